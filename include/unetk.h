@@ -1,0 +1,171 @@
+/*
+ * unetk — C ABI of the B200 (sm_100a) kernel library behind the U-Net / AnomalyUNet hot path of
+ * ukeSJTU/tiaozhanbei-unet.
+ *
+ * The reference has no FFI / plugin interface of its own: its hot path is the Python import
+ * surface of src/model.py and src/train_utils.py, and below that stock PyTorch operators.  This
+ * header is the operator-level boundary the drop-in Python modules (tiaozhanbei-unet_b200/model.py,
+ * train_utils.py) bind with ctypes; every entry point names the reference operator it replaces
+ * (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  All pointers are BORROWED device pointers (the
+ *    library never allocates or frees device memory); `stream` is a cudaStream_t passed as void*.
+ *  - Asynchronous on `stream`.  Returns 0 on success, a negative UNETK_ERR_* code otherwise; the
+ *    message is available from unetk_last_error() (thread-local).
+ *  - Built for sm_100a only.  Any other device -> UNETK_ERR_ARCH.  There is no CPU or library
+ *    fallback.
+ *  - Activations: NHWC bf16, channel count a multiple of 64 (8 for the pure element-wise ops).
+ *    Images / losses / network outputs: NCHW fp32, as the reference's callers hand them over.
+ *  - Packed weights (bf16), produced by unetk_permute_batched from the fp32 reference layouts:
+ *      conv3x3 forward  Wf[co][tap][ci]      = W[co][ci][ky][kx],           tap = 3*ky + kx
+ *      conv3x3 dgrad    Wd[ci][tap][co]      = W[co][ci][2-ky][2-kx]        (taps flipped)
+ *      convT   forward  Wt[tap*Cout+co][ci]  = W[ci][co][ky][kx],           tap = 2*ky + kx
+ *      convT   dgrad    Wtd[ci][tap*Cout+co] = W[ci][co][ky][kx]
+ *    Weight gradients come back fp32 as dW[co][tap][ci] and are re-laid-out to the reference
+ *    layout with unetk_permute_batched.
+ */
+#ifndef UNETK_H_
+#define UNETK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef UNETK_OK
+#define UNETK_OK 0
+#define UNETK_ERR_ARG (-1)       /* bad shape / alignment / null pointer */
+#define UNETK_ERR_ARCH (-2)      /* device is not sm_100 */
+#define UNETK_ERR_CUDA (-3)      /* a CUDA runtime / driver call failed */
+#define UNETK_ERR_WORKSPACE (-4) /* workspace too small */
+#endif
+
+#define UNETK_VERSION 100 /* 0.1.0 */
+
+int unetk_version(void);
+const char* unetk_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, UNETK_ERR_ARCH otherwise. */
+int unetk_check_device(void);
+/* cudaMemsetAsync on the caller's stream (zeroing statistics / gradient accumulators). */
+int unetk_memset_zero(void* ptr, size_t bytes, void* stream);
+
+/* ---- nn.Conv2d(Cin, Cout, 3, padding=1, bias=False): src/model.py:14,17 -------------------- */
+/* y[n,h,w,co] = sum_{tap,ci} cat(src1,src2)[n,h+dy,w+dx,ci] * Wf[co][tap][ci]   (tcgen05 implicit
+ * GEMM).  src2/c2 fold torch.cat([x2, x1], dim=1) of src/model.py:65 into the K loop (c2 = 0: none).
+ * stats != NULL: adds per-channel sum / sum of squares of the fp32 accumulators into stats[2][Cout]
+ * (training BatchNorm, src/model.py:15,18).  scale/shift != NULL: y = relu?(acc*scale+shift)
+ * (eval-mode BatchNorm + ReLU folded in).  stats and scale are mutually exclusive. */
+int unetk_conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wf, void* y,
+                      float* stats, const float* scale, const float* shift, int relu, int n, int h,
+                      int w, int cout, void* stream);
+/* autograd of the above w.r.t. its input: dx = conv(dy, flipped W^T).  Columns [0,c1) go to dx1,
+ * [c1,c1+c2) to dx2 (the two concat sources); accK != 0 accumulates into dxK (skip connections
+ * receive several gradients).  stats != NULL: per-column sums of dx (bias gradient of the
+ * ConvTranspose2d that produced src2). */
+int unetk_conv3x3_dgrad(const void* dy, int cout, const void* wd, void* dx1, int c1, int acc1,
+                        void* dx2, int c2, int acc2, float* stats, int n, int h, int w,
+                        void* stream);
+/* autograd w.r.t. the weight: dw[co][tap][ci] += sum_pix dy * x  (split-K, fp32 atomics; the
+ * caller zeroes dw). */
+int unetk_conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2,
+                        float* dw, int n, int h, int w, int cout, void* stream);
+
+/* First encoder conv, Conv2d(n_channels<=4, 64, 3, padding=1, bias=False) on the caller's NCHW
+ * fp32 image (src/model.py:86 / :168 -> :14); w is the reference OIHW fp32 weight; dw is written
+ * in OIHW directly. */
+int unetk_first_conv_fwd(const float* x, const float* w, void* y, float* stats, int n, int cin,
+                         int h, int w_, int cout, void* stream);
+int unetk_first_conv_wgrad(const float* x, const void* dy, float* dw, int n, int cin, int h, int w_,
+                           int cout, void* stream);
+
+/* ---- nn.ConvTranspose2d(Cin, Cin/2, kernel_size=2, stride=2): src/model.py:51 -------------- */
+/* up[n,2h+ky,2w+kx,co] = bias[co] + sum_ci a[n,h,w,ci] * W[ci][co][ky][kx]  (GEMM + pixel-shuffle
+ * store); n,h,w describe the INPUT grid. */
+int unetk_convt2x2_fwd(const void* a, int cin, const void* wt, const float* bias, void* up, int n,
+                       int h, int w, int cout, void* stream);
+int unetk_convt2x2_dgrad(const void* dup, int cout, const void* wtd, void* da, int cin, int acc,
+                         int n, int h, int w, void* stream);
+/* dw[co][tap][ci] += sum_pix dup[2*pix+tap, co] * a[pix, ci] (caller zeroes dw). */
+int unetk_convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw, int n, int h,
+                         int w, void* stream);
+
+/* ---- nn.BatchNorm2d + nn.ReLU(inplace=True): src/model.py:15-16,18-19 ---------------------- */
+/* Training: batch statistics -> scale = gamma*invstd, shift = beta - mean*scale; updates
+ * running_mean / running_var (momentum, unbiased variance) and num_batches_tracked (int64). */
+int unetk_bn_finalize(const float* stats, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* scale, float* shift, float* mean, float* invstd, int c, double count,
+                      float eps, float momentum, void* stream);
+/* Eval: scale/shift from the running statistics. */
+int unetk_bn_fold(const float* gamma, const float* beta, const float* running_mean,
+                  const float* running_var, float* scale, float* shift, int c, float eps,
+                  void* stream);
+/* a = relu(y*scale + shift) */
+int unetk_bnrelu_apply(const void* y, const float* scale, const float* shift, void* a, int64_t npix,
+                       int c, void* stream);
+/* ---- nn.MaxPool2d(2): src/model.py:32, fused with the BatchNorm+ReLU that feeds it --------- */
+/* apply != 0: a = relu(y*scale+shift) is written too.  pooled = max over 2x2, idx (uint8 per
+ * element, may be NULL) = position 0..3 of the first maximum. */
+int unetk_bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
+                      void* idx, int n, int h, int w, int c, int apply, void* stream);
+int unetk_maxpool_bwd(const void* dpooled, const void* idx, void* da, int n, int h, int w, int c,
+                      int accumulate, void* stream);
+/* BatchNorm+ReLU backward in two passes: sums[2][C] (caller zeroes) then dy, dgamma, dbeta. */
+int unetk_bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, float* sums, int64_t npix, int c,
+                        void* stream);
+int unetk_bn_bwd_apply(const void* da, const void* y, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, const float* sums, void* dy,
+                       float* dgamma, float* dbeta, int64_t npix, int c, void* stream);
+
+/* ---- OutConv = nn.Conv2d(64, n_out, 1) (+ torch.sigmoid): src/model.py:69-75,201,208 ------- */
+int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, int n, int h, int w_,
+                   int c, int n_out, int sigmoid, void* stream);
+int unetk_head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da,
+                   float* dw, float* db, int n, int h, int w_, int c, int n_out, int sigmoid,
+                   void* stream);
+
+/* ---- CombinedLoss.forward / focal_loss: src/train_utils.py:10-44 --------------------------- */
+/* out3 = {total, recon, seg}; d_recon / d_amap (may be NULL) = gradient of `total`. */
+size_t unetk_combined_loss_workspace_bytes(void);
+int unetk_combined_loss(const float* recon, const float* amap, const float* image,
+                        const float* mask, float* d_recon, float* d_amap, float* out3, void* work,
+                        size_t work_bytes, int64_t n_recon, int64_t n_seg, float recon_weight,
+                        float seg_weight, float focal_alpha, float focal_gamma, void* stream);
+int unetk_scale_by_scalar(float* y, const float* scalar, int64_t n, void* stream);
+
+/* ---- SSIMLoss: src/train_utils.py:47-104 --------------------------------------------------- */
+/* sums[n] = per-image sum of the SSIM map; maps (may be NULL; 5 planes of N*C*H*W floats, 3 if
+ * need2 == 0) hold the derivative planes consumed by unetk_ssim_bwd. */
+int unetk_ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int n, int c,
+                   int h, int w, int window_size, int need2, void* stream);
+int unetk_ssim_bwd(const float* img1, const float* img2, const float* maps, const float* gout,
+                   float* grad, int n, int c, int h, int w, int window_size, int which,
+                   int per_image, void* stream);
+
+/* ---- compute_anomaly_score: src/utils.py:205-215 (method 0 = 'mse'/'ssim', 1 = 'l1') ------- */
+int unetk_anomaly_score(const float* recon, const float* orig, float* out, int n, int c, int h,
+                        int w, int method, void* stream);
+
+/* ---- get_optimizer -> torch.optim.{Adam,AdamW,SGD}: src/train_utils.py:263-272 ------------- */
+/* mode 0 Adam (L2 decay in the gradient), 1 AdamW, 2 SGD+momentum (beta1 = momentum, v unused). */
+int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                    int mode, void* stream);
+
+/* ---- layout plumbing ------------------------------------------------------------------------ */
+/* One launch over a table of 64-byte descriptors (see tiaozhanbei-unet_b200/packing.py):
+ * out[d0][d1][d2] = scale * in[i0*s0 + f(i1)*s1 + i2*s2]; out is bf16 (out_bf16 != 0) or fp32. */
+int unetk_permute_batched(const void* descs, int n_desc, int n_chunks, const float* in, void* out,
+                          int out_bf16, float scale, void* stream);
+int unetk_permute_chunk_elems(void);
+int unetk_nchw_to_nhwc(const float* in, void* out, int n, int c, int h, int w, void* stream);
+int unetk_nhwc_to_nchw(const void* in, float* out, int n, int c, int h, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETK_H_ */

@@ -1,0 +1,154 @@
+// extern "C" surface declared in include/unetk.h; forwards 1:1 to the C++ launchers.
+#include "../../include/unetk.h"
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace unetk {
+const char* last_error();
+}
+
+#define S(stream) static_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int unetk_version(void) { return UNETK_VERSION; }
+const char* unetk_last_error(void) { return unetk::last_error(); }
+int unetk_check_device(void) { return unetk::check_device_sm100(); }
+
+int unetk_memset_zero(void* ptr, size_t bytes, void* stream) {
+  if (ptr == nullptr && bytes != 0) {
+    unetk::set_last_error("memset_zero: null pointer");
+    return UNETK_ERR_ARG;
+  }
+  cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, S(stream));
+  if (e != cudaSuccess) {
+    unetk::set_last_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    return UNETK_ERR_CUDA;
+  }
+  return UNETK_OK;
+}
+
+int unetk_conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wf, void* y,
+                      float* stats, const float* scale, const float* shift, int relu, int n, int h,
+                      int w, int cout, void* stream) {
+  return unetk::conv3x3_fwd(src1, c1, src2, c2, wf, y, stats, scale, shift, relu, n, h, w, cout, S(stream));
+}
+int unetk_conv3x3_dgrad(const void* dy, int cout, const void* wd, void* dx1, int c1, int acc1,
+                        void* dx2, int c2, int acc2, float* stats, int n, int h, int w,
+                        void* stream) {
+  return unetk::conv3x3_dgrad(dy, cout, wd, dx1, c1, acc1, dx2, c2, acc2, stats, n, h, w, S(stream));
+}
+int unetk_conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2,
+                        float* dw, int n, int h, int w, int cout, void* stream) {
+  return unetk::conv3x3_wgrad(dy, src1, c1, src2, c2, dw, n, h, w, cout, S(stream));
+}
+int unetk_first_conv_fwd(const float* x, const float* w, void* y, float* stats, int n, int cin,
+                         int h, int w_, int cout, void* stream) {
+  return unetk::first_conv_fwd(x, w, y, stats, n, cin, h, w_, cout, S(stream));
+}
+int unetk_first_conv_wgrad(const float* x, const void* dy, float* dw, int n, int cin, int h, int w_,
+                           int cout, void* stream) {
+  return unetk::first_conv_wgrad(x, dy, dw, n, cin, h, w_, cout, S(stream));
+}
+int unetk_convt2x2_fwd(const void* a, int cin, const void* wt, const float* bias, void* up, int n,
+                       int h, int w, int cout, void* stream) {
+  return unetk::convt2x2_fwd(a, cin, wt, bias, up, n, h, w, cout, S(stream));
+}
+int unetk_convt2x2_dgrad(const void* dup, int cout, const void* wtd, void* da, int cin, int acc,
+                         int n, int h, int w, void* stream) {
+  return unetk::convt2x2_dgrad(dup, cout, wtd, da, cin, acc, n, h, w, S(stream));
+}
+int unetk_convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw, int n, int h,
+                         int w, void* stream) {
+  return unetk::convt2x2_wgrad(a, cin, dup, cout, dw, n, h, w, S(stream));
+}
+int unetk_bn_finalize(const float* stats, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* scale, float* shift, float* mean, float* invstd, int c, double count,
+                      float eps, float momentum, void* stream) {
+  return unetk::bn_finalize(stats, gamma, beta, running_mean, running_var,
+                            reinterpret_cast<long long*>(num_batches_tracked), scale, shift, mean, invstd, c, count,
+                            eps, momentum, S(stream));
+}
+int unetk_bn_fold(const float* gamma, const float* beta, const float* running_mean,
+                  const float* running_var, float* scale, float* shift, int c, float eps,
+                  void* stream) {
+  return unetk::bn_fold(gamma, beta, running_mean, running_var, scale, shift, c, eps, S(stream));
+}
+int unetk_bnrelu_apply(const void* y, const float* scale, const float* shift, void* a, int64_t npix,
+                       int c, void* stream) {
+  return unetk::bnrelu_apply(y, scale, shift, a, static_cast<long>(npix), c, S(stream));
+}
+int unetk_bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
+                      void* idx, int n, int h, int w, int c, int apply, void* stream) {
+  return unetk::bnrelu_pool(y, scale, shift, a, pooled, idx, n, h, w, c, apply, S(stream));
+}
+int unetk_maxpool_bwd(const void* dpooled, const void* idx, void* da, int n, int h, int w, int c,
+                      int accumulate, void* stream) {
+  return unetk::maxpool_bwd(dpooled, idx, da, n, h, w, c, accumulate, S(stream));
+}
+int unetk_bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
+                        const float* mean, const float* invstd, float* sums, int64_t npix, int c,
+                        void* stream) {
+  return unetk::bn_bwd_reduce(da, y, scale, shift, mean, invstd, sums, static_cast<long>(npix), c, S(stream));
+}
+int unetk_bn_bwd_apply(const void* da, const void* y, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, const float* sums, void* dy,
+                       float* dgamma, float* dbeta, int64_t npix, int c, void* stream) {
+  return unetk::bn_bwd_apply(da, y, scale, shift, mean, invstd, sums, dy, dgamma, dbeta, static_cast<long>(npix), c,
+                             S(stream));
+}
+int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, int n, int h, int w_,
+                   int c, int n_out, int sigmoid, void* stream) {
+  return unetk::head_fwd(a, w, b, out, n, h, w_, c, n_out, sigmoid, S(stream));
+}
+int unetk_head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da,
+                   float* dw, float* db, int n, int h, int w_, int c, int n_out, int sigmoid,
+                   void* stream) {
+  return unetk::head_bwd(a, w, dout, out, da, dw, db, n, h, w_, c, n_out, sigmoid, S(stream));
+}
+size_t unetk_combined_loss_workspace_bytes(void) { return unetk::combined_loss_workspace_bytes(); }
+int unetk_combined_loss(const float* recon, const float* amap, const float* image,
+                        const float* mask, float* d_recon, float* d_amap, float* out3, void* work,
+                        size_t work_bytes, int64_t n_recon, int64_t n_seg, float recon_weight,
+                        float seg_weight, float focal_alpha, float focal_gamma, void* stream) {
+  return unetk::combined_loss(recon, amap, image, mask, d_recon, d_amap, out3, work, work_bytes,
+                              static_cast<long>(n_recon), static_cast<long>(n_seg), recon_weight, seg_weight, focal_alpha,
+                              focal_gamma, S(stream));
+}
+int unetk_scale_by_scalar(float* y, const float* scalar, int64_t n, void* stream) {
+  return unetk::scale_by_scalar(y, scalar, static_cast<long>(n), S(stream));
+}
+int unetk_ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int n, int c,
+                   int h, int w, int window_size, int need2, void* stream) {
+  return unetk::ssim_fwd(img1, img2, sums, maps, n, c, h, w, window_size, need2, S(stream));
+}
+int unetk_ssim_bwd(const float* img1, const float* img2, const float* maps, const float* gout,
+                   float* grad, int n, int c, int h, int w, int window_size, int which,
+                   int per_image, void* stream) {
+  return unetk::ssim_bwd(img1, img2, maps, gout, grad, n, c, h, w, window_size, which, per_image, S(stream));
+}
+int unetk_anomaly_score(const float* recon, const float* orig, float* out, int n, int c, int h,
+                        int w, int method, void* stream) {
+  return unetk::anomaly_score(recon, orig, out, n, c, h, w, method, S(stream));
+}
+int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                    int mode, void* stream) {
+  return unetk::adam_step(p, g, m, v, static_cast<long>(n), lr, beta1, beta2, eps, weight_decay,
+                          static_cast<long>(step), grad_scale, mode, S(stream));
+}
+int unetk_permute_batched(const void* descs, int n_desc, int n_chunks, const float* in, void* out,
+                          int out_bf16, float scale, void* stream) {
+  return unetk::permute_batched(descs, n_desc, n_chunks, in, out, out_bf16, scale, S(stream));
+}
+int unetk_permute_chunk_elems(void) { return unetk::permute_chunk_elems(); }
+int unetk_nchw_to_nhwc(const float* in, void* out, int n, int c, int h, int w, void* stream) {
+  return unetk::nchw_to_nhwc(in, out, n, c, h, w, S(stream));
+}
+int unetk_nhwc_to_nchw(const void* in, float* out, int n, int c, int h, int w, void* stream) {
+  return unetk::nhwc_to_nchw(in, out, n, c, h, w, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,445 @@
+// Bandwidth-bound kernels around the convolutions (sm_100a): BatchNorm finalize / apply / backward,
+// ReLU, 2x2 max-pool with index save, NCHW<->NHWC layout conversion.
+//
+// Reference operators being replaced: nn.BatchNorm2d + nn.ReLU(inplace=True) at
+// /root/reference/src/model.py:15-16,18-19 and nn.MaxPool2d(2) at src/model.py:32 (and their
+// autograd).  All tensors are NHWC bf16 with C a multiple of 8; every thread moves 16-byte
+// vectors (8 channels) and keeps its per-channel constants in registers: the grid-stride is a
+// multiple of C/8, so a thread always sees the same 8 channels.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace unetk {
+
+constexpr int kEwThreads = 256;
+
+static inline int ew_grid(long nvec, int cgroups) {
+  // total threads must be a multiple of the channel-group count (<= 256, divides 256 or is a
+  // multiple of it handled by the caller's check)
+  long blocks = (nvec + kEwThreads - 1) / kEwThreads;
+  const long cap = static_cast<long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  // (blocks * 256) % cgroups == 0 must hold: cgroups is a power of two <= 128 in this network, or
+  // otherwise we round blocks up to a multiple of cgroups.
+  if ((blocks * kEwThreads) % cgroups != 0) blocks = ((blocks + cgroups - 1) / cgroups) * cgroups;
+  return static_cast<int>(blocks);
+}
+
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  return u;
+}
+
+// ----------------------------------------------------------------------------------------------
+// BatchNorm finalize: batch statistics -> (scale, shift, mean, invstd), running-stat update.
+// torch semantics (nn.BatchNorm2d, training): biased variance for normalisation, unbiased for
+// running_var, momentum 0.1, num_batches_tracked += 1.
+// ----------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean,
+                                   float* running_var, long long* num_batches_tracked,
+                                   float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   int C, float count, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+  if (c >= C) return;
+  const float mean = stats[c] / count;
+  float var = stats[C + c] / count - mean * mean;
+  var = fmaxf(var, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+  if (running_mean != nullptr) {
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+// Eval mode: fold running statistics into (scale, shift).
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ running_mean,
+                               const float* __restrict__ running_var, float* __restrict__ scale,
+                               float* __restrict__ shift, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - running_mean[c] * sc;
+}
+
+// ----------------------------------------------------------------------------------------------
+// a = relu(y * scale + shift)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+bnrelu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
+                    const float* __restrict__ shift, uint4* __restrict__ a, long nvec, int cgroups) {
+  const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
+  const int cg = static_cast<int>(tid % cgroups);
+  float sc[8], sh[8];
+  load8(scale + cg * 8, sc);
+  load8(shift + cg * 8, sh);
+  for (long i = tid; i < nvec; i += nthreads) {
+    float v[8];
+    unpack8(ldg_nc_v4(y + i), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+    a[i] = pack8(v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// a = relu(y * scale + shift) (optional), pooled = maxpool2x2(a), idx = argmax position (0..3,
+// scan order (0,0),(0,1),(1,0),(1,1), first maximum wins like ATen's max_pool2d_with_indices).
+// apply == 0: the input is already activated (eval path) and `a` is not written.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+bnrelu_pool_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
+                   const float* __restrict__ shift, uint4* __restrict__ a,
+                   uint4* __restrict__ pooled, uint2* __restrict__ idx, int N, int H, int W,
+                   int cgroups, int apply) {
+  const int Hp = H / 2, Wp = W / 2;
+  const long nvec = static_cast<long>(N) * Hp * Wp * cgroups;
+  const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
+  const int cg = static_cast<int>(tid % cgroups);
+  float sc[8], sh[8];
+  if (apply) {
+    load8(scale + cg * 8, sc);
+    load8(shift + cg * 8, sh);
+  }
+  for (long i = tid; i < nvec; i += nthreads) {
+    long pp = i / cgroups;
+    const int px = static_cast<int>(pp % Wp);
+    pp /= Wp;
+    const int py = static_cast<int>(pp % Hp);
+    const int n = static_cast<int>(pp / Hp);
+    const long base = ((static_cast<long>(n) * H + 2 * py) * W + 2 * px) * cgroups + cg;
+    const long offs[4] = {base, base + cgroups, base + static_cast<long>(W) * cgroups,
+                          base + static_cast<long>(W) * cgroups + cgroups};
+    float best[8];
+    uint32_t bi[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      unpack8(ldg_nc_v4(y + offs[k]), v);
+      if (apply) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+        a[offs[k]] = pack8(v);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (k == 0 || v[j] > best[j]) {
+          best[j] = v[j];
+          bi[j] = k;
+        }
+      }
+    }
+    pooled[i] = pack8(best);
+    if (idx != nullptr) {
+      uint2 u;
+      u.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      u.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      idx[i] = u;
+    }
+  }
+}
+
+// dA[argmax position] (+)= dP, other positions (+)= 0
+__global__ void __launch_bounds__(kEwThreads)
+maxpool_bwd_kernel(const uint4* __restrict__ dp, const uint2* __restrict__ idx, uint4* da, int N,
+                   int H, int W, int cgroups, int accumulate) {
+  const int Hp = H / 2, Wp = W / 2;
+  const long nvec = static_cast<long>(N) * Hp * Wp * cgroups;
+  const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
+  const int cg = static_cast<int>(tid % cgroups);
+  for (long i = tid; i < nvec; i += nthreads) {
+    long pp = i / cgroups;
+    const int px = static_cast<int>(pp % Wp);
+    pp /= Wp;
+    const int py = static_cast<int>(pp % Hp);
+    const int n = static_cast<int>(pp / Hp);
+    const long base = ((static_cast<long>(n) * H + 2 * py) * W + 2 * px) * cgroups + cg;
+    const long offs[4] = {base, base + cgroups, base + static_cast<long>(W) * cgroups,
+                          base + static_cast<long>(W) * cgroups + cgroups};
+    float g[8];
+    unpack8(ldg_nc_v4(dp + i), g);
+    const uint2 u = idx[i];
+    uint32_t bi[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bi[j] = (u.x >> (8 * j)) & 0xff;
+      bi[4 + j] = (u.y >> (8 * j)) & 0xff;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      if (accumulate) {
+        unpack8(da[offs[k]], v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += (bi[j] == static_cast<uint32_t>(k)) ? g[j] : 0.f;
+      da[offs[k]] = pack8(v);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// BatchNorm + ReLU backward, pass 1: per-channel  s1 = sum g,  s2 = sum g * xhat
+//   with g = dA * [y*scale + shift > 0],  xhat = (y - mean) * invstd.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                     float* __restrict__ sums, long nvec, int cgroups) {
+  extern __shared__ float sacc[];  // [2][C]
+  const int C = cgroups * 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
+  const int cg = static_cast<int>(tid % cgroups);
+  float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+  load8(scale + cg * 8, sc);
+  load8(shift + cg * 8, sh);
+  load8(mean + cg * 8, mu);
+  load8(invstd + cg * 8, is);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (long i = tid; i < nvec; i += nthreads) {
+    float g[8], v[8];
+    unpack8(ldg_nc_v4(da + i), g);
+    unpack8(ldg_nc_v4(y + i), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gg = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+      s1[j] += gg;
+      s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sacc[cg * 8 + j], s1[j]);
+    atomicAdd(&sacc[C + cg * 8 + j], s2[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, sacc[i]);
+}
+
+// pass 2: dY = scale * (g - s1/M - xhat * s2/M);  block 0 also writes dgamma = s2, dbeta = s1.
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ sums, uint4* __restrict__ dy,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, long nvec, int cgroups,
+                    float inv_count) {
+  const int C = cgroups * 8;
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      dbeta[i] = sums[i];
+      dgamma[i] = sums[C + i];
+    }
+  }
+  const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
+  const int cg = static_cast<int>(tid % cgroups);
+  float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+  load8(scale + cg * 8, sc);
+  load8(shift + cg * 8, sh);
+  load8(mean + cg * 8, mu);
+  load8(invstd + cg * 8, is);
+  load8(sums + cg * 8, m1);
+  load8(sums + C + cg * 8, m2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m1[j] *= inv_count;
+    m2[j] *= inv_count;
+  }
+  for (long i = tid; i < nvec; i += nthreads) {
+    float g[8], v[8];
+    unpack8(ldg_nc_v4(da + i), g);
+    unpack8(ldg_nc_v4(y + i), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gg = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+      const float xh = (v[j] - mu[j]) * is[j];
+      v[j] = sc[j] * (gg - m1[j] - xh * m2[j]);
+    }
+    dy[i] = pack8(v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// layout conversion (for standalone blocks and tests): NCHW fp32 <-> NHWC bf16, 32x32 smem tiles
+// ----------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                    int C, long HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long p0 = static_cast<long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const long p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && p < HW) ? in[(static_cast<long>(n) * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long p = p0 + r;
+    const int c = c0 + threadIdx.x;
+    if (c < C && p < HW) out[(static_cast<long>(n) * HW + p) * C + c] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                    int C, long HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long p0 = static_cast<long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long p = p0 + r;
+    const int c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(in[(static_cast<long>(n) * HW + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const long p = p0 + threadIdx.x;
+    if (c < C && p < HW) out[(static_cast<long>(n) * C + c) * HW + p] = tile[threadIdx.x][r];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host launchers
+// ----------------------------------------------------------------------------------------------
+static int check_c(int C, const char* who) {
+  UNETK_CHECK_ARG(C > 0 && C % 8 == 0, "%s: channel count must be a multiple of 8 (got %d)", who, C);
+  return UNETK_OK;
+}
+
+int bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, long long* nbt, float* scale, float* shift, float* mean,
+                float* invstd, int C, double count, float eps, float momentum, cudaStream_t s) {
+  UNETK_CHECK_ARG(stats && gamma && beta && scale && shift && mean && invstd, "bn_finalize: null pointer");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean,
+                                                     invstd, C, static_cast<float>(count), eps, momentum);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float* scale,
+            float* shift, int C, float eps, cudaStream_t s) {
+  UNETK_CHECK_ARG(gamma && beta && rm && rv && scale && shift, "bn_fold: null pointer");
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, scale, shift, C, eps);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int bnrelu_apply(const void* y, const float* scale, const float* shift, void* a, long npix, int C,
+                 cudaStream_t s) {
+  UNETK_CHECK_ARG(y && scale && shift && a, "bnrelu_apply: null pointer");
+  if (int e = check_c(C, "bnrelu_apply")) return e;
+  const long nvec = npix * (C / 8);
+  bnrelu_apply_kernel<<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(static_cast<const uint4*>(y), scale, shift,
+                                                                  static_cast<uint4*>(a), nvec, C / 8);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
+                void* idx, int N, int H, int W, int C, int apply, cudaStream_t s) {
+  UNETK_CHECK_ARG(y && pooled, "bnrelu_pool: null pointer");
+  UNETK_CHECK_ARG(!apply || (scale && shift && a), "bnrelu_pool: apply needs scale, shift and a");
+  UNETK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "bnrelu_pool: H and W must be even (got %dx%d)", H, W);
+  if (int e = check_c(C, "bnrelu_pool")) return e;
+  const long nvec = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
+  bnrelu_pool_kernel<<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(static_cast<const uint4*>(y), scale, shift,
+                                                                 static_cast<uint4*>(a), static_cast<uint4*>(pooled),
+                                                                 static_cast<uint2*>(idx), N, H, W, C / 8, apply);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, int C, int accumulate,
+                cudaStream_t s) {
+  UNETK_CHECK_ARG(dp && idx && da, "maxpool_bwd: null pointer");
+  UNETK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "maxpool_bwd: H and W must be even");
+  if (int e = check_c(C, "maxpool_bwd")) return e;
+  const long nvec = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool_bwd_kernel<<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(static_cast<const uint4*>(dp), static_cast<const uint2*>(idx),
+                                                                 static_cast<uint4*>(da), N, H, W, C / 8, accumulate);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
+                  const float* mean, const float* invstd, float* sums, long npix, int C,
+                  cudaStream_t s) {
+  UNETK_CHECK_ARG(da && y && scale && shift && mean && invstd && sums, "bn_bwd_reduce: null pointer");
+  if (int e = check_c(C, "bn_bwd_reduce")) return e;
+  const long nvec = npix * (C / 8);
+  int grid = ew_grid(nvec, C / 8);
+  const int cap = num_sms() * 4;
+  if (grid > cap) grid = ((cap * kEwThreads) % (C / 8) == 0) ? cap : grid;
+  bn_bwd_reduce_kernel<<<grid, kEwThreads, 2 * C * sizeof(float), s>>>(static_cast<const uint4*>(da), static_cast<const uint4*>(y),
+                                                                      scale, shift, mean, invstd, sums, nvec, C / 8);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int bn_bwd_apply(const void* da, const void* y, const float* scale, const float* shift,
+                 const float* mean, const float* invstd, const float* sums, void* dy, float* dgamma,
+                 float* dbeta, long npix, int C, cudaStream_t s) {
+  UNETK_CHECK_ARG(da && y && scale && shift && mean && invstd && sums && dy && dgamma && dbeta, "bn_bwd_apply: null pointer");
+  if (int e = check_c(C, "bn_bwd_apply")) return e;
+  const long nvec = npix * (C / 8);
+  bn_bwd_apply_kernel<<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(
+      static_cast<const uint4*>(da), static_cast<const uint4*>(y), scale, shift, mean, invstd, sums,
+      static_cast<uint4*>(dy), dgamma, dbeta, nvec, C / 8, 1.0f / static_cast<float>(npix));
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, cudaStream_t s) {
+  UNETK_CHECK_ARG(in && out, "nchw_to_nhwc: null pointer");
+  const long HW = static_cast<long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, s>>>(in, static_cast<__nv_bfloat16*>(out), C, HW);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int nhwc_to_nchw(const void* in, float* out, int N, int C, int H, int W, cudaStream_t s) {
+  UNETK_CHECK_ARG(in && out, "nhwc_to_nchw: null pointer");
+  const long HW = static_cast<long>(H) * W;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(in), out, C, HW);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+}  // namespace unetk

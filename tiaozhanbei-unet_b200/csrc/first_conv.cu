@@ -1,0 +1,189 @@
+// First layer of the encoder: Conv2d(n_channels <= 4 -> 64, 3x3, pad 1, bias=False) reading the
+// caller's NCHW fp32 image directly (/root/reference/src/model.py:86,168 `inc` = DoubleConv(3, 64),
+// first conv at src/model.py:14).  K = 9 * Cin = 27 is far too short for a tcgen05 tile and the
+// layer is bound by its 128 B/pixel bf16 output, so it is a CUDA-core direct convolution:
+// one thread per output pixel, 64 fp32 accumulators, weights broadcast from shared memory.
+// Forward also emits the BatchNorm statistics (sum, sum of squares per output channel).
+// wgrad: dW[co, ci, tap] = sum_pix dY[pix, co] * X[pix + tap, ci], staged through shared memory.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace unetk {
+
+constexpr int kFcCout = 64;
+constexpr int kFcMaxK = 36;  // 9 taps x up to 4 input channels
+
+__global__ void __launch_bounds__(128)
+first_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                      uint4* __restrict__ y, float* __restrict__ stats, int N, int Cin, int H,
+                      int W) {
+  __shared__ __align__(16) float sw[kFcMaxK][kFcCout];  // [tap * Cin + ci][co]
+  __shared__ float sstat[2][kFcCout];
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < K * kFcCout; i += blockDim.x) {
+    const int k = i / kFcCout, co = i - k * kFcCout;
+    const int tap = k / Cin, ci = k - tap * Cin;
+    sw[k][co] = w[(co * Cin + ci) * 9 + tap];  // OIHW
+  }
+  if (threadIdx.x < kFcCout) sstat[0][threadIdx.x] = sstat[1][threadIdx.x] = 0.f;
+  __syncthreads();
+  const long hw = static_cast<long>(H) * W;
+  const long total = hw * N;
+  const long nblocks = (total + blockDim.x - 1) / blockDim.x;
+  for (long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const long p = blk * blockDim.x + threadIdx.x;
+    const bool valid = p < total;
+    float acc[kFcCout];
+#pragma unroll
+    for (int j = 0; j < kFcCout; ++j) acc[j] = 0.f;
+    if (valid) {
+      const long n = p / hw;
+      const int r = static_cast<int>(p - n * hw);
+      const int yy = r / W, xx = r - yy * W;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+        if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float v = __ldg(x + (n * Cin + ci) * hw + static_cast<long>(sy) * W + sx);
+          const float4* wr = reinterpret_cast<const float4*>(sw[tap * Cin + ci]);
+#pragma unroll
+          for (int j = 0; j < kFcCout / 4; ++j) {
+            const float4 ww = wr[j];
+            acc[4 * j + 0] = fmaf(v, ww.x, acc[4 * j + 0]);
+            acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]);
+            acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 u;
+        u.x = pack_bf16x2(acc[8 * g + 0], acc[8 * g + 1]);
+        u.y = pack_bf16x2(acc[8 * g + 2], acc[8 * g + 3]);
+        u.z = pack_bf16x2(acc[8 * g + 4], acc[8 * g + 5]);
+        u.w = pack_bf16x2(acc[8 * g + 6], acc[8 * g + 7]);
+        y[p * 8 + g] = u;
+      }
+    }
+    if (stats != nullptr) {
+      const int lane = threadIdx.x & 31;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float s[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          s[j] = acc[half * 32 + j];
+          s2[j] = s[j] * s[j];
+        }
+        const float cs = warp_colsum32(s);
+        const float cs2 = warp_colsum32(s2);
+        atomicAdd(&sstat[0][half * 32 + lane], cs);
+        atomicAdd(&sstat[1][half * 32 + lane], cs2);
+      }
+    }
+  }
+  if (stats != nullptr) {
+    __syncthreads();
+    if (threadIdx.x < kFcCout) {
+      atomicAdd(stats + threadIdx.x, sstat[0][threadIdx.x]);
+      atomicAdd(stats + kFcCout + threadIdx.x, sstat[1][threadIdx.x]);
+    }
+  }
+}
+
+// wgrad: block = 256 threads, works on chunks of 96 pixels.  Thread t owns output channel
+// co = t % 64 and the k-range kq = t / 64 (k = tap * Cin + ci split in four groups of 9).
+constexpr int kFwPix = 96;
+
+__global__ void __launch_bounds__(256)
+first_conv_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ dy,
+                        float* __restrict__ dw, int N, int Cin, int H, int W) {
+  __shared__ float sdy[kFwPix][kFcCout + 1];
+  __shared__ float sx[kFwPix][kFcMaxK + 1];
+  const int K = 9 * Cin;
+  const int co = threadIdx.x & 63, kq = threadIdx.x >> 6;
+  const int k0 = kq * 9;
+  float acc[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+  const long hw = static_cast<long>(H) * W;
+  const long total = hw * N;
+  const long nchunks = (total + kFwPix - 1) / kFwPix;
+  for (long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long p0 = ch * kFwPix;
+    __syncthreads();
+    // stage dY (bf16 -> fp32): kFwPix pixels x 8 vectors
+    for (int i = threadIdx.x; i < kFwPix * 8; i += blockDim.x) {
+      const int pp = i >> 3, g = i & 7;
+      const long p = p0 + pp;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (p < total) u = ldg_nc_v4(dy + p * 8 + g);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      float* row = &sdy[pp][g * 8];
+      row[0] = a.x; row[1] = a.y; row[2] = b.x; row[3] = b.y; row[4] = c.x; row[5] = c.y; row[6] = d.x; row[7] = d.y;
+    }
+    // stage the im2col patch of X
+    for (int i = threadIdx.x; i < kFwPix * K; i += blockDim.x) {
+      const int pp = i % kFwPix, k = i / kFwPix;
+      const long p = p0 + pp;
+      float v = 0.f;
+      if (p < total) {
+        const long n = p / hw;
+        const int r = static_cast<int>(p - n * hw);
+        const int yy = r / W, xx = r - yy * W;
+        const int tap = k / Cin, ci = k - tap * Cin;
+        const int sy = yy + tap / 3 - 1, sxx = xx + tap % 3 - 1;
+        if (sy >= 0 && sy < H && sxx >= 0 && sxx < W) v = __ldg(x + (n * Cin + ci) * hw + static_cast<long>(sy) * W + sxx);
+      }
+      sx[pp][k] = v;
+    }
+    __syncthreads();
+    if (k0 < K) {
+      for (int pp = 0; pp < kFwPix; ++pp) {
+        const float g = sdy[pp][co];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) acc[j] = fmaf(g, sx[pp][k0 + j], acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int k = k0 + j;
+    if (k < K) {
+      const int tap = k / Cin, ci = k - tap * Cin;
+      atomicAdd(dw + (co * Cin + ci) * 9 + tap, acc[j]);  // OIHW
+    }
+  }
+}
+
+int first_conv_fwd(const float* x, const float* w, void* y, float* stats, int N, int Cin, int H, int W,
+                   int cout, cudaStream_t s) {
+  UNETK_CHECK_ARG(x && w && y, "first_conv_fwd: null pointer");
+  UNETK_CHECK_ARG(Cin >= 1 && Cin <= 4, "first_conv_fwd: 1..4 input channels supported (got %d)", Cin);
+  UNETK_CHECK_ARG(cout == kFcCout, "first_conv_fwd: 64 output channels required (got %d)", cout);
+  const long total = static_cast<long>(N) * H * W;
+  long blocks = (total + 127) / 128;
+  const long cap = static_cast<long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  first_conv_fwd_kernel<<<static_cast<int>(blocks), 128, 0, s>>>(x, w, static_cast<uint4*>(y), stats, N, Cin, H, W);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int first_conv_wgrad(const float* x, const void* dy, float* dw, int N, int Cin, int H, int W, int cout,
+                     cudaStream_t s) {
+  UNETK_CHECK_ARG(x && dy && dw, "first_conv_wgrad: null pointer");
+  UNETK_CHECK_ARG(Cin >= 1 && Cin <= 4, "first_conv_wgrad: 1..4 input channels supported (got %d)", Cin);
+  UNETK_CHECK_ARG(cout == kFcCout, "first_conv_wgrad: 64 output channels required (got %d)", cout);
+  const long total = static_cast<long>(N) * H * W;
+  long blocks = (total + kFwPix - 1) / kFwPix;
+  const long cap = static_cast<long>(num_sms()) * 2;
+  if (blocks > cap) blocks = cap;
+  UNETK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * cout * Cin * 9, s));
+  first_conv_wgrad_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, static_cast<const uint4*>(dy), dw, N, Cin, H, W);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+}  // namespace unetk

@@ -1,0 +1,481 @@
+// Implicit-GEMM convolution on tcgen05 / TMEM fed by TMA (sm_100a).
+//
+// One kernel covers every K-major contraction of the U-Net hot path:
+//   conv3x3 forward   D[pix, co]  = sum_{tap, ci} A[pix + tap, ci]   * Wf[co, tap, ci]
+//   conv3x3 dgrad     D[pix, ci]  = sum_{tap, co} dY[pix + tap, co]  * Wd[ci, tap, co]   (taps pre-flipped)
+//   convT2x2 forward  D[pix, (tap, co)] = sum_ci A[pix, ci] * Wt[(tap, co), ci]          (pixel-shuffle store)
+//   convT2x2 dgrad    D[pix, ci]  = sum_{tap, co} dUp[2*pix + tap, co] * Wtd[ci, (tap, co)]
+// Reference operators being replaced: nn.Conv2d(3x3, pad 1, bias=False) at
+// /root/reference/src/model.py:14,17 and nn.ConvTranspose2d(k=2, s=2) at src/model.py:51, plus
+// torch.cat([x2, x1], dim=1) at src/model.py:65 (folded into the K loop: two A tensor maps).
+//
+// Layout: activations NHWC bf16; the M tile is a (tn x th x tw) patch of 128 output pixels, loaded
+// per (tap, 64-channel chunk) as one TMA box of 128 rows x 128 B (SWIZZLE_128B) = the canonical
+// K-major UMMA operand.  TMA out-of-bounds zero fill implements the conv zero padding.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2..5 epilogue
+// (TMEM -> registers -> bf16 global, optional per-channel sum / sum-of-squares for BatchNorm,
+// optional per-channel affine + ReLU for eval-mode folded BatchNorm).  Persistent over tiles with
+// a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace unetk {
+
+struct IgemmParams {
+  int n_img, H, W;      // GEMM pixel grid (rows of D)
+  int tw, th, tn;       // pixel tile, tw*th*tn == 128
+  int tiles_x, tiles_y, tiles_n;
+  int n_blocks;         // ceil(Ntot / BN)
+  int Ntot;             // columns of D
+  int num_taps;         // 9 (3x3), 1 (1x1 view), 4 (convT dgrad)
+  int a_mode;           // 0: A box at (c, x+dx, y+dy, n, 0); 1: A box at (c, kx, x, ky, n*H+y)
+  int c1_chunks, c2_chunks;  // 64-channel chunks taken from tmA1 / tmA2
+  int epi_mode;         // 0: NHWC store, 1: convT pixel-shuffle store (+bias)
+  int split;            // columns [0,split) -> out1, [split,Ntot) -> out2
+  __nv_bfloat16* out1;
+  __nv_bfloat16* out2;
+  int ldc1, ldc2;
+  int acc1, acc2;       // 1: read-modify-write (gradient accumulation)
+  float* stats;         // nullable, [2][Ntot]: per-column sum and sum of squares
+  const float* scale;   // nullable per-column affine (eval-mode BatchNorm folded in)
+  const float* shift;
+  int relu;
+  const float* bias;    // epi_mode 1: [cout_t]
+  int cout_t;           // epi_mode 1: channels of the up-sampled tensor
+};
+
+constexpr int kIgemmThreads = 192;
+constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
+
+template <int BN>
+struct IgemmCfg {
+  static constexpr int kStages = (BN == 128) ? 6 : 8;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+             const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+  using Cfg = IgemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* colbuf = reinterpret_cast<float*>(bars + 2 * kStages + 6);  // [2][Ntot] when used
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool use_colbuf = (p.stats != nullptr) || (p.scale != nullptr);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (use_colbuf) {
+    for (int i = threadIdx.x; i < 2 * p.Ntot; i += blockDim.x) {
+      float v = 0.f;
+      if (p.scale != nullptr) v = (i < p.Ntot) ? p.scale[i] : p.shift[i - p.Ntot];
+      colbuf[i] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int total_tiles = tiles_m * p.n_blocks;
+  const int chunks = p.c1_chunks + p.c2_chunks;
+  const int kblocks = p.num_taps * chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nb = t % p.n_blocks;
+        int m = t / p.n_blocks;
+        const int tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int tz = m / p.tiles_y;
+        const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tz * p.tn;
+        const int col0 = nb * BN;
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          int dy = 0, dx = 0;
+          if (p.num_taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          for (int c = 0; c < chunks; ++c) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            const CUtensorMap* mp = (c < p.c1_chunks) ? &tmA1 : &tmA2;
+            const int cc = ((c < p.c1_chunks) ? c : c - p.c1_chunks) * 64;
+            if (p.a_mode == 0) {
+              tma_load_5d(sA + stage * kABytes, mp, &full[stage], cc, x0 + dx, y0 + dy, n0, 0);
+            } else {
+              tma_load_5d(sA + stage * kABytes, mp, &full[stage], cc, tap & 1, x0, tap >> 1,
+                          n0 * p.H + y0);
+            }
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], (tap * chunks + c) * 64,
+                        col0);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + stage * kABytes);
+          const uint32_t b_base = smem_u32(sB + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(a_base + k * 32, 0, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_base + k * 32, 0, 1024);
+            tc_mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty[stage]);
+          if (kb == kblocks - 1) tc_commit(&tfull[as]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rx = row % p.tw;
+    const int ry = (row / p.tw) % p.th;
+    const int rn = row / (p.tw * p.th);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int nb = t % p.n_blocks;
+      int m = t / p.n_blocks;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int tz = m / p.tiles_y;
+      const int x = tx * p.tw + rx, y = ty * p.th + ry, n = tz * p.tn + rn;
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.n_img);
+      const int col0 = nb * BN;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col = col0 + ch * 32;
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + ch * 32, v);
+        tmem_ld_wait();
+        if (col >= p.Ntot) continue;  // warp-uniform
+        if (p.stats != nullptr) {
+          float s[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = valid ? v[j] : 0.f;
+            s[j] = a;
+            s2[j] = a * a;
+          }
+          const float cs = warp_colsum32(s);
+          const float cs2 = warp_colsum32(s2);
+          atomicAdd(&colbuf[col + lane], cs);
+          atomicAdd(&colbuf[p.Ntot + col + lane], cs2);
+        }
+        if (p.scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = fmaf(v[j], colbuf[col + j], colbuf[p.Ntot + col + j]);
+            v[j] = p.relu ? fmaxf(a, 0.f) : a;
+          }
+        }
+        if (!valid) continue;
+        __nv_bfloat16* dst;
+        bool acc;
+        if (p.epi_mode == 0) {
+          const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+          if (col < p.split) {
+            dst = p.out1 + pix * p.ldc1 + col;
+            acc = p.acc1 != 0;
+          } else {
+            dst = p.out2 + pix * p.ldc2 + (col - p.split);
+            acc = p.acc2 != 0;
+          }
+        } else {
+          const int tap = col / p.cout_t;
+          const int co = col - tap * p.cout_t;
+          const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + (2 * y + (tap >> 1))) *
+                                  (2 * p.W) + (2 * x + (tap & 1));
+          dst = p.out1 + opix * p.cout_t + co;
+          acc = false;
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co + j);
+          }
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
+          if (acc) {
+            const uint4 o = d4[g];
+            const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
+            const float2 o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
+            f[0] += o0.x; f[1] += o0.y; f[2] += o1.x; f[3] += o1.y;
+            f[4] += o2.x; f[5] += o2.y; f[6] += o3.x; f[7] += o3.y;
+          }
+          uint4 w;
+          w.x = pack_bf16x2(f[0], f[1]);
+          w.y = pack_bf16x2(f[2], f[3]);
+          w.z = pack_bf16x2(f[4], f[5]);
+          w.w = pack_bf16x2(f[6], f[7]);
+          d4[g] = w;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+    if (p.stats != nullptr) {
+      // all four epilogue warps have finished their smem atomics
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 64;
+      for (int i = et; i < 2 * p.Ntot; i += 128) {
+        const float v = colbuf[i];
+        if (v != 0.f) atomicAdd(p.stats + i, v);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+static int floor_pow2(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+// Pick a (tw, th, tn) patch with tw*th*tn == `pixels` that minimises the padded pixel count.
+void pick_pixel_tile(int n_img, int H, int W, int pixels, int* tw, int* th, int* tn) {
+  long best = -1;
+  for (int w = 1; w <= pixels && w <= 16; w *= 2) {
+    if (w > floor_pow2(W) && w > 1) break;
+    int h = pixels / w;
+    if (h > floor_pow2(H)) h = floor_pow2(H);
+    const int n = pixels / (w * h);
+    const long tiles = static_cast<long>((W + w - 1) / w) * ((H + h - 1) / h) * ((n_img + n - 1) / n);
+    // prefer fewer tiles, then wider rows (longer contiguous runs in NHWC)
+    if (best < 0 || tiles <= best) {
+      best = tiles;
+      *tw = w;
+      *th = h;
+      *tn = n;
+    }
+  }
+}
+
+// Activation tensor map, mode 0: NHWC viewed as (C, W, H, N, 1), box (64, tw, th, tn, 1).
+int make_act_tmap(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int tw, int th,
+                  int tn) {
+  const uint64_t dims[5] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W),
+                            static_cast<uint64_t>(H), static_cast<uint64_t>(N), 1};
+  const uint64_t strides[4] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(W) * C * 2,
+                               static_cast<uint64_t>(H) * W * C * 2,
+                               static_cast<uint64_t>(N) * H * W * C * 2};
+  const uint32_t box[5] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th),
+                           static_cast<uint32_t>(tn), 1};
+  return encode_tmap_bf16(tm, base, 5, dims, strides, box, true);
+}
+
+// Activation tensor map, mode 1 (gather for the 2x2/s2 transposed conv): the fine tensor
+// [N, 2H, 2W, C] viewed as (C, kx(2), X(W), ky(2), N*H), box (64, 1, tw, 1, th*tn).
+int make_act_tmap_up2(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int tw, int th,
+                      int tn) {
+  const uint64_t dims[5] = {static_cast<uint64_t>(C), 2, static_cast<uint64_t>(W), 2,
+                            static_cast<uint64_t>(N) * H};
+  const uint64_t strides[4] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * 4,
+                               static_cast<uint64_t>(W) * C * 4, static_cast<uint64_t>(W) * C * 8};
+  const uint32_t box[5] = {64, 1, static_cast<uint32_t>(tw), 1, static_cast<uint32_t>(th * tn)};
+  return encode_tmap_bf16(tm, base, 5, dims, strides, box, true);
+}
+
+static int make_b_tmap(CUtensorMap* tm, const void* base, int rows, int k, int box_rows) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(k), static_cast<uint64_t>(rows)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(k) * 2};
+  const uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
+  return encode_tmap_bf16(tm, base, 2, dims, strides, box, true);
+}
+
+struct IgemmLaunch {
+  const void* a1;
+  int c1;
+  const void* a2;
+  int c2;
+  const void* b;   // [Ntot][num_taps * (c1 + c2)] bf16
+  int a_fine;      // a_mode 1: A tensors are [N, 2H, 2W, C]
+  IgemmParams p;
+};
+
+static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
+  IgemmParams& p = L.p;
+  UNETK_CHECK_ARG(L.c1 % 64 == 0 && L.c2 % 64 == 0 && L.c1 > 0, "igemm: channel counts must be multiples of 64 (got %d, %d)", L.c1, L.c2);
+  UNETK_CHECK_ARG(p.Ntot % 32 == 0, "igemm: output columns must be a multiple of 32 (got %d)", p.Ntot);
+  UNETK_CHECK_ARG(p.split % 32 == 0, "igemm: column split must be a multiple of 32");
+  UNETK_CHECK_ARG((reinterpret_cast<uintptr_t>(L.a1) & 15) == 0 && (reinterpret_cast<uintptr_t>(L.b) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.out1) & 15) == 0, "igemm: pointers must be 16-byte aligned");
+  if (int e = check_device_sm100()) return e;
+  pick_pixel_tile(p.n_img, p.H, p.W, 128, &p.tw, &p.th, &p.tn);
+  p.tiles_x = (p.W + p.tw - 1) / p.tw;
+  p.tiles_y = (p.H + p.th - 1) / p.th;
+  p.tiles_n = (p.n_img + p.tn - 1) / p.tn;
+  p.c1_chunks = L.c1 / 64;
+  p.c2_chunks = L.c2 / 64;
+  const int bn = (p.Ntot % 128 == 0) ? 128 : 64;
+  UNETK_CHECK_ARG(p.Ntot % bn == 0, "igemm: output columns %d not a multiple of %d", p.Ntot, bn);
+  p.n_blocks = p.Ntot / bn;
+  const bool use_colbuf = p.stats != nullptr || p.scale != nullptr;
+  UNETK_CHECK_ARG(!(p.stats != nullptr && p.scale != nullptr), "igemm: stats and affine epilogues are exclusive");
+  UNETK_CHECK_ARG(!use_colbuf || p.Ntot <= 1024, "igemm: stats/affine epilogue supports at most 1024 columns");
+
+  CUtensorMap tmA1, tmA2, tmB;
+  int e;
+  if (p.a_mode == 0) {
+    if ((e = make_act_tmap(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, p.tw, p.th, p.tn))) return e;
+    if (L.c2 > 0) {
+      if ((e = make_act_tmap(&tmA2, L.a2, p.n_img, p.H, p.W, L.c2, p.tw, p.th, p.tn))) return e;
+    } else {
+      tmA2 = tmA1;
+    }
+  } else {
+    if ((e = make_act_tmap_up2(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, p.tw, p.th, p.tn))) return e;
+    tmA2 = tmA1;
+  }
+  const int K = p.num_taps * (L.c1 + L.c2);
+  if ((e = make_b_tmap(&tmB, L.b, p.Ntot, K, bn))) return e;
+
+  const long total_tiles = static_cast<long>(p.tiles_x) * p.tiles_y * p.tiles_n * p.n_blocks;
+  const int grid = static_cast<int>(total_tiles < num_sms() ? total_tiles : num_sms());
+  const size_t colbytes = use_colbuf ? static_cast<size_t>(2) * p.Ntot * sizeof(float) : 0;
+  if (bn == 128) {
+    using Cfg = IgemmCfg<128>;
+    const size_t smem = 1024 + Cfg::kStages * Cfg::kStageBytes + (2 * Cfg::kStages + 6) * 8 + colbytes;
+    UNETK_CUDA(cudaFuncSetAttribute(igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    igemm_kernel<128><<<grid, kIgemmThreads, smem, stream>>>(tmA1, tmA2, tmB, p);
+  } else {
+    using Cfg = IgemmCfg<64>;
+    const size_t smem = 1024 + Cfg::kStages * Cfg::kStageBytes + (2 * Cfg::kStages + 6) * 8 + colbytes;
+    UNETK_CUDA(cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    igemm_kernel<64><<<grid, kIgemmThreads, smem, stream>>>(tmA1, tmA2, tmB, p);
+  }
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
+                float* stats, const float* scale, const float* shift, int relu, int n, int h, int w,
+                int cout, cudaStream_t stream) {
+  UNETK_CHECK_ARG(src1 && wpk && y, "conv3x3_fwd: null pointer");
+  UNETK_CHECK_ARG(c2 == 0 || src2 != nullptr, "conv3x3_fwd: second source missing");
+  IgemmLaunch L{};
+  L.a1 = src1; L.c1 = c1; L.a2 = src2; L.c2 = c2; L.b = wpk;
+  IgemmParams& p = L.p;
+  p.n_img = n; p.H = h; p.W = w; p.Ntot = cout; p.num_taps = 9; p.a_mode = 0; p.epi_mode = 0;
+  p.split = cout; p.out1 = static_cast<__nv_bfloat16*>(y); p.out2 = nullptr; p.ldc1 = cout; p.ldc2 = 0;
+  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu;
+  return launch_igemm(L, stream);
+}
+
+int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1, int acc1, void* dx2,
+                  int c2, int acc2, float* stats, int n, int h, int w, cudaStream_t stream) {
+  UNETK_CHECK_ARG(dy && wdpk && dx1, "conv3x3_dgrad: null pointer");
+  UNETK_CHECK_ARG(c2 == 0 || dx2 != nullptr, "conv3x3_dgrad: second destination missing");
+  IgemmLaunch L{};
+  L.a1 = dy; L.c1 = cout; L.a2 = nullptr; L.c2 = 0; L.b = wdpk;
+  IgemmParams& p = L.p;
+  p.n_img = n; p.H = h; p.W = w; p.Ntot = c1 + c2; p.num_taps = 9; p.a_mode = 0; p.epi_mode = 0;
+  p.split = c1; p.out1 = static_cast<__nv_bfloat16*>(dx1); p.out2 = static_cast<__nv_bfloat16*>(dx2);
+  p.ldc1 = c1; p.ldc2 = c2; p.acc1 = acc1; p.acc2 = acc2; p.stats = stats;
+  return launch_igemm(L, stream);
+}
+
+int convt2x2_fwd(const void* a, int cin, const void* wpk, const float* bias, void* up, int n, int h,
+                 int w, int cout, cudaStream_t stream) {
+  UNETK_CHECK_ARG(a && wpk && up, "convt2x2_fwd: null pointer");
+  UNETK_CHECK_ARG(cout % 32 == 0, "convt2x2_fwd: cout must be a multiple of 32");
+  IgemmLaunch L{};
+  L.a1 = a; L.c1 = cin; L.b = wpk;
+  IgemmParams& p = L.p;
+  // a 2x2/s2 transposed conv has no spatial coupling: merge N and H into one row dimension
+  p.n_img = 1; p.H = n * h; p.W = w; p.Ntot = 4 * cout; p.num_taps = 1; p.a_mode = 0; p.epi_mode = 1;
+  p.split = p.Ntot; p.out1 = static_cast<__nv_bfloat16*>(up); p.bias = bias; p.cout_t = cout;
+  return launch_igemm(L, stream);
+}
+
+int convt2x2_dgrad(const void* dup, int cout, const void* wdpk, void* da, int cin, int acc, int n,
+                   int h, int w, cudaStream_t stream) {
+  UNETK_CHECK_ARG(dup && wdpk && da, "convt2x2_dgrad: null pointer");
+  IgemmLaunch L{};
+  L.a1 = dup; L.c1 = cout; L.b = wdpk;
+  IgemmParams& p = L.p;
+  p.n_img = 1; p.H = n * h; p.W = w; p.Ntot = cin; p.num_taps = 4; p.a_mode = 1; p.epi_mode = 0;
+  p.split = cin; p.out1 = static_cast<__nv_bfloat16*>(da); p.ldc1 = cin; p.acc1 = acc;
+  return launch_igemm(L, stream);
+}
+
+}  // namespace unetk

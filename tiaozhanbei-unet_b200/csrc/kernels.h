@@ -1,0 +1,79 @@
+// Internal C++ launch interface of the kernel library (one function per fused op).
+// The public C ABI in include/unetk.h forwards to these 1:1.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace unetk {
+
+// igemm.cu — K-major implicit GEMMs (tcgen05)
+int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
+                float* stats, const float* scale, const float* shift, int relu, int n, int h, int w,
+                int cout, cudaStream_t stream);
+int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1, int acc1, void* dx2,
+                  int c2, int acc2, float* stats, int n, int h, int w, cudaStream_t stream);
+int convt2x2_fwd(const void* a, int cin, const void* wpk, const float* bias, void* up, int n, int h,
+                 int w, int cout, cudaStream_t stream);
+int convt2x2_dgrad(const void* dup, int cout, const void* wdpk, void* da, int cin, int acc, int n,
+                   int h, int w, cudaStream_t stream);
+
+// wgrad.cu — MN-major split-K GEMMs (tcgen05)
+int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2, float* dw,
+                  int n, int h, int w, int cout, cudaStream_t stream);
+int convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw, int n, int h, int w,
+                   cudaStream_t stream);
+
+// first_conv.cu
+int first_conv_fwd(const float* x, const float* w, void* y, float* stats, int N, int Cin, int H, int W,
+                   int cout, cudaStream_t s);
+int first_conv_wgrad(const float* x, const void* dy, float* dw, int N, int Cin, int H, int W, int cout,
+                     cudaStream_t s);
+
+// elementwise.cu
+int bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, long long* nbt, float* scale, float* shift, float* mean,
+                float* invstd, int C, double count, float eps, float momentum, cudaStream_t s);
+int bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float* scale,
+            float* shift, int C, float eps, cudaStream_t s);
+int bnrelu_apply(const void* y, const float* scale, const float* shift, void* a, long npix, int C,
+                 cudaStream_t s);
+int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
+                void* idx, int N, int H, int W, int C, int apply, cudaStream_t s);
+int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, int C, int accumulate,
+                cudaStream_t s);
+int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
+                  const float* mean, const float* invstd, float* sums, long npix, int C,
+                  cudaStream_t s);
+int bn_bwd_apply(const void* da, const void* y, const float* scale, const float* shift,
+                 const float* mean, const float* invstd, const float* sums, void* dy, float* dgamma,
+                 float* dbeta, long npix, int C, cudaStream_t s);
+int nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, cudaStream_t s);
+int nhwc_to_nchw(const void* in, float* out, int N, int C, int H, int W, cudaStream_t s);
+
+// head_loss.cu
+int head_fwd(const void* a, const float* w, const float* b, float* out, int N, int H, int W, int C,
+             int n_out, int sigmoid, cudaStream_t s);
+int head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da, float* dw,
+             float* db, int N, int H, int W, int C, int n_out, int sigmoid, cudaStream_t s);
+size_t combined_loss_workspace_bytes();
+int combined_loss(const float* recon, const float* amap, const float* image, const float* mask,
+                  float* d_recon, float* d_amap, float* out3, void* work, size_t work_bytes,
+                  long n_recon, long n_seg, float rw, float sw, float alpha, float gamma,
+                  cudaStream_t s);
+int scale_by_scalar(float* y, const float* s, long n, cudaStream_t st);
+int anomaly_score(const float* recon, const float* orig, float* out, int N, int C, int H, int W,
+                  int method, cudaStream_t s);
+int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int N, int C, int H,
+             int W, int window_size, int need2, cudaStream_t s);
+int ssim_bwd(const float* img1, const float* img2, const float* maps, const float* gout, float* grad,
+             int N, int C, int H, int W, int window_size, int which, int per_image, cudaStream_t s);
+
+// optim.cu
+int adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+              float beta2, float eps, float wd, long step, float grad_scale, int mode,
+              cudaStream_t s);
+int permute_batched(const void* descs, int n_desc, int n_chunks, const float* in, void* out,
+                    int out_bf16, float scale, cudaStream_t s);
+int permute_chunk_elems();
+
+}  // namespace unetk

@@ -1,0 +1,296 @@
+// Weight-gradient contractions on tcgen05 / TMEM fed by TMA (sm_100a).
+//
+//   conv3x3 wgrad   dW[co, tap, ci]  = sum_pix dY[pix, co] * X[pix + tap, ci]
+//   convT2x2 wgrad  dW[co, tap, ci]  = sum_pix dUp[2*pix + tap, co] * A[pix, ci]
+// (autograd of nn.Conv2d at /root/reference/src/model.py:14,17 and nn.ConvTranspose2d at :51).
+//
+// The reduction runs over pixels, which is the OUTER dimension of NHWC tensors, so both operands
+// reach shared memory pixel-row by pixel-row (one TMA box = 64 pixels x 64 channels = 64 rows of
+// 128 B, SWIZZLE_128B) and are consumed through MN-major UMMA descriptors: no transposing copy.
+// UMMA M = 128 input channels (or two taps x 64 channels when Cin == 64), N = BN output channels,
+// K = 16 pixels per instruction.  One CTA owns one (tap row | 4 taps) x 128 ci x BN co block of dW
+// in TMEM and a slice of the pixel range (split-K); partial sums are added to the fp32 gradient
+// with red.global.add.f32.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace unetk {
+
+struct WgradParams {
+  int n_img, H, W;  // pixel grid that is reduced over
+  int tw, th, tn;   // 64-pixel K tile
+  int tiles_x, tiles_y, tiles_n;
+  int cin, cout;
+  int c1_chunks;    // 64-channel chunks of the X operand that live in tensor map 1 (rest: map 2)
+  int ci_tiles, co_tiles;
+  int ksplit;
+  int T;            // taps per weight: 9 or 4
+  float* dw;        // [cout][T][cin]
+};
+
+constexpr int kWgThreads = 192;
+constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 bf16
+
+template <int MODE, int BN, bool M64>
+struct WgCfg {
+  // boxes resident per stage
+  static constexpr int kABoxes = (MODE == 0) ? (M64 ? 4 : 6) : 2;
+  static constexpr int kALoads = (MODE == 0) ? (M64 ? 3 : 6) : 2;
+  static constexpr int kBBoxes = (MODE == 0) ? (BN / 64) : 4 * (BN / 64);
+  static constexpr int kMmas = (MODE == 0) ? (M64 ? 2 : 3) : 4;
+  static constexpr int kStageBytes = (kABoxes + kBBoxes) * kBoxBytes;
+  static constexpr int kStages = (kStageBytes * 4 <= 200 * 1024) ? 4 : (kStageBytes * 3 <= 200 * 1024 ? 3 : 2);
+  static constexpr int kAccCols = kMmas * BN;
+  static constexpr int kTmemCols = kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512));
+};
+
+template <int MODE, int BN, bool M64>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+             const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
+  using Cfg = WgCfg<MODE, BN, M64>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work decomposition
+  int bx = blockIdx.x;
+  const int cot = bx % p.co_tiles;
+  bx /= p.co_tiles;
+  const int cit = bx % p.ci_tiles;
+  const int r = bx / p.ci_tiles;  // tap row (MODE 0), 0 otherwise
+  const int total_k = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int k_begin = static_cast<int>(static_cast<long>(total_k) * blockIdx.y / p.ksplit);
+  const int k_end = static_cast<int>(static_cast<long>(total_k) * (blockIdx.y + 1) / p.ksplit);
+  if (k_end <= k_begin) return;  // uniform for the whole CTA
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX1);
+    tma_prefetch_desc(&tmX2);
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        int m = kt;
+        const int tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int tz = m / p.tiles_y;
+        const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tz * p.tn;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], (Cfg::kALoads + Cfg::kBBoxes) * kBoxBytes);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABoxes * kBoxBytes;
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < Cfg::kALoads; ++j) {
+            const int tap = 3 * r + (M64 ? j : j / 2);
+            const int chunk = M64 ? 0 : cit * 2 + (j & 1);
+            const CUtensorMap* mp = (chunk < p.c1_chunks) ? &tmX1 : &tmX2;
+            const int cc = ((chunk < p.c1_chunks) ? chunk : chunk - p.c1_chunks) * 64;
+            tma_load_5d(sa + j * kBoxBytes, mp, &full[stage], cc, x0 + tap % 3 - 1, y0 + tap / 3 - 1, n0, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < Cfg::kBBoxes; ++j)
+            tma_load_5d(sb + j * kBoxBytes, &tmDY, &full[stage], cot * BN + j * 64, x0, y0, n0, 0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_5d(sa + j * kBoxBytes, &tmX1, &full[stage], (cit * 2 + j) * 64, x0, y0, n0, 0);
+#pragma unroll
+          for (int j = 0; j < Cfg::kBBoxes; ++j) {
+            const int tap = j / (BN / 64);
+            tma_load_5d(sb + j * kBoxBytes, &tmDY, &full[stage], cot * BN + (j % (BN / 64)) * 64,
+                        tap & 1, x0, tap >> 1, n0 * p.H + y0);
+          }
+        }
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = k_begin; kt < k_end; ++kt) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABoxes * kBoxBytes;
+#pragma unroll
+        for (int j = 0; j < Cfg::kMmas; ++j) {
+          const uint32_t a0 = sa + ((MODE == 0) ? 2 * j : 0) * kBoxBytes;
+          const uint32_t b0 = sb + ((MODE == 0) ? 0 : j * (BN / 64)) * kBoxBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // K advances by 16 pixel rows = 2048 B; 64-wide MN atoms are one box (8 KB) apart.
+            const uint64_t da = umma_smem_desc_sw128(a0 + k * 2048, kBoxBytes, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b0 + k * 2048, kBoxBytes, 1024);
+            tc_mma_bf16(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
+          }
+        }
+        tc_commit(&empty[stage]);
+        if (kt == k_end - 1) tc_commit(tfull);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int j = 0; j < Cfg::kMmas; ++j) {
+      int tap, ci;
+      bool valid = true;
+      if (MODE == 0) {
+        if (M64) {
+          const int tj = 2 * j + (row >> 6);
+          tap = 3 * r + tj;
+          ci = row & 63;
+          valid = tj < 3;
+        } else {
+          tap = 3 * r + j;
+          ci = cit * 128 + row;
+        }
+      } else {
+        tap = j;
+        ci = cit * 128 + row;
+      }
+      valid = valid && (ci < p.cin);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * BN + ch * 32, v);
+        tmem_ld_wait();
+        const int co0 = cot * BN + ch * 32;
+        if (valid) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int co = co0 + jj;
+            if (co < p.cout)
+              atomicAdd(p.dw + (static_cast<size_t>(co) * p.T + tap) * p.cin + ci, v[jj]);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// from igemm.cu
+void pick_pixel_tile(int n_img, int H, int W, int pixels, int* tw, int* th, int* tn);
+int make_act_tmap(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int tw, int th, int tn);
+int make_act_tmap_up2(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int tw, int th, int tn);
+
+template <int MODE, int BN, bool M64>
+static int launch_wgrad_t(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& dy,
+                          const WgradParams& p, dim3 grid, cudaStream_t stream) {
+  using Cfg = WgCfg<MODE, BN, M64>;
+  const size_t smem = 1024 + Cfg::kStages * Cfg::kStageBytes + (2 * Cfg::kStages + 2) * 8;
+  UNETK_CUDA(cudaFuncSetAttribute(wgrad_kernel<MODE, BN, M64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  wgrad_kernel<MODE, BN, M64><<<grid, kWgThreads, smem, stream>>>(x1, x2, dy, p);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+static int choose_ksplit(int work_tiles, int total_k) {
+  // aim for >= 4 waves of CTAs while keeping >= 8 K tiles per CTA
+  const int sms = num_sms();
+  int ks = (4 * sms + work_tiles - 1) / work_tiles;
+  if (ks > total_k / 8) ks = total_k / 8;
+  if (ks < 1) ks = 1;
+  return ks;
+}
+
+int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2, float* dw,
+                  int n, int h, int w, int cout, cudaStream_t stream) {
+  UNETK_CHECK_ARG(dy && src1 && dw, "conv3x3_wgrad: null pointer");
+  UNETK_CHECK_ARG(c2 == 0 || src2 != nullptr, "conv3x3_wgrad: second source missing");
+  const int cin = c1 + c2;
+  UNETK_CHECK_ARG(c1 % 64 == 0 && c2 % 64 == 0 && cout % 64 == 0, "conv3x3_wgrad: channels must be multiples of 64");
+  UNETK_CHECK_ARG(cin == 64 || cin % 128 == 0, "conv3x3_wgrad: cin must be 64 or a multiple of 128 (got %d)", cin);
+  if (int e = check_device_sm100()) return e;
+  WgradParams p{};
+  p.n_img = n; p.H = h; p.W = w; p.cin = cin; p.cout = cout; p.c1_chunks = c1 / 64; p.T = 9; p.dw = dw;
+  pick_pixel_tile(n, h, w, 64, &p.tw, &p.th, &p.tn);
+  p.tiles_x = (w + p.tw - 1) / p.tw; p.tiles_y = (h + p.th - 1) / p.th; p.tiles_n = (n + p.tn - 1) / p.tn;
+  const bool m64 = (cin == 64);
+  const int bn = (cout % 128 == 0) ? 128 : 64;
+  p.ci_tiles = m64 ? 1 : cin / 128;
+  p.co_tiles = cout / bn;
+  const int work = 3 * p.ci_tiles * p.co_tiles;
+  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y * p.tiles_n);
+  CUtensorMap x1, x2, tdy;
+  int e;
+  if ((e = make_act_tmap(&x1, src1, n, h, w, c1, p.tw, p.th, p.tn))) return e;
+  if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h, w, c2, p.tw, p.th, p.tn))) return e; } else x2 = x1;
+  if ((e = make_act_tmap(&tdy, dy, n, h, w, cout, p.tw, p.th, p.tn))) return e;
+  dim3 grid(work, p.ksplit);
+  if (m64) return bn == 128 ? launch_wgrad_t<0, 128, true>(x1, x2, tdy, p, grid, stream)
+                            : launch_wgrad_t<0, 64, true>(x1, x2, tdy, p, grid, stream);
+  return bn == 128 ? launch_wgrad_t<0, 128, false>(x1, x2, tdy, p, grid, stream)
+                   : launch_wgrad_t<0, 64, false>(x1, x2, tdy, p, grid, stream);
+}
+
+int convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw, int n, int h, int w,
+                   cudaStream_t stream) {
+  UNETK_CHECK_ARG(a && dup && dw, "convt2x2_wgrad: null pointer");
+  UNETK_CHECK_ARG(cin % 128 == 0 && cout % 64 == 0, "convt2x2_wgrad: cin %% 128 and cout %% 64 required");
+  if (int e = check_device_sm100()) return e;
+  WgradParams p{};
+  // no spatial coupling: merge N and H so that any tile shape is legal for the 5-D gather map
+  p.n_img = 1; p.H = n * h; p.W = w; p.cin = cin; p.cout = cout; p.c1_chunks = cin / 64; p.T = 4; p.dw = dw;
+  pick_pixel_tile(1, p.H, w, 64, &p.tw, &p.th, &p.tn);
+  p.tiles_x = (w + p.tw - 1) / p.tw; p.tiles_y = (p.H + p.th - 1) / p.th; p.tiles_n = 1;
+  const int bn = (cout % 128 == 0) ? 128 : 64;
+  p.ci_tiles = cin / 128;
+  p.co_tiles = cout / bn;
+  const int work = p.ci_tiles * p.co_tiles;
+  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y);
+  CUtensorMap x1, tdy;
+  int e;
+  if ((e = make_act_tmap(&x1, a, 1, p.H, w, cin, p.tw, p.th, p.tn))) return e;
+  if ((e = make_act_tmap_up2(&tdy, dup, 1, p.H, w, cout, p.tw, p.th, p.tn))) return e;
+  dim3 grid(work, p.ksplit);
+  return bn == 128 ? launch_wgrad_t<1, 128, false>(x1, x1, tdy, p, grid, stream)
+                   : launch_wgrad_t<1, 64, false>(x1, x1, tdy, p, grid, stream);
+}
+
+}  // namespace unetk
