@@ -63,8 +63,8 @@ int unetk_conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const 
                       int w, int cout, void* stream);
 /* autograd of the above w.r.t. its input: dx = conv(dy, flipped W^T).  Columns [0,c1) go to dx1,
  * [c1,c1+c2) to dx2 (the two concat sources); accK != 0 accumulates into dxK (skip connections
- * receive several gradients).  stats != NULL: per-column sums of dx (bias gradient of the
- * ConvTranspose2d that produced src2). */
+ * receive several gradients).  stats != NULL: stats[c2] += sum over pixels of dx2 (the bias
+ * gradient of the ConvTranspose2d that produced src2; the caller zeroes it). */
 int unetk_conv3x3_dgrad(const void* dy, int cout, const void* wd, void* dx1, int c1, int acc1,
                         void* dx2, int c2, int acc2, float* stats, int n, int h, int w,
                         void* stream);

@@ -1,0 +1,311 @@
+"""Operator-level parity of the CUDA kernels (through the C ABI) against plain fp32 PyTorch ops
+of the same operator on the same seeded inputs.  Inputs are rounded to bf16 first so that the only
+differences are accumulation order and the bf16 rounding of the stored result.
+
+Tolerances (stated per test): conv-type outputs are stored in bf16 -> relative 2^-8 per element;
+we allow |d| <= 2e-2 * max|ref| (K up to 9216 fp32 accumulation, bf16 store)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from tiaozhanbei_unet_b200 import _lib, ops, packing
+    return _lib, ops, packing
+
+
+def _pack(ops, packing, w, recipe, device, dtype=torch.bfloat16):
+    _lib = ops._lib
+    tab = packing.PermuteTable(_lib.get().unetk_permute_chunk_elems())
+    dims, strides, flip = recipe
+    tab.add(0, 0, dims, strides, flip)
+    tab.finalize(device)
+    out = torch.empty(dims[0] * dims[1] * dims[2], dtype=dtype, device=device)
+    ops.permute_batched(tab, w.contiguous().view(-1), out)
+    return out
+
+
+def _nhwc(x):  # NCHW fp32 -> NHWC bf16
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _nchw(a):  # NHWC bf16 -> NCHW fp32
+    return a.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _close(got, ref, tol, what):
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    assert err <= tol * scale, f"{what}: max abs err {err:.4e} vs scale {scale:.4e} (tol {tol})"
+
+
+CONV_CASES = [
+    # n, h, w, c1, c2, cout
+    (2, 16, 16, 64, 0, 64),
+    (2, 16, 16, 128, 0, 128),
+    (1, 32, 32, 64, 64, 64),      # dual source (decoder concat)
+    (2, 16, 24, 128, 0, 256),     # partial tiles in x, two n-blocks
+    (1, 8, 8, 256, 256, 512),
+    (8, 64, 64, 64, 0, 128),      # more tiles than SMs: persistent loop + double-buffered TMEM
+    (3, 4, 4, 64, 0, 64),         # tile spans several images
+    (1, 32, 88, 64, 0, 64),       # KolektorSDD-like width (not a power of two)
+]
+
+
+@pytest.mark.parametrize("n,h,w,c1,c2,cout", CONV_CASES)
+def test_conv3x3_fwd(cuda_device, n, h, w, c1, c2, cout):
+    _lib, ops, packing = _mods()
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    cin = c1 + c2
+    x = torch.randn(n, cin, h, w, generator=g).to(cuda_device)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)).to(cuda_device)
+    xb = _nhwc(x)
+    wq = wt.to(torch.bfloat16).float()
+    ref = F.conv2d(_nchw(xb), wq, padding=1)
+    wf = _pack(ops, packing, wt, packing.conv_fwd_pack(cout, cin), cuda_device)
+    y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device=cuda_device)
+    stats = torch.zeros(2 * cout, dtype=torch.float32, device=cuda_device)
+    s1 = xb[..., :c1].contiguous()
+    s2 = xb[..., c1:].contiguous() if c2 else None
+    ops.conv3x3_fwd(s1, s2, wf, y, stats=stats)
+    torch.cuda.synchronize()
+    _close(_nchw(y), ref, 2e-2, "conv3x3_fwd")
+    # BatchNorm statistics of the fp32 accumulators
+    _close(stats[:cout], ref.sum(dim=(0, 2, 3)), 2e-3 * (n * h * w) ** 0.5, "sum")
+    _close(stats[cout:], (ref * ref).sum(dim=(0, 2, 3)), 5e-3, "sumsq")
+
+
+def test_conv3x3_fwd_affine_relu(cuda_device):
+    _lib, ops, packing = _mods()
+    g = torch.Generator(device="cpu").manual_seed(7)
+    n, h, w, cin, cout = 2, 16, 16, 64, 128
+    x = torch.randn(n, cin, h, w, generator=g).to(cuda_device)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / 24.0).to(cuda_device)
+    scale = (torch.rand(cout, generator=g) + 0.5).to(cuda_device)
+    shift = torch.randn(cout, generator=g).to(cuda_device) * 0.1
+    xb = _nhwc(x)
+    ref = F.relu(F.conv2d(_nchw(xb), wt.to(torch.bfloat16).float(), padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    wf = _pack(ops, packing, wt, packing.conv_fwd_pack(cout, cin), cuda_device)
+    y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device=cuda_device)
+    ops.conv3x3_fwd(xb, None, wf, y, scale=scale, shift=shift, relu=True)
+    torch.cuda.synchronize()
+    _close(_nchw(y), ref, 2e-2, "conv3x3_fwd affine")
+
+
+@pytest.mark.parametrize("n,h,w,c1,c2,cout", CONV_CASES)
+def test_conv3x3_dgrad(cuda_device, n, h, w, c1, c2, cout):
+    _lib, ops, packing = _mods()
+    g = torch.Generator(device="cpu").manual_seed(99)
+    cin = c1 + c2
+    dy = torch.randn(n, cout, h, w, generator=g).to(cuda_device)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cout ** 0.5)).to(cuda_device)
+    dyb = _nhwc(dy)
+    wq = wt.to(torch.bfloat16).float()
+    ref = F.conv_transpose2d(_nchw(dyb), wq, padding=1)   # = dgrad of conv2d(pad=1)
+    wd = _pack(ops, packing, wt, packing.conv_dgrad_pack(cout, cin), cuda_device)
+    prev1 = torch.randn(n, h, w, c1, generator=g).to(cuda_device).to(torch.bfloat16)
+    dx1 = prev1.clone()
+    dx2 = torch.empty(n, h, w, c2, dtype=torch.bfloat16, device=cuda_device) if c2 else None
+    stats = torch.zeros(c2, dtype=torch.float32, device=cuda_device) if c2 else None
+    ops.conv3x3_dgrad(dyb, wd, dx1, acc1=True, dx2=dx2, acc2=False, stats=stats)
+    torch.cuda.synchronize()
+    _close(_nchw(dx1), ref[:, :c1] + _nchw(prev1), 2e-2, "dgrad dx1 (accumulate)")
+    if c2:
+        _close(_nchw(dx2), ref[:, c1:], 2e-2, "dgrad dx2")
+        _close(stats, ref[:, c1:].sum(dim=(0, 2, 3)), 2e-3 * (n * h * w) ** 0.5, "dgrad column sums")
+
+
+@pytest.mark.parametrize("n,h,w,c1,c2,cout", CONV_CASES)
+def test_conv3x3_wgrad(cuda_device, n, h, w, c1, c2, cout):
+    _lib, ops, packing = _mods()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    cin = c1 + c2
+    x = torch.randn(n, cin, h, w, generator=g).to(cuda_device)
+    dy = torch.randn(n, cout, h, w, generator=g).to(cuda_device)
+    xb, dyb = _nhwc(x), _nhwc(dy)
+    ref = torch.nn.grad.conv2d_weight(_nchw(xb), (cout, cin, 3, 3), _nchw(dyb), padding=1)
+    dwk = torch.zeros(cout * 9 * cin, dtype=torch.float32, device=cuda_device)
+    s1 = xb[..., :c1].contiguous()
+    s2 = xb[..., c1:].contiguous() if c2 else None
+    ops.conv3x3_wgrad(dyb, s1, s2, dwk)
+    got = _pack(ops, packing, dwk, packing.conv_grad_unpack(cout, cin), cuda_device, dtype=torch.float32).view(cout, cin, 3, 3)
+    torch.cuda.synchronize()
+    _close(got, ref, 2e-3, "conv3x3_wgrad")
+
+
+CONVT_CASES = [(2, 8, 8, 128, 64), (1, 16, 16, 256, 128), (2, 4, 4, 1024, 512), (1, 2, 2, 128, 64), (1, 32, 44, 128, 64)]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", CONVT_CASES)
+def test_convt2x2(cuda_device, n, h, w, cin, cout):
+    _lib, ops, packing = _mods()
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a = torch.randn(n, cin, h, w, generator=g).to(cuda_device)
+    wt = (torch.randn(cin, cout, 2, 2, generator=g) / cin ** 0.5).to(cuda_device)
+    bias = torch.randn(cout, generator=g).to(cuda_device)
+    ab = _nhwc(a)
+    wq = wt.to(torch.bfloat16).float()
+    ref = F.conv_transpose2d(_nchw(ab), wq, bias, stride=2)
+    wp = _pack(ops, packing, wt, packing.convt_fwd_pack(cin, cout), cuda_device)
+    up = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.bfloat16, device=cuda_device)
+    ops.convt2x2_fwd(ab, wp, bias, up)
+    torch.cuda.synchronize()
+    _close(_nchw(up), ref, 2e-2, "convt2x2_fwd")
+    # dgrad
+    dup = torch.randn(n, cout, 2 * h, 2 * w, generator=g).to(cuda_device)
+    dupb = _nhwc(dup)
+    ref_da = F.conv2d(_nchw(dupb), wq, stride=2)
+    wpd = _pack(ops, packing, wt, packing.convt_dgrad_pack(cin, cout), cuda_device)
+    da = torch.empty(n, h, w, cin, dtype=torch.bfloat16, device=cuda_device)
+    ops.convt2x2_dgrad(dupb, wpd, da, acc=False)
+    torch.cuda.synchronize()
+    _close(_nchw(da), ref_da, 2e-2, "convt2x2_dgrad")
+    # wgrad: d/dW of conv_transpose2d == conv2d_weight with roles swapped
+    ref_dw = torch.nn.grad.conv2d_weight(_nchw(dupb), (cin, cout, 2, 2), _nchw(ab), stride=2)
+    dwk = torch.zeros(cout * 4 * cin, dtype=torch.float32, device=cuda_device)
+    ops.convt2x2_wgrad(ab, dupb, dwk)
+    got = _pack(ops, packing, dwk, packing.convt_grad_unpack(cin, cout), cuda_device, dtype=torch.float32).view(cin, cout, 2, 2)
+    torch.cuda.synchronize()
+    _close(got, ref_dw, 2e-3, "convt2x2_wgrad")
+
+
+@pytest.mark.parametrize("n,cin,h,w", [(2, 3, 16, 16), (1, 3, 40, 24), (2, 1, 8, 8)])
+def test_first_conv(cuda_device, n, cin, h, w):
+    _lib, ops, packing = _mods()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(n, cin, h, w, generator=g).to(cuda_device)
+    wt = (torch.randn(64, cin, 3, 3, generator=g) / 5.0).to(cuda_device)
+    ref = F.conv2d(x, wt, padding=1)
+    y = torch.empty(n, h, w, 64, dtype=torch.bfloat16, device=cuda_device)
+    stats = torch.zeros(128, dtype=torch.float32, device=cuda_device)
+    ops.first_conv_fwd(x, wt, y, stats)
+    torch.cuda.synchronize()
+    _close(_nchw(y), ref, 1e-2, "first_conv_fwd")
+    _close(stats[:64], ref.sum(dim=(0, 2, 3)), 1e-3 * (n * h * w) ** 0.5, "first conv sum")
+    _close(stats[64:], (ref * ref).sum(dim=(0, 2, 3)), 1e-3, "first conv sumsq")
+    dy = torch.randn(n, 64, h, w, generator=g).to(cuda_device)
+    dyb = _nhwc(dy)
+    ref_dw = torch.nn.grad.conv2d_weight(x, (64, cin, 3, 3), _nchw(dyb), padding=1)
+    dw = torch.empty(64, cin, 3, 3, dtype=torch.float32, device=cuda_device)
+    ops.first_conv_wgrad(x, dyb, dw)
+    torch.cuda.synchronize()
+    _close(dw, ref_dw, 1e-4, "first_conv_wgrad")
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 8, 8, 64), (1, 16, 12, 128), (3, 4, 6, 1024)])
+def test_bn_relu_pool_roundtrip(cuda_device, n, h, w, c):
+    """bn_finalize + bnrelu_apply/pool forward and the two-pass backward against torch autograd of
+    BatchNorm2d(train) -> ReLU -> MaxPool2d(2)."""
+    _lib, ops, packing = _mods()
+    g = torch.Generator(device="cpu").manual_seed(21)
+    dev = cuda_device
+    yb = _nhwc((torch.randn(n, c, h, w, generator=g) * 2 + 0.5).to(dev))
+    gamma = (torch.rand(c, generator=g) + 0.5).to(dev)
+    beta = (torch.randn(c, generator=g) * 0.2).to(dev)
+    yref = _nchw(yb).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(c).to(dev).train()
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta)
+    a_ref = F.relu(bn(yref))
+    p_ref, idx_ref = F.max_pool2d(a_ref, 2, return_indices=True)
+    # ours
+    stats = torch.stack([_nchw(yb).sum(dim=(0, 2, 3)), (_nchw(yb) ** 2).sum(dim=(0, 2, 3))]).contiguous().view(-1)
+    rm = torch.zeros(c, device=dev); rv = torch.ones(c, device=dev); nbt = torch.zeros((), dtype=torch.int64, device=dev)
+    scale = torch.empty(c, device=dev); shift = torch.empty(c, device=dev); mean = torch.empty(c, device=dev); invstd = torch.empty(c, device=dev)
+    ops.bn_finalize(stats, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd, count=n * h * w)
+    a = torch.empty_like(yb)
+    pooled = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=dev)
+    idx = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=dev)
+    ops.bnrelu_pool(yb, scale, shift, a, pooled, idx, apply=True)
+    a2 = torch.empty_like(yb)
+    ops.bnrelu_apply(yb, scale, shift, a2)
+    torch.cuda.synchronize()
+    assert int(nbt.item()) == 1
+    _close(rm, bn.running_mean, 1e-5, "running_mean")
+    _close(rv, bn.running_var, 1e-4, "running_var")
+    _close(_nchw(a), a_ref.detach(), 1e-2, "bnrelu (pool variant)")
+    assert torch.equal(a, a2)
+    _close(_nchw(pooled), p_ref.detach(), 1e-2, "pooled")
+    # backward: upstream gradient on the pooled tensor
+    dp = torch.randn(n, c, h // 2, w // 2, generator=g).to(dev)
+    dpb = _nhwc(dp)
+    p_ref.backward(_nchw(dpb))
+    da = torch.empty_like(yb)
+    ops.maxpool_bwd(dpb, idx, da, accumulate=False)
+    sums = torch.zeros(2 * c, device=dev)
+    ops.bn_bwd_reduce(da, yb, scale, shift, mean, invstd, sums)
+    dy = torch.empty_like(yb); dgamma = torch.empty(c, device=dev); dbeta = torch.empty(c, device=dev)
+    ops.bn_bwd_apply(da, yb, scale, shift, mean, invstd, sums, dy, dgamma, dbeta)
+    torch.cuda.synchronize()
+    _close(dgamma, bn.weight.grad, 2e-2, "dgamma")
+    _close(dbeta, bn.bias.grad, 2e-2, "dbeta")
+    _close(_nchw(dy), yref.grad, 3e-2, "bn backward dy")
+    # accumulate variant
+    base = torch.randn(n, h, w, c, generator=g).to(dev).to(torch.bfloat16)
+    da2 = base.clone()
+    ops.maxpool_bwd(dpb, idx, da2, accumulate=True)
+    torch.cuda.synchronize()
+    _close(da2.float(), base.float() + da.float(), 1e-2, "maxpool_bwd accumulate")
+
+
+@pytest.mark.parametrize("n_out,sigmoid", [(3, True), (1, True), (1, False)])
+def test_head(cuda_device, n_out, sigmoid):
+    _lib, ops, packing = _mods()
+    g = torch.Generator(device="cpu").manual_seed(31)
+    dev = cuda_device
+    n, h, w = 2, 12, 20
+    a = _nhwc(torch.randn(n, 64, h, w, generator=g).to(dev))
+    wt = (torch.randn(n_out, 64, generator=g) / 8).to(dev)
+    b = torch.randn(n_out, generator=g).to(dev)
+    aref = _nchw(a).requires_grad_(True)
+    wref = wt.clone().view(n_out, 64, 1, 1).requires_grad_(True)
+    bref = b.clone().requires_grad_(True)
+    o_ref = F.conv2d(aref, wref, bref)
+    if sigmoid:
+        o_ref = torch.sigmoid(o_ref)
+    out = torch.empty(n, n_out, h, w, device=dev)
+    ops.head_fwd(a, wt, b, out, sigmoid)
+    torch.cuda.synchronize()
+    _close(out, o_ref.detach(), 1e-5, "head_fwd")
+    dout = torch.randn(n, n_out, h, w, generator=g).to(dev)
+    o_ref.backward(dout)
+    da = torch.empty_like(a); dw = torch.empty(n_out, 64, device=dev); db = torch.empty(n_out, device=dev)
+    ops.head_bwd(a, wt, dout, out, da, dw, db, sigmoid)
+    torch.cuda.synchronize()
+    _close(_nchw(da), aref.grad, 1e-2, "head_bwd da")
+    _close(dw, wref.grad.view(n_out, 64), 1e-4, "head_bwd dw")
+    _close(db, bref.grad, 1e-4, "head_bwd db")
+
+
+def test_adam_and_layout(cuda_device):
+    _lib, ops, packing = _mods()
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(41)
+    n = 10007
+    p0 = torch.randn(n, generator=g).to(dev)
+    for mode, make in ((0, lambda p: torch.optim.Adam([p], lr=1e-3, weight_decay=1e-4)),
+                       (1, lambda p: torch.optim.AdamW([p], lr=1e-3, weight_decay=1e-2)),
+                       (2, lambda p: torch.optim.SGD([p], lr=1e-2, momentum=0.9, weight_decay=1e-4))):
+        pref = p0.clone().requires_grad_(True)
+        opt = make(pref)
+        p = torch.zeros(n + 5, device=dev)[:n]  # keep base 16B aligned
+        p.copy_(p0)
+        m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+        wd = opt.param_groups[0]["weight_decay"]; lr = opt.param_groups[0]["lr"]
+        for step in range(1, 4):
+            grad = torch.randn(n, generator=g).to(dev)
+            pref.grad = grad.clone()
+            opt.step()
+            ops.adam_step(p, grad, m, v, lr, 0.9, 0.999, 1e-8, wd, step, 1.0, mode)
+        torch.cuda.synchronize()
+        _close(p, pref.detach(), 1e-6, f"optimizer mode {mode}")
+    x = torch.randn(2, 5, 7, 9, generator=g).to(dev)
+    nh = torch.empty(2, 7, 9, 5, dtype=torch.bfloat16, device=dev)
+    ops.nchw_to_nhwc(x, nh)
+    back = torch.empty_like(x)
+    ops.nhwc_to_nchw(nh, back)
+    torch.cuda.synchronize()
+    assert torch.equal(nh, x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    assert torch.equal(back, x.to(torch.bfloat16).float())

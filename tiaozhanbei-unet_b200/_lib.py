@@ -1,0 +1,99 @@
+"""ctypes binding of csrc/build/libunetk.so (the C ABI declared in include/unetk.h).
+
+The product path fails loudly when the CUDA library is missing or a call returns an error code:
+there is no PyTorch / CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "build", "libunetk.so")
+
+P, I, L, F, D, Z = c_void_p, c_int, c_int64, c_float, c_double, c_size_t
+
+# name -> (restype, argtypes); must mirror include/unetk.h exactly
+SIGNATURES = {
+    "unetk_version": (I, []),
+    "unetk_last_error": (c_char_p, []),
+    "unetk_check_device": (I, []),
+    "unetk_memset_zero": (I, [P, Z, P]),
+    "unetk_conv3x3_fwd": (I, [P, I, P, I, P, P, P, P, P, I, I, I, I, I, P]),
+    "unetk_conv3x3_dgrad": (I, [P, I, P, P, I, I, P, I, I, P, I, I, I, P]),
+    "unetk_conv3x3_wgrad": (I, [P, P, I, P, I, P, I, I, I, I, P]),
+    "unetk_first_conv_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "unetk_first_conv_wgrad": (I, [P, P, P, I, I, I, I, I, P]),
+    "unetk_convt2x2_fwd": (I, [P, I, P, P, P, I, I, I, I, P]),
+    "unetk_convt2x2_dgrad": (I, [P, I, P, P, I, I, I, I, I, P]),
+    "unetk_convt2x2_wgrad": (I, [P, I, P, I, P, I, I, I, P]),
+    "unetk_bn_finalize": (I, [P, P, P, P, P, P, P, P, P, P, I, D, F, F, P]),
+    "unetk_bn_fold": (I, [P, P, P, P, P, P, I, F, P]),
+    "unetk_bnrelu_apply": (I, [P, P, P, P, L, I, P]),
+    "unetk_bnrelu_pool": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
+    "unetk_maxpool_bwd": (I, [P, P, P, I, I, I, I, I, P]),
+    "unetk_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, L, I, P]),
+    "unetk_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, L, I, P]),
+    "unetk_head_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "unetk_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, I, P]),
+    "unetk_combined_loss_workspace_bytes": (Z, []),
+    "unetk_combined_loss": (I, [P, P, P, P, P, P, P, P, Z, L, L, F, F, F, F, P]),
+    "unetk_scale_by_scalar": (I, [P, P, L, P]),
+    "unetk_ssim_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "unetk_ssim_bwd": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "unetk_anomaly_score": (I, [P, P, P, I, I, I, I, I, P]),
+    "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),
+    "unetk_permute_batched": (I, [P, I, I, P, P, I, F, P]),
+    "unetk_permute_chunk_elems": (I, []),
+    "unetk_nchw_to_nhwc": (I, [P, P, I, I, I, I, P]),
+    "unetk_nhwc_to_nchw": (I, [P, P, I, I, I, I, P]),
+}
+
+
+class UnetkError(RuntimeError):
+    pass
+
+
+_lib = None
+_launches = 0  # number of kernel-launching C-ABI calls made by this process (bench: gpu_launches)
+
+
+def get():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if os.environ.get("UNETK_AUTOBUILD", "0") == "1":
+            from . import build as _build
+            _build.build()
+        else:
+            raise UnetkError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale: loud on purpose
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = get().unetk_last_error()
+    return msg.decode() if msg else ""
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point and raise UnetkError on a non-zero code."""
+    global _launches
+    rc = getattr(get(), name)(*args)
+    _launches += 1
+    if rc != 0:
+        raise UnetkError(f"{name} failed with code {rc}: {last_error()}")
+
+
+def launch_count() -> int:
+    return _launches

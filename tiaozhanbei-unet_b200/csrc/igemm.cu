@@ -36,7 +36,9 @@ struct IgemmParams {
   __nv_bfloat16* out2;
   int ldc1, ldc2;
   int acc1, acc2;       // 1: read-modify-write (gradient accumulation)
-  float* stats;         // nullable, [2][Ntot]: per-column sum and sum of squares
+  float* stats;         // nullable: per-column sums for columns [stats_from, Ntot), stats[col - stats_from]
+  float* stats_sq;      // nullable: per-column sums of squares, same indexing
+  int stats_from;
   const float* scale;   // nullable per-column affine (eval-mode BatchNorm folded in)
   const float* shift;
   int relu;
@@ -214,18 +216,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + ch * 32, v);
         tmem_ld_wait();
         if (col >= p.Ntot) continue;  // warp-uniform
-        if (p.stats != nullptr) {
-          float s[32], s2[32];
+        if (p.stats != nullptr && col >= p.stats_from) {
+          float s[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = valid ? v[j] : 0.f;
-            s[j] = a;
-            s2[j] = a * a;
-          }
+          for (int j = 0; j < 32; ++j) s[j] = valid ? v[j] : 0.f;
           const float cs = warp_colsum32(s);
-          const float cs2 = warp_colsum32(s2);
           atomicAdd(&colbuf[col + lane], cs);
-          atomicAdd(&colbuf[p.Ntot + col + lane], cs2);
+          if (p.stats_sq != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = valid ? v[j] : 0.f;
+              s[j] = a * a;
+            }
+            const float cs2 = warp_colsum32(s);
+            atomicAdd(&colbuf[p.Ntot + col + lane], cs2);
+          }
         }
         if (p.scale != nullptr) {
 #pragma unroll
@@ -287,9 +292,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       // all four epilogue warps have finished their smem atomics
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = threadIdx.x - 64;
-      for (int i = et; i < 2 * p.Ntot; i += 128) {
+      for (int i = p.stats_from + et; i < p.Ntot; i += 128) {
         const float v = colbuf[i];
-        if (v != 0.f) atomicAdd(p.stats + i, v);
+        if (v != 0.f) atomicAdd(p.stats + (i - p.stats_from), v);
+        if (p.stats_sq != nullptr) {
+          const float v2 = colbuf[p.Ntot + i];
+          if (v2 != 0.f) atomicAdd(p.stats_sq + (i - p.stats_from), v2);
+        }
       }
     }
   }
@@ -437,7 +446,8 @@ int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* 
   IgemmParams& p = L.p;
   p.n_img = n; p.H = h; p.W = w; p.Ntot = cout; p.num_taps = 9; p.a_mode = 0; p.epi_mode = 0;
   p.split = cout; p.out1 = static_cast<__nv_bfloat16*>(y); p.out2 = nullptr; p.ldc1 = cout; p.ldc2 = 0;
-  p.stats = stats; p.scale = scale; p.shift = shift; p.relu = relu;
+  p.stats = stats; p.stats_sq = stats ? stats + cout : nullptr; p.stats_from = 0;
+  p.scale = scale; p.shift = shift; p.relu = relu;
   return launch_igemm(L, stream);
 }
 
@@ -450,7 +460,10 @@ int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1,
   IgemmParams& p = L.p;
   p.n_img = n; p.H = h; p.W = w; p.Ntot = c1 + c2; p.num_taps = 9; p.a_mode = 0; p.epi_mode = 0;
   p.split = c1; p.out1 = static_cast<__nv_bfloat16*>(dx1); p.out2 = static_cast<__nv_bfloat16*>(dx2);
-  p.ldc1 = c1; p.ldc2 = c2; p.acc1 = acc1; p.acc2 = acc2; p.stats = stats;
+  p.ldc1 = c1; p.ldc2 = c2; p.acc1 = acc1; p.acc2 = acc2;
+  // bias gradient of the ConvTranspose2d that produced the second concat source: sum over pixels of dx2
+  p.stats = stats; p.stats_sq = nullptr; p.stats_from = c1;
+  UNETK_CHECK_ARG(stats == nullptr || c2 > 0, "conv3x3_dgrad: stats requested without a second destination");
   return launch_igemm(L, stream);
 }
 

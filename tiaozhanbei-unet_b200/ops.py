@@ -1,0 +1,238 @@
+"""Tensor-level wrappers around the C ABI (include/unetk.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every computation is a
+call into libunetk.so.  All wrappers are asynchronous on torch's current CUDA stream.
+Activations are NHWC bf16 tensors of shape [N, H, W, C]; images / outputs are NCHW fp32.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _p(t):
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.UnetkError(f"{name}: expected a CUDA tensor (this library has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.UnetkError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.UnetkError(f"{name}: expected a contiguous tensor")
+
+
+def zero_(t):
+    _lib.call("unetk_memset_zero", _p(t), t.numel() * t.element_size(), _s())
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# convolutions
+# ---------------------------------------------------------------------------------------------
+def conv3x3_fwd(src1, src2, wf, y, stats=None, scale=None, shift=None, relu=False):
+    """y = conv3x3(cat(src1, src2)) with packed weights wf [Cout][9][Cin]."""
+    _chk(src1, bf16, "src1"); _chk(wf, bf16, "wf"); _chk(y, bf16, "y")
+    n, h, w, c1 = src1.shape
+    c2 = 0
+    if src2 is not None:
+        _chk(src2, bf16, "src2")
+        c2 = src2.shape[3]
+    cout = y.shape[3]
+    _lib.call("unetk_conv3x3_fwd", _p(src1), c1, _p(src2), c2, _p(wf), _p(y), _p(stats), _p(scale),
+              _p(shift), int(relu), n, h, w, cout, _s())
+    return y
+
+
+def conv3x3_dgrad(dy, wd, dx1, acc1=False, dx2=None, acc2=False, stats=None):
+    _chk(dy, bf16, "dy"); _chk(wd, bf16, "wd"); _chk(dx1, bf16, "dx1")
+    n, h, w, cout = dy.shape
+    c1 = dx1.shape[3]
+    c2 = 0
+    if dx2 is not None:
+        _chk(dx2, bf16, "dx2")
+        c2 = dx2.shape[3]
+    _lib.call("unetk_conv3x3_dgrad", _p(dy), cout, _p(wd), _p(dx1), c1, int(acc1), _p(dx2), c2,
+              int(acc2), _p(stats), n, h, w, _s())
+
+
+def conv3x3_wgrad(dy, src1, src2, dw):
+    """dw[co][tap][ci] += ... (fp32, caller zeroes)."""
+    _chk(dy, bf16, "dy"); _chk(src1, bf16, "src1"); _chk(dw, f32, "dw")
+    n, h, w, cout = dy.shape
+    c1 = src1.shape[3]
+    c2 = 0
+    if src2 is not None:
+        _chk(src2, bf16, "src2")
+        c2 = src2.shape[3]
+    _lib.call("unetk_conv3x3_wgrad", _p(dy), _p(src1), c1, _p(src2), c2, _p(dw), n, h, w, cout, _s())
+
+
+def first_conv_fwd(x, w, y, stats=None):
+    _chk(x, f32, "x"); _chk(w, f32, "w"); _chk(y, bf16, "y")
+    n, cin, h, ww = x.shape
+    _lib.call("unetk_first_conv_fwd", _p(x), _p(w), _p(y), _p(stats), n, cin, h, ww, y.shape[3], _s())
+    return y
+
+
+def first_conv_wgrad(x, dy, dw):
+    _chk(x, f32, "x"); _chk(dy, bf16, "dy"); _chk(dw, f32, "dw")
+    n, cin, h, ww = x.shape
+    _lib.call("unetk_first_conv_wgrad", _p(x), _p(dy), _p(dw), n, cin, h, ww, dy.shape[3], _s())
+
+
+def convt2x2_fwd(a, wt, bias, up):
+    _chk(a, bf16, "a"); _chk(wt, bf16, "wt"); _chk(up, bf16, "up")
+    n, h, w, cin = a.shape
+    _lib.call("unetk_convt2x2_fwd", _p(a), cin, _p(wt), _p(bias), _p(up), n, h, w, up.shape[3], _s())
+    return up
+
+
+def convt2x2_dgrad(dup, wtd, da, acc=False):
+    _chk(dup, bf16, "dup"); _chk(wtd, bf16, "wtd"); _chk(da, bf16, "da")
+    n, h, w, cin = da.shape
+    _lib.call("unetk_convt2x2_dgrad", _p(dup), dup.shape[3], _p(wtd), _p(da), cin, int(acc), n, h, w, _s())
+
+
+def convt2x2_wgrad(a, dup, dw):
+    _chk(a, bf16, "a"); _chk(dup, bf16, "dup"); _chk(dw, f32, "dw")
+    n, h, w, cin = a.shape
+    _lib.call("unetk_convt2x2_wgrad", _p(a), cin, _p(dup), dup.shape[3], _p(dw), n, h, w, _s())
+
+
+# ---------------------------------------------------------------------------------------------
+# batch norm / relu / pool
+# ---------------------------------------------------------------------------------------------
+def bn_finalize(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd,
+                count, eps=1e-5, momentum=0.1):
+    c = gamma.numel()
+    _lib.call("unetk_bn_finalize", _p(stats), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+              _p(nbt), _p(scale), _p(shift), _p(mean), _p(invstd), c, float(count), eps, momentum, _s())
+
+
+def bn_fold(gamma, beta, running_mean, running_var, scale, shift, eps=1e-5):
+    _lib.call("unetk_bn_fold", _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(scale),
+              _p(shift), gamma.numel(), eps, _s())
+
+
+def bnrelu_apply(y, scale, shift, a):
+    _chk(y, bf16, "y"); _chk(a, bf16, "a")
+    c = y.shape[-1]
+    _lib.call("unetk_bnrelu_apply", _p(y), _p(scale), _p(shift), _p(a), y.numel() // c, c, _s())
+    return a
+
+
+def bnrelu_pool(y, scale, shift, a, pooled, idx, apply=True):
+    _chk(y, bf16, "y"); _chk(pooled, bf16, "pooled")
+    n, h, w, c = y.shape
+    _lib.call("unetk_bnrelu_pool", _p(y), _p(scale), _p(shift), _p(a), _p(pooled), _p(idx), n, h, w, c,
+              int(apply), _s())
+
+
+def maxpool_bwd(dpooled, idx, da, accumulate):
+    _chk(dpooled, bf16, "dpooled"); _chk(da, bf16, "da")
+    n, h, w, c = da.shape
+    _lib.call("unetk_maxpool_bwd", _p(dpooled), _p(idx), _p(da), n, h, w, c, int(accumulate), _s())
+
+
+def bn_bwd_reduce(da, y, scale, shift, mean, invstd, sums):
+    c = y.shape[-1]
+    _lib.call("unetk_bn_bwd_reduce", _p(da), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums),
+              y.numel() // c, c, _s())
+
+
+def bn_bwd_apply(da, y, scale, shift, mean, invstd, sums, dy, dgamma, dbeta):
+    c = y.shape[-1]
+    _lib.call("unetk_bn_bwd_apply", _p(da), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums),
+              _p(dy), _p(dgamma), _p(dbeta), y.numel() // c, c, _s())
+
+
+# ---------------------------------------------------------------------------------------------
+# head / losses / scoring
+# ---------------------------------------------------------------------------------------------
+def head_fwd(a, w, b, out, sigmoid):
+    _chk(a, bf16, "a"); _chk(out, f32, "out")
+    n, h, ww, c = a.shape
+    _lib.call("unetk_head_fwd", _p(a), _p(w), _p(b), _p(out), n, h, ww, c, out.shape[1], int(sigmoid), _s())
+    return out
+
+
+def head_bwd(a, w, dout, out, da, dw, db, sigmoid):
+    _chk(a, bf16, "a"); _chk(dout, f32, "dout"); _chk(da, bf16, "da")
+    n, h, ww, c = a.shape
+    _lib.call("unetk_head_bwd", _p(a), _p(w), _p(dout), _p(out), _p(da), _p(dw), _p(db), n, h, ww, c,
+              dout.shape[1], int(sigmoid), _s())
+
+
+def combined_loss_workspace(device):
+    nbytes = _lib.get().unetk_combined_loss_workspace_bytes()
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+
+def combined_loss(recon, amap, image, mask, d_recon, d_amap, out3, work, rw, sw, alpha, gamma):
+    for t, nm in ((recon, "reconstruction"), (amap, "anomaly_map"), (image, "original_image"), (mask, "true_mask")):
+        _chk(t, f32, nm)
+    _lib.call("unetk_combined_loss", _p(recon), _p(amap), _p(image), _p(mask), _p(d_recon), _p(d_amap),
+              _p(out3), _p(work), work.numel(), recon.numel(), amap.numel(), rw, sw, alpha, gamma, _s())
+
+
+def scale_by_scalar(y, scalar):
+    _lib.call("unetk_scale_by_scalar", _p(y), _p(scalar), y.numel(), _s())
+
+
+def ssim_fwd(img1, img2, sums, maps, window_size, need2):
+    _chk(img1, f32, "img1"); _chk(img2, f32, "img2")
+    n, c, h, w = img1.shape
+    _lib.call("unetk_ssim_fwd", _p(img1), _p(img2), _p(sums), _p(maps), n, c, h, w, window_size, int(need2), _s())
+
+
+def ssim_bwd(img1, img2, maps, gout, grad, window_size, which, per_image):
+    n, c, h, w = img1.shape
+    _lib.call("unetk_ssim_bwd", _p(img1), _p(img2), _p(maps), _p(gout), _p(grad), n, c, h, w, window_size,
+              which, int(per_image), _s())
+
+
+def anomaly_score(recon, orig, out, method=0):
+    _chk(recon, f32, "reconstruction"); _chk(orig, f32, "original")
+    n, c, h, w = recon.shape
+    _lib.call("unetk_anomaly_score", _p(recon), _p(orig), _p(out), n, c, h, w, method, _s())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# optimizer / layout
+# ---------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, mode=0):
+    _lib.call("unetk_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, wd, step,
+              grad_scale, mode, _s())
+
+
+def permute_batched(table, src, dst, scale=1.0):
+    """table: packing.PermuteTable (device descriptor array)."""
+    _lib.call("unetk_permute_batched", _p(table.device_descs), table.n_desc, table.n_chunks, _p(src), _p(dst),
+              int(dst.dtype == bf16), scale, _s())
+
+
+def nchw_to_nhwc(x, out):
+    _chk(x, f32, "x"); _chk(out, bf16, "out")
+    n, c, h, w = x.shape
+    _lib.call("unetk_nchw_to_nhwc", _p(x), _p(out), n, c, h, w, _s())
+    return out
+
+
+def nhwc_to_nchw(a, out):
+    _chk(a, bf16, "a"); _chk(out, f32, "out")
+    n, h, w, c = a.shape
+    _lib.call("unetk_nhwc_to_nchw", _p(a), _p(out), n, c, h, w, _s())
+    return out
