@@ -142,6 +142,9 @@ int unetk_scale_by_scalar(float* y, const float* scalar, int64_t n, void* stream
  * need2 == 0) hold the derivative planes consumed by unetk_ssim_bwd. */
 int unetk_ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int n, int c,
                    int h, int w, int window_size, int need2, void* stream);
+/* out = 1 - mean(ssim_map): out[0] when size_average, else out[n] (one value per image). */
+int unetk_ssim_finalize(const float* sums, float* out, int n, int c, int h, int w, int size_average,
+                        void* stream);
 int unetk_ssim_bwd(const float* img1, const float* img2, const float* maps, const float* gout,
                    float* grad, int n, int c, int h, int w, int window_size, int which,
                    int per_image, void* stream);

@@ -1,0 +1,123 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol of
+include/unetk.h, the drop-in modules have the reference's parameter layout / state_dict keys /
+initialisation stream, the packing recipes are the right permutations, and the product path fails
+loudly (no CPU fallback)."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import unet_oracle as O  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    from tiaozhanbei_unet_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "unetk.h")).read()
+    declared = set(re.findall(r"\b(unetk_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    lib = _lib.get()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/unetk.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table and header disagree"
+    assert lib.unetk_version() == 100
+
+
+@pytest.mark.parametrize("arch", ["unet", "anomaly_unet"])
+def test_state_dict_layout_matches_reference(arch):
+    from tiaozhanbei_unet_b200.model import AnomalyUNet, UNet
+    m = UNet(3, 1) if arch == "unet" else AnomalyUNet(3)
+    sd = m.state_dict()
+    spec = O.state_dict_spec(arch)   # pinned against the reference by tests/test_oracle.py
+    assert list(sd.keys()) == list(spec.keys())
+    for k, (shape, dtype) in spec.items():
+        assert tuple(sd[k].shape) == tuple(shape) and sd[k].dtype == dtype, k
+    n = sum(p.numel() for p in m.parameters())
+    assert n == (31037633 if arch == "unet" else 43228228)
+    # strict load of a reference-shaped state_dict
+    m.load_state_dict(O.synthetic_state_dict(arch, seed=1), strict=True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="live reference only in the build container")
+def test_initialisation_stream_matches_reference():
+    """Same seed -> same initial weights as the reference constructors (src/train.py:106 seeds 42)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import import_reference
+    ref = import_reference()
+    from tiaozhanbei_unet_b200.model import AnomalyUNet
+    torch.manual_seed(42)
+    a = ref["model"].AnomalyUNet(3).state_dict()
+    torch.manual_seed(42)
+    b = AnomalyUNet(3).state_dict()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_packing_recipes_are_the_documented_permutations():
+    from tiaozhanbei_unet_b200 import packing
+
+    def apply(recipe, src):
+        (d0, d1, d2), (s0, s1, s2), flip = recipe
+        out = np.empty(d0 * d1 * d2, dtype=src.dtype)
+        for i0 in range(d0):
+            for i1 in range(d1):
+                j1 = d1 - 1 - i1 if flip else i1
+                for i2 in range(d2):
+                    out[(i0 * d1 + i1) * d2 + i2] = src[i0 * s0 + j1 * s1 + i2 * s2]
+        return out
+
+    co, ci = 4, 3
+    w = np.arange(co * ci * 9, dtype=np.float32).reshape(co, ci, 3, 3)
+    wf = apply(packing.conv_fwd_pack(co, ci), w.ravel()).reshape(co, 9, ci)
+    assert np.array_equal(wf, w.reshape(co, ci, 9).transpose(0, 2, 1))
+    wd = apply(packing.conv_dgrad_pack(co, ci), w.ravel()).reshape(ci, 9, co)
+    assert np.array_equal(wd, w[:, :, ::-1, ::-1].reshape(co, ci, 9).transpose(1, 2, 0))
+    back = apply(packing.conv_grad_unpack(co, ci), wf.ravel()).reshape(co, ci, 3, 3)
+    assert np.array_equal(back, w)
+    wt = np.arange(ci * co * 4, dtype=np.float32).reshape(ci, co, 2, 2)
+    tf = apply(packing.convt_fwd_pack(ci, co), wt.ravel()).reshape(4, co, ci)
+    assert np.array_equal(tf, wt.reshape(ci, co, 4).transpose(2, 1, 0))
+    td = apply(packing.convt_dgrad_pack(ci, co), wt.ravel()).reshape(ci, 4, co)
+    assert np.array_equal(td, wt.reshape(ci, co, 4).transpose(0, 2, 1))
+    gk = wt.reshape(ci, co, 4).transpose(1, 2, 0).copy()      # [co][tap][ci]
+    assert np.array_equal(apply(packing.convt_grad_unpack(ci, co), gk.ravel()).reshape(ci, co, 2, 2), wt)
+    tab = packing.PermuteTable(2048)
+    tab.add(0, 0, *packing.conv_fwd_pack(64, 64))
+    tab.add(100, 200, *packing.identity(5000))
+    arr, chunks = tab.numpy()
+    assert arr.dtype.itemsize == 64 and chunks == 18 + 3 and arr[1]["chunk_begin"] == 18
+
+
+def test_no_cpu_fallback():
+    from tiaozhanbei_unet_b200 import train_utils
+    from tiaozhanbei_unet_b200.model import UNet, Up
+    m = UNet(3, 1)
+    with pytest.raises(Exception) as e:
+        m(torch.randn(1, 3, 32, 32))
+    assert "CUDA" in str(e.value) or "cuda" in str(e.value)
+    with pytest.raises(RuntimeError):
+        train_utils.CombinedLoss()(torch.rand(1, 3, 8, 8), torch.rand(1, 1, 8, 8), torch.rand(1, 3, 8, 8), torch.rand(1, 1, 8, 8))
+    with pytest.raises(NotImplementedError):
+        Up(128, 64, bilinear=True)
+
+
+def test_optimizer_state_dict_is_torch_shaped():
+    from tiaozhanbei_unet_b200 import train_utils
+    lin = torch.nn.Linear(4, 3)
+    ours = train_utils.get_optimizer(lin, "adam", 1e-3, 1e-4)
+    ref = torch.optim.Adam(lin.parameters(), lr=1e-3, weight_decay=1e-4)
+    a, b = ours.state_dict(), ref.state_dict()
+    assert a["param_groups"][0].keys() == b["param_groups"][0].keys()
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad"):
+        assert a["param_groups"][0][k] == b["param_groups"][0][k]
+    ours.load_state_dict(b)          # a torch-Adam checkpoint loads
+    ref.load_state_dict(a)
+    with pytest.raises(ValueError):
+        train_utils.get_optimizer(lin, "rmsprop")
+    sch = train_utils.get_scheduler(ours, "cosine", 10)
+    assert isinstance(sch, torch.optim.lr_scheduler.CosineAnnealingLR)
+    assert train_utils.get_scheduler(ours, "none") is None

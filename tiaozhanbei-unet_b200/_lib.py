@@ -41,6 +41,7 @@ SIGNATURES = {
     "unetk_combined_loss": (I, [P, P, P, P, P, P, P, P, Z, L, L, F, F, F, F, P]),
     "unetk_scale_by_scalar": (I, [P, P, L, P]),
     "unetk_ssim_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "unetk_ssim_finalize": (I, [P, P, I, I, I, I, I, P]),
     "unetk_ssim_bwd": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P]),
     "unetk_anomaly_score": (I, [P, P, P, I, I, I, I, I, P]),
     "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),

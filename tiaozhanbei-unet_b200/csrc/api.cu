@@ -124,6 +124,10 @@ int unetk_ssim_fwd(const float* img1, const float* img2, float* sums, float* map
                    int h, int w, int window_size, int need2, void* stream) {
   return unetk::ssim_fwd(img1, img2, sums, maps, n, c, h, w, window_size, need2, S(stream));
 }
+int unetk_ssim_finalize(const float* sums, float* out, int n, int c, int h, int w, int size_average,
+                        void* stream) {
+  return unetk::ssim_finalize(sums, out, n, c, h, w, size_average, S(stream));
+}
 int unetk_ssim_bwd(const float* img1, const float* img2, const float* maps, const float* gout,
                    float* grad, int n, int c, int h, int w, int window_size, int which,
                    int per_image, void* stream) {

@@ -408,6 +408,21 @@ ssim_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
   }
 }
 
+// out = 1 - mean(ssim_map): one scalar (size_average) or one value per image
+__global__ void ssim_finalize_kernel(const float* __restrict__ sums, float* __restrict__ out, int n,
+                                     float per_image_count, int size_average) {
+  if (size_average) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < n; ++i) s += sums[i];
+      out[0] = static_cast<float>(1.0 - s / (static_cast<double>(per_image_count) * n));
+    }
+  } else {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.f - sums[i] / per_image_count;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------------------------
@@ -512,6 +527,14 @@ int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int
   UNETK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * N, s));
   dim3 grid((W + kSsimT - 1) / kSsimT, (H + kSsimT - 1) / kSsimT, N * C);
   ssim_fwd_kernel<<<grid, 256, 0, s>>>(img1, img2, sums, maps, C, H, W, win, need2);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int ssim_finalize(const float* sums, float* out, int N, int C, int H, int W, int size_average,
+                  cudaStream_t s) {
+  UNETK_CHECK_ARG(sums && out, "ssim_finalize: null pointer");
+  ssim_finalize_kernel<<<(N + 127) / 128, 128, 0, s>>>(sums, out, N, static_cast<float>(C) * H * W, size_average);
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }

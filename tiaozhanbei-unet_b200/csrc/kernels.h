@@ -65,6 +65,8 @@ int anomaly_score(const float* recon, const float* orig, float* out, int N, int 
                   int method, cudaStream_t s);
 int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int N, int C, int H,
              int W, int window_size, int need2, cudaStream_t s);
+int ssim_finalize(const float* sums, float* out, int N, int C, int H, int W, int size_average,
+                  cudaStream_t s);
 int ssim_bwd(const float* img1, const float* img2, const float* maps, const float* gout, float* grad,
              int N, int C, int H, int W, int window_size, int which, int per_image, cudaStream_t s);
 

@@ -1,0 +1,492 @@
+"""Static execution plan of one U-Net / AnomalyUNet: flat parameter storage, packed bf16 weights,
+pre-allocated NHWC bf16 activations and the forward / backward kernel sequences.
+
+What the reference does with nn.Module.__call__ + autograd (src/model.py:97-108, :188-210 and the
+`total_loss.backward()` of src/train_utils.py:132), this file does with explicit launches of the
+kernels declared in include/unetk.h, in a fixed order on torch's current stream:
+
+  forward (train)   conv -> [BN stats in the conv epilogue] -> bn_finalize -> bnrelu(+pool+idx)
+  forward (eval)    conv with folded BN + ReLU in the epilogue -> pool
+  backward          head_bwd -> per conv: bn_bwd_reduce / bn_bwd_apply -> wgrad + dgrad;
+                    skip connections accumulate their 2-3 gradients in place (dgrad epilogue /
+                    pool backward read-modify-write); weight gradients are staged in
+                    [Cout][tap][Cin] and re-laid-out to the reference layouts by one launch.
+
+Parameters stay `nn.Parameter`s under the reference's attribute paths (state_dict identical);
+their storage is re-pointed to slices of ONE flat fp32 buffer so the optimizer step, the weight
+re-packing, the gradient un-packing and the data-parallel all-reduce are each one launch / one
+contiguous range.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops, packing
+
+WIDTHS = [64, 128, 256, 512, 1024]
+ALIGN = 64  # elements; keeps every slice 256-byte aligned
+
+
+def _align(n):
+    return (n + ALIGN - 1) // ALIGN * ALIGN
+
+
+class _ConvBN:
+    """One conv3x3 + BatchNorm record (tensor views are filled in by Engine._build_views)."""
+
+    def __init__(self, name, conv, bn, cin1, cin2, cout, first=False):
+        self.name, self.conv, self.bn = name, conv, bn
+        self.cin1, self.cin2, self.cout, self.first = cin1, cin2, cout, first
+
+
+class _ConvT:
+    def __init__(self, name, mod, cin, cout):
+        self.name, self.mod, self.cin, self.cout = name, mod, cin, cout
+
+
+class _Head:
+    def __init__(self, name, mod, n_out, sigmoid):
+        self.name, self.mod, self.n_out, self.sigmoid = name, mod, n_out, sigmoid
+
+
+class Plan:
+    """Buffers for one input shape."""
+
+    def __init__(self, eng, n, h, w, device):
+        self.n, self.h, self.w = n, h, w
+        self.generation = 0
+        bf = torch.bfloat16
+
+        def act(lvl, c):
+            return torch.empty(n, h >> lvl, w >> lvl, c, dtype=bf, device=device)
+
+        self.enc = []
+        for l in range(5):
+            c = WIDTHS[l]
+            d = {"y1": act(l, c), "a1": act(l, c), "y2": act(l, c), "a2": act(l, c)}
+            if l < 4:
+                d["p"] = act(l + 1, c)
+                d["idx"] = torch.empty(n, h >> (l + 1), w >> (l + 1), c, dtype=torch.uint8, device=device)
+            self.enc.append(d)
+        self.dec = []
+        for _ in eng.decoders:
+            stages = []
+            for k in range(1, 5):
+                lv = 4 - k
+                c = WIDTHS[lv]
+                stages.append({"up": act(lv, c), "y1": act(lv, c), "a1": act(lv, c), "y2": act(lv, c),
+                               "a2": act(lv, c)})
+            self.dec.append(stages)
+        self._act = act
+        self.grads_ready = False
+
+    def alloc_grads(self):
+        if self.grads_ready:
+            return
+        act = self._act
+        self.d_skip = [act(l, WIDTHS[l]) for l in range(5)]   # d(a2) of every encoder level
+        self.d_t = act(0, 64)       # running decoder gradient d(a2) of the current stage (max size)
+        self.d_a1 = act(0, 64)      # gradient wrt a DoubleConv's inner activation (max size)
+        self.d_y = act(0, 64)       # gradient wrt a raw conv output (max size)
+        self.d_up = act(0, 64)      # gradient wrt an up-sampled tensor (max size)
+        self.d_p = act(1, 64)       # gradient wrt a pooled tensor (max size)
+        self.grads_ready = True
+
+    @staticmethod
+    def view(buf, like):
+        return buf.view(-1)[: like.numel()].view(like.shape)
+
+
+class Engine:
+    def __init__(self, module, arch, n_channels, head_specs):
+        """head_specs: list of (suffix, n_out, sigmoid) — one decoder each."""
+        self.module = module
+        self.arch = arch
+        self.n_channels = n_channels
+        self.device = None
+        self.plans = {}
+        self.flat_p = None
+        self._sig = None
+        self.ddp = None           # set by distributed.attach()
+        self.weights_dirty = True
+        self.fold_dirty = True
+        m = module
+        self.convbn = []
+        self.encoder = []
+        dcs = [("inc", m.inc)] + [(f"down{k}.maxpool_conv.1", getattr(m, f"down{k}").maxpool_conv[1]) for k in range(1, 5)]
+        for l, (name, dc) in enumerate(dcs):
+            cin = n_channels if l == 0 else WIDTHS[l - 1]
+            c1 = _ConvBN(f"{name}.double_conv.0", dc.double_conv[0], dc.double_conv[1], cin, 0, WIDTHS[l], first=(l == 0))
+            c2 = _ConvBN(f"{name}.double_conv.3", dc.double_conv[3], dc.double_conv[4], WIDTHS[l], 0, WIDTHS[l])
+            self.encoder.append((c1, c2))
+            self.convbn += [c1, c2]
+        self.decoders = []
+        for suffix, n_out, sigmoid in head_specs:
+            stages = []
+            for k in range(1, 5):
+                up = getattr(m, f"up{k}{suffix}")
+                cin = WIDTHS[5 - k]
+                ct = _ConvT(f"up{k}{suffix}.up", up.up, cin, cin // 2)
+                c1 = _ConvBN(f"up{k}{suffix}.conv.double_conv.0", up.conv.double_conv[0], up.conv.double_conv[1],
+                             cin // 2, cin // 2, cin // 2)
+                c2 = _ConvBN(f"up{k}{suffix}.conv.double_conv.3", up.conv.double_conv[3], up.conv.double_conv[4],
+                             cin // 2, 0, cin // 2)
+                stages.append((ct, c1, c2))
+                self.convbn += [c1, c2]
+            head = _Head(f"outc{suffix}.conv", getattr(m, f"outc{suffix}").conv, n_out, sigmoid)
+            self.decoders.append((stages, head))
+
+    # ------------------------------------------------------------------------------------------
+    # parameter storage
+    # ------------------------------------------------------------------------------------------
+    def _signature(self):
+        ps = list(self.module.parameters())
+        return (ps[0].data_ptr(), ps[-1].data_ptr(), ps[0].device)
+
+    def ensure(self, device):
+        """(Re)flatten parameters when the module moved (`.to()`, `.cuda()`) or on first use."""
+        if self.flat_p is not None and self._sig == self._signature() and self.device == device:
+            return
+        if device.type != "cuda":
+            raise _lib.UnetkError("this implementation has no CPU path: move the model and inputs to a CUDA (sm_100a) device")
+        rc = _lib.get().unetk_check_device()
+        if rc != 0:
+            raise _lib.UnetkError(_lib.last_error())
+        self.device = device
+        named = list(self.module.named_parameters())
+        self.param_names = [k for k, _ in named]
+        self.params = [p for _, p in named]
+        offs, total = {}, 0
+        for k, p in named:
+            offs[k] = total
+            total += _align(p.numel())
+        self.offsets, self.total = offs, total
+        flat = torch.zeros(total, dtype=torch.float32, device=device)
+        for k, p in named:
+            v = flat[offs[k]: offs[k] + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+        self.flat_p = flat
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=device)
+        self.gstage = torch.zeros(total, dtype=torch.float32, device=device)
+        self._build_views(device)
+        self.plans = {}
+        self._sig = self._signature()
+        self.weights_dirty = True
+        self.fold_dirty = True
+
+    def _slice(self, buf, key, shape=None):
+        p = dict(zip(self.param_names, self.params))[key]
+        v = buf[self.offsets[key]: self.offsets[key] + p.numel()]
+        return v.view(shape if shape is not None else p.shape)
+
+    def _build_views(self, device):
+        chunk = _lib.get().unetk_permute_chunk_elems()
+        pack = packing.PermuteTable(chunk)
+        unpack = packing.PermuteTable(chunk)
+        pdict = dict(zip(self.param_names, self.params))
+        wsize = 0
+
+        def walloc(n):
+            nonlocal wsize
+            o = wsize
+            wsize += _align(n)
+            return o
+
+        # small per-BN buffers: [stats 2C | sums 2C] regions are contiguous over layers (one memset each)
+        tot_c = sum(L.cout for L in self.convbn)
+        self.bn_stats_all = torch.zeros(2 * tot_c, dtype=torch.float32, device=device)
+        self.bn_sums_all = torch.zeros(2 * tot_c, dtype=torch.float32, device=device)
+        self.bn_aux = torch.zeros(4 * tot_c, dtype=torch.float32, device=device)
+        co = 0
+        wplan = []
+        handled = set()
+        for L in self.convbn:
+            c = L.cout
+            L.stats = self.bn_stats_all[2 * co: 2 * co + 2 * c]
+            L.sums = self.bn_sums_all[2 * co: 2 * co + 2 * c]
+            L.scale = self.bn_aux[4 * co: 4 * co + c]
+            L.shift = self.bn_aux[4 * co + c: 4 * co + 2 * c]
+            L.mean = self.bn_aux[4 * co + 2 * c: 4 * co + 3 * c]
+            L.invstd = self.bn_aux[4 * co + 3 * c: 4 * co + 4 * c]
+            co += c
+            wk, gk, bk = L.name + ".weight", None, None
+            bnname = L.name.rsplit(".", 1)[0] + "." + str(int(L.name.rsplit(".", 1)[1]) + 1)
+            gk, bk = bnname + ".weight", bnname + ".bias"
+            L.w = self._slice(self.flat_p, wk)
+            L.gamma, L.beta = self._slice(self.flat_p, gk), self._slice(self.flat_p, bk)
+            L.g_gamma, L.g_beta = self._slice(self.gstage, gk), self._slice(self.gstage, bk)
+            L.rm, L.rv, L.nbt = L.bn.running_mean, L.bn.running_var, L.bn.num_batches_tracked
+            cin = L.cin1 + L.cin2
+            n = pdict[wk].numel()
+            if L.first:
+                L.g_w = self._slice(self.gstage, wk)            # written in OIHW directly
+                unpack.add(self.offsets[wk], self.offsets[wk], *packing.identity(n))
+            else:
+                L.g_w = self._slice(self.gstage, wk, (n,))      # [Cout][tap][Cin]
+                unpack.add(self.offsets[wk], self.offsets[wk], *packing.conv_grad_unpack(L.cout, cin))
+                of, od = walloc(n), walloc(n)
+                pack.add(self.offsets[wk], of, *packing.conv_fwd_pack(L.cout, cin))
+                pack.add(self.offsets[wk], od, *packing.conv_dgrad_pack(L.cout, cin))
+                wplan.append((L, "wf", of, n))
+                wplan.append((L, "wd", od, n))
+            for k in (gk, bk):
+                unpack.add(self.offsets[k], self.offsets[k], *packing.identity(pdict[k].numel()))
+            handled.update((wk, gk, bk))
+        for stages, head in self.decoders:
+            for ct, _, _ in stages:
+                wk, bk = ct.name + ".weight", ct.name + ".bias"
+                n = pdict[wk].numel()
+                ct.bias = self._slice(self.flat_p, bk)
+                ct.g_w = self._slice(self.gstage, wk, (n,))
+                ct.g_bias = self._slice(self.gstage, bk)
+                of, od = walloc(n), walloc(n)
+                pack.add(self.offsets[wk], of, *packing.convt_fwd_pack(ct.cin, ct.cout))
+                pack.add(self.offsets[wk], od, *packing.convt_dgrad_pack(ct.cin, ct.cout))
+                wplan.append((ct, "wf", of, n))
+                wplan.append((ct, "wd", od, n))
+                unpack.add(self.offsets[wk], self.offsets[wk], *packing.convt_grad_unpack(ct.cin, ct.cout))
+                unpack.add(self.offsets[bk], self.offsets[bk], *packing.identity(ct.cout))
+                handled.update((wk, bk))
+            wk, bk = head.name + ".weight", head.name + ".bias"
+            head.w = self._slice(self.flat_p, wk, (head.n_out, 64))
+            head.b = self._slice(self.flat_p, bk)
+            head.g_w = self._slice(self.gstage, wk, (head.n_out, 64))
+            head.g_b = self._slice(self.gstage, bk)
+            unpack.add(self.offsets[wk], self.offsets[wk], *packing.identity(head.n_out * 64))
+            unpack.add(self.offsets[bk], self.offsets[bk], *packing.identity(head.n_out))
+            handled.update((wk, bk))
+        missing = set(self.param_names) - handled
+        if missing:
+            raise _lib.UnetkError(f"engine does not cover parameters {sorted(missing)}")
+        self.wpack = torch.zeros(max(wsize, ALIGN), dtype=torch.bfloat16, device=device)
+        for obj, attr, off, n in wplan:
+            setattr(obj, attr, self.wpack[off: off + n])
+        self.pack_table = pack.finalize(device)
+        self.unpack_table = unpack.finalize(device)
+
+    def mark_weights_dirty(self):
+        self.weights_dirty = True
+        self.fold_dirty = True
+
+    def _version_sig(self):
+        """Sum of autograd version counters: changes whenever torch code (load_state_dict, a stock
+        optimizer) writes parameters or buffers in place.  Our own optimizer calls
+        mark_weights_dirty() instead (its kernels write through raw pointers)."""
+        v = 0
+        for p in self.params:
+            v += p._version
+        for L in self.convbn:
+            v += L.rm._version + L.rv._version
+        return v
+
+    def _pack_weights(self):
+        if self.weights_dirty:
+            ops.permute_batched(self.pack_table, self.flat_p, self.wpack)
+            self.weights_dirty = False
+
+    def grad_views(self):
+        """Fresh views of the flat gradient buffer, one per parameter (autograd takes ownership)."""
+        out = []
+        for k, p in zip(self.param_names, self.params):
+            o = self.offsets[k]
+            out.append(self.flat_g[o: o + p.numel()].view(p.shape))
+        return out
+
+    def plan_for(self, n, h, w):
+        key = (n, h, w)
+        pl = self.plans.get(key)
+        if pl is None:
+            if h % 16 or w % 16:
+                raise ValueError(f"input size {h}x{w} is not a multiple of 16: the F.pad path of the reference "
+                                 "(src/model.py:57-61) is not implemented in this version")
+            if len(self.plans) >= 3:      # e.g. train batch, last ragged batch, validation batch
+                self.plans.pop(next(iter(self.plans)))
+            pl = Plan(self, n, h, w, self.device)
+            self.plans[key] = pl
+        return pl
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def _check_input(self, x):
+        if x.dim() != 4 or x.shape[1] != self.n_channels:
+            raise ValueError(f"expected input [N, {self.n_channels}, H, W], got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise _lib.UnetkError("input must be a CUDA tensor (no CPU path)")
+        if x.dtype != torch.float32:
+            x = x.float()
+        return x.contiguous()
+
+    def forward(self, x, training):
+        x = self._check_input(x)
+        self.ensure(x.device)
+        n, _, h, w = x.shape
+        pl = self.plan_for(n, h, w)
+        pl.generation += 1
+        sig = self._version_sig()
+        if training or sig != getattr(self, "_vsig", None):
+            self.mark_weights_dirty()
+            self._vsig = sig
+        self._pack_weights()
+        if training:
+            outs = self._forward_train(pl, x)
+            self.fold_dirty = True   # running statistics moved
+        else:
+            outs = self._forward_eval(pl, x)
+        pl.x = x
+        return outs, pl, pl.generation
+
+    def _bn_train(self, L, y, a, count, pool=None):
+        ops.bn_finalize(L.stats, L.gamma, L.beta, L.rm, L.rv, L.nbt, L.scale, L.shift, L.mean, L.invstd,
+                        count, L.bn.eps, L.bn.momentum if L.bn.momentum is not None else 0.1)
+        if pool is None:
+            ops.bnrelu_apply(y, L.scale, L.shift, a)
+        else:
+            ops.bnrelu_pool(y, L.scale, L.shift, a, pool[0], pool[1], apply=True)
+
+    def _forward_train(self, pl, x):
+        ops.zero_(self.bn_stats_all)
+        n = pl.n
+        for l, (c1, c2) in enumerate(self.encoder):
+            e = pl.enc[l]
+            count = n * (pl.h >> l) * (pl.w >> l)
+            if l == 0:
+                ops.first_conv_fwd(x, c1.w, e["y1"], c1.stats)
+            else:
+                ops.conv3x3_fwd(pl.enc[l - 1]["p"], None, c1.wf, e["y1"], stats=c1.stats)
+            self._bn_train(c1, e["y1"], e["a1"], count)
+            ops.conv3x3_fwd(e["a1"], None, c2.wf, e["y2"], stats=c2.stats)
+            self._bn_train(c2, e["y2"], e["a2"], count, pool=(e["p"], e["idx"]) if l < 4 else None)
+        outs = []
+        for d, (stages, head) in enumerate(self.decoders):
+            t = pl.enc[4]["a2"]
+            for k, (ct, c1, c2) in enumerate(stages):
+                lv = 3 - k
+                s = pl.dec[d][k]
+                count = n * (pl.h >> lv) * (pl.w >> lv)
+                ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
+                ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["y1"], stats=c1.stats)
+                self._bn_train(c1, s["y1"], s["a1"], count)
+                ops.conv3x3_fwd(s["a1"], None, c2.wf, s["y2"], stats=c2.stats)
+                self._bn_train(c2, s["y2"], s["a2"], count)
+                t = s["a2"]
+            out = torch.empty(n, head.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device)
+            ops.head_fwd(t, head.w, head.b, out, head.sigmoid)
+            outs.append(out)
+        return outs
+
+    def _fold(self):
+        if self.fold_dirty:
+            for L in self.convbn:
+                ops.bn_fold(L.gamma, L.beta, L.rm, L.rv, L.scale, L.shift, L.bn.eps)
+            self.fold_dirty = False
+
+    def _forward_eval(self, pl, x):
+        self._fold()
+        n = pl.n
+        for l, (c1, c2) in enumerate(self.encoder):
+            e = pl.enc[l]
+            if l == 0:
+                ops.first_conv_fwd(x, c1.w, e["y1"], None)
+                ops.bnrelu_apply(e["y1"], c1.scale, c1.shift, e["a1"])
+            else:
+                ops.conv3x3_fwd(pl.enc[l - 1]["p"], None, c1.wf, e["a1"], scale=c1.scale, shift=c1.shift, relu=True)
+            ops.conv3x3_fwd(e["a1"], None, c2.wf, e["a2"], scale=c2.scale, shift=c2.shift, relu=True)
+            if l < 4:
+                ops.bnrelu_pool(e["a2"], None, None, None, e["p"], None, apply=False)
+        outs = []
+        for d, (stages, head) in enumerate(self.decoders):
+            t = pl.enc[4]["a2"]
+            for k, (ct, c1, c2) in enumerate(stages):
+                lv = 3 - k
+                s = pl.dec[d][k]
+                ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
+                ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["a1"], scale=c1.scale, shift=c1.shift, relu=True)
+                ops.conv3x3_fwd(s["a1"], None, c2.wf, s["a2"], scale=c2.scale, shift=c2.shift, relu=True)
+                t = s["a2"]
+            out = torch.empty(n, head.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device)
+            ops.head_fwd(t, head.w, head.b, out, head.sigmoid)
+            outs.append(out)
+        return outs
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def _bn_bwd(self, L, d_a, y, d_y):
+        ops.bn_bwd_reduce(d_a, y, L.scale, L.shift, L.mean, L.invstd, L.sums)
+        ops.bn_bwd_apply(d_a, y, L.scale, L.shift, L.mean, L.invstd, L.sums, d_y, L.g_gamma, L.g_beta)
+
+    def backward(self, pl, generation, grad_outs, outs):
+        if generation != pl.generation:
+            raise RuntimeError("backward() after another forward() through the same model and input shape: the saved "
+                               "activations of this graph were overwritten (only one live graph per shape is supported)")
+        pl.alloc_grads()
+        V = Plan.view
+        ops.zero_(self.gstage)
+        ops.zero_(self.bn_sums_all)
+        skip_written = [False] * 5
+        n_dec = len(self.decoders)
+        for d in reversed(range(n_dec)):
+            stages, head = self.decoders[d]
+            g = grad_outs[d]
+            last = pl.dec[d][3]
+            d_t = V(pl.d_t, last["a2"])
+            if g is None:
+                g = ops.zero_(torch.empty_like(outs[d]))
+            g = g.contiguous().float()
+            ops.head_bwd(last["a2"], head.w, g, outs[d], d_t, head.g_w, head.g_b, head.sigmoid)
+            for k in reversed(range(4)):
+                ct, c1, c2 = stages[k]
+                lv = 3 - k
+                s = pl.dec[d][k]
+                d_t = V(pl.d_t, s["a2"])
+                d_y = V(pl.d_y, s["y2"])
+                d_a1 = V(pl.d_a1, s["a1"])
+                d_up = V(pl.d_up, s["up"])
+                skip = pl.enc[lv]["a2"]
+                # second conv of the DoubleConv
+                self._bn_bwd(c2, d_t, s["y2"], d_y)
+                ops.conv3x3_wgrad(d_y, s["a1"], None, c2.g_w)
+                ops.conv3x3_dgrad(d_y, c2.wd, d_a1)
+                # first conv: two sources (skip, up)
+                self._bn_bwd(c1, d_a1, s["y1"], d_y)
+                ops.conv3x3_wgrad(d_y, skip, s["up"], c1.g_w)
+                ops.conv3x3_dgrad(d_y, c1.wd, pl.d_skip[lv], acc1=skip_written[lv], dx2=d_up, acc2=False,
+                                  stats=ct.g_bias)
+                skip_written[lv] = True
+                # transposed conv
+                t_in = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
+                ops.convt2x2_wgrad(t_in, d_up, ct.g_w)
+                if k > 0:
+                    ops.convt2x2_dgrad(d_up, ct.wd, V(pl.d_t, t_in), acc=False)
+                else:
+                    ops.convt2x2_dgrad(d_up, ct.wd, pl.d_skip[4], acc=skip_written[4])
+                    skip_written[4] = True
+            if self.ddp is not None:
+                self.ddp.segment_ready(self, ("dec", d))
+        for l in reversed(range(5)):
+            c1, c2 = self.encoder[l]
+            e = pl.enc[l]
+            d_y = V(pl.d_y, e["y2"])
+            d_a1 = V(pl.d_a1, e["a1"])
+            self._bn_bwd(c2, pl.d_skip[l], e["y2"], d_y)
+            ops.conv3x3_wgrad(d_y, e["a1"], None, c2.g_w)
+            ops.conv3x3_dgrad(d_y, c2.wd, d_a1)
+            self._bn_bwd(c1, d_a1, e["y1"], d_y)
+            if l == 0:
+                ops.first_conv_wgrad(pl.x, d_y, c1.g_w)
+            else:
+                src = pl.enc[l - 1]["p"]
+                d_p = V(pl.d_p, src)
+                ops.conv3x3_wgrad(d_y, src, None, c1.g_w)
+                ops.conv3x3_dgrad(d_y, c1.wd, d_p)
+                ops.maxpool_bwd(d_p, pl.enc[l - 1]["idx"], pl.d_skip[l - 1], accumulate=skip_written[l - 1])
+                skip_written[l - 1] = True
+            if self.ddp is not None and l in (3, 0):
+                self.ddp.segment_ready(self, ("enc", l))
+        scale = 1.0
+        if self.ddp is not None:
+            scale = self.ddp.finish(self)
+        ops.permute_batched(self.unpack_table, self.gstage, self.flat_g, scale)
+        return self.grad_views()

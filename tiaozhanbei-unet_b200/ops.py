@@ -197,6 +197,11 @@ def ssim_fwd(img1, img2, sums, maps, window_size, need2):
     _lib.call("unetk_ssim_fwd", _p(img1), _p(img2), _p(sums), _p(maps), n, c, h, w, window_size, int(need2), _s())
 
 
+def ssim_finalize(sums, out, shape, size_average):
+    n, c, h, w = shape
+    _lib.call("unetk_ssim_finalize", _p(sums), _p(out), n, c, h, w, int(size_average), _s())
+
+
 def ssim_bwd(img1, img2, maps, gout, grad, window_size, which, per_image):
     n, c, h, w = img1.shape
     _lib.call("unetk_ssim_bwd", _p(img1), _p(img2), _p(maps), _p(gout), _p(grad), n, c, h, w, window_size,

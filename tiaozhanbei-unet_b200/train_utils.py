@@ -1,0 +1,287 @@
+"""Drop-in replacement for the reference's `src/train_utils.py`.
+
+Same public names and call signatures (src/train.py:17-24 imports CombinedLoss, SSIMLoss,
+get_optimizer, get_scheduler, train_epoch, validate_epoch); the losses are CUDA kernels
+(csrc/head_loss.cu) wrapped in autograd nodes, the optimizer is optim.FusedOptimizer.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd.function import once_differentiable
+
+from . import ops
+from .optim import FusedOptimizer
+from .utils import AverageMeter, calculate_metrics, compute_anomaly_score
+
+try:  # progress bars are cosmetic; the reference uses tqdm (src/train_utils.py:5)
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, **kwargs):
+        return it
+
+
+def _as_f32_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the loss kernels have no CPU path")
+    return t.detach().float().contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# CombinedLoss — src/train_utils.py:10-44
+# ---------------------------------------------------------------------------------------------
+class _CombinedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, reconstruction, anomaly_map, original_image, true_mask, owner):
+        r = _as_f32_cuda(reconstruction, "reconstruction")
+        a = _as_f32_cuda(anomaly_map, "anomaly_map")
+        x = _as_f32_cuda(original_image, "original_image")
+        t = _as_f32_cuda(true_mask, "true_mask")
+        if r.shape != x.shape or a.shape != t.shape:
+            raise ValueError(f"shape mismatch: reconstruction {tuple(r.shape)} vs image {tuple(x.shape)}, "
+                             f"anomaly_map {tuple(a.shape)} vs mask {tuple(t.shape)}")
+        need_r, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d_r = torch.empty_like(r) if need_r else None
+        d_a = torch.empty_like(a) if need_a else None
+        out3 = torch.empty(3, dtype=torch.float32, device=r.device)
+        ops.combined_loss(r, a, x, t, d_r, d_a, out3, owner._workspace(r.device), owner.recon_weight,
+                          owner.seg_weight, owner.focal_alpha, owner.focal_gamma)
+        ctx.d_r, ctx.d_a = d_r, d_a
+        owner._last = out3
+        total, rl, sl = out3[0], out3[1], out3[2]
+        ctx.mark_non_differentiable(rl, sl)
+        return total, rl, sl
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_total, _g1, _g2):
+        d_r, d_a = ctx.d_r, ctx.d_a
+        ctx.d_r = ctx.d_a = None
+        g = g_total.detach().float().contiguous().view(1)
+        if d_r is not None:
+            ops.scale_by_scalar(d_r, g)
+        if d_a is not None:
+            ops.scale_by_scalar(d_a, g)
+        return d_r, d_a, None, None, None
+
+
+class CombinedLoss(nn.Module):
+    """recon_weight * MSE(reconstruction, image) + seg_weight * focal(anomaly_map, mask)."""
+
+    def __init__(self, recon_weight=1.0, seg_weight=1.0, focal_alpha=0.25, focal_gamma=2.0):
+        super().__init__()
+        self.recon_weight = recon_weight
+        self.seg_weight = seg_weight
+        self.focal_alpha = focal_alpha
+        self.focal_gamma = focal_gamma
+        self._work = None
+        self._last = None
+
+    def _workspace(self, device):
+        if self._work is None or self._work.device != device:
+            self._work = ops.combined_loss_workspace(device)
+        return self._work
+
+    def focal_loss(self, pred, target):
+        """Focal loss alone (src/train_utils.py:23-28): same kernel with recon_weight 0."""
+        dummy = ops.zero_(torch.empty(4, dtype=torch.float32, device=pred.device))
+        _, _, sl = _FocalOnlyFn.apply(pred, target, self, dummy)
+        return sl
+
+    def forward(self, reconstruction, anomaly_map, original_image, true_mask):
+        total, rl, sl = _CombinedLossFn.apply(reconstruction, anomaly_map, original_image, true_mask, self)
+        return {"total_loss": total, "recon_loss": rl, "seg_loss": sl}
+
+    def last_values(self):
+        """(total, recon, seg) of the most recent forward as python floats: ONE device->host copy
+        instead of the three `.item()` syncs of src/train_utils.py:137-139."""
+        return tuple(self._last.tolist())
+
+
+class _FocalOnlyFn(torch.autograd.Function):
+    """focal(pred, target) with gradient w.r.t. pred; reuses the combined kernel on a 4-element dummy
+    reconstruction pair so that no second kernel is needed."""
+
+    @staticmethod
+    def forward(ctx, pred, target, owner, dummy):
+        a = _as_f32_cuda(pred, "pred")
+        t = _as_f32_cuda(target, "target")
+        d_a = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        out3 = torch.empty(3, dtype=torch.float32, device=a.device)
+        ops.combined_loss(dummy, a, dummy, t, None, d_a, out3, owner._workspace(a.device), 0.0, 1.0,
+                          owner.focal_alpha, owner.focal_gamma)
+        ctx.d_a = d_a
+        return out3[0], out3[1], out3[2]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, _g0, _g1, g_seg):
+        d_a = ctx.d_a
+        ctx.d_a = None
+        if d_a is not None:
+            ops.scale_by_scalar(d_a, g_seg.detach().float().contiguous().view(1))
+        return d_a, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# SSIMLoss — src/train_utils.py:47-104
+# ---------------------------------------------------------------------------------------------
+class _SSIMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img1, img2, window_size, size_average):
+        a = _as_f32_cuda(img1, "img1")
+        b = _as_f32_cuda(img2, "img2")
+        if a.shape != b.shape or a.dim() != 4:
+            raise ValueError(f"SSIMLoss expects two [N, C, H, W] tensors of equal shape, got {tuple(a.shape)} and {tuple(b.shape)}")
+        n = a.shape[0]
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        maps = None
+        if need1 or need2:
+            maps = torch.empty((5 if need2 else 3,) + tuple(a.shape), dtype=torch.float32, device=a.device)
+        sums = torch.empty(n, dtype=torch.float32, device=a.device)
+        ops.ssim_fwd(a, b, sums, maps, window_size, need2)
+        out = torch.empty(() if size_average else (n,), dtype=torch.float32, device=a.device)
+        ops.ssim_finalize(sums, out, a.shape, size_average)
+        ctx.saved = (a, b, maps, window_size, size_average, need1, need2)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        a, b, maps, window_size, size_average, need1, need2 = ctx.saved
+        ctx.saved = None
+        g = gout.detach().float().contiguous().view(-1)
+        g1 = g2 = None
+        if need1:
+            g1 = torch.empty_like(a)
+            ops.ssim_bwd(a, b, maps, g, g1, window_size, 0, not size_average)
+        if need2:
+            g2 = torch.empty_like(b)
+            ops.ssim_bwd(a, b, maps, g, g2, window_size, 1, not size_average)
+        return g1, g2, None, None
+
+
+class SSIMLoss(nn.Module):
+    """1 - SSIM with an 11x11 gaussian window (sigma 1.5), zero padding 5."""
+
+    def __init__(self, window_size=11, size_average=True):
+        super().__init__()
+        self.window_size = window_size
+        self.size_average = size_average
+        self.channel = 1
+
+    def forward(self, img1, img2):
+        self.channel = img1.size(1)
+        return _SSIMFn.apply(img1, img2, self.window_size, self.size_average)
+
+
+# ---------------------------------------------------------------------------------------------
+# training / validation loops — src/train_utils.py:107-260
+# ---------------------------------------------------------------------------------------------
+def _loss_values(criterion, loss_dict):
+    if isinstance(criterion, CombinedLoss):
+        return criterion.last_values()
+    return (loss_dict["total_loss"].item(), loss_dict["recon_loss"].item(), loss_dict["seg_loss"].item())
+
+
+def train_epoch(model, train_loader, criterion, optimizer, device, epoch):
+    """Train for one epoch; returns the same dict of three running averages as the reference."""
+    model.train()
+    losses, recon_losses, seg_losses = AverageMeter(), AverageMeter(), AverageMeter()
+    pbar = tqdm(train_loader, desc=f"Epoch {epoch}")
+    for batch_idx, batch in enumerate(pbar):
+        images = batch["image"].to(device, non_blocking=True)
+        masks = batch["mask"].to(device, non_blocking=True)
+        reconstruction, anomaly_map = model(images)
+        loss_dict = criterion(reconstruction, anomaly_map, images, masks)
+        total_loss = loss_dict["total_loss"]
+        optimizer.zero_grad()
+        total_loss.backward()
+        optimizer.step()
+        batch_size = images.size(0)
+        t, r, s = _loss_values(criterion, loss_dict)
+        losses.update(t, batch_size)
+        recon_losses.update(r, batch_size)
+        seg_losses.update(s, batch_size)
+        if hasattr(pbar, "set_postfix"):
+            pbar.set_postfix({"Loss": f"{losses.avg:.4f}", "Recon": f"{recon_losses.avg:.4f}",
+                              "Seg": f"{seg_losses.avg:.4f}"})
+    return {"total_loss": losses.avg, "recon_loss": recon_losses.avg, "seg_loss": seg_losses.avg}
+
+
+def validate_epoch(model, val_loader, criterion, device):
+    """Validate for one epoch (same flow, keys and thresholds as src/train_utils.py:155-260)."""
+    model.eval()
+    losses, recon_losses, seg_losses = AverageMeter(), AverageMeter(), AverageMeter()
+    all_labels, all_scores, all_masks_true, all_masks_pred = [], [], [], []
+    with torch.no_grad():
+        pbar = tqdm(val_loader, desc="Validation")
+        for batch in pbar:
+            images = batch["image"].to(device)
+            masks = batch["mask"].to(device)
+            labels = batch["label"].numpy()
+            reconstruction, anomaly_map = model(images)
+            loss_dict = criterion(reconstruction, anomaly_map, images, masks)
+            batch_size = images.size(0)
+            t, r, s = _loss_values(criterion, loss_dict)
+            losses.update(t, batch_size)
+            recon_losses.update(r, batch_size)
+            seg_losses.update(s, batch_size)
+            anomaly_scores = compute_anomaly_score(reconstruction, images).cpu().numpy()
+            all_labels.extend(labels)
+            all_scores.extend(anomaly_scores)
+            all_masks_true.extend(masks.cpu().numpy())
+            all_masks_pred.extend(anomaly_map.cpu().numpy())
+            if hasattr(pbar, "set_postfix"):
+                pbar.set_postfix({"Loss": f"{losses.avg:.4f}", "Recon": f"{recon_losses.avg:.4f}",
+                                  "Seg": f"{seg_losses.avg:.4f}"})
+    all_labels = np.array(all_labels)
+    all_scores = np.array(all_scores)
+    all_masks_true = np.array(all_masks_true)
+    all_masks_pred = np.array(all_masks_pred)
+    if len(np.unique(all_labels)) > 1:
+        threshold = np.percentile(all_scores, 95)
+        predictions = (all_scores > threshold).astype(int)
+        image_metrics = calculate_metrics(all_labels, predictions, all_scores)
+    else:
+        normal = all_labels[0] == 0
+        image_metrics = {"accuracy": 1.0 if normal else 0.0, "precision": 0.0, "recall": 0.0,
+                         "specificity": 1.0 if normal else 0.0, "f1_score": 0.0, "auroc": 0.0, "auprc": 0.0}
+    pixel_metrics = {}
+    anomaly_indices = all_labels == 1
+    if np.sum(anomaly_indices) > 0:
+        for threshold in [0.3, 0.5, 0.7]:
+            pred_flat = (all_masks_pred[anomaly_indices] > threshold).astype(np.uint8).flatten()
+            true_flat = (all_masks_true[anomaly_indices] > 0.5).astype(np.uint8).flatten()
+            if len(np.unique(true_flat)) > 1:
+                pixel_metrics[f"pixel_f1_@{threshold}"] = calculate_metrics(true_flat, pred_flat)["f1_score"]
+    return {
+        "total_loss": losses.avg, "recon_loss": recon_losses.avg, "seg_loss": seg_losses.avg,
+        "image_metrics": image_metrics, "pixel_metrics": pixel_metrics,
+        "predictions": {"labels": all_labels, "scores": all_scores, "masks_true": all_masks_true,
+                        "masks_pred": all_masks_pred},
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# optimizer / scheduler factories — src/train_utils.py:263-284
+# ---------------------------------------------------------------------------------------------
+def get_optimizer(model, optimizer_name="adam", learning_rate=1e-3, weight_decay=1e-4):
+    name = optimizer_name.lower()
+    if name not in ("adam", "adamw", "sgd"):
+        raise ValueError(f"Unknown optimizer: {optimizer_name}")
+    engine = model._engine() if hasattr(model, "_engine") else None
+    return FusedOptimizer(model.parameters(), name, lr=learning_rate, weight_decay=weight_decay, engine=engine)
+
+
+def get_scheduler(optimizer, scheduler_name="cosine", num_epochs=100, eta_min=1e-6):
+    """Host-side learning-rate schedules, identical to the reference's choices."""
+    name = scheduler_name.lower()
+    if name == "cosine":
+        return torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=num_epochs, eta_min=eta_min)
+    if name == "step":
+        return torch.optim.lr_scheduler.StepLR(optimizer, step_size=num_epochs // 3, gamma=0.1)
+    if name == "plateau":
+        return torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", patience=10, factor=0.5)
+    return None
