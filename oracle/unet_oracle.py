@@ -107,56 +107,90 @@ def synthetic_state_dict(arch="anomaly_unet", seed=0, n_channels=3, n_classes=1,
 
 
 # ---------------------------------------------------------------------------------------------
+# storage contract of the B200 build (optional): bf16 storage, fp32 accumulation
+# ---------------------------------------------------------------------------------------------
+class _RoundBF16(torch.autograd.Function):
+    """Value round trip through bf16 in forward AND backward: marks the tensors the CUDA path keeps
+    in bf16 in HBM (conv / transposed-conv outputs, post-ReLU activations, their gradients, the
+    packed conv weights).  Everything else (accumulation, BatchNorm statistics, heads, losses,
+    optimizer) stays fp32, exactly like the reference algorithm above it."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _rounder(storage):
+    if storage == "fp32":
+        return lambda t: t
+    if storage == "bf16":
+        return _RoundBF16.apply
+    raise ValueError(storage)
+
+
+# ---------------------------------------------------------------------------------------------
 # forward
 # ---------------------------------------------------------------------------------------------
-def _double_conv(sd, prefix, x, training):
+def _double_conv(sd, prefix, x, training, r, first=False):
     # (conv3x3 pad 1 no bias -> BN -> ReLU) x 2                      src/model.py:13-20
     for i_conv, i_bn in ((0, 1), (3, 4)):
-        x = F.conv2d(x, sd[f"{prefix}.double_conv.{i_conv}.weight"], None, padding=1)
+        w = sd[f"{prefix}.double_conv.{i_conv}.weight"]
+        if not (first and i_conv == 0):      # the first conv reads the fp32 image with fp32 weights
+            w = r(w)
+        x = F.conv2d(x, w, None, padding=1)
+        if training or (first and i_conv == 0):
+            x = r(x)      # eval mode folds BN + ReLU into the conv epilogue: the raw output is never stored
         b = f"{prefix}.double_conv.{i_bn}"
         if training:
             sd[b + ".num_batches_tracked"] += 1
         x = F.batch_norm(x, sd[b + ".running_mean"], sd[b + ".running_var"], sd[b + ".weight"],
                          sd[b + ".bias"], training, BN_MOMENTUM, BN_EPS)
-        x = F.relu(x)
+        x = r(F.relu(x))
     return x
 
 
-def _up(sd, prefix, x1, x2, training):
+def _up(sd, prefix, x1, x2, training, r):
     # ConvTranspose2d(k2, s2) -> pad to the skip's size -> cat([skip, up]) -> DoubleConv
     #                                                                   src/model.py:51,54-66
-    x1 = F.conv_transpose2d(x1, sd[prefix + ".up.weight"], sd[prefix + ".up.bias"], stride=2)
+    x1 = r(F.conv_transpose2d(x1, r(sd[prefix + ".up.weight"]), sd[prefix + ".up.bias"], stride=2))
     dy = x2.size(2) - x1.size(2)
     dx = x2.size(3) - x1.size(3)
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
-    return _double_conv(sd, prefix + ".conv", torch.cat([x2, x1], dim=1), training)
+    return _double_conv(sd, prefix + ".conv", torch.cat([x2, x1], dim=1), training, r)
 
 
-def _encoder(sd, x, training):
-    feats = [_double_conv(sd, "inc", x, training)]
+def _encoder(sd, x, training, r):
+    feats = [_double_conv(sd, "inc", x, training, r, first=True)]
     for k in range(1, 5):
-        feats.append(_double_conv(sd, f"down{k}.maxpool_conv.1", F.max_pool2d(feats[-1], 2), training))
+        feats.append(_double_conv(sd, f"down{k}.maxpool_conv.1", F.max_pool2d(feats[-1], 2), training, r))
     return feats
 
 
-def _decoder(sd, feats, suffix, training):
+def _decoder(sd, feats, suffix, training, r):
     x = feats[4]
     for k in range(1, 5):
-        x = _up(sd, f"up{k}{suffix}", x, feats[4 - k], training)
+        x = _up(sd, f"up{k}{suffix}", x, feats[4 - k], training, r)
     return F.conv2d(x, sd[f"outc{suffix}.conv.weight"], sd[f"outc{suffix}.conv.bias"])
 
 
-def unet_forward(sd, x, training=False):
+def unet_forward(sd, x, training=False, storage="fp32"):
     """UNet.forward -> logits (no sigmoid).  src/model.py:97-108.  BN buffers in `sd` are updated
-    in place when training, like nn.BatchNorm2d."""
-    return _decoder(sd, _encoder(sd, x, training), "", training)
+    in place when training, like nn.BatchNorm2d.  storage="bf16" applies the build's storage
+    contract (see _RoundBF16); the default is the reference's plain fp32."""
+    r = _rounder(storage)
+    return _decoder(sd, _encoder(sd, x, training, r), "", training, r)
 
 
-def anomaly_unet_forward(sd, x, training=False):
+def anomaly_unet_forward(sd, x, training=False, storage="fp32"):
     """AnomalyUNet.forward -> (sigmoid reconstruction, sigmoid anomaly map).  src/model.py:188-210."""
-    feats = _encoder(sd, x, training)
-    recon = torch.sigmoid(_decoder(sd, feats, "_recon", training))
-    amap = torch.sigmoid(_decoder(sd, feats, "_seg", training))
+    r = _rounder(storage)
+    feats = _encoder(sd, x, training, r)
+    recon = torch.sigmoid(_decoder(sd, feats, "_recon", training, r))
+    amap = torch.sigmoid(_decoder(sd, feats, "_seg", training, r))
     return recon, amap
 
 
@@ -227,18 +261,19 @@ def adam_update(p, g, m, v, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_
     p.addcdiv_(m, denom, value=-(lr / bc1))
 
 
-def train_step(sd, image, mask, arch="anomaly_unet", opt_state=None, step=1, lr=1e-3, weight_decay=1e-4):
+def train_step(sd, image, mask, arch="anomaly_unet", opt_state=None, step=1, lr=1e-3, weight_decay=1e-4,
+               storage="fp32"):
     """Forward + loss + backward (+ Adam when opt_state is a dict).  Returns (loss dict, grads)."""
     params = {k: v for k, v in sd.items() if not is_buffer(k)}
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
     work = OrderedDict((k, leaves[k] if k in leaves else v) for k, v in sd.items())
     if arch == "anomaly_unet":
-        recon, amap = anomaly_unet_forward(work, image, training=True)
+        recon, amap = anomaly_unet_forward(work, image, training=True, storage=storage)
         losses = combined_loss(recon, amap, image, mask)
     else:
         # UNet cannot go through train_epoch (SURVEY.md §4 defect 2): config 1's step is
         # p = sigmoid(UNet(x)); loss = MSE(p, mask) + focal(p, mask)
-        p = torch.sigmoid(unet_forward(work, image, training=True))
+        p = torch.sigmoid(unet_forward(work, image, training=True, storage=storage))
         rl = F.mse_loss(p, mask)
         sl = focal_loss(p, mask)
         losses = {"total_loss": rl + sl, "recon_loss": rl, "seg_loss": sl}
@@ -249,4 +284,4 @@ def train_step(sd, image, mask, arch="anomaly_unet", opt_state=None, step=1, lr=
             for k in leaves:
                 st = opt_state.setdefault(k, {"m": torch.zeros_like(sd[k]), "v": torch.zeros_like(sd[k])})
                 adam_update(sd[k], grads[k], st["m"], st["v"], step, lr=lr, weight_decay=weight_decay)
-    return {k: float(v) for k, v in losses.items()}, grads
+    return {k: float(v.detach()) for k, v in losses.items()}, grads

@@ -57,7 +57,8 @@ class UnetkError(RuntimeError):
 
 
 _lib = None
-_launches = 0  # number of kernel-launching C-ABI calls made by this process (bench: gpu_launches)
+_launches = 0  # number of C-ABI calls made by this process
+_kernel_launches = 0  # ... of which launch at least one of our kernels (bench: gpu_launches)
 
 
 def get():
@@ -89,12 +90,18 @@ def last_error() -> str:
 
 def call(name: str, *args) -> None:
     """Call an int-returning entry point and raise UnetkError on a non-zero code."""
-    global _launches
+    global _launches, _kernel_launches
     rc = getattr(get(), name)(*args)
     _launches += 1
+    if name != "unetk_memset_zero":
+        _kernel_launches += 1
     if rc != 0:
         raise UnetkError(f"{name} failed with code {rc}: {last_error()}")
 
 
 def launch_count() -> int:
     return _launches
+
+
+def kernel_launch_count() -> int:
+    return _kernel_launches

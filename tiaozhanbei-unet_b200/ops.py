@@ -33,6 +33,36 @@ def _chk(t, dtype, name):
         raise _lib.UnetkError(f"{name}: expected a contiguous tensor")
 
 
+# Optional instrumentation (bench.py roofline): CUDA events around every tensor-core conv launch.
+_timing = None
+
+
+def enable_conv_timing():
+    global _timing
+    _timing = []
+    return _timing
+
+
+def collect_conv_timing(rec):
+    """-> (algorithmic FLOPs, summed kernel milliseconds, launches); disables the instrumentation."""
+    global _timing
+    _timing = None
+    flops = sum(f for f, _, _ in rec)
+    ms = sum(a.elapsed_time(b) for _, a, b in rec)
+    return flops, ms, len(rec)
+
+
+def _timed(flops, name, *args):
+    if _timing is None:
+        _lib.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call(name, *args)
+    e1.record()
+    _timing.append((flops, e0, e1))
+
+
 def zero_(t):
     _lib.call("unetk_memset_zero", _p(t), t.numel() * t.element_size(), _s())
     return t
@@ -50,7 +80,7 @@ def conv3x3_fwd(src1, src2, wf, y, stats=None, scale=None, shift=None, relu=Fals
         _chk(src2, bf16, "src2")
         c2 = src2.shape[3]
     cout = y.shape[3]
-    _lib.call("unetk_conv3x3_fwd", _p(src1), c1, _p(src2), c2, _p(wf), _p(y), _p(stats), _p(scale),
+    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "unetk_conv3x3_fwd", _p(src1), c1, _p(src2), c2, _p(wf), _p(y), _p(stats), _p(scale),
               _p(shift), int(relu), n, h, w, cout, _s())
     return y
 
@@ -63,7 +93,7 @@ def conv3x3_dgrad(dy, wd, dx1, acc1=False, dx2=None, acc2=False, stats=None):
     if dx2 is not None:
         _chk(dx2, bf16, "dx2")
         c2 = dx2.shape[3]
-    _lib.call("unetk_conv3x3_dgrad", _p(dy), cout, _p(wd), _p(dx1), c1, int(acc1), _p(dx2), c2,
+    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "unetk_conv3x3_dgrad", _p(dy), cout, _p(wd), _p(dx1), c1, int(acc1), _p(dx2), c2,
               int(acc2), _p(stats), n, h, w, _s())
 
 
@@ -76,7 +106,7 @@ def conv3x3_wgrad(dy, src1, src2, dw):
     if src2 is not None:
         _chk(src2, bf16, "src2")
         c2 = src2.shape[3]
-    _lib.call("unetk_conv3x3_wgrad", _p(dy), _p(src1), c1, _p(src2), c2, _p(dw), n, h, w, cout, _s())
+    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "unetk_conv3x3_wgrad", _p(dy), _p(src1), c1, _p(src2), c2, _p(dw), n, h, w, cout, _s())
 
 
 def first_conv_fwd(x, w, y, stats=None):
@@ -95,20 +125,20 @@ def first_conv_wgrad(x, dy, dw):
 def convt2x2_fwd(a, wt, bias, up):
     _chk(a, bf16, "a"); _chk(wt, bf16, "wt"); _chk(up, bf16, "up")
     n, h, w, cin = a.shape
-    _lib.call("unetk_convt2x2_fwd", _p(a), cin, _p(wt), _p(bias), _p(up), n, h, w, up.shape[3], _s())
+    _timed(2.0 * n * h * w * cin * 4 * up.shape[3], "unetk_convt2x2_fwd", _p(a), cin, _p(wt), _p(bias), _p(up), n, h, w, up.shape[3], _s())
     return up
 
 
 def convt2x2_dgrad(dup, wtd, da, acc=False):
     _chk(dup, bf16, "dup"); _chk(wtd, bf16, "wtd"); _chk(da, bf16, "da")
     n, h, w, cin = da.shape
-    _lib.call("unetk_convt2x2_dgrad", _p(dup), dup.shape[3], _p(wtd), _p(da), cin, int(acc), n, h, w, _s())
+    _timed(2.0 * n * h * w * cin * 4 * dup.shape[3], "unetk_convt2x2_dgrad", _p(dup), dup.shape[3], _p(wtd), _p(da), cin, int(acc), n, h, w, _s())
 
 
 def convt2x2_wgrad(a, dup, dw):
     _chk(a, bf16, "a"); _chk(dup, bf16, "dup"); _chk(dw, f32, "dw")
     n, h, w, cin = a.shape
-    _lib.call("unetk_convt2x2_wgrad", _p(a), cin, _p(dup), dup.shape[3], _p(dw), n, h, w, _s())
+    _timed(2.0 * n * h * w * cin * 4 * dup.shape[3], "unetk_convt2x2_wgrad", _p(a), cin, _p(dup), dup.shape[3], _p(dw), n, h, w, _s())
 
 
 # ---------------------------------------------------------------------------------------------
