@@ -9,13 +9,21 @@
 // /root/reference/src/model.py:14,17 and nn.ConvTranspose2d(k=2, s=2) at src/model.py:51, plus
 // torch.cat([x2, x1], dim=1) at src/model.py:65 (folded into the K loop: two A tensor maps).
 //
-// Layout: activations NHWC bf16; the M tile is a (tn x th x tw) patch of 128 output pixels, loaded
-// per (tap, 64-channel chunk) as one TMA box of 128 rows x 128 B (SWIZZLE_128B) = the canonical
-// K-major UMMA operand.  TMA out-of-bounds zero fill implements the conv zero padding.
+// Data movement (the kernel is L2-bandwidth bound, not tensor bound, unless operands are reused):
+//  * One CTA tile is a 16x16-pixel region = two 8x16 sub-tiles of 128 GEMM rows each.
+//  * For a 3x3 conv the A operand of ALL NINE taps comes from ONE TMA load per 64-channel chunk:
+//    the 18x18-pixel halo of the region (324 rows x 128 B, SWIZZLE_128B, zero-filled outside the
+//    image = the conv padding).  A tap shift is a descriptor START OFFSET of (dy*18 + dx) rows:
+//    the 128B swizzle is a function of absolute shared-memory address bits, so a start that is a
+//    multiple of 128 B (not 1024 B) addresses the same swizzled data (measured:
+//    profiles/umma_probe_r01.txt).  8-pixel tile rows are the 8-row core-matrix groups, the next
+//    tile row is SBO = 18*128 B away.  A traffic drops 7x versus one load per tap.
+//  * Each weight stage (BN x 64, one tap x one channel chunk) is multiplied into BOTH sub-tiles
+//    (two TMEM accumulators), halving weight traffic per FLOP.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2..5 epilogue
 // (TMEM -> registers -> bf16 global, optional per-channel sum / sum-of-squares for BatchNorm,
 // optional per-channel affine + ReLU for eval-mode folded BatchNorm).  Persistent over tiles with
-// a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.
+// double-buffered TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -23,12 +31,12 @@ namespace unetk {
 
 struct IgemmParams {
   int n_img, H, W;      // GEMM pixel grid (rows of D)
-  int tw, th, tn;       // pixel tile, tw*th*tn == 128
-  int tiles_x, tiles_y, tiles_n;
-  int n_blocks;         // ceil(Ntot / BN)
+  int regions_x, regions_y;
+  int n_blocks;         // Ntot / BN
   int Ntot;             // columns of D
   int num_taps;         // 9 (3x3), 1 (1x1 view), 4 (convT dgrad)
   int a_mode;           // 0: A box at (c, x+dx, y+dy, n, 0); 1: A box at (c, kx, x, ky, n*H+y)
+  int halo;             // 1 for the 3x3 conv (one halo load serves 9 taps), else 0
   int c1_chunks, c2_chunks;  // 64-channel chunks taken from tmA1 / tmA2
   int epi_mode;         // 0: NHWC store, 1: convT pixel-shuffle store (+bias)
   int split;            // columns [0,split) -> out1, [split,Ntot) -> out2
@@ -47,14 +55,18 @@ struct IgemmParams {
 };
 
 constexpr int kIgemmThreads = 192;
-constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
+constexpr int kRegion = 16;                   // CTA tile: 16 x 16 output pixels
+constexpr int kSubW = 8;                      // sub-tile: 8 wide x 16 tall = 128 GEMM rows
+constexpr int kABufBytes = 41 * 1024;         // >= 18*18*128 B, multiple of 1024
+constexpr int kNumABufs = 2;
 
 template <int BN>
 struct IgemmCfg {
-  static constexpr int kStages = (BN == 128) ? 6 : 8;
+  static constexpr int kBStages = (BN == 128) ? 6 : 8;
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kTmemCols = 4 * BN;    // 2 accumulator stages x 2 sub-tiles
+  static constexpr int kSmemMain = kNumABufs * kABufBytes + kBStages * kBBytes;
+  static constexpr int kNumBars = 2 * kNumABufs + 2 * kBStages + 4;
 };
 
 template <int BN>
@@ -62,32 +74,36 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
   using Cfg = IgemmCfg<BN>;
-  constexpr int kStages = Cfg::kStages;
+  constexpr int kBStages = Cfg::kBStages;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kStages;
-  uint64_t* tfull = bars + 2 * kStages;
-  uint64_t* tempty = bars + 2 * kStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  float* colbuf = reinterpret_cast<float*>(bars + 2 * kStages + 6);  // [2][Ntot] when used
+  uint8_t* sB = smem + kNumABufs * kABufBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kSmemMain);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kNumABufs;
+  uint64_t* b_full = a_empty + kNumABufs;
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* tfull = b_empty + kBStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* colbuf = reinterpret_cast<float*>(tempty + 4);  // affine: [2][Ntot]; stats: [4][2][Ntot]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool use_colbuf = (p.stats != nullptr) || (p.scale != nullptr);
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+    for (int i = 0; i < kNumABufs; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -96,59 +112,64 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
-  if (use_colbuf) {
-    for (int i = threadIdx.x; i < 2 * p.Ntot; i += blockDim.x) {
-      float v = 0.f;
-      if (p.scale != nullptr) v = (i < p.Ntot) ? p.scale[i] : p.shift[i - p.Ntot];
-      colbuf[i] = v;
-    }
+  if (p.scale != nullptr) {          // [2][Ntot]: scale, shift
+    for (int i = threadIdx.x; i < 2 * p.Ntot; i += blockDim.x)
+      colbuf[i] = (i < p.Ntot) ? p.scale[i] : p.shift[i - p.Ntot];
+  } else if (p.stats != nullptr) {   // [4 epilogue warps][2][Ntot]: sum, sum of squares
+    for (int i = threadIdx.x; i < 8 * p.Ntot; i += blockDim.x) colbuf[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_m = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int total_tiles = tiles_m * p.n_blocks;
+  const int regions = p.regions_x * p.regions_y * p.n_img;
+  const int total_tiles = regions * p.n_blocks;
   const int chunks = p.c1_chunks + p.c2_chunks;
-  const int kblocks = p.num_taps * chunks;
+  const int pitch = kRegion + 2 * p.halo;               // halo tile row pitch in pixels
+  const uint32_t a_bytes = static_cast<uint32_t>(pitch * pitch * 128);
+  // A loads per tile: one per channel chunk (halo mode: serves all taps) or one per (tap, chunk)
+  const int taps_per_load = p.halo ? p.num_taps : 1;
+  const int a_loads = p.halo ? chunks : p.num_taps * chunks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nb = t % p.n_blocks;
         int m = t / p.n_blocks;
-        const int tx = m % p.tiles_x;
-        m /= p.tiles_x;
-        const int ty = m % p.tiles_y;
-        const int tz = m / p.tiles_y;
-        const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tz * p.tn;
+        const int rx = m % p.regions_x;
+        m /= p.regions_x;
+        const int ry = m % p.regions_y;
+        const int n0 = m / p.regions_y;
+        const int x0 = rx * kRegion, y0 = ry * kRegion;
         const int col0 = nb * BN;
-        for (int tap = 0; tap < p.num_taps; ++tap) {
-          int dy = 0, dx = 0;
-          if (p.num_taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
+        for (int al = 0; al < a_loads; ++al) {
+          const int c = p.halo ? al : al % chunks;
+          const int tap0 = p.halo ? 0 : al / chunks;
+          mbar_wait(&a_empty[as], aph ^ 1);
+          mbar_expect_tx(&a_full[as], a_bytes);
+          const CUtensorMap* mp = (c < p.c1_chunks) ? &tmA1 : &tmA2;
+          const int cc = ((c < p.c1_chunks) ? c : c - p.c1_chunks) * 64;
+          if (p.a_mode == 0) {
+            tma_load_5d(sA + as * kABufBytes, mp, &a_full[as], cc, x0 - p.halo, y0 - p.halo, n0, 0);
+          } else {
+            tma_load_5d(sA + as * kABufBytes, mp, &a_full[as], cc, tap0 & 1, x0, tap0 >> 1, n0 * p.H + y0);
           }
-          for (int c = 0; c < chunks; ++c) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-            const CUtensorMap* mp = (c < p.c1_chunks) ? &tmA1 : &tmA2;
-            const int cc = ((c < p.c1_chunks) ? c : c - p.c1_chunks) * 64;
-            if (p.a_mode == 0) {
-              tma_load_5d(sA + stage * kABytes, mp, &full[stage], cc, x0 + dx, y0 + dy, n0, 0);
-            } else {
-              tma_load_5d(sA + stage * kABytes, mp, &full[stage], cc, tap & 1, x0, tap >> 1,
-                          n0 * p.H + y0);
-            }
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full[stage], (tap * chunks + c) * 64,
-                        col0);
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
+          if (++as == kNumABufs) {
+            as = 0;
+            aph ^= 1;
+          }
+          for (int tt = 0; tt < taps_per_load; ++tt) {
+            const int tap = tap0 + tt;
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            mbar_expect_tx(&b_full[bs], Cfg::kBBytes);
+            tma_load_2d(sB + bs * Cfg::kBBytes, &tmB, &b_full[bs], (tap * chunks + c) * 64, col0);
+            if (++bs == kBStages) {
+              bs = 0;
+              bph ^= 1;
             }
           }
         }
@@ -158,147 +179,174 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
+      const uint32_t sbo = static_cast<uint32_t>(pitch * 128);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty[as], aphase ^ 1);
+        const int acc = it & 1;
+        const uint32_t accph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], accph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full[stage], phase);
+        const uint32_t d_tmem = tmem_base + acc * (2 * BN);
+        uint32_t first = 1;
+        for (int al = 0; al < a_loads; ++al) {
+          mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + stage * kABytes);
-          const uint32_t b_base = smem_u32(sB + stage * Cfg::kBBytes);
+          const uint32_t a_base = smem_u32(sA + as * kABufBytes);
+          for (int tt = 0; tt < taps_per_load; ++tt) {
+            // tap (dy, dx) in {-1,0,1}^2 = rows (dy+1)*pitch + (dx+1) into the halo tile
+            const uint32_t tap_off = p.halo ? static_cast<uint32_t>(((tt / 3) * pitch + (tt % 3)) * 128) : 0u;
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(sB + bs * Cfg::kBBytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(a_base + k * 32, 0, 1024);
-            const uint64_t db = umma_smem_desc_sw128(b_base + k * 32, 0, 1024);
-            tc_mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = umma_smem_desc_sw128(a_base + tap_off + sub * (kSubW * 128) + k * 32, 0, sbo);
+                const uint64_t db = umma_smem_desc_sw128(b_base + k * 32, 0, 1024);
+                tc_mma_bf16(d_tmem + sub * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            first = 0;
+            tc_commit(&b_empty[bs]);
+            if (++bs == kBStages) {
+              bs = 0;
+              bph ^= 1;
+            }
           }
-          tc_commit(&empty[stage]);
-          if (kb == kblocks - 1) tc_commit(&tfull[as]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+          tc_commit(&a_empty[as]);
+          if (++as == kNumABufs) {
+            as = 0;
+            aph ^= 1;
           }
         }
+        tc_commit(&tfull[acc]);
       }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const int rx = row % p.tw;
-    const int ry = (row / p.tw) % p.th;
-    const int rn = row / (p.tw * p.th);
+    float* wbuf = colbuf + (warp - 2) * 2 * p.Ntot;   // this warp's private [2][Ntot] statistics slot
+    const int sx = row & 7;   // pixel inside the 8 x 16 sub-tile
+    const int sy = row >> 3;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int acc = it & 1;
+      const uint32_t accph = (it >> 1) & 1;
       const int nb = t % p.n_blocks;
       int m = t / p.n_blocks;
-      const int tx = m % p.tiles_x;
-      m /= p.tiles_x;
-      const int ty = m % p.tiles_y;
-      const int tz = m / p.tiles_y;
-      const int x = tx * p.tw + rx, y = ty * p.th + ry, n = tz * p.tn + rn;
-      const bool valid = (x < p.W) && (y < p.H) && (n < p.n_img);
+      const int rx = m % p.regions_x;
+      m /= p.regions_x;
+      const int ry = m % p.regions_y;
+      const int n = m / p.regions_y;
+      const int y = ry * kRegion + sy;
       const int col0 = nb * BN;
-      mbar_wait(&tfull[as], aphase);
+      mbar_wait(&tfull[acc], accph);
       tc_fence_after();
+      const int xs[2] = {rx * kRegion + sx, rx * kRegion + kSubW + sx};
+      const bool valids[2] = {(xs[0] < p.W) && (y < p.H), (xs[1] < p.W) && (y < p.H)};
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         const int col = col0 + ch * 32;
-        float v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + ch * 32, v);
+        float v2[2][32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (2 * BN) + ch * 32, v2[0]);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (2 * BN) + BN + ch * 32, v2[1]);
         tmem_ld_wait();
-        if (col >= p.Ntot) continue;  // warp-uniform
         if (p.stats != nullptr && col >= p.stats_from) {
+          // both sub-tiles share the columns: add them first, then ONE transposing butterfly each
+          // for the sum and the sum of squares; per-warp smem slots (no shared-memory atomics)
           float s[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s[j] = valid ? v[j] : 0.f;
+          for (int j = 0; j < 32; ++j) s[j] = (valids[0] ? v2[0][j] : 0.f) + (valids[1] ? v2[1][j] : 0.f);
           const float cs = warp_colsum32(s);
-          atomicAdd(&colbuf[col + lane], cs);
+          wbuf[col + lane] += cs;
           if (p.stats_sq != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float a = valid ? v[j] : 0.f;
-              s[j] = a * a;
+              const float a = valids[0] ? v2[0][j] : 0.f, b = valids[1] ? v2[1][j] : 0.f;
+              s[j] = fmaf(a, a, b * b);
             }
             const float cs2 = warp_colsum32(s);
-            atomicAdd(&colbuf[p.Ntot + col + lane], cs2);
+            wbuf[p.Ntot + col + lane] += cs2;
           }
         }
-        if (p.scale != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float a = fmaf(v[j], colbuf[col + j], colbuf[p.Ntot + col + j]);
-            v[j] = p.relu ? fmaxf(a, 0.f) : a;
+        for (int sub = 0; sub < 2; ++sub) {
+          float (&v)[32] = v2[sub];
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float a = fmaf(v[j], colbuf[col + j], colbuf[p.Ntot + col + j]);
+              v[j] = p.relu ? fmaxf(a, 0.f) : a;
+            }
           }
-        }
-        if (!valid) continue;
-        __nv_bfloat16* dst;
-        bool acc;
-        if (p.epi_mode == 0) {
-          const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
-          if (col < p.split) {
-            dst = p.out1 + pix * p.ldc1 + col;
-            acc = p.acc1 != 0;
+          if (!valids[sub]) continue;
+          const int x = xs[sub];
+          __nv_bfloat16* dst;
+          bool accum;
+          if (p.epi_mode == 0) {
+            const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+            if (col < p.split) {
+              dst = p.out1 + pix * p.ldc1 + col;
+              accum = p.acc1 != 0;
+            } else {
+              dst = p.out2 + pix * p.ldc2 + (col - p.split);
+              accum = p.acc2 != 0;
+            }
           } else {
-            dst = p.out2 + pix * p.ldc2 + (col - p.split);
-            acc = p.acc2 != 0;
-          }
-        } else {
-          const int tap = col / p.cout_t;
-          const int co = col - tap * p.cout_t;
-          const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + (2 * y + (tap >> 1))) *
-                                  (2 * p.W) + (2 * x + (tap & 1));
-          dst = p.out1 + opix * p.cout_t + co;
-          acc = false;
-          if (p.bias != nullptr) {
+            const int tap = col / p.cout_t;
+            const int co = col - tap * p.cout_t;
+            const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + (2 * y + (tap >> 1))) * (2 * p.W) +
+                                (2 * x + (tap & 1));
+            dst = p.out1 + opix * p.cout_t + co;
+            accum = false;
+            if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co + j);
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co + j);
+            }
           }
-        }
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
+          for (int g = 0; g < 4; ++g) {
+            float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
-          if (acc) {
-            const uint4 o = d4[g];
-            const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
-            const float2 o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
-            f[0] += o0.x; f[1] += o0.y; f[2] += o1.x; f[3] += o1.y;
-            f[4] += o2.x; f[5] += o2.y; f[6] += o3.x; f[7] += o3.y;
+            for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
+            if (accum) {
+              const uint4 o = d4[g];
+              const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
+              const float2 o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
+              f[0] += o0.x; f[1] += o0.y; f[2] += o1.x; f[3] += o1.y;
+              f[4] += o2.x; f[5] += o2.y; f[6] += o3.x; f[7] += o3.y;
+            }
+            uint4 w;
+            w.x = pack_bf16x2(f[0], f[1]);
+            w.y = pack_bf16x2(f[2], f[3]);
+            w.z = pack_bf16x2(f[4], f[5]);
+            w.w = pack_bf16x2(f[6], f[7]);
+            d4[g] = w;
           }
-          uint4 w;
-          w.x = pack_bf16x2(f[0], f[1]);
-          w.y = pack_bf16x2(f[2], f[3]);
-          w.z = pack_bf16x2(f[4], f[5]);
-          w.w = pack_bf16x2(f[6], f[7]);
-          d4[g] = w;
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
     if (p.stats != nullptr) {
       // all four epilogue warps have finished their smem atomics
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = threadIdx.x - 64;
       for (int i = p.stats_from + et; i < p.Ntot; i += 128) {
-        const float v = colbuf[i];
-        if (v != 0.f) atomicAdd(p.stats + (i - p.stats_from), v);
-        if (p.stats_sq != nullptr) {
-          const float v2 = colbuf[p.Ntot + i];
-          if (v2 != 0.f) atomicAdd(p.stats_sq + (i - p.stats_from), v2);
+        float v = 0.f, v2 = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+          v += colbuf[w4 * 2 * p.Ntot + i];
+          v2 += colbuf[w4 * 2 * p.Ntot + p.Ntot + i];
         }
+        if (v != 0.f) atomicAdd(p.stats + (i - p.stats_from), v);
+        if (p.stats_sq != nullptr && v2 != 0.f) atomicAdd(p.stats_sq + (i - p.stats_from), v2);
       }
     }
   }
@@ -320,7 +368,8 @@ static int floor_pow2(int v) {
   return p;
 }
 
-// Pick a (tw, th, tn) patch with tw*th*tn == `pixels` that minimises the padded pixel count.
+// Pick a (tw, th, tn) patch with tw*th*tn == `pixels` that minimises the padded pixel count
+// (used by the weight-gradient kernel for its K tiles).
 void pick_pixel_tile(int n_img, int H, int W, int pixels, int* tw, int* th, int* tn) {
   long best = -1;
   for (int w = 1; w <= pixels && w <= 16; w *= 2) {
@@ -377,58 +426,56 @@ struct IgemmLaunch {
   const void* a2;
   int c2;
   const void* b;   // [Ntot][num_taps * (c1 + c2)] bf16
-  int a_fine;      // a_mode 1: A tensors are [N, 2H, 2W, C]
   IgemmParams p;
 };
 
 static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
   IgemmParams& p = L.p;
   UNETK_CHECK_ARG(L.c1 % 64 == 0 && L.c2 % 64 == 0 && L.c1 > 0, "igemm: channel counts must be multiples of 64 (got %d, %d)", L.c1, L.c2);
-  UNETK_CHECK_ARG(p.Ntot % 32 == 0, "igemm: output columns must be a multiple of 32 (got %d)", p.Ntot);
+  UNETK_CHECK_ARG(p.Ntot % 64 == 0, "igemm: output columns must be a multiple of 64 (got %d)", p.Ntot);
   UNETK_CHECK_ARG(p.split % 32 == 0, "igemm: column split must be a multiple of 32");
   UNETK_CHECK_ARG((reinterpret_cast<uintptr_t>(L.a1) & 15) == 0 && (reinterpret_cast<uintptr_t>(L.b) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(p.out1) & 15) == 0, "igemm: pointers must be 16-byte aligned");
   if (int e = check_device_sm100()) return e;
-  pick_pixel_tile(p.n_img, p.H, p.W, 128, &p.tw, &p.th, &p.tn);
-  p.tiles_x = (p.W + p.tw - 1) / p.tw;
-  p.tiles_y = (p.H + p.th - 1) / p.th;
-  p.tiles_n = (p.n_img + p.tn - 1) / p.tn;
+  p.halo = (p.num_taps == 9) ? 1 : 0;
+  p.regions_x = (p.W + kRegion - 1) / kRegion;
+  p.regions_y = (p.H + kRegion - 1) / kRegion;
   p.c1_chunks = L.c1 / 64;
   p.c2_chunks = L.c2 / 64;
   const int bn = (p.Ntot % 128 == 0) ? 128 : 64;
-  UNETK_CHECK_ARG(p.Ntot % bn == 0, "igemm: output columns %d not a multiple of %d", p.Ntot, bn);
   p.n_blocks = p.Ntot / bn;
   const bool use_colbuf = p.stats != nullptr || p.scale != nullptr;
   UNETK_CHECK_ARG(!(p.stats != nullptr && p.scale != nullptr), "igemm: stats and affine epilogues are exclusive");
   UNETK_CHECK_ARG(!use_colbuf || p.Ntot <= 1024, "igemm: stats/affine epilogue supports at most 1024 columns");
 
+  const int box = kRegion + 2 * p.halo;
   CUtensorMap tmA1, tmA2, tmB;
   int e;
   if (p.a_mode == 0) {
-    if ((e = make_act_tmap(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, p.tw, p.th, p.tn))) return e;
+    if ((e = make_act_tmap(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, box, box, 1))) return e;
     if (L.c2 > 0) {
-      if ((e = make_act_tmap(&tmA2, L.a2, p.n_img, p.H, p.W, L.c2, p.tw, p.th, p.tn))) return e;
+      if ((e = make_act_tmap(&tmA2, L.a2, p.n_img, p.H, p.W, L.c2, box, box, 1))) return e;
     } else {
       tmA2 = tmA1;
     }
   } else {
-    if ((e = make_act_tmap_up2(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, p.tw, p.th, p.tn))) return e;
+    if ((e = make_act_tmap_up2(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, kRegion, kRegion, 1))) return e;
     tmA2 = tmA1;
   }
   const int K = p.num_taps * (L.c1 + L.c2);
   if ((e = make_b_tmap(&tmB, L.b, p.Ntot, K, bn))) return e;
 
-  const long total_tiles = static_cast<long>(p.tiles_x) * p.tiles_y * p.tiles_n * p.n_blocks;
+  const long total_tiles = static_cast<long>(p.regions_x) * p.regions_y * p.n_img * p.n_blocks;
   const int grid = static_cast<int>(total_tiles < num_sms() ? total_tiles : num_sms());
-  const size_t colbytes = use_colbuf ? static_cast<size_t>(2) * p.Ntot * sizeof(float) : 0;
+  const size_t colbytes = (p.stats != nullptr ? 8 : (use_colbuf ? 2 : 0)) * static_cast<size_t>(p.Ntot) * sizeof(float);
   if (bn == 128) {
     using Cfg = IgemmCfg<128>;
-    const size_t smem = 1024 + Cfg::kStages * Cfg::kStageBytes + (2 * Cfg::kStages + 6) * 8 + colbytes;
+    const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;
     UNETK_CUDA(cudaFuncSetAttribute(igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     igemm_kernel<128><<<grid, kIgemmThreads, smem, stream>>>(tmA1, tmA2, tmB, p);
   } else {
     using Cfg = IgemmCfg<64>;
-    const size_t smem = 1024 + Cfg::kStages * Cfg::kStageBytes + (2 * Cfg::kStages + 6) * 8 + colbytes;
+    const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;
     UNETK_CUDA(cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     igemm_kernel<64><<<grid, kIgemmThreads, smem, stream>>>(tmA1, tmA2, tmB, p);
   }
@@ -455,6 +502,7 @@ int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1,
                   int c2, int acc2, float* stats, int n, int h, int w, cudaStream_t stream) {
   UNETK_CHECK_ARG(dy && wdpk && dx1, "conv3x3_dgrad: null pointer");
   UNETK_CHECK_ARG(c2 == 0 || dx2 != nullptr, "conv3x3_dgrad: second destination missing");
+  UNETK_CHECK_ARG(stats == nullptr || c2 > 0, "conv3x3_dgrad: stats requested without a second destination");
   IgemmLaunch L{};
   L.a1 = dy; L.c1 = cout; L.a2 = nullptr; L.c2 = 0; L.b = wdpk;
   IgemmParams& p = L.p;
@@ -463,7 +511,6 @@ int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1,
   p.ldc1 = c1; p.ldc2 = c2; p.acc1 = acc1; p.acc2 = acc2;
   // bias gradient of the ConvTranspose2d that produced the second concat source: sum over pixels of dx2
   p.stats = stats; p.stats_sq = nullptr; p.stats_from = c1;
-  UNETK_CHECK_ARG(stats == nullptr || c2 > 0, "conv3x3_dgrad: stats requested without a second destination");
   return launch_igemm(L, stream);
 }
 

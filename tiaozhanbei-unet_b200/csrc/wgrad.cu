@@ -11,6 +11,10 @@
 // K = 16 pixels per instruction.  One CTA owns one (tap row | 4 taps) x 128 ci x BN co block of dW
 // in TMEM and a slice of the pixel range (split-K); partial sums are added to the fp32 gradient
 // with red.global.add.f32.
+// conv3x3: the K tile is an 8x8 pixel patch; the X operand of the three dx taps of a tap row comes
+// from ONE 10x8 halo box per 64-channel chunk (80 rows x 128 B): a dx shift is a descriptor start
+// offset of dx*128 B, 8-pixel patch rows are the 8-row K groups with SBO = 10*128 B (the 128B
+// swizzle is address based, profiles/umma_probe_r01.txt).  X traffic drops 2.4x.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,17 +33,21 @@ struct WgradParams {
 };
 
 constexpr int kWgThreads = 192;
-constexpr int kBoxBytes = 64 * 128;  // 64 pixels x 64 bf16
+constexpr int kBoxBytes = 64 * 128;   // 64 pixels x 64 bf16
+constexpr int kHaloBytes = 80 * 128;  // 10 x 8 pixels x 64 bf16 (conv3x3 X operand)
+constexpr int kHaloPitch = 10 * 128;  // bytes between patch rows inside the halo box
 
 template <int MODE, int BN, bool M64>
 struct WgCfg {
-  // boxes resident per stage
-  static constexpr int kABoxes = (MODE == 0) ? (M64 ? 4 : 6) : 2;
-  static constexpr int kALoads = (MODE == 0) ? (M64 ? 3 : 6) : 2;
+  // per stage: A (X operand) and B (dY / dUp operand) regions
+  static constexpr int kALoads = (MODE == 0) ? (M64 ? 1 : 2) : 2;
+  static constexpr int kABoxBytes = (MODE == 0) ? kHaloBytes : kBoxBytes;
+  // M64: the second tap of the last pair reads 3 rows past the box; keep that inside the stage
+  static constexpr int kABytes = kALoads * kABoxBytes + ((MODE == 0 && M64) ? 1024 : 0);
   static constexpr int kBBoxes = (MODE == 0) ? (BN / 64) : 4 * (BN / 64);
   static constexpr int kMmas = (MODE == 0) ? (M64 ? 2 : 3) : 4;
-  static constexpr int kStageBytes = (kABoxes + kBBoxes) * kBoxBytes;
-  static constexpr int kStages = (kStageBytes * 4 <= 200 * 1024) ? 4 : (kStageBytes * 3 <= 200 * 1024 ? 3 : 2);
+  static constexpr int kStageBytes = kABytes + kBBoxes * kBoxBytes;
+  static constexpr int kStages = (kStageBytes * 6 <= 200 * 1024) ? 6 : (kStageBytes * 4 <= 200 * 1024 ? 4 : (kStageBytes * 3 <= 200 * 1024 ? 3 : 2));
   static constexpr int kAccCols = kMmas * BN;
   static constexpr int kTmemCols = kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512));
 };
@@ -102,17 +110,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
         const int tz = m / p.tiles_y;
         const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tz * p.tn;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], (Cfg::kALoads + Cfg::kBBoxes) * kBoxBytes);
+        mbar_expect_tx(&full[stage], Cfg::kALoads * Cfg::kABoxBytes + Cfg::kBBoxes * kBoxBytes);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABoxes * kBoxBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
         if (MODE == 0) {
 #pragma unroll
           for (int j = 0; j < Cfg::kALoads; ++j) {
-            const int tap = 3 * r + (M64 ? j : j / 2);
-            const int chunk = M64 ? 0 : cit * 2 + (j & 1);
+            const int chunk = M64 ? 0 : cit * 2 + j;
             const CUtensorMap* mp = (chunk < p.c1_chunks) ? &tmX1 : &tmX2;
             const int cc = ((chunk < p.c1_chunks) ? chunk : chunk - p.c1_chunks) * 64;
-            tma_load_5d(sa + j * kBoxBytes, mp, &full[stage], cc, x0 + tap % 3 - 1, y0 + tap / 3 - 1, n0, 0);
+            // halo box of tap row r: pixels (x0-1 .. x0+8, y0+r-1 .. y0+r+6)
+            tma_load_5d(sa + j * kHaloBytes, mp, &full[stage], cc, x0 - 1, y0 + r - 1, n0, 0);
           }
 #pragma unroll
           for (int j = 0; j < Cfg::kBBoxes; ++j)
@@ -143,16 +151,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABoxes * kBoxBytes;
+        const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
         for (int j = 0; j < Cfg::kMmas; ++j) {
-          const uint32_t a0 = sa + ((MODE == 0) ? 2 * j : 0) * kBoxBytes;
           const uint32_t b0 = sb + ((MODE == 0) ? 0 : j * (BN / 64)) * kBoxBytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // K advances by 16 pixel rows = 2048 B; 64-wide MN atoms are one box (8 KB) apart.
-            const uint64_t da = umma_smem_desc_sw128(a0 + k * 2048, kBoxBytes, 1024);
+            // B: K advances by 16 pixel rows = 2048 B; 64-wide MN atoms are one box (8 KB) apart.
             const uint64_t db = umma_smem_desc_sw128(b0 + k * 2048, kBoxBytes, 1024);
+            uint64_t da;
+            if (MODE == 0) {
+              // X halo: tap dx starts dx rows in; 16 pixels = two patch rows of the 10-wide halo.
+              // !M64: M = 128 ci = two halo boxes (LBO).  M64: M = taps (2j, 2j+1) x 64 ci (LBO = 1 row).
+              const uint32_t a0 = sa + (M64 ? 2 * j : j) * 128 + k * 2 * kHaloPitch;
+              da = umma_smem_desc_sw128(a0, M64 ? 128 : kHaloBytes, kHaloPitch);
+            } else {
+              da = umma_smem_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
+            }
             tc_mma_bf16(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
           }
         }
@@ -198,8 +213,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
             const int co = co0 + jj;
-            if (co < p.cout)
-              atomicAdd(p.dw + (static_cast<size_t>(co) * p.T + tap) * p.cin + ci, v[jj]);
+            if (co < p.cout) {
+              float* dst = p.dw + (static_cast<size_t>(co) * p.T + tap) * p.cin + ci;
+              if (p.ksplit == 1) *dst = v[jj]; else atomicAdd(dst, v[jj]);
+            }
           }
         }
       }
@@ -230,13 +247,27 @@ static int launch_wgrad_t(const CUtensorMap& x1, const CUtensorMap& x2, const CU
   return UNETK_OK;
 }
 
-static int choose_ksplit(int work_tiles, int total_k) {
-  // aim for >= 4 waves of CTAs while keeping >= 8 K tiles per CTA
+// Split-K factor from a small cost model (units: microseconds).  Every split pays one epilogue:
+// red.global.add when ksplit > 1 (atomics on the same addresses serialise in L2, so their cost
+// grows with the number of splits), plain stores when ksplit == 1.  Measured on B200
+// (profiles/ncu_conv_r01a): 594 CTAs x 49 K atomics took about as long as their main loops.
+static int choose_ksplit(int work_tiles, int total_k, double us_per_ktile, double out_elems_per_cta) {
   const int sms = num_sms();
-  int ks = (4 * sms + work_tiles - 1) / work_tiles;
-  if (ks > total_k / 8) ks = total_k / 8;
-  if (ks < 1) ks = 1;
-  return ks;
+  int best = 1;
+  double best_t = 1e30;
+  const int max_ks = total_k < 512 ? total_k : 512;
+  for (int ks = 1; ks <= max_ks; ++ks) {
+    const long ctas = static_cast<long>(work_tiles) * ks;
+    const double waves = static_cast<double>((ctas + sms - 1) / sms);
+    const double main_us = (static_cast<double>((total_k + ks - 1) / ks)) * us_per_ktile;
+    const double epi_us = (ks == 1) ? out_elems_per_cta * 4e-5 : out_elems_per_cta * (1.2e-4 + 2.0e-6 * ks);
+    const double t = waves * (main_us + epi_us + 3.0);
+    if (t < best_t) {
+      best_t = t;
+      best = ks;
+    }
+  }
+  return best;
 }
 
 int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2, float* dw,
@@ -249,19 +280,21 @@ int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, in
   if (int e = check_device_sm100()) return e;
   WgradParams p{};
   p.n_img = n; p.H = h; p.W = w; p.cin = cin; p.cout = cout; p.c1_chunks = c1 / 64; p.T = 9; p.dw = dw;
-  pick_pixel_tile(n, h, w, 64, &p.tw, &p.th, &p.tn);
-  p.tiles_x = (w + p.tw - 1) / p.tw; p.tiles_y = (h + p.th - 1) / p.th; p.tiles_n = (n + p.tn - 1) / p.tn;
+  p.tw = 8; p.th = 8; p.tn = 1;   // 8x8 pixel K tiles, X read through 10x8 halo boxes
+  p.tiles_x = (w + 7) / 8; p.tiles_y = (h + 7) / 8; p.tiles_n = n;
   const bool m64 = (cin == 64);
   const int bn = (cout % 128 == 0) ? 128 : 64;
   p.ci_tiles = m64 ? 1 : cin / 128;
   p.co_tiles = cout / bn;
   const int work = 3 * p.ci_tiles * p.co_tiles;
-  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y * p.tiles_n);
+  // one K tile = (2 or 3) x 4 MMAs of 128 x bn x 16 (M64: N = bn at half the tile rows)
+  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y * p.tiles_n, (m64 ? 8 : 12) * bn / 256.0 / 1.7 + 0.05,
+                           (m64 ? 3 * 64 : 3 * 128) * static_cast<double>(bn));
   CUtensorMap x1, x2, tdy;
   int e;
-  if ((e = make_act_tmap(&x1, src1, n, h, w, c1, p.tw, p.th, p.tn))) return e;
-  if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h, w, c2, p.tw, p.th, p.tn))) return e; } else x2 = x1;
-  if ((e = make_act_tmap(&tdy, dy, n, h, w, cout, p.tw, p.th, p.tn))) return e;
+  if ((e = make_act_tmap(&x1, src1, n, h, w, c1, 10, 8, 1))) return e;
+  if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h, w, c2, 10, 8, 1))) return e; } else x2 = x1;
+  if ((e = make_act_tmap(&tdy, dy, n, h, w, cout, 8, 8, 1))) return e;
   dim3 grid(work, p.ksplit);
   if (m64) return bn == 128 ? launch_wgrad_t<0, 128, true>(x1, x2, tdy, p, grid, stream)
                             : launch_wgrad_t<0, 64, true>(x1, x2, tdy, p, grid, stream);
@@ -283,7 +316,7 @@ int convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw,
   p.ci_tiles = cin / 128;
   p.co_tiles = cout / bn;
   const int work = p.ci_tiles * p.co_tiles;
-  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y);
+  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y, 16 * bn / 256.0 / 1.7 + 0.05, 4 * 128.0 * bn);
   CUtensorMap x1, tdy;
   int e;
   if ((e = make_act_tmap(&x1, a, 1, p.H, w, cin, p.tw, p.th, p.tn))) return e;
