@@ -31,6 +31,15 @@ def _align(n):
     return (n + ALIGN - 1) // ALIGN * ALIGN
 
 
+def param_layout(named_params):
+    """Offsets (in elements) of every parameter inside the flat buffers, in named_parameters() order."""
+    offs, total = {}, 0
+    for k, p in named_params:
+        offs[k] = total
+        total += _align(p.numel())
+    return offs, total
+
+
 class _ConvBN:
     """One conv3x3 + BatchNorm record (tensor views are filled in by Engine._build_views)."""
 
@@ -156,10 +165,7 @@ class Engine:
         named = list(self.module.named_parameters())
         self.param_names = [k for k, _ in named]
         self.params = [p for _, p in named]
-        offs, total = {}, 0
-        for k, p in named:
-            offs[k] = total
-            total += _align(p.numel())
+        offs, total = param_layout(named)
         self.offsets, self.total = offs, total
         flat = torch.zeros(total, dtype=torch.float32, device=device)
         for k, p in named:

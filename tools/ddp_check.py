@@ -1,0 +1,78 @@
+"""Run under torchrun (N ranks, one GPU each): data-parallel gradient parity.
+Every rank trains on its own shard; after backward all ranks must hold bit-identical gradients, and
+those must equal the mean of the per-shard gradients (checked on rank 0 against the fp32 oracle run
+on every shard: SURVEY.md §7.2 item 6, "reference per shard + gradient mean")."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import unet_oracle as O  # noqa: E402
+from tiaozhanbei_unet_b200 import distributed as D, train_utils  # noqa: E402
+from tiaozhanbei_unet_b200.model import AnomalyUNet  # noqa: E402
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+
+sd = O.synthetic_state_dict("anomaly_unet", seed=3)
+m = AnomalyUNet(3)
+m.load_state_dict(sd)
+m = m.to(dev).train()
+D.broadcast_parameters(m)
+red = D.attach(m)
+crit = train_utils.CombinedLoss()
+opt = train_utils.get_optimizer(m)
+n, h, w = 4, 64, 64
+
+
+def shard(r):
+    g = torch.Generator().manual_seed(500 + r)
+    return torch.randn(n, 3, h, w, generator=g), (torch.rand(n, 1, h, w, generator=g) > 0.95).float()
+
+
+image, mask = (t.to(dev) for t in shard(rank))
+r_, a_ = m(image)
+ld = crit(r_, a_, image, mask)
+opt.zero_grad()
+ld["total_loss"].backward()
+torch.cuda.synchronize()
+flat = m._engine().flat_g
+# 1) identical on all ranks
+chk = torch.stack([flat.double().sum(), flat.double().abs().sum()])
+allc = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(allc, chk)
+same = all(torch.equal(allc[0], c) for c in allc)
+ok = same
+msg = f"identical across ranks: {same}; reduced {red.bytes_reduced / 1e6:.1f} MB in buckets"
+if rank == 0:
+    ref = None
+    for r in range(world):
+        im, mk = (t.to(dev) for t in shard(r))
+        _, g = O.train_step({k: v.to(dev).clone() for k, v in sd.items()}, im, mk, arch="anomaly_unet")
+        ref = g if ref is None else {k: ref[k] + g[k] for k in g}
+    ref = {k: v / world for k, v in ref.items()}
+    worst_cos, head = 1.0, 0.0
+    for k, p in m.named_parameters():
+        g, gr = p.grad, ref[k]
+        cos = ((g * gr).sum() / (g.norm() * gr.norm() + 1e-30)).item()
+        worst_cos = min(worst_cos, cos)
+        if k.startswith("outc"):
+            head = max(head, ((g - gr).norm() / gr.norm()).item())
+        nr = abs(g.norm().item() - gr.norm().item()) / gr.norm().item()
+        ok = ok and cos > 0.6 and nr < 0.2
+    ok = ok and head < 3e-2
+    msg += f"; vs mean of per-shard oracle grads: worst cosine {worst_cos:.3f}, head rel err {head:.2e}"
+opt.step()
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(("DDP CHECK PASSED: " if flag.item() else "DDP CHECK FAILED: ") + msg, flush=True)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() else 1)
