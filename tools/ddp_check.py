@@ -19,7 +19,8 @@ torch.backends.cuda.matmul.allow_tf32 = False
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+import datetime
+dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 
 sd = O.synthetic_state_dict("anomaly_unet", seed=3)
 m = AnomalyUNet(3)
