@@ -107,7 +107,11 @@ def cpu_reference_rate(steps, warmup, budget_s):
     threads) on a bounded sample: the per-step batch is shrunk so the whole run fits the budget."""
     import torch
     from oracle import unet_oracle as O
-    threads = torch.get_num_threads()
+    try:                      # torchrun exports OMP_NUM_THREADS=1: take every core we are allowed to use
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     sd = O.synthetic_state_dict("anomaly_unet", seed=42)
     g = torch.Generator().manual_seed(0)
 
