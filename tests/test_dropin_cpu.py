@@ -1,0 +1,60 @@
+"""The UNMODIFIED reference training script on top of this package (build container only: needs
+/root/reference).  On a machine without a GPU the run must get through the reference's own argument
+parsing, dataset, model / criterion / optimizer / scheduler construction and into the first training
+step, and stop there with OUR loud "no CPU path" error — proving the flat-import drop-in wiring
+ without any CPU fallback existing."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF_TRAIN = "/root/reference/src/train.py"
+
+
+def _make_mvtec_tree(root, category="synth", n_train=4, n_test=2, size=40):
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    for split, n in (("train", n_train), ("test", n_test)):
+        d = os.path.join(root, category, split, "good")
+        os.makedirs(d, exist_ok=True)
+        for i in range(n):
+            Image.fromarray(rng.integers(0, 255, (size, size, 3), dtype=np.uint8)).save(os.path.join(d, f"{i:03d}.png"))
+    os.makedirs(os.path.join(root, category, "ground_truth"), exist_ok=True)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TRAIN), reason="reference sources only exist in the build container")
+def test_reference_train_script_runs_on_top_of_this_package(tmp_path, monkeypatch):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU wiring test")
+    pytest.importorskip("torchvision")
+    from tiaozhanbei_unet_b200 import _lib
+    from tiaozhanbei_unet_b200.dropin import launch
+    data = str(tmp_path / "mvtec")
+    _make_mvtec_tree(data)
+    saved_modules = {k: sys.modules.get(k) for k in ("model", "train_utils", "utils", "dataset", "matplotlib", "seaborn")}
+    saved_argv, saved_path = list(sys.argv), list(sys.path)
+    monkeypatch.chdir(os.path.dirname(REF_TRAIN))
+    try:
+        with pytest.raises((_lib.UnetkError, RuntimeError)) as e:
+            launch.run(REF_TRAIN, ["--data_root", data, "--category", "synth", "--image_size", "32", "--epochs", "1",
+                                   "--batch_size", "2", "--num_workers", "0", "--use_ssim", "--model", "anomaly_unet",
+                                   "--save_dir", str(tmp_path / "out"), "--device", "cpu"])
+        assert "CUDA" in str(e.value) or "CPU" in str(e.value)
+        # the script really used OUR modules under the reference's flat names
+        import model as flat_model
+        import train_utils as flat_tu
+        assert flat_model.AnomalyUNet.__module__ == "tiaozhanbei_unet_b200.model"
+        assert flat_tu.CombinedLoss.__module__ == "tiaozhanbei_unet_b200.train_utils"
+        assert os.path.isdir(str(tmp_path / "out"))      # experiment directory + args.json were written first
+    finally:
+        sys.argv[:] = saved_argv
+        sys.path[:] = saved_path
+        for k, v in saved_modules.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

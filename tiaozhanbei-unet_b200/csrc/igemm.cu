@@ -177,7 +177,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the loops (warp-uniform control flow keeps the descriptors in uniform
+    // registers); one elected lane issues the tcgen05 instructions.
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
       const uint32_t sbo = static_cast<uint32_t>(pitch * 128);
       int as = 0, bs = 0;
@@ -192,37 +194,41 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         uint32_t first = 1;
         for (int al = 0; al < a_loads; ++al) {
           mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + as * kABufBytes);
+          // descriptor of sub-tile 0, tap (0,0), k = 0; everything else is a start-address offset
+          const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(sA + as * kABufBytes), 0, sbo);
           for (int tt = 0; tt < taps_per_load; ++tt) {
             // tap (dy, dx) in {-1,0,1}^2 = rows (dy+1)*pitch + (dx+1) into the halo tile
-            const uint32_t tap_off = p.halo ? static_cast<uint32_t>(((tt / 3) * pitch + (tt % 3)) * 128) : 0u;
+            const uint32_t tap_off16 = p.halo ? static_cast<uint32_t>(((tt / 3) * pitch + (tt % 3)) * 8) : 0u;
             mbar_wait(&b_full[bs], bph);
             tc_fence_after();
-            const uint32_t b_base = smem_u32(sB + bs * Cfg::kBBytes);
+            const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(sB + bs * Cfg::kBBytes), 0, 1024);
+            if (elect_one()) {
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
+              for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = umma_smem_desc_sw128(a_base + tap_off + sub * (kSubW * 128) + k * 32, 0, sbo);
-                const uint64_t db = umma_smem_desc_sw128(b_base + k * 32, 0, 1024);
-                tc_mma_bf16(d_tmem + sub * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                for (int k = 0; k < 4; ++k) {
+                  // start-address field is (addr >> 4): offsets in 16-byte units
+                  const uint64_t da = a_desc0 + (tap_off16 + sub * (kSubW * 8) + k * 2);
+                  const uint64_t db = b_desc0 + (k * 2);
+                  tc_mma_bf16(d_tmem + sub * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                }
               }
+              tc_commit(&b_empty[bs]);
+              if (tt == taps_per_load - 1) tc_commit(&a_empty[as]);
+              if (tt == taps_per_load - 1 && al == a_loads - 1) tc_commit(&tfull[acc]);
             }
+            __syncwarp();
             first = 0;
-            tc_commit(&b_empty[bs]);
             if (++bs == kBStages) {
               bs = 0;
               bph ^= 1;
             }
           }
-          tc_commit(&a_empty[as]);
           if (++as == kNumABufs) {
             as = 0;
             aph ^= 1;
           }
         }
-        tc_commit(&tfull[acc]);
       }
     }
   } else {

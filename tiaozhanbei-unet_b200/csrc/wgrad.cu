@@ -143,7 +143,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // warp-uniform loop, one elected lane issues (keeps descriptors in uniform registers)
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
       int stage = 0;
       uint32_t phase = 0;
@@ -152,27 +153,28 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + Cfg::kABytes;
+        // base descriptors; per-MMA variation is a start-address offset in 16-byte units
+        const uint64_t a_desc0 = (MODE == 0) ? umma_smem_desc_sw128(sa, M64 ? 128 : kHaloBytes, kHaloPitch)
+                                             : umma_smem_desc_sw128(sa, kBoxBytes, 1024);
+        const uint64_t b_desc0 = umma_smem_desc_sw128(sb, kBoxBytes, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < Cfg::kMmas; ++j) {
-          const uint32_t b0 = sb + ((MODE == 0) ? 0 : j * (BN / 64)) * kBoxBytes;
+          for (int j = 0; j < Cfg::kMmas; ++j) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // B: K advances by 16 pixel rows = 2048 B; 64-wide MN atoms are one box (8 KB) apart.
-            const uint64_t db = umma_smem_desc_sw128(b0 + k * 2048, kBoxBytes, 1024);
-            uint64_t da;
-            if (MODE == 0) {
-              // X halo: tap dx starts dx rows in; 16 pixels = two patch rows of the 10-wide halo.
-              // !M64: M = 128 ci = two halo boxes (LBO).  M64: M = taps (2j, 2j+1) x 64 ci (LBO = 1 row).
-              const uint32_t a0 = sa + (M64 ? 2 * j : j) * 128 + k * 2 * kHaloPitch;
-              da = umma_smem_desc_sw128(a0, M64 ? 128 : kHaloBytes, kHaloPitch);
-            } else {
-              da = umma_smem_desc_sw128(sa + k * 2048, kBoxBytes, 1024);
+            for (int k = 0; k < 4; ++k) {
+              // B: K advances by 16 pixel rows = 2048 B; 64-wide MN atoms are one box (8 KB) apart.
+              const uint64_t db = b_desc0 + (((MODE == 0) ? 0 : j * (BN / 64)) * (kBoxBytes / 16) + k * 128);
+              // X halo (MODE 0): tap dx starts dx rows in; 16 pixels = two patch rows of the 10-wide
+              // halo.  !M64: M = 128 ci = two halo boxes (LBO).  M64: M = taps (2j, 2j+1) x 64 ci.
+              const uint64_t da = (MODE == 0) ? a_desc0 + ((M64 ? 2 * j : j) * 8 + k * 2 * (kHaloPitch / 16))
+                                              : a_desc0 + (k * 128);
+              tc_mma_bf16(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
             }
-            tc_mma_bf16(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
           }
+          tc_commit(&empty[stage]);
+          if (kt == k_end - 1) tc_commit(tfull);
         }
-        tc_commit(&empty[stage]);
-        if (kt == k_end - 1) tc_commit(tfull);
+        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
