@@ -165,6 +165,13 @@ int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, flo
 int unetk_permute_batched(const void* descs, int n_desc, int n_chunks, const float* in, void* out,
                           int out_bf16, float scale, void* stream);
 int unetk_permute_chunk_elems(void);
+/* Tiled fast paths for the conv3x3 layers (64-byte descriptors {src_off, dst_off, dst2_off, cout, cin,
+ * block_begin}, see tiaozhanbei-unet_b200/packing.py): OIHW fp32 -> Wf and Wd bf16 in one launch
+ * (one block per 32x32 (co, ci) tile), and staged dW[co][tap][ci] -> OIHW fp32 * scale (one block per co). */
+int unetk_pack_conv_weights(const void* descs, int n_desc, int n_blocks, const float* flat_p, void* wpack,
+                            void* stream);
+int unetk_unpack_conv_grads(const void* descs, int n_desc, int n_blocks, int max_cin, const float* gstage,
+                            float* flat_g, float scale, void* stream);
 int unetk_nchw_to_nhwc(const float* in, void* out, int n, int c, int h, int w, void* stream);
 int unetk_nhwc_to_nchw(const void* in, float* out, int n, int c, int h, int w, void* stream);
 

@@ -47,6 +47,8 @@ SIGNATURES = {
     "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),
     "unetk_permute_batched": (I, [P, I, I, P, P, I, F, P]),
     "unetk_permute_chunk_elems": (I, []),
+    "unetk_pack_conv_weights": (I, [P, I, I, P, P, P]),
+    "unetk_unpack_conv_grads": (I, [P, I, I, I, P, P, F, P]),
     "unetk_nchw_to_nhwc": (I, [P, P, I, I, I, I, P]),
     "unetk_nhwc_to_nchw": (I, [P, P, I, I, I, I, P]),
 }

@@ -147,6 +147,14 @@ int unetk_permute_batched(const void* descs, int n_desc, int n_chunks, const flo
                           int out_bf16, float scale, void* stream) {
   return unetk::permute_batched(descs, n_desc, n_chunks, in, out, out_bf16, scale, S(stream));
 }
+int unetk_pack_conv_weights(const void* descs, int n_desc, int n_blocks, const float* flat_p, void* wpack,
+                            void* stream) {
+  return unetk::pack_conv_weights(descs, n_desc, n_blocks, flat_p, wpack, S(stream));
+}
+int unetk_unpack_conv_grads(const void* descs, int n_desc, int n_blocks, int max_cin, const float* gstage,
+                            float* flat_g, float scale, void* stream) {
+  return unetk::unpack_conv_grads(descs, n_desc, n_blocks, max_cin, gstage, flat_g, scale, S(stream));
+}
 int unetk_permute_chunk_elems(void) { return unetk::permute_chunk_elems(); }
 int unetk_nchw_to_nhwc(const float* in, void* out, int n, int c, int h, int w, void* stream) {
   return unetk::nchw_to_nhwc(in, out, n, c, h, w, S(stream));

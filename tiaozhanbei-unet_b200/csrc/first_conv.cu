@@ -92,43 +92,46 @@ first_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }
 }
 
-// wgrad: block = 256 threads, works on chunks of 96 pixels.  Thread t owns output channel
-// co = t % 64 and the k-range kq = t / 64 (k = tap * Cin + ci split in four groups of 9).
-constexpr int kFwPix = 96;
+// wgrad: block = 256 threads = 4 pixel slices x 64 threads; thread (slice, t) owns a 4 co x 7 k
+// register tile (co = 4*(t%16).., k = 7*(t/16)..; k = tap*Cin + ci, 28 slots >= 27) and walks every
+// fourth pixel of a 128-pixel chunk staged in shared memory: 3 vector LDS per 28 FMAs.
+constexpr int kFwPix = 128;
+constexpr int kFwK = 28;
 
 __global__ void __launch_bounds__(256)
 first_conv_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ dy,
                         float* __restrict__ dw, int N, int Cin, int H, int W) {
-  __shared__ float sdy[kFwPix][kFcCout + 1];
-  __shared__ float sx[kFwPix][kFcMaxK + 1];
+  __shared__ __align__(16) float sdy[kFwPix][kFcCout];      // 32 KB
+  __shared__ __align__(16) float sx[kFwPix][kFwK];          // 14 KB
   const int K = 9 * Cin;
-  const int co = threadIdx.x & 63, kq = threadIdx.x >> 6;
-  const int k0 = kq * 9;
-  float acc[9];
+  const int t = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int co0 = (t & 15) * 4, k0 = (t >> 4) * 7;
+  float acc[4][7];
 #pragma unroll
-  for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
   const long hw = static_cast<long>(H) * W;
   const long total = hw * N;
   const long nchunks = (total + kFwPix - 1) / kFwPix;
   for (long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const long p0 = ch * kFwPix;
     __syncthreads();
-    // stage dY (bf16 -> fp32): kFwPix pixels x 8 vectors
     for (int i = threadIdx.x; i < kFwPix * 8; i += blockDim.x) {
       const int pp = i >> 3, g = i & 7;
       const long p = p0 + pp;
       uint4 u = make_uint4(0, 0, 0, 0);
       if (p < total) u = ldg_nc_v4(dy + p * 8 + g);
       const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-      float* row = &sdy[pp][g * 8];
-      row[0] = a.x; row[1] = a.y; row[2] = b.x; row[3] = b.y; row[4] = c.x; row[5] = c.y; row[6] = d.x; row[7] = d.y;
+      float4* row = reinterpret_cast<float4*>(&sdy[pp][g * 8]);
+      row[0] = make_float4(a.x, a.y, b.x, b.y);
+      row[1] = make_float4(c.x, c.y, d.x, d.y);
     }
-    // stage the im2col patch of X
-    for (int i = threadIdx.x; i < kFwPix * K; i += blockDim.x) {
+    for (int i = threadIdx.x; i < kFwPix * kFwK; i += blockDim.x) {
       const int pp = i % kFwPix, k = i / kFwPix;
       const long p = p0 + pp;
       float v = 0.f;
-      if (p < total) {
+      if (p < total && k < K) {
         const long n = p / hw;
         const int r = static_cast<int>(p - n * hw);
         const int yy = r / W, xx = r - yy * W;
@@ -139,22 +142,29 @@ first_conv_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ d
       sx[pp][k] = v;
     }
     __syncthreads();
-    if (k0 < K) {
-      for (int pp = 0; pp < kFwPix; ++pp) {
-        const float g = sdy[pp][co];
+#pragma unroll 4
+    for (int pp = slice; pp < kFwPix; pp += 4) {
+      const float4 g = *reinterpret_cast<const float4*>(&sdy[pp][co0]);
+      float xv[7];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) acc[j] = fmaf(g, sx[pp][k0 + j], acc[j]);
+      for (int j = 0; j < 7; ++j) xv[j] = sx[pp][k0 + j];
+      const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int k = k0 + j;
+      if (k < K) {
+        const int tap = k / Cin, ci = k - tap * Cin;
+        atomicAdd(dw + ((co0 + i) * Cin + ci) * 9 + tap, acc[i][j]);  // OIHW
       }
     }
-  }
-#pragma unroll
-  for (int j = 0; j < 9; ++j) {
-    const int k = k0 + j;
-    if (k < K) {
-      const int tap = k / Cin, ci = k - tap * Cin;
-      atomicAdd(dw + (co * Cin + ci) * 9 + tap, acc[j]);  // OIHW
-    }
-  }
 }
 
 int first_conv_fwd(const float* x, const float* w, void* y, float* stats, int N, int Cin, int H, int W,

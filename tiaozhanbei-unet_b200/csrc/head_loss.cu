@@ -55,75 +55,100 @@ head_fwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const 
 // head backward.  dlogit = dout * out * (1 - out) if sigmoid else dout.
 //   dA[p, c] = sum_j dlogit[p, j] * w[j, c]          (bf16 NHWC)
 //   dW[j, c] = sum_p dlogit[p, j] * a[p, c],  db[j] = sum_p dlogit[p, j]   (fp32, atomically added)
-// One warp walks 32 consecutive pixels at a time; lane l owns channels 2l, 2l+1.
+// 8 lanes cover one pixel (16-byte vectors of 8 channels), a warp covers 4 pixels per step and every
+// thread keeps four steps in flight; weights and the dW partial sums live in registers.
 // ----------------------------------------------------------------------------------------------
+template <int NOUT>
 __global__ void __launch_bounds__(256)
-head_bwd_kernel(const uint32_t* __restrict__ a, const float* __restrict__ w,
+head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
                 const float* __restrict__ dout, const float* __restrict__ out,
-                uint32_t* __restrict__ da, float* __restrict__ dw, float* __restrict__ db,
-                long npix_total, long hw, int n_out, int sigmoid) {
-  __shared__ float sdw[kHeadMaxOut * kHeadC];
-  __shared__ float sdb[kHeadMaxOut];
-  for (int i = threadIdx.x; i < kHeadMaxOut * kHeadC; i += blockDim.x) sdw[i] = 0.f;
-  if (threadIdx.x < kHeadMaxOut) sdb[threadIdx.x] = 0.f;
+                uint4* __restrict__ da, float* __restrict__ dw, float* __restrict__ db,
+                long npix_total, long hw, int sigmoid) {
+  __shared__ float sdw[NOUT * kHeadC];
+  __shared__ float sdb[NOUT];
+  for (int i = threadIdx.x; i < NOUT * kHeadC; i += blockDim.x) sdw[i] = 0.f;
+  if (threadIdx.x < NOUT) sdb[threadIdx.x] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  const int cg = lane & 7;          // channel group: channels 8*cg .. 8*cg+7
+  const int pl = lane >> 3;         // pixel slot inside the warp step
+  float wr[NOUT][8], gw[NOUT][8], gb[NOUT];
+#pragma unroll
+  for (int j = 0; j < NOUT; ++j) {
+    gb[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      wr[j][k] = w[j * kHeadC + cg * 8 + k];
+      gw[j][k] = 0.f;
+    }
+  }
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
-  float w0[kHeadMaxOut], w1[kHeadMaxOut], g0[kHeadMaxOut], g1[kHeadMaxOut], gb[kHeadMaxOut];
+  constexpr int U = 4;              // steps in flight per thread
+  for (long base = warp * (4 * U); base < npix_total; base += nwarps * (4 * U)) {
+    uint4 av[U];
+    float dl[U][NOUT];
+    bool ok[U];
 #pragma unroll
-  for (int j = 0; j < kHeadMaxOut; ++j) {
-    w0[j] = (j < n_out) ? w[j * kHeadC + 2 * lane] : 0.f;
-    w1[j] = (j < n_out) ? w[j * kHeadC + 2 * lane + 1] : 0.f;
-    g0[j] = g1[j] = gb[j] = 0.f;
-  }
-  for (long base = warp * 32; base < npix_total; base += nwarps * 32) {
-    const long p = base + lane;
-    float dl[kHeadMaxOut];
+    for (int u = 0; u < U; ++u) {
+      const long p = base + u * 4 + pl;
+      ok[u] = p < npix_total;
+      av[u] = ok[u] ? ldg_nc_v4(a + p * 8 + cg) : make_uint4(0, 0, 0, 0);
+      const long n = ok[u] ? p / hw : 0, r = ok[u] ? p - n * hw : 0;
 #pragma unroll
-    for (int j = 0; j < kHeadMaxOut; ++j) {
-      dl[j] = 0.f;
-      if (j < n_out && p < npix_total) {
-        const long n = p / hw, r = p - n * hw;
-        const long o = (n * n_out + j) * hw + r;
-        float d = dout[o];
-        if (sigmoid) {
-          const float s = out[o];
-          d *= s * (1.f - s);
+      for (int j = 0; j < NOUT; ++j) {
+        const long o = (n * NOUT + j) * hw + r;
+        float d = ok[u] ? __ldg(dout + o) : 0.f;
+        if (sigmoid && ok[u]) {
+          const float sg = __ldg(out + o);
+          d *= sg * (1.f - sg);
         }
-        dl[j] = d;
-        gb[j] += d;
+        dl[u][j] = d;
       }
     }
-    const int cnt = static_cast<int>(min(32L, npix_total - base));
-    for (int i = 0; i < cnt; ++i) {
-      const float2 x = unpack_bf16x2(a[(base + i) * 32 + lane]);
-      float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < kHeadMaxOut; ++j) {
-        if (j < n_out) {
-          const float d = __shfl_sync(0xffffffffu, dl[j], i);
-          d0 = fmaf(d, w0[j], d0);
-          d1 = fmaf(d, w1[j], d1);
-          g0[j] = fmaf(d, x.x, g0[j]);
-          g1[j] = fmaf(d, x.y, g1[j]);
+    for (int u = 0; u < U; ++u) {
+      float x[8], g[8];
+      const float2 f0 = unpack_bf16x2(av[u].x), f1 = unpack_bf16x2(av[u].y), f2 = unpack_bf16x2(av[u].z), f3 = unpack_bf16x2(av[u].w);
+      x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y; x[4] = f2.x; x[5] = f2.y; x[6] = f3.x; x[7] = f3.y;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j) {
+        const float d = dl[u][j];
+        if (cg == 0) gb[j] += d;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          g[k] = fmaf(d, wr[j][k], g[k]);
+          gw[j][k] = fmaf(d, x[k], gw[j][k]);
         }
       }
-      da[(base + i) * 32 + lane] = pack_bf16x2(d0, d1);
+      if (ok[u]) {
+        uint4 o4;
+        o4.x = pack_bf16x2(g[0], g[1]); o4.y = pack_bf16x2(g[2], g[3]);
+        o4.z = pack_bf16x2(g[4], g[5]); o4.w = pack_bf16x2(g[6], g[7]);
+        da[(base + u * 4 + pl) * 8 + cg] = o4;
+      }
     }
   }
+  // fold the four pixel slots of the warp, then one shared atomic per (j, channel) per warp
 #pragma unroll
-  for (int j = 0; j < kHeadMaxOut; ++j) {
-    if (j < n_out) {
-      atomicAdd(&sdw[j * kHeadC + 2 * lane], g0[j]);
-      atomicAdd(&sdw[j * kHeadC + 2 * lane + 1], g1[j]);
-      const float s = warp_sum(gb[j]);
-      if (lane == 0) atomicAdd(&sdb[j], s);
+  for (int j = 0; j < NOUT; ++j) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = gw[j][k];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (pl == 0) atomicAdd(&sdw[j * kHeadC + cg * 8 + k], v);
     }
+    float bsum = gb[j];
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 8);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 16);
+    if (lane == 0) atomicAdd(&sdb[j], bsum);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_out * kHeadC; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
-  if (threadIdx.x < n_out) atomicAdd(db + threadIdx.x, sdb[threadIdx.x]);
+  for (int i = threadIdx.x; i < NOUT * kHeadC; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
+  if (threadIdx.x < NOUT) atomicAdd(db + threadIdx.x, sdb[threadIdx.x]);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -453,11 +478,17 @@ int head_bwd(const void* a, const float* w, const float* dout, const float* out,
   const long hw = static_cast<long>(H) * W, np = hw * N;
   UNETK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * n_out * kHeadC, s));
   UNETK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * n_out, s));
-  int blocks = ew_blocks((np + 31) / 32, 8);
+  int blocks = ew_blocks((np + 127) / 128, 1);
   const int cap = num_sms() * 4;
   if (blocks > cap) blocks = cap;
-  head_bwd_kernel<<<blocks, 256, 0, s>>>(static_cast<const uint32_t*>(a), w, dout, out, static_cast<uint32_t*>(da), dw, db, np,
-                                        hw, n_out, sigmoid);
+  const uint4* a4 = static_cast<const uint4*>(a);
+  uint4* da4 = static_cast<uint4*>(da);
+  switch (n_out) {
+    case 1: head_bwd_kernel<1><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid); break;
+    case 2: head_bwd_kernel<2><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid); break;
+    case 3: head_bwd_kernel<3><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid); break;
+    default: head_bwd_kernel<4><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid); break;
+  }
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }

@@ -77,5 +77,9 @@ int adam_step(float* p, const float* g, float* m, float* v, long n, float lr, fl
 int permute_batched(const void* descs, int n_desc, int n_chunks, const float* in, void* out,
                     int out_bf16, float scale, cudaStream_t s);
 int permute_chunk_elems();
+int pack_conv_weights(const void* descs, int n_desc, int n_blocks, const float* flat_p, void* wpack,
+                      cudaStream_t s);
+int unpack_conv_grads(const void* descs, int n_desc, int n_blocks, int max_cin, const float* gstage,
+                      float* flat_g, float scale, cudaStream_t s);
 
 }  // namespace unetk

@@ -108,6 +108,95 @@ permute_batched_kernel(const PermuteDesc* __restrict__ descs, int n_desc,
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Tiled conv3x3 weight packing / gradient un-packing (the generic permute above reads with a
+// 36-byte stride; these move >= 64-byte runs on both sides through a shared-memory tile).
+// ----------------------------------------------------------------------------------------------
+struct ConvPackDesc {
+  long long src_off;   // pack: OIHW fp32 weight in the flat parameter buffer | unpack: staged [co][tap][ci] gradient
+  long long dst_off;   // pack: Wf [co][tap][ci] bf16                        | unpack: OIHW fp32 gradient
+  long long dst2_off;  // pack: Wd [ci][8-tap][co] bf16                      | unpack: unused
+  int cout, cin;
+  int block_begin;     // first block id of this layer
+  int pad[7];
+};
+static_assert(sizeof(ConvPackDesc) == 64, "ConvPackDesc layout is part of the C ABI");
+
+__device__ __forceinline__ ConvPackDesc find_layer(const ConvPackDesc* descs, int n, int block) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].block_begin <= block) lo = mid; else hi = mid - 1;
+  }
+  return descs[lo];
+}
+
+// one block = 32 output channels x 32 input channels x 9 taps
+__global__ void __launch_bounds__(256)
+pack_conv_weights_kernel(const ConvPackDesc* __restrict__ descs, int n_desc, const float* __restrict__ flat_p,
+                         __nv_bfloat16* __restrict__ wpack) {
+  __shared__ float tile[32][289];
+  const ConvPackDesc d = find_layer(descs, n_desc, blockIdx.x);
+  const int tiles_ci = d.cin / 32;
+  const int tix = blockIdx.x - d.block_begin;
+  const int co0 = (tix / tiles_ci) * 32, ci0 = (tix % tiles_ci) * 32;
+  for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
+    const int r = i / 288, j = i - r * 288;
+    tile[r][j] = flat_p[d.src_off + (static_cast<long long>(co0 + r) * d.cin + ci0) * 9 + j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
+    const int c = i & 31, rt = i >> 5;          // rt = r * 9 + tap
+    const int r = rt / 9, tap = rt - r * 9;
+    wpack[d.dst_off + (static_cast<long long>(co0 + r) * 9 + tap) * d.cin + ci0 + c] = __float2bfloat16(tile[r][c * 9 + tap]);
+  }
+  for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
+    const int r = i & 31, ct = i >> 5;          // ct = c * 9 + tap'
+    const int c = ct / 9, tapf = ct - c * 9;    // tap' = 8 - tap (180-degree rotation for dgrad)
+    wpack[d.dst2_off + (static_cast<long long>(ci0 + c) * 9 + tapf) * d.cout + co0 + r] = __float2bfloat16(tile[r][c * 9 + (8 - tapf)]);
+  }
+}
+
+// one block = one output channel: [tap][ci] -> [ci][tap], scaled
+__global__ void __launch_bounds__(256)
+unpack_conv_grads_kernel(const ConvPackDesc* __restrict__ descs, int n_desc, const float* __restrict__ gstage,
+                         float* __restrict__ flat_g, float scale) {
+  extern __shared__ float row[];               // [9][cin + 1]
+  const ConvPackDesc d = find_layer(descs, n_desc, blockIdx.x);
+  const int co = blockIdx.x - d.block_begin;
+  const int n = 9 * d.cin, pitch = d.cin + 1;
+  const float* src = gstage + d.src_off + static_cast<long long>(co) * n;
+  float* dst = flat_g + d.dst_off + static_cast<long long>(co) * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int tap = i / d.cin, ci = i - tap * d.cin;
+    row[tap * pitch + ci] = src[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci = i / 9, tap = i - ci * 9;
+    dst[i] = row[tap * pitch + ci] * scale;
+  }
+}
+
+int pack_conv_weights(const void* descs, int n_desc, int n_blocks, const float* flat_p, void* wpack,
+                      cudaStream_t s) {
+  UNETK_CHECK_ARG(descs && flat_p && wpack && n_desc > 0 && n_blocks > 0, "pack_conv_weights: bad arguments");
+  pack_conv_weights_kernel<<<n_blocks, 256, 0, s>>>(static_cast<const ConvPackDesc*>(descs), n_desc, flat_p,
+                                                   static_cast<__nv_bfloat16*>(wpack));
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int unpack_conv_grads(const void* descs, int n_desc, int n_blocks, int max_cin, const float* gstage,
+                      float* flat_g, float scale, cudaStream_t s) {
+  UNETK_CHECK_ARG(descs && gstage && flat_g && n_desc > 0 && n_blocks > 0, "unpack_conv_grads: bad arguments");
+  UNETK_CHECK_ARG(max_cin > 0 && max_cin <= 1024, "unpack_conv_grads: cin up to 1024 supported");
+  const size_t smem = static_cast<size_t>(9) * (max_cin + 1) * sizeof(float);
+  unpack_conv_grads_kernel<<<n_blocks, 256, smem, s>>>(static_cast<const ConvPackDesc*>(descs), n_desc, gstage, flat_g, scale);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
 int adam_step(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
               float beta2, float eps, float wd, long step, float grad_scale, int mode,
               cudaStream_t s) {

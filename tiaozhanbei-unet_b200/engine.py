@@ -190,6 +190,8 @@ class Engine:
         chunk = _lib.get().unetk_permute_chunk_elems()
         pack = packing.PermuteTable(chunk)
         unpack = packing.PermuteTable(chunk)
+        conv_pack = packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32))
+        conv_unpack = packing.ConvTable(lambda cout, cin: cout)
         pdict = dict(zip(self.param_names, self.params))
         wsize = 0
 
@@ -230,10 +232,9 @@ class Engine:
                 unpack.add(self.offsets[wk], self.offsets[wk], *packing.identity(n))
             else:
                 L.g_w = self._slice(self.gstage, wk, (n,))      # [Cout][tap][Cin]
-                unpack.add(self.offsets[wk], self.offsets[wk], *packing.conv_grad_unpack(L.cout, cin))
                 of, od = walloc(n), walloc(n)
-                pack.add(self.offsets[wk], of, *packing.conv_fwd_pack(L.cout, cin))
-                pack.add(self.offsets[wk], od, *packing.conv_dgrad_pack(L.cout, cin))
+                conv_unpack.add(self.offsets[wk], self.offsets[wk], 0, L.cout, cin)
+                conv_pack.add(self.offsets[wk], of, od, L.cout, cin)
                 wplan.append((L, "wf", of, n))
                 wplan.append((L, "wd", od, n))
             for k in (gk, bk):
@@ -270,6 +271,8 @@ class Engine:
             setattr(obj, attr, self.wpack[off: off + n])
         self.pack_table = pack.finalize(device)
         self.unpack_table = unpack.finalize(device)
+        self.conv_pack_table = conv_pack.finalize(device)
+        self.conv_unpack_table = conv_unpack.finalize(device)
 
     def mark_weights_dirty(self):
         self.weights_dirty = True
@@ -288,7 +291,8 @@ class Engine:
 
     def _pack_weights(self):
         if self.weights_dirty:
-            ops.permute_batched(self.pack_table, self.flat_p, self.wpack)
+            ops.pack_conv_weights(self.conv_pack_table, self.flat_p, self.wpack)     # conv3x3 layers (tiled)
+            ops.permute_batched(self.pack_table, self.flat_p, self.wpack)            # transposed convs
             self.weights_dirty = False
 
     def grad_views(self):
@@ -494,5 +498,6 @@ class Engine:
         scale = 1.0
         if self.ddp is not None:
             scale = self.ddp.finish(self)
+        ops.unpack_conv_grads(self.conv_unpack_table, self.gstage, self.flat_g, scale)
         ops.permute_batched(self.unpack_table, self.gstage, self.flat_g, scale)
         return self.grad_views()

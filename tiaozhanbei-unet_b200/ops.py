@@ -259,6 +259,15 @@ def permute_batched(table, src, dst, scale=1.0):
               int(dst.dtype == bf16), scale, _s())
 
 
+def pack_conv_weights(table, flat_p, wpack):
+    _lib.call("unetk_pack_conv_weights", _p(table.device_descs), table.n_desc, table.n_blocks, _p(flat_p), _p(wpack), _s())
+
+
+def unpack_conv_grads(table, gstage, flat_g, scale=1.0):
+    _lib.call("unetk_unpack_conv_grads", _p(table.device_descs), table.n_desc, table.n_blocks, table.max_cin,
+              _p(gstage), _p(flat_g), scale, _s())
+
+
 def nchw_to_nhwc(x, out):
     _chk(x, f32, "x"); _chk(out, bf16, "out")
     n, c, h, w = x.shape

@@ -80,3 +80,36 @@ def convt_grad_unpack(cin, cout):
 
 def identity(n):
     return (1, 1, n), (0, 0, 1), False
+
+
+# ---- tiled conv3x3 fast path (unetk_pack_conv_weights / unetk_unpack_conv_grads) -----------------
+CONV_DESC_DTYPE = np.dtype([("src_off", "<i8"), ("dst_off", "<i8"), ("dst2_off", "<i8"), ("cout", "<i4"), ("cin", "<i4"),
+                            ("block_begin", "<i4"), ("pad", "<i4", (7,))])
+assert CONV_DESC_DTYPE.itemsize == 64
+
+
+class ConvTable:
+    """blocks_per_layer(cout, cin): 32x32 tiles for packing, one block per output channel for un-packing."""
+
+    def __init__(self, blocks_per_layer):
+        self.blocks_per_layer = blocks_per_layer
+        self.entries = []
+        self.device_descs = None
+        self.n_desc = self.n_blocks = self.max_cin = 0
+
+    def add(self, src_off, dst_off, dst2_off, cout, cin):
+        if cout % 32 or cin % 32:
+            raise ValueError("tiled conv packing needs channel counts that are multiples of 32")
+        self.entries.append((src_off, dst_off, dst2_off, cout, cin))
+
+    def finalize(self, device):
+        arr = np.zeros(len(self.entries), dtype=CONV_DESC_DTYPE)
+        blk = 0
+        for i, (so, do, d2, cout, cin) in enumerate(self.entries):
+            arr[i]["src_off"], arr[i]["dst_off"], arr[i]["dst2_off"] = so, do, d2
+            arr[i]["cout"], arr[i]["cin"], arr[i]["block_begin"] = cout, cin, blk
+            blk += self.blocks_per_layer(cout, cin)
+            self.max_cin = max(self.max_cin, cin)
+        self.n_desc, self.n_blocks = len(self.entries), blk
+        self.device_descs = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+        return self
