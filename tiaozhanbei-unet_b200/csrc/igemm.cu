@@ -54,7 +54,7 @@ struct IgemmParams {
   int cout_t;           // epi_mode 1: channels of the up-sampled tensor
 };
 
-constexpr int kIgemmThreads = 192;
+constexpr int kIgemmThreads = 192;                 // warps: 0 TMA, 1 MMA, 2..5 epilogue (one per TMEM lane quarter)
 constexpr int kRegion = 16;                   // CTA tile: 16 x 16 output pixels
 constexpr int kSubW = 8;                      // sub-tile: 8 wide x 16 tall = 128 GEMM rows
 constexpr int kABufBytes = 41 * 1024;         // >= 18*18*128 B, multiple of 1024
@@ -62,7 +62,7 @@ constexpr int kNumABufs = 2;
 
 template <int BN>
 struct IgemmCfg {
-  static constexpr int kBStages = (BN == 128) ? 6 : 8;
+  static constexpr int kBStages = (BN == 128) ? 8 : 14;   // >= L2 latency / MMA time per stage
   static constexpr int kBBytes = BN * 128;
   static constexpr int kTmemCols = 4 * BN;    // 2 accumulator stages x 2 sub-tiles
   static constexpr int kSmemMain = kNumABufs * kABufBytes + kBStages * kBBytes;
@@ -89,7 +89,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   uint64_t* tfull = b_empty + kBStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* colbuf = reinterpret_cast<float*>(tempty + 4);  // affine: [2][Ntot]; stats: [4][2][Ntot]
+  float* colbuf = reinterpret_cast<float*>(tempty + 4);  // affine: [2][Ntot]; stats: [4][2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,8 +115,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   if (p.scale != nullptr) {          // [2][Ntot]: scale, shift
     for (int i = threadIdx.x; i < 2 * p.Ntot; i += blockDim.x)
       colbuf[i] = (i < p.Ntot) ? p.scale[i] : p.shift[i - p.Ntot];
-  } else if (p.stats != nullptr) {   // [4 epilogue warps][2][Ntot]: sum, sum of squares
-    for (int i = threadIdx.x; i < 8 * p.Ntot; i += blockDim.x) colbuf[i] = 0.f;
+  } else if (p.stats != nullptr) {   // [4 epilogue warps][2][BN]: sum, sum of squares of the current column block
+    for (int i = threadIdx.x; i < 8 * BN; i += blockDim.x) colbuf[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -138,8 +138,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nb = t % p.n_blocks;
-        int m = t / p.n_blocks;
+        // region-fastest order: CTAs running together share the weight tile (and the statistics slot)
+        const int nb = t / regions;
+        int m = t - nb * regions;
         const int rx = m % p.regions_x;
         m /= p.regions_x;
         const int ry = m % p.regions_y;
@@ -235,20 +236,42 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    float* wbuf = colbuf + (warp - 2) * 2 * p.Ntot;   // this warp's private [2][Ntot] statistics slot
+    float* wbuf = colbuf + (warp - 2) * 2 * BN;       // this warp's private [2][BN] statistics slot
+    int cur_nb = -1;
+    // add this warp's partial column sums of column block `nbk` to the global statistics
+    auto flush_stats = [&](int nbk) {
+      for (int i = lane; i < BN; i += 32) {
+        const int col = nbk * BN + i;
+        if (col >= p.stats_from) {
+          const float v = wbuf[i];
+          if (v != 0.f) atomicAdd(p.stats + (col - p.stats_from), v);
+          if (p.stats_sq != nullptr) {
+            const float v2 = wbuf[BN + i];
+            if (v2 != 0.f) atomicAdd(p.stats_sq + (col - p.stats_from), v2);
+          }
+        }
+        wbuf[i] = 0.f;
+        wbuf[BN + i] = 0.f;
+      }
+      __syncwarp();
+    };
     const int sx = row & 7;   // pixel inside the 8 x 16 sub-tile
     const int sy = row >> 3;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
-      const int nb = t % p.n_blocks;
-      int m = t / p.n_blocks;
+      const int nb = t / regions;
+      int m = t - nb * regions;
       const int rx = m % p.regions_x;
       m /= p.regions_x;
       const int ry = m % p.regions_y;
       const int n = m / p.regions_y;
       const int y = ry * kRegion + sy;
+      if (p.stats != nullptr && nb != cur_nb) {
+        if (cur_nb >= 0) flush_stats(cur_nb);
+        cur_nb = nb;
+      }
       const int col0 = nb * BN;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
@@ -268,7 +291,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) s[j] = (valids[0] ? v2[0][j] : 0.f) + (valids[1] ? v2[1][j] : 0.f);
           const float cs = warp_colsum32(s);
-          wbuf[col + lane] += cs;
+          wbuf[ch * 32 + lane] += cs;
           if (p.stats_sq != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -276,7 +299,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               s[j] = fmaf(a, a, b * b);
             }
             const float cs2 = warp_colsum32(s);
-            wbuf[p.Ntot + col + lane] += cs2;
+            wbuf[BN + ch * 32 + lane] += cs2;
           }
         }
 #pragma unroll
@@ -340,21 +363,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    if (p.stats != nullptr) {
-      // all four epilogue warps have finished their smem atomics
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = threadIdx.x - 64;
-      for (int i = p.stats_from + et; i < p.Ntot; i += 128) {
-        float v = 0.f, v2 = 0.f;
-#pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) {
-          v += colbuf[w4 * 2 * p.Ntot + i];
-          v2 += colbuf[w4 * 2 * p.Ntot + p.Ntot + i];
-        }
-        if (v != 0.f) atomicAdd(p.stats + (i - p.stats_from), v);
-        if (p.stats_sq != nullptr && v2 != 0.f) atomicAdd(p.stats_sq + (i - p.stats_from), v2);
-      }
-    }
+    if (p.stats != nullptr && cur_nb >= 0) flush_stats(cur_nb);
   }
   __syncwarp();
   tc_fence_before();
@@ -473,7 +482,7 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
 
   const long total_tiles = static_cast<long>(p.regions_x) * p.regions_y * p.n_img * p.n_blocks;
   const int grid = static_cast<int>(total_tiles < num_sms() ? total_tiles : num_sms());
-  const size_t colbytes = (p.stats != nullptr ? 8 : (use_colbuf ? 2 : 0)) * static_cast<size_t>(p.Ntot) * sizeof(float);
+  const size_t colbytes = (p.stats != nullptr ? static_cast<size_t>(8) * bn : (use_colbuf ? static_cast<size_t>(2) * p.Ntot : 0)) * sizeof(float);
   if (bn == 128) {
     using Cfg = IgemmCfg<128>;
     const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;

@@ -47,7 +47,8 @@ struct WgCfg {
   static constexpr int kBBoxes = (MODE == 0) ? (BN / 64) : 4 * (BN / 64);
   static constexpr int kMmas = (MODE == 0) ? (M64 ? 2 : 3) : 4;
   static constexpr int kStageBytes = kABytes + kBBoxes * kBoxBytes;
-  static constexpr int kStages = (kStageBytes * 6 <= 200 * 1024) ? 6 : (kStageBytes * 4 <= 200 * 1024 ? 4 : (kStageBytes * 3 <= 200 * 1024 ? 3 : 2));
+  static constexpr int kMaxFit = (210 * 1024) / kStageBytes;
+  static constexpr int kStages = kMaxFit > 10 ? 10 : (kMaxFit < 2 ? 2 : kMaxFit);
   static constexpr int kAccCols = kMmas * BN;
   static constexpr int kTmemCols = kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512));
 };

@@ -21,7 +21,12 @@ def run(h, c1, c2, cout, reps=2):
         ops.conv3x3_dgrad(y, wd, dx1, False, dx2, False)
         ops.conv3x3_wgrad(y, s1, s2, dw)
     torch.cuda.synchronize()
-run(256, 64, 0, 64)      # inc.3 / up4.3: N=64, K=576
-run(128, 128, 0, 128)    # down1.3 / up3.3
-run(32, 512, 512, 512)   # up1.0: long K
+import sys as _s
+which = _s.argv[1] if len(_s.argv) > 1 else "all"
+if which in ("all", "n64"):
+    run(256, 64, 0, 64)      # inc.3 / up4.3: N=64, K=576
+    run(128, 64, 0, 128)     # down1.0: N=128, K=576
+if which in ("all", "mid"):
+    run(128, 128, 0, 128)    # down1.3 / up3.3
+    run(32, 512, 512, 512)   # up1.0: long K
 print("done")
