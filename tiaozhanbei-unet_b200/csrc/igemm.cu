@@ -24,6 +24,8 @@
 // (TMEM -> registers -> bf16 global, optional per-channel sum / sum-of-squares for BatchNorm,
 // optional per-channel affine + ReLU for eval-mode folded BatchNorm).  Persistent over tiles with
 // double-buffered TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -55,26 +57,40 @@ struct IgemmParams {
 };
 
 constexpr int kIgemmThreads = 192;                 // warps: 0 TMA, 1 MMA, 2..5 epilogue (one per TMEM lane quarter)
-constexpr int kRegion = 16;                   // CTA tile: 16 x 16 output pixels
+constexpr int kRegionH = 16;                  // CTA tile: (8*SUBS) x 16 output pixels
 constexpr int kSubW = 8;                      // sub-tile: 8 wide x 16 tall = 128 GEMM rows
-constexpr int kABufBytes = 41 * 1024;         // >= 18*18*128 B, multiple of 1024
 constexpr int kNumABufs = 2;
 
-template <int BN>
+// BN   : columns of D per tile (per CTA pair when CTAS == 2)
+// SUBS : 8x16 sub-tiles per CTA (1 or 2), each with its own TMEM accumulator
+// CTAS : 1, or 2 = cta_group::2: two CTAs of a cluster (one region each, M = 256 per instruction) share
+//        every weight stage: each CTA stages only BN/2 weight rows, the leader CTA issues the MMAs.
+//        SS-mode UMMA fetches its operands from shared memory at ~64 B/clk/SM (measured: N=128 -> 50 %,
+//        N=64 -> 33 % tensor-pipe activity with everything else waiting on the MMA), so halving the B
+//        bytes per CTA is what lifts the tensor pipe: 256x256 pair tiles read A 4 KB + B 4 KB per
+//        128-cycle instruction.
+template <int BN, int SUBS, int CTAS>
 struct IgemmCfg {
-  static constexpr int kBStages = (BN == 128) ? 8 : 14;   // >= L2 latency / MMA time per stage
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kTmemCols = 4 * BN;    // 2 accumulator stages x 2 sub-tiles
+  static constexpr int kBNLocal = BN / CTAS;
+  static constexpr int kBBytes = kBNLocal * 128;
+  static constexpr int kABufBytes = (SUBS == 2) ? 41 * 1024 : 23 * 1024;   // >= (8*SUBS+2)*18*128, 1 KB multiple
+  static constexpr int kBudget = 196 * 1024;
+  static constexpr int kFit = (kBudget - kNumABufs * kABufBytes) / kBBytes;
+  static constexpr int kBStages = kFit > 16 ? 16 : kFit;
+  static constexpr int kTmemCols = 2 * SUBS * BN;    // 2 accumulator stages x SUBS sub-tiles
   static constexpr int kSmemMain = kNumABufs * kABufBytes + kBStages * kBBytes;
   static constexpr int kNumBars = 2 * kNumABufs + 2 * kBStages + 4;
+  static_assert(kTmemCols <= 512 && kBStages >= 4, "bad igemm configuration");
 };
 
-template <int BN>
+template <int BN, int SUBS, int CTAS>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, SUBS, CTAS>;
   constexpr int kBStages = Cfg::kBStages;
+  constexpr int kABufBytes = Cfg::kABufBytes;
+  constexpr int kRegionW = kSubW * SUBS;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -93,6 +109,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmA2);
@@ -107,11 +124,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[i], 4 * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (CTAS == 2) cluster_sync_all();     // pair TMEM allocation needs both CTAs resident
+  if (warp == 1) {
+    if (CTAS == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   if (p.scale != nullptr) {          // [2][Ntot]: scale, shift
     for (int i = threadIdx.x; i < 2 * p.Ntot; i += blockDim.x)
       colbuf[i] = (i < p.Ntot) ? p.scale[i] : p.shift[i - p.Ntot];
@@ -119,45 +140,51 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     for (int i = threadIdx.x; i < 8 * BN; i += blockDim.x) colbuf[i] = 0.f;
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // barrier inits visible to the peer's TMA / arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int regions = p.regions_x * p.regions_y * p.n_img;
-  const int total_tiles = regions * p.n_blocks;
+  const int region_slots = (regions + CTAS - 1) / CTAS;      // one slot = one region per CTA of the pair
+  const int total_tiles = region_slots * p.n_blocks;
+  const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
   const int chunks = p.c1_chunks + p.c2_chunks;
-  const int pitch = kRegion + 2 * p.halo;               // halo tile row pitch in pixels
-  const uint32_t a_bytes = static_cast<uint32_t>(pitch * pitch * 128);
+  const int pitch = kRegionW + 2 * p.halo;              // halo tile row pitch in pixels
+  const uint32_t a_bytes = static_cast<uint32_t>(pitch * (kRegionH + 2 * p.halo) * 128);
   // A loads per tile: one per channel chunk (halo mode: serves all taps) or one per (tap, chunk)
   const int taps_per_load = p.halo ? p.num_taps : 1;
   const int a_loads = p.halo ? chunks : p.num_taps * chunks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (each CTA feeds its own shared memory) =====================
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < total_tiles; t += tile_step) {
         // region-fastest order: CTAs running together share the weight tile (and the statistics slot)
-        const int nb = t / regions;
-        int m = t - nb * regions;
+        const int nb = t / region_slots;
+        int m = (t - nb * region_slots) * CTAS + static_cast<int>(rank);
+        const bool live = m < regions;                  // odd region count: the last pair has one idle CTA
         const int rx = m % p.regions_x;
         m /= p.regions_x;
         const int ry = m % p.regions_y;
-        const int n0 = m / p.regions_y;
-        const int x0 = rx * kRegion, y0 = ry * kRegion;
-        const int col0 = nb * BN;
+        const int n0 = live ? m / p.regions_y : p.n_img;   // idle CTA: everything out of bounds -> zeros
+        const int x0 = rx * kRegionW, y0 = ry * kRegionH;
+        const int col0 = nb * BN + static_cast<int>(rank) * Cfg::kBNLocal;
         for (int al = 0; al < a_loads; ++al) {
           const int c = p.halo ? al : al % chunks;
           const int tap0 = p.halo ? 0 : al / chunks;
           mbar_wait(&a_empty[as], aph ^ 1);
-          mbar_expect_tx(&a_full[as], a_bytes);
+          if (rank == 0) mbar_expect_tx(&a_full[as], a_bytes * CTAS);
           const CUtensorMap* mp = (c < p.c1_chunks) ? &tmA1 : &tmA2;
           const int cc = ((c < p.c1_chunks) ? c : c - p.c1_chunks) * 64;
+          uint8_t* dstA = sA + as * kABufBytes;
           if (p.a_mode == 0) {
-            tma_load_5d(sA + as * kABufBytes, mp, &a_full[as], cc, x0 - p.halo, y0 - p.halo, n0, 0);
+            if (CTAS == 2) tma_load_5d_pair(dstA, mp, &a_full[as], cc, x0 - p.halo, y0 - p.halo, n0, 0);
+            else tma_load_5d(dstA, mp, &a_full[as], cc, x0 - p.halo, y0 - p.halo, n0, 0);
           } else {
-            tma_load_5d(sA + as * kABufBytes, mp, &a_full[as], cc, tap0 & 1, x0, tap0 >> 1, n0 * p.H + y0);
+            if (CTAS == 2) tma_load_5d_pair(dstA, mp, &a_full[as], cc, tap0 & 1, x0, tap0 >> 1, n0 * p.H + y0);
+            else tma_load_5d(dstA, mp, &a_full[as], cc, tap0 & 1, x0, tap0 >> 1, n0 * p.H + y0);
           }
           if (++as == kNumABufs) {
             as = 0;
@@ -166,8 +193,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
           for (int tt = 0; tt < taps_per_load; ++tt) {
             const int tap = tap0 + tt;
             mbar_wait(&b_empty[bs], bph ^ 1);
-            mbar_expect_tx(&b_full[bs], Cfg::kBBytes);
-            tma_load_2d(sB + bs * Cfg::kBBytes, &tmB, &b_full[bs], (tap * chunks + c) * 64, col0);
+            if (rank == 0) mbar_expect_tx(&b_full[bs], Cfg::kBBytes * CTAS);
+            if (CTAS == 2) tma_load_2d_pair(sB + bs * Cfg::kBBytes, &tmB, &b_full[bs], (tap * chunks + c) * 64, col0);
+            else tma_load_2d(sB + bs * Cfg::kBBytes, &tmB, &b_full[bs], (tap * chunks + c) * 64, col0);
             if (++bs == kBStages) {
               bs = 0;
               bph ^= 1;
@@ -177,21 +205,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (leader CTA only when CTAS == 2) =====================
     // The whole warp walks the loops (warp-uniform control flow keeps the descriptors in uniform
     // registers); one elected lane issues the tcgen05 instructions.
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, false, false);
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CTAS, BN, false, false);
       const uint32_t sbo = static_cast<uint32_t>(pitch * 128);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = tile0; t < total_tiles; t += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t accph = (it >> 1) & 1;
         mbar_wait(&tempty[acc], accph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (2 * BN);
+        const uint32_t d_tmem = tmem_base + acc * (SUBS * BN);
         uint32_t first = 1;
         for (int al = 0; al < a_loads; ++al) {
           mbar_wait(&a_full[as], aph);
@@ -205,18 +233,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(sB + bs * Cfg::kBBytes), 0, 1024);
             if (elect_one()) {
 #pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {
+              for (int sub = 0; sub < SUBS; ++sub) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   // start-address field is (addr >> 4): offsets in 16-byte units
                   const uint64_t da = a_desc0 + (tap_off16 + sub * (kSubW * 8) + k * 2);
                   const uint64_t db = b_desc0 + (k * 2);
-                  tc_mma_bf16(d_tmem + sub * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                  if (CTAS == 2) tc_mma_bf16_pair(d_tmem + sub * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
+                  else tc_mma_bf16(d_tmem + sub * BN, da, db, idesc, (first && k == 0) ? 0u : 1u);
                 }
               }
-              tc_commit(&b_empty[bs]);
-              if (tt == taps_per_load - 1) tc_commit(&a_empty[as]);
-              if (tt == taps_per_load - 1 && al == a_loads - 1) tc_commit(&tfull[acc]);
+              const bool last_tap = tt == taps_per_load - 1;
+              if (CTAS == 2) {
+                tc_commit_pair(&b_empty[bs]);
+                if (last_tap) tc_commit_pair(&a_empty[as]);
+                if (last_tap && al == a_loads - 1) tc_commit_pair(&tfull[acc]);
+              } else {
+                tc_commit(&b_empty[bs]);
+                if (last_tap) tc_commit(&a_empty[as]);
+                if (last_tap && al == a_loads - 1) tc_commit(&tfull[acc]);
+              }
             }
             __syncwarp();
             first = 0;
@@ -258,16 +294,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     const int sx = row & 7;   // pixel inside the 8 x 16 sub-tile
     const int sy = row >> 3;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < total_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t accph = (it >> 1) & 1;
-      const int nb = t / regions;
-      int m = t - nb * regions;
+      const int nb = t / region_slots;
+      int m = (t - nb * region_slots) * CTAS + static_cast<int>(rank);
+      const bool live = m < regions;
       const int rx = m % p.regions_x;
       m /= p.regions_x;
       const int ry = m % p.regions_y;
       const int n = m / p.regions_y;
-      const int y = ry * kRegion + sy;
+      const int y = ry * kRegionH + sy;
       if (p.stats != nullptr && nb != cur_nb) {
         if (cur_nb >= 0) flush_stats(cur_nb);
         cur_nb = nb;
@@ -275,102 +312,123 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       const int col0 = nb * BN;
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
-      const int xs[2] = {rx * kRegion + sx, rx * kRegion + kSubW + sx};
-      const bool valids[2] = {(xs[0] < p.W) && (y < p.H), (xs[1] < p.W) && (y < p.H)};
+      int xs[SUBS];
+      bool valids[SUBS];
+#pragma unroll
+      for (int sub = 0; sub < SUBS; ++sub) {
+        xs[sub] = rx * kRegionW + sub * kSubW + sx;
+        valids[sub] = live && (xs[sub] < p.W) && (y < p.H);
+      }
+      if (live) {
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int col = col0 + ch * 32;
-        float v2[2][32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (2 * BN) + ch * 32, v2[0]);
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (2 * BN) + BN + ch * 32, v2[1]);
-        tmem_ld_wait();
-        if (p.stats != nullptr && col >= p.stats_from) {
-          // both sub-tiles share the columns: add them first, then ONE transposing butterfly each
-          // for the sum and the sum of squares; per-warp smem slots (no shared-memory atomics)
-          float s[32];
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          const int col = col0 + ch * 32;
+          float v2[SUBS][32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s[j] = (valids[0] ? v2[0][j] : 0.f) + (valids[1] ? v2[1][j] : 0.f);
-          const float cs = warp_colsum32(s);
-          wbuf[ch * 32 + lane] += cs;
-          if (p.stats_sq != nullptr) {
+          for (int sub = 0; sub < SUBS; ++sub)
+            tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (SUBS * BN) + sub * BN + ch * 32, v2[sub]);
+          tmem_ld_wait();
+          if (p.stats != nullptr && col >= p.stats_from) {
+            // the sub-tiles share the columns: add them first, then ONE transposing butterfly each
+            // for the sum and the sum of squares; per-warp smem slots (no shared-memory atomics)
+            float s[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float a = valids[0] ? v2[0][j] : 0.f, b = valids[1] ? v2[1][j] : 0.f;
-              s[j] = fmaf(a, a, b * b);
+              float a = valids[0] ? v2[0][j] : 0.f;
+              if (SUBS == 2) a += valids[SUBS - 1] ? v2[SUBS - 1][j] : 0.f;
+              s[j] = a;
             }
-            const float cs2 = warp_colsum32(s);
-            wbuf[BN + ch * 32 + lane] += cs2;
-          }
-        }
+            const float cs = warp_colsum32(s);
+            wbuf[ch * 32 + lane] += cs;
+            if (p.stats_sq != nullptr) {
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          float (&v)[32] = v2[sub];
-          if (p.scale != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float a = fmaf(v[j], colbuf[col + j], colbuf[p.Ntot + col + j]);
-              v[j] = p.relu ? fmaxf(a, 0.f) : a;
+              for (int j = 0; j < 32; ++j) {
+                const float a = valids[0] ? v2[0][j] : 0.f;
+                float sq = a * a;
+                if (SUBS == 2) {
+                  const float b = valids[SUBS - 1] ? v2[SUBS - 1][j] : 0.f;
+                  sq = fmaf(b, b, sq);
+                }
+                s[j] = sq;
+              }
+              const float cs2 = warp_colsum32(s);
+              wbuf[BN + ch * 32 + lane] += cs2;
             }
           }
-          if (!valids[sub]) continue;
-          const int x = xs[sub];
-          __nv_bfloat16* dst;
-          bool accum;
-          if (p.epi_mode == 0) {
-            const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
-            if (col < p.split) {
-              dst = p.out1 + pix * p.ldc1 + col;
-              accum = p.acc1 != 0;
+#pragma unroll
+          for (int sub = 0; sub < SUBS; ++sub) {
+            float (&v)[32] = v2[sub];
+            if (p.scale != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float a = fmaf(v[j], colbuf[col + j], colbuf[p.Ntot + col + j]);
+                v[j] = p.relu ? fmaxf(a, 0.f) : a;
+              }
+            }
+            if (!valids[sub]) continue;
+            const int x = xs[sub];
+            __nv_bfloat16* dst;
+            bool accum;
+            if (p.epi_mode == 0) {
+              const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+              if (col < p.split) {
+                dst = p.out1 + pix * p.ldc1 + col;
+                accum = p.acc1 != 0;
+              } else {
+                dst = p.out2 + pix * p.ldc2 + (col - p.split);
+                accum = p.acc2 != 0;
+              }
             } else {
-              dst = p.out2 + pix * p.ldc2 + (col - p.split);
-              accum = p.acc2 != 0;
-            }
-          } else {
-            const int tap = col / p.cout_t;
-            const int co = col - tap * p.cout_t;
-            const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + (2 * y + (tap >> 1))) * (2 * p.W) +
-                                (2 * x + (tap & 1));
-            dst = p.out1 + opix * p.cout_t + co;
-            accum = false;
-            if (p.bias != nullptr) {
+              const int tap = col / p.cout_t;
+              const int co = col - tap * p.cout_t;
+              const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + (2 * y + (tap >> 1))) * (2 * p.W) +
+                                  (2 * x + (tap & 1));
+              dst = p.out1 + opix * p.cout_t + co;
+              accum = false;
+              if (p.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co + j);
+                for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co + j);
+              }
             }
-          }
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
-            if (accum) {
-              const uint4 o = d4[g];
-              const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
-              const float2 o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
-              f[0] += o0.x; f[1] += o0.y; f[2] += o1.x; f[3] += o1.y;
-              f[4] += o2.x; f[5] += o2.y; f[6] += o3.x; f[7] += o3.y;
+              for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
+              if (accum) {
+                const uint4 o = d4[g];
+                const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
+                const float2 o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
+                f[0] += o0.x; f[1] += o0.y; f[2] += o1.x; f[3] += o1.y;
+                f[4] += o2.x; f[5] += o2.y; f[6] += o3.x; f[7] += o3.y;
+              }
+              uint4 w;
+              w.x = pack_bf16x2(f[0], f[1]);
+              w.y = pack_bf16x2(f[2], f[3]);
+              w.z = pack_bf16x2(f[4], f[5]);
+              w.w = pack_bf16x2(f[6], f[7]);
+              d4[g] = w;
             }
-            uint4 w;
-            w.x = pack_bf16x2(f[0], f[1]);
-            w.y = pack_bf16x2(f[2], f[3]);
-            w.z = pack_bf16x2(f[4], f[5]);
-            w.w = pack_bf16x2(f[6], f[7]);
-            d4[g] = w;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(&tempty[acc], 0);   // the leader's MMA warp waits on its own barrier
+        else mbar_arrive(&tempty[acc]);
+      }
     }
     if (p.stats != nullptr && cur_nb >= 0) flush_stats(cur_nb);
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -444,6 +502,29 @@ struct IgemmLaunch {
   IgemmParams p;
 };
 
+template <int BN, int SUBS, int CTAS>
+static int launch_cfg(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB, const IgemmParams& p,
+                      int grid, size_t colbytes, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BN, SUBS, CTAS>;
+  const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;
+  auto kern = igemm_kernel<BN, SUBS, CTAS>;
+  UNETK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kIgemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UNETK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA1, tmA2, tmB, p));
+  return UNETK_OK;
+}
+
 static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
   IgemmParams& p = L.p;
   UNETK_CHECK_ARG(L.c1 % 64 == 0 && L.c2 % 64 == 0 && L.c1 > 0, "igemm: channel counts must be multiples of 64 (got %d, %d)", L.c1, L.c2);
@@ -453,49 +534,49 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
                       (reinterpret_cast<uintptr_t>(p.out1) & 15) == 0, "igemm: pointers must be 16-byte aligned");
   if (int e = check_device_sm100()) return e;
   p.halo = (p.num_taps == 9) ? 1 : 0;
-  p.regions_x = (p.W + kRegion - 1) / kRegion;
-  p.regions_y = (p.H + kRegion - 1) / kRegion;
   p.c1_chunks = L.c1 / 64;
   p.c2_chunks = L.c2 / 64;
-  const int bn = (p.Ntot % 128 == 0) ? 128 : 64;
+  // configuration: CTA pairs with 256-wide column blocks where the layer is wide enough
+  static const bool pair_ok = (getenv("UNETK_IGEMM_1CTA") == nullptr);
+  int bn, subs, ctas;
+  if (pair_ok && p.Ntot % 256 == 0) { bn = 256; subs = 1; ctas = 2; }
+  else if (pair_ok) { bn = (p.Ntot % 128 == 0) ? 128 : 64; subs = 2; ctas = 2; }
+  else { bn = (p.Ntot % 128 == 0) ? 128 : 64; subs = 2; ctas = 1; }
+  const int region_w = kSubW * subs;
+  p.regions_x = (p.W + region_w - 1) / region_w;
+  p.regions_y = (p.H + kRegionH - 1) / kRegionH;
   p.n_blocks = p.Ntot / bn;
   const bool use_colbuf = p.stats != nullptr || p.scale != nullptr;
   UNETK_CHECK_ARG(!(p.stats != nullptr && p.scale != nullptr), "igemm: stats and affine epilogues are exclusive");
   UNETK_CHECK_ARG(!use_colbuf || p.Ntot <= 1024, "igemm: stats/affine epilogue supports at most 1024 columns");
 
-  const int box = kRegion + 2 * p.halo;
+  const int box_w = region_w + 2 * p.halo, box_h = kRegionH + 2 * p.halo;
   CUtensorMap tmA1, tmA2, tmB;
   int e;
   if (p.a_mode == 0) {
-    if ((e = make_act_tmap(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, box, box, 1))) return e;
+    if ((e = make_act_tmap(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, box_w, box_h, 1))) return e;
     if (L.c2 > 0) {
-      if ((e = make_act_tmap(&tmA2, L.a2, p.n_img, p.H, p.W, L.c2, box, box, 1))) return e;
+      if ((e = make_act_tmap(&tmA2, L.a2, p.n_img, p.H, p.W, L.c2, box_w, box_h, 1))) return e;
     } else {
       tmA2 = tmA1;
     }
   } else {
-    if ((e = make_act_tmap_up2(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, kRegion, kRegion, 1))) return e;
+    if ((e = make_act_tmap_up2(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, region_w, kRegionH, 1))) return e;
     tmA2 = tmA1;
   }
   const int K = p.num_taps * (L.c1 + L.c2);
-  if ((e = make_b_tmap(&tmB, L.b, p.Ntot, K, bn))) return e;
+  if ((e = make_b_tmap(&tmB, L.b, p.Ntot, K, bn / ctas))) return e;
 
-  const long total_tiles = static_cast<long>(p.regions_x) * p.regions_y * p.n_img * p.n_blocks;
-  const int grid = static_cast<int>(total_tiles < num_sms() ? total_tiles : num_sms());
+  const long regions = static_cast<long>(p.regions_x) * p.regions_y * p.n_img;
+  const long total_tiles = ((regions + ctas - 1) / ctas) * p.n_blocks;     // per CTA (pair)
+  const int max_units = num_sms() / ctas;
+  const int grid = static_cast<int>(total_tiles < max_units ? total_tiles : max_units) * ctas;
   const size_t colbytes = (p.stats != nullptr ? static_cast<size_t>(8) * bn : (use_colbuf ? static_cast<size_t>(2) * p.Ntot : 0)) * sizeof(float);
-  if (bn == 128) {
-    using Cfg = IgemmCfg<128>;
-    const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;
-    UNETK_CUDA(cudaFuncSetAttribute(igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    igemm_kernel<128><<<grid, kIgemmThreads, smem, stream>>>(tmA1, tmA2, tmB, p);
-  } else {
-    using Cfg = IgemmCfg<64>;
-    const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;
-    UNETK_CUDA(cudaFuncSetAttribute(igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    igemm_kernel<64><<<grid, kIgemmThreads, smem, stream>>>(tmA1, tmA2, tmB, p);
-  }
-  UNETK_CUDA(cudaGetLastError());
-  return UNETK_OK;
+  if (bn == 256) return launch_cfg<256, 1, 2>(tmA1, tmA2, tmB, p, grid, colbytes, stream);
+  if (ctas == 2) return bn == 128 ? launch_cfg<128, 2, 2>(tmA1, tmA2, tmB, p, grid, colbytes, stream)
+                                  : launch_cfg<64, 2, 2>(tmA1, tmA2, tmB, p, grid, colbytes, stream);
+  return bn == 128 ? launch_cfg<128, 2, 1>(tmA1, tmA2, tmB, p, grid, colbytes, stream)
+                   : launch_cfg<64, 2, 1>(tmA1, tmA2, tmB, p, grid, colbytes, stream);
 }
 
 int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
