@@ -92,28 +92,30 @@ first_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
   }
 }
 
-// wgrad: block = 256 threads = 4 pixel slices x 64 threads; thread (slice, t) owns a 4 co x 7 k
-// register tile (co = 4*(t%16).., k = 7*(t/16)..; k = tap*Cin + ci, 28 slots >= 27) and walks every
-// fourth pixel of a 128-pixel chunk staged in shared memory: 3 vector LDS per 28 FMAs.
+// wgrad: block = 256 threads = 4 pixel slices x 64 threads; thread (slice, t) owns a 4 co x 8 k
+// register tile (co = 4*(t%16).., k = 8*(t/16)..; k = tap*Cin + ci, 32 slots >= 27) and walks every
+// fourth pixel of a 128-pixel chunk staged in shared memory: 3 vector LDS per 32 FMAs.
 constexpr int kFwPix = 128;
-constexpr int kFwK = 28;
+constexpr int kFwK = 32;
 
 __global__ void __launch_bounds__(256)
 first_conv_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ dy,
                         float* __restrict__ dw, int N, int Cin, int H, int W) {
   __shared__ __align__(16) float sdy[kFwPix][kFcCout];      // 32 KB
-  __shared__ __align__(16) float sx[kFwPix][kFwK];          // 14 KB
+  __shared__ __align__(16) float sx[kFwPix][kFwK];          // 16 KB
   const int K = 9 * Cin;
   const int t = threadIdx.x & 63, slice = threadIdx.x >> 6;
-  const int co0 = (t & 15) * 4, k0 = (t >> 4) * 7;
-  float acc[4][7];
+  const int co0 = (t & 15) * 4, k0 = (t >> 4) * 8;
+  float acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 7; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const long hw = static_cast<long>(H) * W;
   const long total = hw * N;
   const long nchunks = (total + kFwPix - 1) / kFwPix;
+  // staging role of this thread: pixel pp = tid % 128 (fixed), k = tid / 128, +2, +4, ...
+  const int spp = threadIdx.x & (kFwPix - 1), sk0 = threadIdx.x >> 7;
   for (long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const long p0 = ch * kFwPix;
     __syncthreads();
@@ -127,38 +129,45 @@ first_conv_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ d
       row[0] = make_float4(a.x, a.y, b.x, b.y);
       row[1] = make_float4(c.x, c.y, d.x, d.y);
     }
-    for (int i = threadIdx.x; i < kFwPix * kFwK; i += blockDim.x) {
-      const int pp = i % kFwPix, k = i / kFwPix;
-      const long p = p0 + pp;
-      float v = 0.f;
-      if (p < total && k < K) {
-        const long n = p / hw;
-        const int r = static_cast<int>(p - n * hw);
-        const int yy = r / W, xx = r - yy * W;
-        const int tap = k / Cin, ci = k - tap * Cin;
-        const int sy = yy + tap / 3 - 1, sxx = xx + tap % 3 - 1;
-        if (sy >= 0 && sy < H && sxx >= 0 && sxx < W) v = __ldg(x + (n * Cin + ci) * hw + static_cast<long>(sy) * W + sxx);
+    {
+      // one pixel per thread: decode (n, y, x) once, then walk this thread's k slots
+      const long p = p0 + spp;
+      const bool pv = p < total;
+      const long n = pv ? p / hw : 0;
+      const int r = static_cast<int>(p - n * hw);
+      const int yy = r / W, xx = r - yy * W;
+      const float* xb = x + n * Cin * hw;
+      int tap = 0, ci = sk0;          // k = tap * Cin + ci, advanced by 2 each step
+      while (ci >= Cin) { ci -= Cin; ++tap; }
+      for (int k = sk0; k < kFwK; k += 2) {
+        float v = 0.f;
+        if (pv && k < K) {
+          const int sy = yy + tap / 3 - 1, sxx = xx + tap % 3 - 1;
+          if (sy >= 0 && sy < H && sxx >= 0 && sxx < W) v = __ldg(xb + ci * hw + static_cast<long>(sy) * W + sxx);
+        }
+        sx[spp][k] = v;
+        ci += 2;
+        while (ci >= Cin) { ci -= Cin; ++tap; }
       }
-      sx[pp][k] = v;
     }
     __syncthreads();
 #pragma unroll 4
     for (int pp = slice; pp < kFwPix; pp += 4) {
       const float4 g = *reinterpret_cast<const float4*>(&sdy[pp][co0]);
-      float xv[7];
-#pragma unroll
-      for (int j = 0; j < 7; ++j) xv[j] = sx[pp][k0 + j];
+      const float4 x0 = *reinterpret_cast<const float4*>(&sx[pp][k0]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&sx[pp][k0 + 4]);
       const float gv[4] = {g.x, g.y, g.z, g.w};
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 7; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
     }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int k = k0 + j;
       if (k < K) {
         const int tap = k / Cin, ci = k - tap * Cin;

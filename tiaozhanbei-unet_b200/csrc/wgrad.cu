@@ -15,6 +15,8 @@
 // from ONE 10x8 halo box per 64-channel chunk (80 rows x 128 B): a dx shift is a descriptor start
 // offset of dx*128 B, 8-pixel patch rows are the 8-row K groups with SBO = 10*128 B (the 128B
 // swizzle is address based, profiles/umma_probe_r01.txt).  X traffic drops 2.4x.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -37,14 +39,17 @@ constexpr int kBoxBytes = 64 * 128;   // 64 pixels x 64 bf16
 constexpr int kHaloBytes = 80 * 128;  // 10 x 8 pixels x 64 bf16 (conv3x3 X operand)
 constexpr int kHaloPitch = 10 * 128;  // bytes between patch rows inside the halo box
 
-template <int MODE, int BN, bool M64>
+// CTAS == 2 (conv3x3, BN == 128): cta_group::2 pairs.  The two CTAs own different (tap row, ci tile)
+// units (M = 256 per instruction) and each stages only 64 of the 128 dY channels: per CTA an MMA
+// fetches A 4 KB + B 2 KB from shared memory instead of 4 + 4 (SS-mode operand fetch is the limiter).
+template <int MODE, int BN, bool M64, int CTAS = 1>
 struct WgCfg {
   // per stage: A (X operand) and B (dY / dUp operand) regions
   static constexpr int kALoads = (MODE == 0) ? (M64 ? 1 : 2) : 2;
   static constexpr int kABoxBytes = (MODE == 0) ? kHaloBytes : kBoxBytes;
   // M64: the second tap of the last pair reads 3 rows past the box; keep that inside the stage
   static constexpr int kABytes = kALoads * kABoxBytes + ((MODE == 0 && M64) ? 1024 : 0);
-  static constexpr int kBBoxes = (MODE == 0) ? (BN / 64) : 4 * (BN / 64);
+  static constexpr int kBBoxes = (MODE == 0) ? (BN / 64 / CTAS) : 4 * (BN / 64);   // per CTA
   static constexpr int kMmas = (MODE == 0) ? (M64 ? 2 : 3) : 4;
   static constexpr int kStageBytes = kABytes + kBBoxes * kBoxBytes;
   static constexpr int kMaxFit = (210 * 1024) / kStageBytes;
@@ -53,11 +58,12 @@ struct WgCfg {
   static constexpr int kTmemCols = kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : (kAccCols <= 256 ? 256 : 512));
 };
 
-template <int MODE, int BN, bool M64>
+template <int MODE, int BN, bool M64, int CTAS>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
              const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
-  using Cfg = WgCfg<MODE, BN, M64>;
+  using Cfg = WgCfg<MODE, BN, M64, CTAS>;
+  static_assert(CTAS == 1 || (MODE == 0 && BN == 128), "CTA pairs: conv3x3 with 128-wide co tiles only");
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -71,12 +77,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // work decomposition
-  int bx = blockIdx.x;
+  // work decomposition: unit = (tap row r, ci tile); a CTA pair takes two consecutive units
+  const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  int bx = blockIdx.x / CTAS;
   const int cot = bx % p.co_tiles;
   bx /= p.co_tiles;
-  const int cit = bx % p.ci_tiles;
-  const int r = bx / p.ci_tiles;  // tap row (MODE 0), 0 otherwise
+  const int unit = bx * CTAS + static_cast<int>(rank);
+  const int n_units = (MODE == 0 ? 3 : 1) * p.ci_tiles;
+  const bool live = unit < n_units;          // odd unit count: the last pair has one idle CTA
+  const int cit = unit % p.ci_tiles;
+  const int r = unit / p.ci_tiles;  // tap row (MODE 0), 0 otherwise
   const int total_k = p.tiles_x * p.tiles_y * p.tiles_n;
   const int k_begin = static_cast<int>(static_cast<long>(total_k) * blockIdx.y / p.ksplit);
   const int k_end = static_cast<int>(static_cast<long>(total_k) * (blockIdx.y + 1) / p.ksplit);
@@ -93,9 +103,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (CTAS == 2) cluster_sync_all();
+  if (warp == 1) {
+    if (CTAS == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -110,8 +124,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
         const int ty = m % p.tiles_y;
         const int tz = m / p.tiles_y;
         const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tz * p.tn;
+        const int n0a = live ? n0 : p.n_img;   // idle CTA of a pair: X out of bounds -> zeros
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], Cfg::kALoads * Cfg::kABoxBytes + Cfg::kBBoxes * kBoxBytes);
+        if (rank == 0) mbar_expect_tx(&full[stage], (Cfg::kALoads * Cfg::kABoxBytes + Cfg::kBBoxes * kBoxBytes) * CTAS);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
         if (MODE == 0) {
@@ -121,11 +136,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
             const CUtensorMap* mp = (chunk < p.c1_chunks) ? &tmX1 : &tmX2;
             const int cc = ((chunk < p.c1_chunks) ? chunk : chunk - p.c1_chunks) * 64;
             // halo box of tap row r: pixels (x0-1 .. x0+8, y0+r-1 .. y0+r+6)
-            tma_load_5d(sa + j * kHaloBytes, mp, &full[stage], cc, x0 - 1, y0 + r - 1, n0, 0);
+            if (CTAS == 2) tma_load_5d_pair(sa + j * kHaloBytes, mp, &full[stage], cc, x0 - 1, y0 + r - 1, n0a, 0);
+            else tma_load_5d(sa + j * kHaloBytes, mp, &full[stage], cc, x0 - 1, y0 + r - 1, n0a, 0);
           }
 #pragma unroll
-          for (int j = 0; j < Cfg::kBBoxes; ++j)
-            tma_load_5d(sb + j * kBoxBytes, &tmDY, &full[stage], cot * BN + j * 64, x0, y0, n0, 0);
+          for (int j = 0; j < Cfg::kBBoxes; ++j) {
+            const int co = cot * BN + (static_cast<int>(rank) * Cfg::kBBoxes + j) * 64;   // this CTA's share of dY
+            if (CTAS == 2) tma_load_5d_pair(sb + j * kBoxBytes, &tmDY, &full[stage], co, x0, y0, n0, 0);
+            else tma_load_5d(sb + j * kBoxBytes, &tmDY, &full[stage], co, x0, y0, n0, 0);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 2; ++j)
@@ -144,9 +163,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    {
+    if (rank == 0) {
       // warp-uniform loop, one elected lane issues (keeps descriptors in uniform registers)
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, true, true);
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CTAS, BN, true, true);
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = k_begin; kt < k_end; ++kt) {
@@ -169,11 +188,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
               // halo.  !M64: M = 128 ci = two halo boxes (LBO).  M64: M = taps (2j, 2j+1) x 64 ci.
               const uint64_t da = (MODE == 0) ? a_desc0 + ((M64 ? 2 * j : j) * 8 + k * 2 * (kHaloPitch / 16))
                                               : a_desc0 + (k * 128);
-              tc_mma_bf16(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
+              if (CTAS == 2) tc_mma_bf16_pair(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
+              else tc_mma_bf16(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
             }
           }
-          tc_commit(&empty[stage]);
-          if (kt == k_end - 1) tc_commit(tfull);
+          if (CTAS == 2) {
+            tc_commit_pair(&empty[stage]);
+            if (kt == k_end - 1) tc_commit_pair(tfull);
+          } else {
+            tc_commit(&empty[stage]);
+            if (kt == k_end - 1) tc_commit(tfull);
+          }
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -205,7 +230,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
         tap = j;
         ci = cit * 128 + row;
       }
-      valid = valid && (ci < p.cin);
+      valid = valid && live && (ci < p.cin);
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         float v[32];
@@ -227,10 +252,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -239,14 +265,26 @@ void pick_pixel_tile(int n_img, int H, int W, int pixels, int* tw, int* th, int*
 int make_act_tmap(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int tw, int th, int tn);
 int make_act_tmap_up2(CUtensorMap* tm, const void* base, int N, int H, int W, int C, int tw, int th, int tn);
 
-template <int MODE, int BN, bool M64>
+template <int MODE, int BN, bool M64, int CTAS = 1>
 static int launch_wgrad_t(const CUtensorMap& x1, const CUtensorMap& x2, const CUtensorMap& dy,
                           const WgradParams& p, dim3 grid, cudaStream_t stream) {
-  using Cfg = WgCfg<MODE, BN, M64>;
+  using Cfg = WgCfg<MODE, BN, M64, CTAS>;
   const size_t smem = 1024 + Cfg::kStages * Cfg::kStageBytes + (2 * Cfg::kStages + 2) * 8;
-  UNETK_CUDA(cudaFuncSetAttribute(wgrad_kernel<MODE, BN, M64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  wgrad_kernel<MODE, BN, M64><<<grid, kWgThreads, smem, stream>>>(x1, x2, dy, p);
-  UNETK_CUDA(cudaGetLastError());
+  auto kern = wgrad_kernel<MODE, BN, M64, CTAS>;
+  UNETK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kWgThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UNETK_CUDA(cudaLaunchKernelEx(&cfg, kern, x1, x2, dy, p));
   return UNETK_OK;
 }
 
@@ -289,7 +327,10 @@ int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, in
   const int bn = (cout % 128 == 0) ? 128 : 64;
   p.ci_tiles = m64 ? 1 : cin / 128;
   p.co_tiles = cout / bn;
-  const int work = 3 * p.ci_tiles * p.co_tiles;
+  static const bool pair_ok = (getenv("UNETK_WGRAD_1CTA") == nullptr);
+  const int ctas = (pair_ok && bn == 128) ? 2 : 1;
+  const int unit_slots = (3 * p.ci_tiles + ctas - 1) / ctas;       // (tap row, ci tile) units per CTA (pair)
+  const int work = unit_slots * ctas * p.co_tiles;                  // CTAs in grid.x
   // one K tile = (2 or 3) x 4 MMAs of 128 x bn x 16 (M64: N = bn at half the tile rows)
   p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y * p.tiles_n, (m64 ? 8 : 12) * bn / 256.0 / 1.7 + 0.05,
                            (m64 ? 3 * 64 : 3 * 128) * static_cast<double>(bn));
@@ -299,6 +340,8 @@ int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, in
   if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h, w, c2, 10, 8, 1))) return e; } else x2 = x1;
   if ((e = make_act_tmap(&tdy, dy, n, h, w, cout, 8, 8, 1))) return e;
   dim3 grid(work, p.ksplit);
+  if (ctas == 2) return m64 ? launch_wgrad_t<0, 128, true, 2>(x1, x2, tdy, p, grid, stream)
+                            : launch_wgrad_t<0, 128, false, 2>(x1, x2, tdy, p, grid, stream);
   if (m64) return bn == 128 ? launch_wgrad_t<0, 128, true>(x1, x2, tdy, p, grid, stream)
                             : launch_wgrad_t<0, 64, true>(x1, x2, tdy, p, grid, stream);
   return bn == 128 ? launch_wgrad_t<0, 128, false>(x1, x2, tdy, p, grid, stream)
