@@ -45,6 +45,19 @@ extern "C" {
 
 #define UNETK_VERSION 100 /* 0.1.0 */
 
+/* Optional fused first pass of a BatchNorm+ReLU backward (HOST struct, read at launch; NULL = off).
+ * A kernel that completes a gradient dA of an activation a = relu(y*scale+shift) also accumulates
+ *   sums[0..C) += sum g,  sums[C..2C) += sum g*xhat,   g = dA*[y*scale+shift > 0], xhat = (y-mean)*invstd
+ * (what unetk_bn_bwd_reduce computes), saving one pass over dA and y.  The caller zeroes sums. */
+typedef struct {
+  const void* y;          /* raw conv output of the producing layer, NHWC bf16, same shape as dA */
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  float* sums;            /* [2][C] */
+} unetk_bn_ctx;
+
 int unetk_version(void);
 const char* unetk_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x, UNETK_ERR_ARCH otherwise. */
@@ -66,8 +79,8 @@ int unetk_conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const 
  * receive several gradients).  stats != NULL: stats[c2] += sum over pixels of dx2 (the bias
  * gradient of the ConvTranspose2d that produced src2; the caller zeroes it). */
 int unetk_conv3x3_dgrad(const void* dy, int cout, const void* wd, void* dx1, int c1, int acc1,
-                        void* dx2, int c2, int acc2, float* stats, int n, int h, int w,
-                        void* stream);
+                        void* dx2, int c2, int acc2, float* stats, const unetk_bn_ctx* bn, int n, int h,
+                        int w, void* stream);
 /* autograd w.r.t. the weight: dw[co][tap][ci] += sum_pix dy * x  (split-K, fp32 atomics; the
  * caller zeroes dw). */
 int unetk_conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2,
@@ -80,6 +93,13 @@ int unetk_first_conv_fwd(const float* x, const float* w, void* y, float* stats, 
                          int h, int w_, int cout, void* stream);
 int unetk_first_conv_wgrad(const float* x, const void* dy, float* dw, int n, int cin, int h, int w_,
                            int cout, void* stream);
+/* Tensor-core route for the same gradient.  unetk_image_to_nhwc64 writes channels [0,8) of the NHWC
+ * bf16 image x64[n,h,w,64] (the caller zeroes x64 ONCE: the padding channels are never written);
+ * unetk_first_conv_wgrad_tc runs the 64->64 conv3x3 weight gradient on it (scratch: 64*9*64 floats,
+ * zeroed by the call) and gathers dw in OIHW [64][cin][3][3] (overwritten). */
+int unetk_image_to_nhwc64(const float* x, void* x64, int n, int cin, int h, int w_, void* stream);
+int unetk_first_conv_wgrad_tc(const void* x64, const void* dy, float* scratch, float* dw, int n,
+                              int cin, int h, int w_, int cout, void* stream);
 
 /* ---- nn.ConvTranspose2d(Cin, Cin/2, kernel_size=2, stride=2): src/model.py:51 -------------- */
 /* up[n,2h+ky,2w+kx,co] = bias[co] + sum_ci a[n,h,w,ci] * W[ci][co][ky][kx]  (GEMM + pixel-shuffle
@@ -87,7 +107,7 @@ int unetk_first_conv_wgrad(const float* x, const void* dy, float* dw, int n, int
 int unetk_convt2x2_fwd(const void* a, int cin, const void* wt, const float* bias, void* up, int n,
                        int h, int w, int cout, void* stream);
 int unetk_convt2x2_dgrad(const void* dup, int cout, const void* wtd, void* da, int cin, int acc,
-                         int n, int h, int w, void* stream);
+                         const unetk_bn_ctx* bn, int n, int h, int w, void* stream);
 /* dw[co][tap][ci] += sum_pix dup[2*pix+tap, co] * a[pix, ci] (caller zeroes dw). */
 int unetk_convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw, int n, int h,
                          int w, void* stream);
@@ -112,7 +132,7 @@ int unetk_bnrelu_apply(const void* y, const float* scale, const float* shift, vo
 int unetk_bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
                       void* idx, int n, int h, int w, int c, int apply, void* stream);
 int unetk_maxpool_bwd(const void* dpooled, const void* idx, void* da, int n, int h, int w, int c,
-                      int accumulate, void* stream);
+                      int accumulate, const unetk_bn_ctx* bn, void* stream);
 /* BatchNorm+ReLU backward in two passes: sums[2][C] (caller zeroes) then dy, dgamma, dbeta. */
 int unetk_bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
                         const float* mean, const float* invstd, float* sums, int64_t npix, int c,
@@ -126,7 +146,7 @@ int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, in
                    int c, int n_out, int sigmoid, void* stream);
 int unetk_head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da,
                    float* dw, float* db, int n, int h, int w_, int c, int n_out, int sigmoid,
-                   void* stream);
+                   const unetk_bn_ctx* bn, void* stream);
 
 /* ---- CombinedLoss.forward / focal_loss: src/train_utils.py:10-44 --------------------------- */
 /* out3 = {total, recon, seg}; d_recon / d_amap (may be NULL) = gradient of `total`. */

@@ -12,8 +12,10 @@ BatchNorm/ReLU layers, not a property of these kernels (each kernel is checked t
 tests/test_ops_gpu.py).  Hence, against the fp32 reference numbers:
   * outputs: mean |d| <= 8e-3 * max|ref|, max |d| <= 1.5e-1 * max|ref|
   * losses: relative 2e-3
-  * gradients: per tensor cosine >= 0.6 and norm within 20 %; the output-side tensors (heads and the
-    last BatchNorm), which see no accumulated noise, within 3e-2 relative L2
+  * gradients: per tensor cosine >= 0.6 and norm within 30 % (the bf16-contract ORACLE is itself 18 % off
+    the fp32 norm on inc.double_conv.1.weight of the 2x32x32 UNet case, 7 % on the others, so 20 % had no
+    margin: the case flipped between runs with the order of the fp32 atomics); the output-side tensors
+    (heads and the last BatchNorm), which see no accumulated noise, within 3e-2 relative L2
   * threshold masks: bit-exact wherever the reference margin |p - 0.5| exceeds 1.5e-1, and fewer than
     0.2 % flips outside a 5e-2 margin
   * loss curve over 20 Adam steps within 1 %
@@ -31,7 +33,7 @@ sys.path.insert(0, ROOT)
 from oracle import unet_oracle as O  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "unet_golden.pt")
-OUT_MAX, OUT_MEAN, LOSS_REL, GRAD_COS, GRAD_NORM, GRAD_REL_HEAD, MARGIN, SOFT_MARGIN = 1.5e-1, 8e-3, 2e-3, 0.6, 0.2, 3e-2, 1.5e-1, 5e-2
+OUT_MAX, OUT_MEAN, LOSS_REL, GRAD_COS, GRAD_NORM, GRAD_REL_HEAD, MARGIN, SOFT_MARGIN = 1.5e-1, 8e-3, 2e-3, 0.6, 0.3, 3e-2, 1.5e-1, 5e-2
 HEAD_KEYS = ("outc", "up4.conv.double_conv.4", "up4_recon.conv.double_conv.4", "up4_seg.conv.double_conv.4")
 
 

@@ -115,6 +115,18 @@ def test_conv3x3_dgrad(cuda_device, n, h, w, c1, c2, cout):
     if c2:
         _close(_nchw(dx2), ref[:, c1:], 2e-2, "dgrad dx2")
         _close(stats, ref[:, c1:].sum(dim=(0, 2, 3)), 2e-3 * (n * h * w) ** 0.5, "dgrad column sums")
+    else:
+        # fused first pass of the BatchNorm backward of the producing layer (single destination)
+        yb = _nhwc(torch.randn(n, c1, h, w, generator=g).to(cuda_device))
+        sc = (torch.rand(c1, generator=g) + 0.5).to(cuda_device); sh = torch.randn(c1, generator=g).to(cuda_device) * 0.3
+        mu = torch.randn(c1, generator=g).to(cuda_device) * 0.2; iv = (torch.rand(c1, generator=g) + 0.5).to(cuda_device)
+        fused = torch.zeros(2 * c1, device=cuda_device); ref_sums = torch.zeros(2 * c1, device=cuda_device)
+        dx3 = prev1.clone()
+        ops.conv3x3_dgrad(dyb, wd, dx3, acc1=True, bn=ops.bn_ctx(yb, sc, sh, mu, iv, fused))
+        ops.bn_bwd_reduce(dx3, yb, sc, sh, mu, iv, ref_sums)
+        torch.cuda.synchronize()
+        assert torch.equal(dx3, dx1)
+        _close(fused, ref_sums, 1e-4, "dgrad fused BN reduction")
 
 
 @pytest.mark.parametrize("n,h,w,c1,c2,cout", CONV_CASES)
@@ -162,6 +174,16 @@ def test_convt2x2(cuda_device, n, h, w, cin, cout):
     ops.convt2x2_dgrad(dupb, wpd, da, acc=False)
     torch.cuda.synchronize()
     _close(_nchw(da), ref_da, 2e-2, "convt2x2_dgrad")
+    yb = _nhwc(torch.randn(n, cin, h, w, generator=g).to(cuda_device))
+    sc = (torch.rand(cin, generator=g) + 0.5).to(cuda_device); sh = torch.randn(cin, generator=g).to(cuda_device) * 0.3
+    mu = torch.randn(cin, generator=g).to(cuda_device) * 0.2; iv = (torch.rand(cin, generator=g) + 0.5).to(cuda_device)
+    fused = torch.zeros(2 * cin, device=cuda_device); ref_sums = torch.zeros(2 * cin, device=cuda_device)
+    da2 = torch.empty_like(da)
+    ops.convt2x2_dgrad(dupb, wpd, da2, acc=False, bn=ops.bn_ctx(yb, sc, sh, mu, iv, fused))
+    ops.bn_bwd_reduce(da2, yb, sc, sh, mu, iv, ref_sums)
+    torch.cuda.synchronize()
+    assert torch.equal(da2, da)
+    _close(fused, ref_sums, 1e-4, "convt2x2_dgrad fused BN reduction")
     # wgrad: d/dW of conv_transpose2d == conv2d_weight with roles swapped
     ref_dw = torch.nn.grad.conv2d_weight(_nchw(dupb), (cin, cout, 2, 2), _nchw(ab), stride=2)
     dwk = torch.zeros(cout * 4 * cin, dtype=torch.float32, device=cuda_device)
@@ -192,6 +214,19 @@ def test_first_conv(cuda_device, n, cin, h, w):
     ops.first_conv_wgrad(x, dyb, dw)
     torch.cuda.synchronize()
     _close(dw, ref_dw, 1e-4, "first_conv_wgrad")
+    # tensor-core route: channel-padded bf16 image + the 64->64 nine-tap weight-gradient kernel
+    x64 = torch.zeros(n, h, w, 64, dtype=torch.bfloat16, device=cuda_device)
+    ops.image_to_nhwc64(x, x64)
+    torch.cuda.synchronize()
+    assert torch.equal(x64[..., :cin].float(), x.to(torch.bfloat16).float().permute(0, 2, 3, 1))
+    assert float(x64[..., cin:].abs().max()) == 0.0
+    ref_dw_bf = torch.nn.grad.conv2d_weight(x.to(torch.bfloat16).float(), (64, cin, 3, 3), _nchw(dyb), padding=1)
+    scratch = torch.empty(64 * 9 * 64, dtype=torch.float32, device=cuda_device)
+    dw2 = torch.full((64, cin, 3, 3), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.first_conv_wgrad_tc(x64, dyb, scratch, dw2)
+    torch.cuda.synchronize()
+    _close(dw2, ref_dw_bf, 1e-4, "first_conv_wgrad_tc (bf16 image)")
+    _close(dw2, ref_dw, 1e-2, "first_conv_wgrad_tc vs fp32 image")
 
 
 @pytest.mark.parametrize("n,h,w,c", [(2, 8, 8, 64), (1, 16, 12, 128), (3, 4, 6, 1024)])
@@ -248,6 +283,15 @@ def test_bn_relu_pool_roundtrip(cuda_device, n, h, w, c):
     ops.maxpool_bwd(dpb, idx, da2, accumulate=True)
     torch.cuda.synchronize()
     _close(da2.float(), base.float() + da.float(), 1e-2, "maxpool_bwd accumulate")
+    # fused first pass of the BatchNorm backward == the stand-alone reduction on the finished gradient
+    da3 = base.clone()
+    fused = torch.zeros(2 * c, device=dev)
+    ops.maxpool_bwd(dpb, idx, da3, accumulate=True, bn=ops.bn_ctx(yb, scale, shift, mean, invstd, fused))
+    ref_sums = torch.zeros(2 * c, device=dev)
+    ops.bn_bwd_reduce(da3, yb, scale, shift, mean, invstd, ref_sums)
+    torch.cuda.synchronize()
+    assert torch.equal(da3, da2)
+    _close(fused, ref_sums, 1e-4, "maxpool_bwd fused BN reduction")
 
 
 @pytest.mark.parametrize("n_out,sigmoid", [(3, True), (1, True), (1, False)])
@@ -277,6 +321,25 @@ def test_head(cuda_device, n_out, sigmoid):
     _close(_nchw(da), aref.grad, 1e-2, "head_bwd da")
     _close(dw, wref.grad.view(n_out, 64), 1e-4, "head_bwd dw")
     _close(db, bref.grad, 1e-4, "head_bwd db")
+    # fused first pass of the BatchNorm backward of the layer that produced the head's input:
+    # a2 = relu(y*scale + shift) (the kernel recovers xhat from the activation it already holds)
+    yb = _nhwc(torch.randn(n, 64, h, w, generator=g).to(dev))
+    sc = (torch.rand(64, generator=g) + 0.5).to(dev); sh = torch.randn(64, generator=g).to(dev) * 0.3
+    iv = (torch.rand(64, generator=g) + 0.5).to(dev)
+    mu = -sh / sc + torch.randn(64, generator=g).to(dev) * 0.05     # consistent BatchNorm constants (beta small)
+    a2 = torch.empty_like(yb)
+    ops.bnrelu_apply(yb, sc, sh, a2)
+    for scale_case in (sc, torch.cat([sc[:5] * 0, sc[5:]])):     # second case: gamma == 0 channels (direct route)
+        if scale_case is not sc:
+            ops.bnrelu_apply(yb, scale_case, sh, a2)
+        fused = torch.zeros(128, device=dev); ref_sums = torch.zeros(128, device=dev)
+        da2 = torch.empty_like(a); da3 = torch.empty_like(a)
+        ops.head_bwd(a2, wt, dout, out, da3, dw, db, sigmoid)
+        ops.head_bwd(a2, wt, dout, out, da2, dw, db, sigmoid, bn=ops.bn_ctx(yb, scale_case, sh, mu, iv, fused))
+        ops.bn_bwd_reduce(da2, yb, scale_case, sh, mu, iv, ref_sums)
+        torch.cuda.synchronize()
+        assert torch.equal(da2, da3)
+        _close(fused, ref_sums, 5e-3, "head_bwd fused BN reduction")
 
 
 def test_adam_and_layout(cuda_device):

@@ -21,22 +21,24 @@ SIGNATURES = {
     "unetk_check_device": (I, []),
     "unetk_memset_zero": (I, [P, Z, P]),
     "unetk_conv3x3_fwd": (I, [P, I, P, I, P, P, P, P, P, I, I, I, I, I, P]),
-    "unetk_conv3x3_dgrad": (I, [P, I, P, P, I, I, P, I, I, P, I, I, I, P]),
+    "unetk_conv3x3_dgrad": (I, [P, I, P, P, I, I, P, I, I, P, P, I, I, I, P]),
     "unetk_conv3x3_wgrad": (I, [P, P, I, P, I, P, I, I, I, I, P]),
     "unetk_first_conv_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "unetk_first_conv_wgrad": (I, [P, P, P, I, I, I, I, I, P]),
+    "unetk_image_to_nhwc64": (I, [P, P, I, I, I, I, P]),
+    "unetk_first_conv_wgrad_tc": (I, [P, P, P, P, I, I, I, I, I, P]),
     "unetk_convt2x2_fwd": (I, [P, I, P, P, P, I, I, I, I, P]),
-    "unetk_convt2x2_dgrad": (I, [P, I, P, P, I, I, I, I, I, P]),
+    "unetk_convt2x2_dgrad": (I, [P, I, P, P, I, I, P, I, I, I, P]),
     "unetk_convt2x2_wgrad": (I, [P, I, P, I, P, I, I, I, P]),
     "unetk_bn_finalize": (I, [P, P, P, P, P, P, P, P, P, P, I, D, F, F, P]),
     "unetk_bn_fold": (I, [P, P, P, P, P, P, I, F, P]),
     "unetk_bnrelu_apply": (I, [P, P, P, P, L, I, P]),
     "unetk_bnrelu_pool": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
-    "unetk_maxpool_bwd": (I, [P, P, P, I, I, I, I, I, P]),
+    "unetk_maxpool_bwd": (I, [P, P, P, I, I, I, I, I, P, P]),
     "unetk_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, L, I, P]),
     "unetk_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, L, I, P]),
     "unetk_head_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P]),
-    "unetk_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, I, P]),
+    "unetk_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, I, P, P]),
     "unetk_combined_loss_workspace_bytes": (Z, []),
     "unetk_combined_loss": (I, [P, P, P, P, P, P, P, P, Z, L, L, F, F, F, F, P]),
     "unetk_scale_by_scalar": (I, [P, P, L, P]),
@@ -56,6 +58,12 @@ SIGNATURES = {
 
 class UnetkError(RuntimeError):
     pass
+
+
+class BnCtx(ctypes.Structure):
+    """Mirror of `unetk_bn_ctx` (include/unetk.h): fused BatchNorm-backward first pass."""
+    _fields_ = [("y", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("mean", c_void_p), ("invstd", c_void_p),
+                ("sums", c_void_p)]
 
 
 _lib = None

@@ -34,10 +34,13 @@ int unetk_conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const 
                       int w, int cout, void* stream) {
   return unetk::conv3x3_fwd(src1, c1, src2, c2, wf, y, stats, scale, shift, relu, n, h, w, cout, S(stream));
 }
+static const unetk::BnReduceCtx* B(const unetk_bn_ctx* bn) { return reinterpret_cast<const unetk::BnReduceCtx*>(bn); }
+static_assert(sizeof(unetk_bn_ctx) == sizeof(unetk::BnReduceCtx), "unetk_bn_ctx mirrors BnReduceCtx");
+
 int unetk_conv3x3_dgrad(const void* dy, int cout, const void* wd, void* dx1, int c1, int acc1,
-                        void* dx2, int c2, int acc2, float* stats, int n, int h, int w,
+                        void* dx2, int c2, int acc2, float* stats, const unetk_bn_ctx* bn, int n, int h, int w,
                         void* stream) {
-  return unetk::conv3x3_dgrad(dy, cout, wd, dx1, c1, acc1, dx2, c2, acc2, stats, n, h, w, S(stream));
+  return unetk::conv3x3_dgrad(dy, cout, wd, dx1, c1, acc1, dx2, c2, acc2, stats, B(bn), n, h, w, S(stream));
 }
 int unetk_conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2,
                         float* dw, int n, int h, int w, int cout, void* stream) {
@@ -46,6 +49,13 @@ int unetk_conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* sr
 int unetk_first_conv_fwd(const float* x, const float* w, void* y, float* stats, int n, int cin,
                          int h, int w_, int cout, void* stream) {
   return unetk::first_conv_fwd(x, w, y, stats, n, cin, h, w_, cout, S(stream));
+}
+int unetk_image_to_nhwc64(const float* x, void* x64, int n, int cin, int h, int w_, void* stream) {
+  return unetk::image_to_nhwc64(x, x64, n, cin, h, w_, S(stream));
+}
+int unetk_first_conv_wgrad_tc(const void* x64, const void* dy, float* scratch, float* dw, int n,
+                              int cin, int h, int w_, int cout, void* stream) {
+  return unetk::first_conv_wgrad_tc(x64, dy, scratch, dw, n, cin, h, w_, cout, S(stream));
 }
 int unetk_first_conv_wgrad(const float* x, const void* dy, float* dw, int n, int cin, int h, int w_,
                            int cout, void* stream) {
@@ -56,8 +66,8 @@ int unetk_convt2x2_fwd(const void* a, int cin, const void* wt, const float* bias
   return unetk::convt2x2_fwd(a, cin, wt, bias, up, n, h, w, cout, S(stream));
 }
 int unetk_convt2x2_dgrad(const void* dup, int cout, const void* wtd, void* da, int cin, int acc,
-                         int n, int h, int w, void* stream) {
-  return unetk::convt2x2_dgrad(dup, cout, wtd, da, cin, acc, n, h, w, S(stream));
+                         const unetk_bn_ctx* bn, int n, int h, int w, void* stream) {
+  return unetk::convt2x2_dgrad(dup, cout, wtd, da, cin, acc, B(bn), n, h, w, S(stream));
 }
 int unetk_convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw, int n, int h,
                          int w, void* stream) {
@@ -85,8 +95,8 @@ int unetk_bnrelu_pool(const void* y, const float* scale, const float* shift, voi
   return unetk::bnrelu_pool(y, scale, shift, a, pooled, idx, n, h, w, c, apply, S(stream));
 }
 int unetk_maxpool_bwd(const void* dpooled, const void* idx, void* da, int n, int h, int w, int c,
-                      int accumulate, void* stream) {
-  return unetk::maxpool_bwd(dpooled, idx, da, n, h, w, c, accumulate, S(stream));
+                      int accumulate, const unetk_bn_ctx* bn, void* stream) {
+  return unetk::maxpool_bwd(dpooled, idx, da, n, h, w, c, accumulate, B(bn), S(stream));
 }
 int unetk_bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
                         const float* mean, const float* invstd, float* sums, int64_t npix, int c,
@@ -105,8 +115,8 @@ int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, in
 }
 int unetk_head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da,
                    float* dw, float* db, int n, int h, int w_, int c, int n_out, int sigmoid,
-                   void* stream) {
-  return unetk::head_bwd(a, w, dout, out, da, dw, db, n, h, w_, c, n_out, sigmoid, S(stream));
+                   const unetk_bn_ctx* bn, void* stream) {
+  return unetk::head_bwd(a, w, dout, out, da, dw, db, n, h, w_, c, n_out, sigmoid, B(bn), S(stream));
 }
 size_t unetk_combined_loss_workspace_bytes(void) { return unetk::combined_loss_workspace_bytes(); }
 int unetk_combined_loss(const float* recon, const float* amap, const float* image,

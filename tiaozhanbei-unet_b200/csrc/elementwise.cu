@@ -163,15 +163,36 @@ bnrelu_pool_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
   }
 }
 
-// dA[argmax position] (+)= dP, other positions (+)= 0
+// dA[argmax position] (+)= dP, other positions (+)= 0.  When `bn_y` is given, dA is final after this
+// kernel and the first pass of the producing layer's BatchNorm+ReLU backward is fused in:
+// sums[0..C) += sum g, sums[C..2C) += sum g*xhat  (g = dA*[y*scale+shift > 0], xhat = (y-mean)*invstd).
 __global__ void __launch_bounds__(kEwThreads)
 maxpool_bwd_kernel(const uint4* __restrict__ dp, const uint2* __restrict__ idx, uint4* da, int N,
-                   int H, int W, int cgroups, int accumulate) {
+                   int H, int W, int cgroups, int accumulate, const uint4* __restrict__ bn_y,
+                   const float* __restrict__ scale, const float* __restrict__ shift,
+                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                   float* __restrict__ sums) {
+  extern __shared__ float sacc[];  // [2][C] when bn_y != nullptr
+  const int C = cgroups * 8;
+  const bool bn = bn_y != nullptr;
+  if (bn) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+  }
   const int Hp = H / 2, Wp = W / 2;
   const long nvec = static_cast<long>(N) * Hp * Wp * cgroups;
   const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
   const int cg = static_cast<int>(tid % cgroups);
+  float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+  if (bn) {
+    load8(scale + cg * 8, sc);
+    load8(shift + cg * 8, sh);
+    load8(mean + cg * 8, mu);
+    load8(invstd + cg * 8, is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  }
   for (long i = tid; i < nvec; i += nthreads) {
     long pp = i / cgroups;
     const int px = static_cast<int>(pp % Wp);
@@ -201,8 +222,29 @@ maxpool_bwd_kernel(const uint4* __restrict__ dp, const uint2* __restrict__ idx, 
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += (bi[j] == static_cast<uint32_t>(k)) ? g[j] : 0.f;
-      da[offs[k]] = pack8(v);
+      const uint4 packed = pack8(v);
+      da[offs[k]] = packed;
+      if (bn) {
+        float r[8], yv[8];
+        unpack8(packed, r);                       // the stored (bf16) gradient
+        unpack8(ldg_nc_v4(bn_y + offs[k]), yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = (fmaf(yv[j], sc[j], sh[j]) > 0.f) ? r[j] : 0.f;
+          s1[j] += gg;
+          s2[j] = fmaf(gg, (yv[j] - mu[j]) * is[j], s2[j]);
+        }
+      }
     }
+  }
+  if (bn) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sacc[cg * 8 + j], s1[j]);
+      atomicAdd(&sacc[C + cg * 8 + j], s2[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, sacc[i]);
   }
 }
 
@@ -385,13 +427,20 @@ int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, 
 }
 
 int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, int C, int accumulate,
-                cudaStream_t s) {
+                const BnReduceCtx* bn, cudaStream_t s) {
   UNETK_CHECK_ARG(dp && idx && da, "maxpool_bwd: null pointer");
   UNETK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "maxpool_bwd: H and W must be even");
   if (int e = check_c(C, "maxpool_bwd")) return e;
   const long nvec = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
-  maxpool_bwd_kernel<<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(static_cast<const uint4*>(dp), static_cast<const uint2*>(idx),
-                                                                 static_cast<uint4*>(da), N, H, W, C / 8, accumulate);
+  const bool fuse = bn != nullptr && bn->y != nullptr;
+  UNETK_CHECK_ARG(!fuse || (bn->scale && bn->shift && bn->mean && bn->invstd && bn->sums), "maxpool_bwd: incomplete BatchNorm context");
+  int grid = ew_grid(nvec, C / 8);
+  const int cap = num_sms() * 4;
+  if (fuse && grid > cap && (static_cast<long>(cap) * kEwThreads) % (C / 8) == 0) grid = cap;   // fewer global atomics
+  maxpool_bwd_kernel<<<grid, kEwThreads, fuse ? 2 * C * sizeof(float) : 0, s>>>(
+      static_cast<const uint4*>(dp), static_cast<const uint2*>(idx), static_cast<uint4*>(da), N, H, W, C / 8, accumulate,
+      fuse ? static_cast<const uint4*>(bn->y) : nullptr, fuse ? bn->scale : nullptr, fuse ? bn->shift : nullptr,
+      fuse ? bn->mean : nullptr, fuse ? bn->invstd : nullptr, fuse ? bn->sums : nullptr);
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -402,9 +451,9 @@ int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float
   UNETK_CHECK_ARG(da && y && scale && shift && mean && invstd && sums, "bn_bwd_reduce: null pointer");
   if (int e = check_c(C, "bn_bwd_reduce")) return e;
   const long nvec = npix * (C / 8);
-  int grid = ew_grid(nvec, C / 8);
-  const int cap = num_sms() * 4;
-  if (grid > cap) grid = ((cap * kEwThreads) % (C / 8) == 0) ? cap : grid;
+  // full grid (8 blocks per SM): at 4 per SM the two read streams ran at 3.9 TB/s, latency bound; an
+  // unrolled variant with four loads in flight per thread was slower still (3.2 TB/s)
+  const int grid = ew_grid(nvec, C / 8);
   bn_bwd_reduce_kernel<<<grid, kEwThreads, 2 * C * sizeof(float), s>>>(static_cast<const uint4*>(da), static_cast<const uint4*>(y),
                                                                       scale, shift, mean, invstd, sums, nvec, C / 8);
   UNETK_CUDA(cudaGetLastError());

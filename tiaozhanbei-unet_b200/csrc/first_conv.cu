@@ -176,6 +176,62 @@ first_conv_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ d
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Tensor-core route for the weight gradient: the image is re-laid-out as NHWC bf16 with the channels
+// zero-padded to 64 (only the first 16-byte group of every 128-byte pixel row is ever written; the
+// caller zeroes the buffer once) and the gradient is the ordinary conv3x3 weight gradient of a
+// 64 -> 64 layer (nine-tap tcgen05 kernel, wgrad.cu MODE 2) followed by a 64*Cin*9-element gather into
+// OIHW.  0.36 ms -> ~0.1 ms at 16 x 256 x 256 (the CUDA-core kernel above is LDS bound).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+image_to_nhwc64_kernel(const float* __restrict__ x, uint4* __restrict__ x64, int Cin, long hw, long total) {
+  for (long p = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
+       p += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long n = p / hw, r = p - n * hw;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < Cin) v[c] = __ldg(x + (n * Cin + c) * hw + r);
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    x64[p * 8] = u;
+  }
+}
+
+// scratch [64 co][9 taps][64 ci] -> dw OIHW [64][Cin][3][3]
+__global__ void first_conv_gather_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kFcCout * Cin * 9) return;
+  const int tap = i % 9, ci = (i / 9) % Cin, co = i / (9 * Cin);
+  dw[i] = scratch[(co * 9 + tap) * 64 + ci];
+}
+
+int image_to_nhwc64(const float* x, void* x64, int N, int Cin, int H, int W, cudaStream_t s) {
+  UNETK_CHECK_ARG(x && x64, "image_to_nhwc64: null pointer");
+  UNETK_CHECK_ARG(Cin >= 1 && Cin <= 8, "image_to_nhwc64: 1..8 input channels supported (got %d)", Cin);
+  const long hw = static_cast<long>(H) * W, total = hw * N;
+  long blocks = (total + 255) / 256;
+  const long cap = static_cast<long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  image_to_nhwc64_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(x, static_cast<uint4*>(x64), Cin, hw, total);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int first_conv_wgrad_tc(const void* x64, const void* dy, float* scratch, float* dw, int N, int Cin, int H, int W,
+                        int cout, cudaStream_t s) {
+  UNETK_CHECK_ARG(x64 && dy && scratch && dw, "first_conv_wgrad_tc: null pointer");
+  UNETK_CHECK_ARG(Cin >= 1 && Cin <= 8, "first_conv_wgrad_tc: 1..8 input channels supported (got %d)", Cin);
+  UNETK_CHECK_ARG(cout == kFcCout, "first_conv_wgrad_tc: 64 output channels required (got %d)", cout);
+  UNETK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * kFcCout * 9 * 64, s));
+  if (int e = conv3x3_wgrad(dy, x64, 64, nullptr, 0, scratch, N, H, W, cout, s)) return e;
+  const int n = kFcCout * Cin * 9;
+  first_conv_gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(scratch, dw, Cin);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
 int first_conv_fwd(const float* x, const float* w, void* y, float* stats, int N, int Cin, int H, int W,
                    int cout, cudaStream_t s) {
   UNETK_CHECK_ARG(x && w && y, "first_conv_fwd: null pointer");

@@ -58,21 +58,41 @@ head_fwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const 
 // 8 lanes cover one pixel (16-byte vectors of 8 channels), a warp covers 4 pixels per step and every
 // thread keeps four steps in flight; weights and the dW partial sums live in registers.
 // ----------------------------------------------------------------------------------------------
+// Optional fusion (bn_y != nullptr): first pass of the BatchNorm+ReLU backward of the layer that
+// produced `a` (y = its raw conv output): sums[0..64) += sum g, sums[64..128) += sum g*xhat.
 template <int NOUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
                 const float* __restrict__ dout, const float* __restrict__ out,
                 uint4* __restrict__ da, float* __restrict__ dw, float* __restrict__ db,
-                long npix_total, long hw, int sigmoid) {
+                long npix_total, long hw, int sigmoid, const uint4* __restrict__ bn_y,
+                const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
+                float* __restrict__ bn_sums) {
   __shared__ float sdw[NOUT * kHeadC];
   __shared__ float sdb[NOUT];
+  __shared__ float sbn[2 * kHeadC];
   for (int i = threadIdx.x; i < NOUT * kHeadC; i += blockDim.x) sdw[i] = 0.f;
   if (threadIdx.x < NOUT) sdb[threadIdx.x] = 0.f;
+  if (threadIdx.x < 2 * kHeadC) sbn[threadIdx.x] = 0.f;
   __syncthreads();
+  const bool bn = bn_y != nullptr;
   const int lane = threadIdx.x & 31;
   const int cg = lane & 7;          // channel group: channels 8*cg .. 8*cg+7
   const int pl = lane >> 3;         // pixel slot inside the warp step
   float wr[NOUT][8], gw[NOUT][8], gb[NOUT];
+  // BatchNorm fusion: a = relu(y*scale + shift) is already in registers, and where a > 0
+  //   xhat = (y - mean)*invstd = (a - shift)/scale*invstd - mean*invstd = A*a + B,
+  // so the reduction needs only s1 = sum g and s2 = sum g*a (g = dA*[a > 0]); A, B are applied once per
+  // block.  A channel whose scale is exactly 0 (gamma == 0) cannot be inverted: it takes the direct route
+  // through y (never in practice; kept for exactness).
+  float s1[8], s2[8];
+  bool degenerate = false;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s1[k] = s2[k] = 0.f;
+    if (bn && bn_scale[cg * 8 + k] == 0.f) degenerate = true;
+  }
 #pragma unroll
   for (int j = 0; j < NOUT; ++j) {
     gb[j] = 0.f;
@@ -84,7 +104,7 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
   }
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
-  constexpr int U = 4;              // steps in flight per thread
+  constexpr int U = (NOUT >= 3) ? 2 : 4;   // steps in flight per thread (two blocks per SM)
   for (long base = warp * (4 * U); base < npix_total; base += nwarps * (4 * U)) {
     uint4 av[U];
     float dl[U][NOUT];
@@ -128,6 +148,29 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
         o4.x = pack_bf16x2(g[0], g[1]); o4.y = pack_bf16x2(g[2], g[3]);
         o4.z = pack_bf16x2(g[4], g[5]); o4.w = pack_bf16x2(g[6], g[7]);
         da[(base + u * 4 + pl) * 8 + cg] = o4;
+        if (bn) {
+          const float2 r0 = unpack_bf16x2(o4.x), r1 = unpack_bf16x2(o4.y), r2 = unpack_bf16x2(o4.z), r3 = unpack_bf16x2(o4.w);
+          const float rr[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};   // the stored (bf16) gradient
+          if (!degenerate) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float gg = (x[k] > 0.f) ? rr[k] : 0.f;
+              s1[k] += gg;
+              s2[k] = fmaf(gg, x[k], s2[k]);
+            }
+          } else {
+            const uint4 yv4 = ldg_nc_v4(bn_y + (base + u * 4 + pl) * 8 + cg);
+            const float2 y0 = unpack_bf16x2(yv4.x), y1 = unpack_bf16x2(yv4.y), y2 = unpack_bf16x2(yv4.z), y3 = unpack_bf16x2(yv4.w);
+            const float yy[8] = {y0.x, y0.y, y1.x, y1.y, y2.x, y2.y, y3.x, y3.y};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int c = cg * 8 + k;
+              const float gg = (fmaf(yy[k], bn_scale[c], bn_shift[c]) > 0.f) ? rr[k] : 0.f;
+              s1[k] += gg;
+              s2[k] = fmaf(gg, (yy[k] - bn_mean[c]) * bn_invstd[c], s2[k]);
+            }
+          }
+        }
       }
     }
   }
@@ -146,9 +189,29 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
     bsum += __shfl_xor_sync(0xffffffffu, bsum, 16);
     if (lane == 0) atomicAdd(&sdb[j], bsum);
   }
+  if (bn) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v1 = s1[k], v2 = s2[k];
+      if (!degenerate) {          // sum g*a -> sum g*xhat
+        const int c = cg * 8 + k;
+        const float inv = bn_invstd[c] / bn_scale[c];
+        v2 = inv * (v2 - bn_shift[c] * v1) - bn_mean[c] * bn_invstd[c] * v1;
+      }
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 8);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, 8);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, 16);
+      if (pl == 0) {
+        atomicAdd(&sbn[cg * 8 + k], v1);
+        atomicAdd(&sbn[kHeadC + cg * 8 + k], v2);
+      }
+    }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < NOUT * kHeadC; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
   if (threadIdx.x < NOUT) atomicAdd(db + threadIdx.x, sdb[threadIdx.x]);
+  if (bn && threadIdx.x < 2 * kHeadC) atomicAdd(bn_sums + threadIdx.x, sbn[threadIdx.x]);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -470,7 +533,7 @@ int head_fwd(const void* a, const float* w, const float* b, float* out, int N, i
 }
 
 int head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da, float* dw,
-             float* db, int N, int H, int W, int C, int n_out, int sigmoid, cudaStream_t s) {
+             float* db, int N, int H, int W, int C, int n_out, int sigmoid, const BnReduceCtx* bn, cudaStream_t s) {
   UNETK_CHECK_ARG(a && w && dout && da && dw && db, "head_bwd: null pointer");
   UNETK_CHECK_ARG(!sigmoid || out, "head_bwd: sigmoid backward needs the forward output");
   UNETK_CHECK_ARG(C == kHeadC, "head_bwd: input channels must be 64 (got %d)", C);
@@ -479,15 +542,21 @@ int head_bwd(const void* a, const float* w, const float* dout, const float* out,
   UNETK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * n_out * kHeadC, s));
   UNETK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * n_out, s));
   int blocks = ew_blocks((np + 127) / 128, 1);
-  const int cap = num_sms() * 4;
+  const int cap = num_sms() * 2;     // two resident blocks per SM, grid-stride
   if (blocks > cap) blocks = cap;
   const uint4* a4 = static_cast<const uint4*>(a);
   uint4* da4 = static_cast<uint4*>(da);
+  const bool fuse = bn != nullptr && bn->y != nullptr;
+  UNETK_CHECK_ARG(!fuse || (bn->scale && bn->shift && bn->mean && bn->invstd && bn->sums), "head_bwd: incomplete BatchNorm context");
+  const uint4* by = fuse ? static_cast<const uint4*>(bn->y) : nullptr;
+  const float* b1 = fuse ? bn->scale : nullptr; const float* b2 = fuse ? bn->shift : nullptr;
+  const float* b3 = fuse ? bn->mean : nullptr;  const float* b4 = fuse ? bn->invstd : nullptr;
+  float* b5 = fuse ? bn->sums : nullptr;
   switch (n_out) {
-    case 1: head_bwd_kernel<1><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid); break;
-    case 2: head_bwd_kernel<2><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid); break;
-    case 3: head_bwd_kernel<3><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid); break;
-    default: head_bwd_kernel<4><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid); break;
+    case 1: head_bwd_kernel<1><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5); break;
+    case 2: head_bwd_kernel<2><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5); break;
+    case 3: head_bwd_kernel<3><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5); break;
+    default: head_bwd_kernel<4><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5); break;
   }
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;

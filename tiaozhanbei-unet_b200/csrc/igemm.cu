@@ -54,12 +54,24 @@ struct IgemmParams {
   int relu;
   const float* bias;    // epi_mode 1: [cout_t]
   int cout_t;           // epi_mode 1: channels of the up-sampled tensor
+  // Fused first pass of the BatchNorm+ReLU backward of the layer that PRODUCED this gradient's
+  // activation (epi_mode 0, single destination): with y that layer's raw conv output,
+  //   g = d * [y*scale + shift > 0],  stats += sum g,  stats_sq += sum g * (y - mean) * invstd
+  const __nv_bfloat16* bn_y;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_invstd;
 };
 
-constexpr int kIgemmThreads = 192;                 // warps: 0 TMA, 1 MMA, 2..5 epilogue (one per TMEM lane quarter)
+// warps: 0 TMA, 1 MMA, 2.. epilogue.  One epilogue warp per TMEM lane quarter: two per quarter (8 warps,
+// 320 threads, 168-register cap) measured SLOWER on the K=576 layers (fwd 0.107 -> 0.113 ms, dgrad
+// 0.086 -> 0.099 ms at 64 ch x 256^2 x 16), so the epilogue is not what limits them.
+constexpr int kEpiWarps = 4;
+constexpr int kEpiPerQuarter = kEpiWarps / 4;
+constexpr int kIgemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kRegionH = 16;                  // CTA tile: (8*SUBS) x 16 output pixels
 constexpr int kSubW = 8;                      // sub-tile: 8 wide x 16 tall = 128 GEMM rows
-constexpr int kNumABufs = 2;
 
 // BN   : columns of D per tile (per CTA pair when CTAS == 2)
 // SUBS : 8x16 sub-tiles per CTA (1 or 2), each with its own TMEM accumulator
@@ -75,6 +87,8 @@ struct IgemmCfg {
   static constexpr int kBBytes = kBNLocal * 128;
   static constexpr int kABufBytes = (SUBS == 2) ? 41 * 1024 : 23 * 1024;   // >= (8*SUBS+2)*18*128, 1 KB multiple
   static constexpr int kBudget = 196 * 1024;
+  // halo buffers in flight (a third buffer for the narrow BN = 64 tiles was measured: no change)
+  static constexpr int kNumABufs = 2;
   static constexpr int kFit = (kBudget - kNumABufs * kABufBytes) / kBBytes;
   static constexpr int kBStages = kFit > 16 ? 16 : kFit;
   static constexpr int kTmemCols = 2 * SUBS * BN;    // 2 accumulator stages x SUBS sub-tiles
@@ -83,13 +97,16 @@ struct IgemmCfg {
   static_assert(kTmemCols <= 512 && kBStages >= 4, "bad igemm configuration");
 };
 
-template <int BN, int SUBS, int CTAS>
+// BNRED: the epilogue also runs the first pass of the BatchNorm+ReLU backward of the layer that produced
+//        the activation whose gradient this kernel completes (IgemmParams::bn_*), see unetk_bn_ctx.
+template <int BN, int SUBS, int CTAS, bool BNRED>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
   using Cfg = IgemmCfg<BN, SUBS, CTAS>;
   constexpr int kBStages = Cfg::kBStages;
   constexpr int kABufBytes = Cfg::kABufBytes;
+  constexpr int kNumABufs = Cfg::kNumABufs;
   constexpr int kRegionW = kSubW * SUBS;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment.
@@ -124,7 +141,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4 * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tempty[i], kEpiWarps * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
@@ -136,8 +153,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   if (p.scale != nullptr) {          // [2][Ntot]: scale, shift
     for (int i = threadIdx.x; i < 2 * p.Ntot; i += blockDim.x)
       colbuf[i] = (i < p.Ntot) ? p.scale[i] : p.shift[i - p.Ntot];
-  } else if (p.stats != nullptr) {   // [4 epilogue warps][2][BN]: sum, sum of squares of the current column block
+  } else if (p.stats != nullptr) {   // [4 lane quarters][2][BN]: sum, sum of squares of the current column block
     for (int i = threadIdx.x; i < 8 * BN; i += blockDim.x) colbuf[i] = 0.f;
+    if (BNRED) {                     // + per-column BatchNorm constants {scale, shift, mean, invstd}
+      float4* bnc = reinterpret_cast<float4*>(colbuf + 8 * BN);
+      for (int i = threadIdx.x; i < p.Ntot; i += blockDim.x)
+        bnc[i] = make_float4(p.bn_scale[i], p.bn_shift[i], p.bn_mean[i], p.bn_invstd[i]);
+    }
   }
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // barrier inits visible to the peer's TMA / arrives
@@ -269,14 +291,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..) =====================
+    // A warp may only touch the TMEM lane quarter (warp % 4); the warps of a quarter interleave the
+    // 32-column chunks of the tile.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    float* wbuf = colbuf + (warp - 2) * 2 * BN;       // this warp's private [2][BN] statistics slot
+    float* wbuf = colbuf + q * 2 * BN;       // this lane quarter's [2][BN] statistics slot (chunks are disjoint per warp)
     int cur_nb = -1;
     // add this warp's partial column sums of column block `nbk` to the global statistics
     auto flush_stats = [&](int nbk) {
-      for (int i = lane; i < BN; i += 32) {
+      for (int c = half; c < BN / 32; c += kEpiPerQuarter) {
+        const int i = c * 32 + lane;
         const int col = nbk * BN + i;
         if (col >= p.stats_from) {
           const float v = wbuf[i];
@@ -310,8 +336,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         cur_nb = nb;
       }
       const int col0 = nb * BN;
-      mbar_wait(&tfull[acc], accph);
-      tc_fence_after();
       int xs[SUBS];
       bool valids[SUBS];
 #pragma unroll
@@ -319,18 +343,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
         xs[sub] = rx * kRegionW + sub * kSubW + sx;
         valids[sub] = live && (xs[sub] < p.W) && (y < p.H);
       }
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
       if (live) {
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = half; ch < BN / 32; ch += kEpiPerQuarter) {
           const int col = col0 + ch * 32;
+          // BNRED: fetch the producing layer's raw conv output under the TMEM load latency
+          uint4 yv[BNRED ? SUBS : 1][4];
+          if constexpr (BNRED) {
+#pragma unroll
+            for (int sub = 0; sub < SUBS; ++sub) {
+              const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + xs[sub];
+              const uint4* src = reinterpret_cast<const uint4*>(p.bn_y + pix * p.ldc1 + col);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) yv[sub][g] = valids[sub] ? ldg_nc_v4(src + g) : make_uint4(0, 0, 0, 0);
+            }
+          }
           float v2[SUBS][32];
 #pragma unroll
           for (int sub = 0; sub < SUBS; ++sub)
             tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (SUBS * BN) + sub * BN + ch * 32, v2[sub]);
           tmem_ld_wait();
-          if (p.stats != nullptr && col >= p.stats_from) {
+          if (!BNRED && p.stats != nullptr && col >= p.stats_from) {
             // the sub-tiles share the columns: add them first, then ONE transposing butterfly each
-            // for the sum and the sum of squares; per-warp smem slots (no shared-memory atomics)
+            // for the sum and the sum of squares; per-quarter smem slots (no shared-memory atomics)
             float s[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -355,23 +392,34 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               wbuf[BN + ch * 32 + lane] += cs2;
             }
           }
+          float gx[32];                  // BNRED: sum over the sub-tiles of g * xhat (dead otherwise)
+          if (BNRED) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gx[j] = 0.f;
+          }
 #pragma unroll
           for (int sub = 0; sub < SUBS; ++sub) {
             float (&v)[32] = v2[sub];
-            if (p.scale != nullptr) {
+            if (!BNRED && p.scale != nullptr) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 float a = fmaf(v[j], colbuf[col + j], colbuf[p.Ntot + col + j]);
                 v[j] = p.relu ? fmaxf(a, 0.f) : a;
               }
             }
-            if (!valids[sub]) continue;
+            if (!valids[sub]) {
+              if (BNRED) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              }
+              continue;
+            }
             const int x = xs[sub];
             __nv_bfloat16* dst;
             bool accum;
-            if (p.epi_mode == 0) {
+            if (BNRED || p.epi_mode == 0) {
               const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
-              if (col < p.split) {
+              if (BNRED || col < p.split) {
                 dst = p.out1 + pix * p.ldc1 + col;
                 accum = p.acc1 != 0;
               } else {
@@ -409,7 +457,34 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               w.z = pack_bf16x2(f[4], f[5]);
               w.w = pack_bf16x2(f[6], f[7]);
               d4[g] = w;
+              if constexpr (BNRED) {
+                // g = the STORED (accumulated, bf16-rounded) gradient masked by the ReLU of the producing
+                // layer; keep g in v[] and g * xhat in gx[] for the column reduction below
+                const uint4 yq = yv[sub][g];
+                const float2 y0 = unpack_bf16x2(yq.x), y1 = unpack_bf16x2(yq.y), y2 = unpack_bf16x2(yq.z), y3 = unpack_bf16x2(yq.w);
+                const float2 r0 = unpack_bf16x2(w.x), r1 = unpack_bf16x2(w.y), r2 = unpack_bf16x2(w.z), r3 = unpack_bf16x2(w.w);
+                const float yy[8] = {y0.x, y0.y, y1.x, y1.y, y2.x, y2.y, y3.x, y3.y};
+                const float rr[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
+                const float4* bnc = reinterpret_cast<const float4*>(colbuf + 8 * BN) + col + g * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 c = bnc[j];                  // {scale, shift, mean, invstd}
+                  const float gg = (fmaf(yy[j], c.x, c.y) > 0.f) ? rr[j] : 0.f;
+                  v[g * 8 + j] = gg;
+                  gx[g * 8 + j] = fmaf(gg, (yy[j] - c.z) * c.w, gx[g * 8 + j]);
+                }
+              }
             }
+          }
+          if constexpr (BNRED) {
+            if (SUBS == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v2[0][j] += v2[SUBS - 1][j];
+            }
+            const float cs = warp_colsum32(v2[0]);
+            wbuf[ch * 32 + lane] += cs;
+            const float cs2 = warp_colsum32(gx);
+            wbuf[BN + ch * 32 + lane] += cs2;
           }
         }
       }
@@ -502,12 +577,12 @@ struct IgemmLaunch {
   IgemmParams p;
 };
 
-template <int BN, int SUBS, int CTAS>
+template <int BN, int SUBS, int CTAS, bool BNRED>
 static int launch_cfg(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB, const IgemmParams& p,
                       int grid, size_t colbytes, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, SUBS, CTAS>;
   const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;
-  auto kern = igemm_kernel<BN, SUBS, CTAS>;
+  auto kern = igemm_kernel<BN, SUBS, CTAS, BNRED>;
   UNETK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -571,12 +646,16 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
   const long total_tiles = ((regions + ctas - 1) / ctas) * p.n_blocks;     // per CTA (pair)
   const int max_units = num_sms() / ctas;
   const int grid = static_cast<int>(total_tiles < max_units ? total_tiles : max_units) * ctas;
-  const size_t colbytes = (p.stats != nullptr ? static_cast<size_t>(8) * bn : (use_colbuf ? static_cast<size_t>(2) * p.Ntot : 0)) * sizeof(float);
-  if (bn == 256) return launch_cfg<256, 1, 2>(tmA1, tmA2, tmB, p, grid, colbytes, stream);
-  if (ctas == 2) return bn == 128 ? launch_cfg<128, 2, 2>(tmA1, tmA2, tmB, p, grid, colbytes, stream)
-                                  : launch_cfg<64, 2, 2>(tmA1, tmA2, tmB, p, grid, colbytes, stream);
-  return bn == 128 ? launch_cfg<128, 2, 1>(tmA1, tmA2, tmB, p, grid, colbytes, stream)
-                   : launch_cfg<64, 2, 1>(tmA1, tmA2, tmB, p, grid, colbytes, stream);
+  const size_t colbytes = (p.stats != nullptr ? static_cast<size_t>(8) * bn + (p.bn_y != nullptr ? 4 * static_cast<size_t>(p.Ntot) : 0)
+                                              : (use_colbuf ? static_cast<size_t>(2) * p.Ntot : 0)) * sizeof(float);
+  const bool red = p.bn_y != nullptr;
+#define UNETK_IGEMM_LAUNCH(BN_, SUBS_, CTAS_)                                                             \
+  (red ? launch_cfg<BN_, SUBS_, CTAS_, true>(tmA1, tmA2, tmB, p, grid, colbytes, stream)                 \
+       : launch_cfg<BN_, SUBS_, CTAS_, false>(tmA1, tmA2, tmB, p, grid, colbytes, stream))
+  if (bn == 256) return UNETK_IGEMM_LAUNCH(256, 1, 2);
+  if (ctas == 2) return bn == 128 ? UNETK_IGEMM_LAUNCH(128, 2, 2) : UNETK_IGEMM_LAUNCH(64, 2, 2);
+  return bn == 128 ? UNETK_IGEMM_LAUNCH(128, 2, 1) : UNETK_IGEMM_LAUNCH(64, 2, 1);
+#undef UNETK_IGEMM_LAUNCH
 }
 
 int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
@@ -594,8 +673,18 @@ int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* 
   return launch_igemm(L, stream);
 }
 
+static int apply_bn_ctx(IgemmParams& p, const BnReduceCtx* bn, const char* who) {
+  if (bn == nullptr || bn->y == nullptr) return UNETK_OK;
+  UNETK_CHECK_ARG(bn->scale && bn->shift && bn->mean && bn->invstd && bn->sums, "%s: incomplete BatchNorm context", who);
+  UNETK_CHECK_ARG(p.stats == nullptr && p.split == p.Ntot, "%s: BatchNorm reduction needs a single destination and no bias sums", who);
+  p.bn_y = static_cast<const __nv_bfloat16*>(bn->y);
+  p.bn_scale = bn->scale; p.bn_shift = bn->shift; p.bn_mean = bn->mean; p.bn_invstd = bn->invstd;
+  p.stats = bn->sums; p.stats_sq = bn->sums + p.Ntot; p.stats_from = 0;
+  return UNETK_OK;
+}
+
 int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1, int acc1, void* dx2,
-                  int c2, int acc2, float* stats, int n, int h, int w, cudaStream_t stream) {
+                  int c2, int acc2, float* stats, const BnReduceCtx* bn, int n, int h, int w, cudaStream_t stream) {
   UNETK_CHECK_ARG(dy && wdpk && dx1, "conv3x3_dgrad: null pointer");
   UNETK_CHECK_ARG(c2 == 0 || dx2 != nullptr, "conv3x3_dgrad: second destination missing");
   UNETK_CHECK_ARG(stats == nullptr || c2 > 0, "conv3x3_dgrad: stats requested without a second destination");
@@ -607,6 +696,7 @@ int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1,
   p.ldc1 = c1; p.ldc2 = c2; p.acc1 = acc1; p.acc2 = acc2;
   // bias gradient of the ConvTranspose2d that produced the second concat source: sum over pixels of dx2
   p.stats = stats; p.stats_sq = nullptr; p.stats_from = c1;
+  if (int e = apply_bn_ctx(p, bn, "conv3x3_dgrad")) return e;
   return launch_igemm(L, stream);
 }
 
@@ -623,14 +713,15 @@ int convt2x2_fwd(const void* a, int cin, const void* wpk, const float* bias, voi
   return launch_igemm(L, stream);
 }
 
-int convt2x2_dgrad(const void* dup, int cout, const void* wdpk, void* da, int cin, int acc, int n,
-                   int h, int w, cudaStream_t stream) {
+int convt2x2_dgrad(const void* dup, int cout, const void* wdpk, void* da, int cin, int acc,
+                   const BnReduceCtx* bn, int n, int h, int w, cudaStream_t stream) {
   UNETK_CHECK_ARG(dup && wdpk && da, "convt2x2_dgrad: null pointer");
   IgemmLaunch L{};
   L.a1 = dup; L.c1 = cout; L.b = wdpk;
   IgemmParams& p = L.p;
   p.n_img = 1; p.H = n * h; p.W = w; p.Ntot = cin; p.num_taps = 4; p.a_mode = 1; p.epi_mode = 0;
   p.split = cin; p.out1 = static_cast<__nv_bfloat16*>(da); p.ldc1 = cin; p.acc1 = acc;
+  if (int e = apply_bn_ctx(p, bn, "convt2x2_dgrad")) return e;
   return launch_igemm(L, stream);
 }
 

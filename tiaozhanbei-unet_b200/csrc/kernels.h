@@ -6,16 +6,28 @@
 
 namespace unetk {
 
+// Optional fused first pass of a BatchNorm+ReLU backward (same layout as unetk_bn_ctx in unetk.h):
+// the kernel that finishes a gradient dA also accumulates sums[0..C) += sum g, sums[C..2C) += sum g*xhat
+// with g = dA * [y*scale+shift > 0], xhat = (y-mean)*invstd, for the layer whose raw output is y.
+struct BnReduceCtx {
+  const void* y;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  float* sums;
+};
+
 // igemm.cu — K-major implicit GEMMs (tcgen05)
 int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
                 float* stats, const float* scale, const float* shift, int relu, int n, int h, int w,
                 int cout, cudaStream_t stream);
 int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1, int acc1, void* dx2,
-                  int c2, int acc2, float* stats, int n, int h, int w, cudaStream_t stream);
+                  int c2, int acc2, float* stats, const BnReduceCtx* bn, int n, int h, int w, cudaStream_t stream);
 int convt2x2_fwd(const void* a, int cin, const void* wpk, const float* bias, void* up, int n, int h,
                  int w, int cout, cudaStream_t stream);
-int convt2x2_dgrad(const void* dup, int cout, const void* wdpk, void* da, int cin, int acc, int n,
-                   int h, int w, cudaStream_t stream);
+int convt2x2_dgrad(const void* dup, int cout, const void* wdpk, void* da, int cin, int acc,
+                   const BnReduceCtx* bn, int n, int h, int w, cudaStream_t stream);
 
 // wgrad.cu — MN-major split-K GEMMs (tcgen05)
 int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2, float* dw,
@@ -26,6 +38,9 @@ int convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw,
 // first_conv.cu
 int first_conv_fwd(const float* x, const float* w, void* y, float* stats, int N, int Cin, int H, int W,
                    int cout, cudaStream_t s);
+int image_to_nhwc64(const float* x, void* x64, int N, int Cin, int H, int W, cudaStream_t s);
+int first_conv_wgrad_tc(const void* x64, const void* dy, float* scratch, float* dw, int N, int Cin, int H, int W,
+                        int cout, cudaStream_t s);
 int first_conv_wgrad(const float* x, const void* dy, float* dw, int N, int Cin, int H, int W, int cout,
                      cudaStream_t s);
 
@@ -40,7 +55,7 @@ int bnrelu_apply(const void* y, const float* scale, const float* shift, void* a,
 int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
                 void* idx, int N, int H, int W, int C, int apply, cudaStream_t s);
 int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, int C, int accumulate,
-                cudaStream_t s);
+                const BnReduceCtx* bn, cudaStream_t s);
 int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
                   const float* mean, const float* invstd, float* sums, long npix, int C,
                   cudaStream_t s);
@@ -54,7 +69,7 @@ int nhwc_to_nchw(const void* in, float* out, int N, int C, int H, int W, cudaStr
 int head_fwd(const void* a, const float* w, const float* b, float* out, int N, int H, int W, int C,
              int n_out, int sigmoid, cudaStream_t s);
 int head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da, float* dw,
-             float* db, int N, int H, int W, int C, int n_out, int sigmoid, cudaStream_t s);
+             float* db, int N, int H, int W, int C, int n_out, int sigmoid, const BnReduceCtx* bn, cudaStream_t s);
 size_t combined_loss_workspace_bytes();
 int combined_loss(const float* recon, const float* amap, const float* image, const float* mask,
                   float* d_recon, float* d_amap, float* out3, void* work, size_t work_bytes,

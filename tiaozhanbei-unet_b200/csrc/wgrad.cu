@@ -15,6 +15,10 @@
 // from ONE 10x8 halo box per 64-channel chunk (80 rows x 128 B): a dx shift is a descriptor start
 // offset of dx*128 B, 8-pixel patch rows are the 8-row K groups with SBO = 10*128 B (the 128B
 // swizzle is address based, profiles/umma_probe_r01.txt).  X traffic drops 2.4x.
+// MODE 2 (narrow layers, Cin*Cout <= 64*128, where the tap-row kernel is L2-bandwidth bound because
+// three CTAs re-read the same pixels): one CTA owns ALL NINE taps of a 64 ci x 64 co block -- M = two
+// taps x 64 ci per instruction (five tap pairs, the last half empty), X from ONE 10x10 halo box per
+// K tile.  The second tap of a pair is an LBO away (128 B for a dx step, 1024 B from tap (0,2) to (1,0)).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -38,6 +42,7 @@ constexpr int kWgThreads = 192;
 constexpr int kBoxBytes = 64 * 128;   // 64 pixels x 64 bf16
 constexpr int kHaloBytes = 80 * 128;  // 10 x 8 pixels x 64 bf16 (conv3x3 X operand)
 constexpr int kHaloPitch = 10 * 128;  // bytes between patch rows inside the halo box
+constexpr int kHalo9Bytes = 100 * 128;  // 10 x 10 pixels x 64 bf16 (MODE 2)
 
 // CTAS == 2 (conv3x3, BN == 128): cta_group::2 pairs.  The two CTAs own different (tap row, ci tile)
 // units (M = 256 per instruction) and each stages only 64 of the 128 dY channels: per CTA an MMA
@@ -45,12 +50,12 @@ constexpr int kHaloPitch = 10 * 128;  // bytes between patch rows inside the hal
 template <int MODE, int BN, bool M64, int CTAS = 1>
 struct WgCfg {
   // per stage: A (X operand) and B (dY / dUp operand) regions
-  static constexpr int kALoads = (MODE == 0) ? (M64 ? 1 : 2) : 2;
-  static constexpr int kABoxBytes = (MODE == 0) ? kHaloBytes : kBoxBytes;
-  // M64: the second tap of the last pair reads 3 rows past the box; keep that inside the stage
-  static constexpr int kABytes = kALoads * kABoxBytes + ((MODE == 0 && M64) ? 1024 : 0);
-  static constexpr int kBBoxes = (MODE == 0) ? (BN / 64 / CTAS) : 4 * (BN / 64);   // per CTA
-  static constexpr int kMmas = (MODE == 0) ? (M64 ? 2 : 3) : 4;
+  static constexpr int kALoads = (MODE == 2) ? 1 : (MODE == 0) ? (M64 ? 1 : 2) : 2;
+  static constexpr int kABoxBytes = (MODE == 2) ? kHalo9Bytes : (MODE == 0) ? kHaloBytes : kBoxBytes;
+  // M64 / MODE 2: the second tap of the last pair reads a few rows past the box; keep that inside the stage
+  static constexpr int kABytes = (MODE == 2) ? 13 * 1024 : kALoads * kABoxBytes + ((MODE == 0 && M64) ? 1024 : 0);
+  static constexpr int kBBoxes = (MODE == 2) ? 1 : (MODE == 0) ? (BN / 64 / CTAS) : 4 * (BN / 64);   // per CTA
+  static constexpr int kMmas = (MODE == 2) ? 5 : (MODE == 0) ? (M64 ? 2 : 3) : 4;
   static constexpr int kStageBytes = kABytes + kBBoxes * kBoxBytes;
   static constexpr int kMaxFit = (210 * 1024) / kStageBytes;
   static constexpr int kStages = kMaxFit > 10 ? 10 : (kMaxFit < 2 ? 2 : kMaxFit);
@@ -64,6 +69,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
              const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
   using Cfg = WgCfg<MODE, BN, M64, CTAS>;
   static_assert(CTAS == 1 || (MODE == 0 && BN == 128), "CTA pairs: conv3x3 with 128-wide co tiles only");
+  static_assert(MODE != 2 || (BN == 64 && CTAS == 1), "nine-tap mode: 64 x 64 blocks, single CTA");
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -83,7 +89,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
   const int cot = bx % p.co_tiles;
   bx /= p.co_tiles;
   const int unit = bx * CTAS + static_cast<int>(rank);
-  const int n_units = (MODE == 0 ? 3 : 1) * p.ci_tiles;
+  const int n_units = (MODE == 0 ? 3 : 1) * p.ci_tiles;   // MODE 2: ci_tiles counts 64-channel chunks
   const bool live = unit < n_units;          // odd unit count: the last pair has one idle CTA
   const int cit = unit % p.ci_tiles;
   const int r = unit / p.ci_tiles;  // tap row (MODE 0), 0 otherwise
@@ -129,7 +135,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
         if (rank == 0) mbar_expect_tx(&full[stage], (Cfg::kALoads * Cfg::kABoxBytes + Cfg::kBBoxes * kBoxBytes) * CTAS);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
-        if (MODE == 0) {
+        if (MODE == 2) {
+          const CUtensorMap* mp = (cit < p.c1_chunks) ? &tmX1 : &tmX2;
+          const int cc = ((cit < p.c1_chunks) ? cit : cit - p.c1_chunks) * 64;
+          tma_load_5d(sa, mp, &full[stage], cc, x0 - 1, y0 - 1, n0, 0);      // 10x10 halo: all nine taps
+          tma_load_5d(sb, &tmDY, &full[stage], cot * BN, x0, y0, n0, 0);
+        } else if (MODE == 0) {
 #pragma unroll
           for (int j = 0; j < Cfg::kALoads; ++j) {
             const int chunk = M64 ? 0 : cit * 2 + j;
@@ -174,8 +185,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint32_t sb = sa + Cfg::kABytes;
         // base descriptors; per-MMA variation is a start-address offset in 16-byte units
-        const uint64_t a_desc0 = (MODE == 0) ? umma_smem_desc_sw128(sa, M64 ? 128 : kHaloBytes, kHaloPitch)
-                                             : umma_smem_desc_sw128(sa, kBoxBytes, 1024);
+        const uint64_t a_desc0 = (MODE == 2) ? umma_smem_desc_sw128(sa, 0, kHaloPitch)
+                                 : (MODE == 0) ? umma_smem_desc_sw128(sa, M64 ? 128 : kHaloBytes, kHaloPitch)
+                                               : umma_smem_desc_sw128(sa, kBoxBytes, 1024);
         const uint64_t b_desc0 = umma_smem_desc_sw128(sb, kBoxBytes, 1024);
         if (elect_one()) {
 #pragma unroll
@@ -183,10 +195,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // B: K advances by 16 pixel rows = 2048 B; 64-wide MN atoms are one box (8 KB) apart.
-              const uint64_t db = b_desc0 + (((MODE == 0) ? 0 : j * (BN / 64)) * (kBoxBytes / 16) + k * 128);
+              const uint64_t db = b_desc0 + (((MODE == 1) ? j * (BN / 64) : 0) * (kBoxBytes / 16) + k * 128);
               // X halo (MODE 0): tap dx starts dx rows in; 16 pixels = two patch rows of the 10-wide
               // halo.  !M64: M = 128 ci = two halo boxes (LBO).  M64: M = taps (2j, 2j+1) x 64 ci.
-              const uint64_t da = (MODE == 0) ? a_desc0 + ((M64 ? 2 * j : j) * 8 + k * 2 * (kHaloPitch / 16))
+              // MODE 2: tap t = 2j sits ((t/3)*10 + t%3) pixel rows into the 10x10 halo, tap t+1 an LBO further
+              const int t0 = 2 * j, t1 = 2 * j + 1;                                       // (8, -): the pad half is discarded
+              const uint32_t off0 = static_cast<uint32_t>((t0 / 3) * 10 + t0 % 3) * 8;     // 16-byte units
+              const uint32_t off1 = (t1 < 9) ? static_cast<uint32_t>((t1 / 3) * 10 + t1 % 3) * 8 : off0 + 8;
+              const uint64_t da = (MODE == 2) ? a_desc0 + (off0 + k * 2 * (kHaloPitch / 16)) + (static_cast<uint64_t>(off1 - off0) << 16)
+                                : (MODE == 0) ? a_desc0 + ((M64 ? 2 * j : j) * 8 + k * 2 * (kHaloPitch / 16))
                                               : a_desc0 + (k * 128);
               if (CTAS == 2) tc_mma_bf16_pair(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
               else tc_mma_bf16(tmem_base + j * BN, da, db, idesc, (kt > k_begin) || (k > 0));
@@ -216,7 +233,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
     for (int j = 0; j < Cfg::kMmas; ++j) {
       int tap, ci;
       bool valid = true;
-      if (MODE == 0) {
+      if (MODE == 2) {
+        tap = 2 * j + (row >> 6);
+        ci = cit * 64 + (row & 63);
+        valid = tap < 9;
+      } else if (MODE == 0) {
         if (M64) {
           const int tj = 2 * j + (row >> 6);
           tap = 3 * r + tj;
@@ -288,11 +309,15 @@ static int launch_wgrad_t(const CUtensorMap& x1, const CUtensorMap& x2, const CU
   return UNETK_OK;
 }
 
-// Split-K factor from a small cost model (units: microseconds).  Every split pays one epilogue:
-// red.global.add when ksplit > 1 (atomics on the same addresses serialise in L2, so their cost
-// grows with the number of splits), plain stores when ksplit == 1.  Measured on B200
-// (profiles/ncu_conv_r01a): 594 CTAs x 49 K atomics took about as long as their main loops.
+// Split-K factor from a small cost model (units: microseconds), fitted to a sweep of every layer shape of
+// the B=16 @256^2 step on a B200 (tools/wgrad_sweep.py -> profiles/wgrad_sweep_r01.txt): a CTA costs a fixed
+// ~10 us (launch, prologue, pipeline fill, drain) + its K tiles + its epilogue (red.global.add when
+// ksplit > 1, plain stores otherwise); the model picks the measured optimum for all 13 conv shapes.
 static int choose_ksplit(int work_tiles, int total_k, double us_per_ktile, double out_elems_per_cta) {
+  if (const char* f = getenv("UNETK_WGRAD_KSPLIT")) {       // tuning override (tools/wgrad_sweep.py)
+    const int v = atoi(f);
+    if (v >= 1) return v < total_k ? v : total_k;
+  }
   const int sms = num_sms();
   int best = 1;
   double best_t = 1e30;
@@ -301,8 +326,8 @@ static int choose_ksplit(int work_tiles, int total_k, double us_per_ktile, doubl
     const long ctas = static_cast<long>(work_tiles) * ks;
     const double waves = static_cast<double>((ctas + sms - 1) / sms);
     const double main_us = (static_cast<double>((total_k + ks - 1) / ks)) * us_per_ktile;
-    const double epi_us = (ks == 1) ? out_elems_per_cta * 4e-5 : out_elems_per_cta * (1.2e-4 + 2.0e-6 * ks);
-    const double t = waves * (main_us + epi_us + 3.0);
+    const double epi_us = out_elems_per_cta * ((ks == 1) ? 4e-5 : 1e-4);
+    const double t = waves * (main_us + epi_us + 10.0);
     if (t < best_t) {
       best_t = t;
       best = ks;
@@ -323,6 +348,21 @@ int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, in
   p.n_img = n; p.H = h; p.W = w; p.cin = cin; p.cout = cout; p.c1_chunks = c1 / 64; p.T = 9; p.dw = dw;
   p.tw = 8; p.th = 8; p.tn = 1;   // 8x8 pixel K tiles, X read through 10x8 halo boxes
   p.tiles_x = (w + 7) / 8; p.tiles_y = (h + 7) / 8; p.tiles_n = n;
+  static const bool nine_ok = (getenv("UNETK_WGRAD_NO9") == nullptr);
+  if (nine_ok && static_cast<long>(cin) * cout <= 64 * 128) {
+    // narrow layer: nine-tap units of 64 ci x 64 co (see the header comment)
+    p.ci_tiles = cin / 64;
+    p.co_tiles = cout / 64;
+    const int work = p.ci_tiles * p.co_tiles;
+    // one K tile = 5 x 4 MMAs of 128 x 64 x 16, shared-memory bound at ~48 cycles each
+    p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y * p.tiles_n, 0.65, 5 * 128 * 64.0);
+    CUtensorMap x1, x2, tdy;
+    int e;
+    if ((e = make_act_tmap(&x1, src1, n, h, w, c1, 10, 10, 1))) return e;
+    if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h, w, c2, 10, 10, 1))) return e; } else x2 = x1;
+    if ((e = make_act_tmap(&tdy, dy, n, h, w, cout, 8, 8, 1))) return e;
+    return launch_wgrad_t<2, 64, true>(x1, x2, tdy, p, dim3(work, p.ksplit), stream);
+  }
   const bool m64 = (cin == 64);
   const int bn = (cout % 128 == 0) ? 128 : 64;
   p.ci_tiles = m64 ? 1 : cin / 128;
@@ -331,8 +371,9 @@ int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, in
   const int ctas = (pair_ok && bn == 128) ? 2 : 1;
   const int unit_slots = (3 * p.ci_tiles + ctas - 1) / ctas;       // (tap row, ci tile) units per CTA (pair)
   const int work = unit_slots * ctas * p.co_tiles;                  // CTAs in grid.x
-  // one K tile = (2 or 3) x 4 MMAs of 128 x bn x 16 (M64: N = bn at half the tile rows)
-  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y * p.tiles_n, (m64 ? 8 : 12) * bn / 256.0 / 1.7 + 0.05,
+  // one K tile = (2 or 3) x 4 MMAs of 128 x bn x 16 (M64: N = bn at half the tile rows): 0.40 us measured
+  // for the pair configuration, proportionally less for the narrower ones
+  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y * p.tiles_n, 0.40 * (ctas == 2 ? 1.0 : bn / 128.0) * (m64 ? 0.7 : 1.0),
                            (m64 ? 3 * 64 : 3 * 128) * static_cast<double>(bn));
   CUtensorMap x1, x2, tdy;
   int e;
@@ -362,7 +403,7 @@ int convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw,
   p.ci_tiles = cin / 128;
   p.co_tiles = cout / bn;
   const int work = p.ci_tiles * p.co_tiles;
-  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y, 16 * bn / 256.0 / 1.7 + 0.05, 4 * 128.0 * bn);
+  p.ksplit = choose_ksplit(work, p.tiles_x * p.tiles_y, 0.55 * bn / 128.0, 4 * 128.0 * bn);
   CUtensorMap x1, tdy;
   int e;
   if ((e = make_act_tmap(&x1, a, 1, p.H, w, cin, p.tw, p.th, p.tn))) return e;

@@ -23,7 +23,22 @@ import torch
 
 from . import _lib, ops, packing
 
+import os
+
 WIDTHS = [64, 128, 256, 512, 1024]
+# Which producers of an activation gradient also run the first pass (per-channel sums) of the BatchNorm
+# backward of the layer below them: "head" (default: the 1x1 head backward already holds the activation in
+# registers, +0.01 ms instead of a 0.07 ms pass), "all" (+ conv / transposed-conv dgrad epilogues and the
+# pool backward: measured slower at B=16 @256^2, the extra global loads sit on the epilogue's critical
+# path), "0" (stand-alone reductions everywhere).
+FUSE_BN_REDUCE = os.environ.get("UNETK_FUSE_BN_REDUCE", "head")
+FUSE_CHECK = os.environ.get("UNETK_FUSE_CHECK", "0") == "1"
+FIRST_WGRAD_TC = os.environ.get("UNETK_FIRST_WGRAD_TC", "1") != "0"
+# Weight gradients are off the critical path of backward (nothing downstream reads them before the
+# optimizer): they run on a side stream, each one released only after the data gradient of the same layer,
+# so the tensor-bound wgrad kernel shares the SMs with the memory-bound BatchNorm-backward passes of the
+# next layer instead of queueing in front of them.
+OVERLAP_WGRAD = os.environ.get("UNETK_OVERLAP_WGRAD", "1") != "0"
 ALIGN = 64  # elements; keeps every slice 256-byte aligned
 
 
@@ -88,6 +103,8 @@ class Plan:
             self.dec.append(stages)
         self._act = act
         self.grads_ready = False
+        self.bnctx = {}
+        self.fused = set()
 
     def alloc_grads(self):
         if self.grads_ready:
@@ -96,9 +113,14 @@ class Plan:
         self.d_skip = [act(l, WIDTHS[l]) for l in range(5)]   # d(a2) of every encoder level
         self.d_t = act(0, 64)       # running decoder gradient d(a2) of the current stage (max size)
         self.d_a1 = act(0, 64)      # gradient wrt a DoubleConv's inner activation (max size)
-        self.d_y = act(0, 64)       # gradient wrt a raw conv output (max size)
-        self.d_up = act(0, 64)      # gradient wrt an up-sampled tensor (max size)
+        # gradient wrt a raw conv output / an up-sampled tensor (max size).  Two slots each: the weight
+        # gradient that reads slot i runs on the side stream while the main stream already fills slot i^1
+        self.d_y = [act(0, 64), act(0, 64)]
+        self.d_up = [act(0, 64), act(0, 64)]
         self.d_p = act(1, 64)       # gradient wrt a pooled tensor (max size)
+        # first conv weight gradient on the tensor cores: channel-padded image (padding written once here)
+        self.x64 = ops.zero_(act(0, 64))
+        self.fc_scratch = torch.empty(64 * 9 * 64, dtype=torch.float32, device=self.x64.device)
         self.grads_ready = True
 
     @staticmethod
@@ -117,6 +139,8 @@ class Engine:
         self.flat_p = None
         self._sig = None
         self.ddp = None           # set by distributed.attach()
+        self.fuse_check = []      # (layer, relative error) records of UNETK_FUSE_CHECK=1
+        self.wstream = None       # side stream of the weight gradients (OVERLAP_WGRAD)
         self.weights_dirty = True
         self.fold_dirty = True
         m = module
@@ -423,9 +447,32 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # backward
     # ------------------------------------------------------------------------------------------
-    def _bn_bwd(self, L, d_a, y, d_y):
-        ops.bn_bwd_reduce(d_a, y, L.scale, L.shift, L.mean, L.invstd, L.sums)
+    def _bn_apply_bwd(self, pl, L, d_a, y, d_y):
+        """BatchNorm+ReLU backward of layer L: per-channel sums (first pass) unless the kernel that
+        finished d_a already produced them (see FUSE_BN_REDUCE), then dy / dgamma / dbeta."""
+        if L.name in pl.fused:
+            pl.fused.discard(L.name)
+            if FUSE_CHECK:      # debug: the fused sums against the stand-alone reduction on the same d_a
+                ref = ops.zero_(torch.empty_like(L.sums))
+                ops.bn_bwd_reduce(d_a, y, L.scale, L.shift, L.mean, L.invstd, ref)
+                err = ((L.sums - ref).abs().max() / (ref.abs().max() + 1e-20)).item()
+                self.fuse_check.append((L.name, err))
+        else:
+            ops.bn_bwd_reduce(d_a, y, L.scale, L.shift, L.mean, L.invstd, L.sums)
         ops.bn_bwd_apply(d_a, y, L.scale, L.shift, L.mean, L.invstd, L.sums, d_y, L.g_gamma, L.g_beta)
+
+    @staticmethod
+    def _ctx(pl, L, y, kind="igemm"):
+        """unetk_bn_ctx for the producer of layer L's activation gradient, or None when that producer does
+        not fuse the reduction."""
+        if FUSE_BN_REDUCE != "all" and not (FUSE_BN_REDUCE == "head" and kind == "head"):
+            return None
+        pl.fused.add(L.name)
+        key = (L.name, y.data_ptr())
+        c = pl.bnctx.get(key)
+        if c is None:
+            c = pl.bnctx[key] = ops.bn_ctx(y, L.scale, L.shift, L.mean, L.invstd, L.sums)
+        return c
 
     def backward(self, pl, generation, grad_outs, outs):
         if generation != pl.generation:
@@ -433,10 +480,48 @@ class Engine:
                                "activations of this graph were overwritten (only one live graph per shape is supported)")
         pl.alloc_grads()
         V = Plan.view
+        ctx = self._ctx
+        s0 = torch.cuda.current_stream(self.device)
+        overlap = OVERLAP_WGRAD and not ops.timing_enabled()
+        if overlap and self.wstream is None:
+            self.wstream = torch.cuda.Stream(device=self.device)
+        sw = self.wstream if overlap else None
+        last_w = [None]                 # last event recorded on the side stream
+        free_dy = [None, None]          # event after which d_y[slot] / d_up[slot] may be overwritten
+        free_up = [None, None]
+        slot_y = [0]
+        slot_u = [0]
+
+        def side(fn):
+            """Run the weight-gradient launches of `fn` on the side stream, after everything enqueued on the
+            main stream so far (the data gradient of the same layer included)."""
+            if sw is None:
+                fn()
+                return None
+            ev = torch.cuda.Event()
+            ev.record(s0)
+            sw.wait_event(ev)
+            with torch.cuda.stream(sw):
+                fn()
+                done = torch.cuda.Event()
+                done.record(sw)
+            last_w[0] = done
+            return done
+
+        def take(bufs, free, slot, like):
+            """Next slot of a double-buffered scratch tensor, viewed like `like`."""
+            slot[0] ^= 1
+            i = slot[0]
+            if free[i] is not None:
+                s0.wait_event(free[i])
+                free[i] = None
+            return i, V(bufs[i], like)
+
         ops.zero_(self.gstage)
         ops.zero_(self.bn_sums_all)
         skip_written = [False] * 5
         n_dec = len(self.decoders)
+        enc4 = self.encoder[4][1]
         for d in reversed(range(n_dec)):
             stages, head = self.decoders[d]
             g = grad_outs[d]
@@ -445,56 +530,72 @@ class Engine:
             if g is None:
                 g = ops.zero_(torch.empty_like(outs[d]))
             g = g.contiguous().float()
-            ops.head_bwd(last["a2"], head.w, g, outs[d], d_t, head.g_w, head.g_b, head.sigmoid)
+            ops.head_bwd(last["a2"], head.w, g, outs[d], d_t, head.g_w, head.g_b, head.sigmoid,
+                         bn=ctx(pl, stages[3][2], last["y2"], kind="head"))
             for k in reversed(range(4)):
                 ct, c1, c2 = stages[k]
                 lv = 3 - k
                 s = pl.dec[d][k]
                 d_t = V(pl.d_t, s["a2"])
-                d_y = V(pl.d_y, s["y2"])
                 d_a1 = V(pl.d_a1, s["a1"])
-                d_up = V(pl.d_up, s["up"])
                 skip = pl.enc[lv]["a2"]
                 # second conv of the DoubleConv
-                self._bn_bwd(c2, d_t, s["y2"], d_y)
-                ops.conv3x3_wgrad(d_y, s["a1"], None, c2.g_w)
-                ops.conv3x3_dgrad(d_y, c2.wd, d_a1)
+                iy, d_y = take(pl.d_y, free_dy, slot_y, s["y2"])
+                self._bn_apply_bwd(pl, c2, d_t, s["y2"], d_y)
+                ops.conv3x3_dgrad(d_y, c2.wd, d_a1, bn=ctx(pl, c1, s["y1"]))
+                free_dy[iy] = side(lambda d_y=d_y, s=s, c2=c2: ops.conv3x3_wgrad(d_y, s["a1"], None, c2.g_w))
                 # first conv: two sources (skip, up)
-                self._bn_bwd(c1, d_a1, s["y1"], d_y)
-                ops.conv3x3_wgrad(d_y, skip, s["up"], c1.g_w)
+                iy, d_y = take(pl.d_y, free_dy, slot_y, s["y1"])
+                iu, d_up = take(pl.d_up, free_up, slot_u, s["up"])
+                self._bn_apply_bwd(pl, c1, d_a1, s["y1"], d_y)
                 ops.conv3x3_dgrad(d_y, c1.wd, pl.d_skip[lv], acc1=skip_written[lv], dx2=d_up, acc2=False,
                                   stats=ct.g_bias)
                 skip_written[lv] = True
+                free_dy[iy] = side(lambda d_y=d_y, s=s, c1=c1, skip=skip: ops.conv3x3_wgrad(d_y, skip, s["up"], c1.g_w))
                 # transposed conv
                 t_in = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
-                ops.convt2x2_wgrad(t_in, d_up, ct.g_w)
                 if k > 0:
-                    ops.convt2x2_dgrad(d_up, ct.wd, V(pl.d_t, t_in), acc=False)
+                    prev = stages[k - 1][2]
+                    ops.convt2x2_dgrad(d_up, ct.wd, V(pl.d_t, t_in), acc=False, bn=ctx(pl, prev, pl.dec[d][k - 1]["y2"]))
                 else:
-                    ops.convt2x2_dgrad(d_up, ct.wd, pl.d_skip[4], acc=skip_written[4])
+                    # the bottleneck gradient is complete after the LAST decoder processed (d == 0)
+                    ops.convt2x2_dgrad(d_up, ct.wd, pl.d_skip[4], acc=skip_written[4],
+                                       bn=ctx(pl, enc4, pl.enc[4]["y2"]) if d == 0 else None)
                     skip_written[4] = True
+                free_up[iu] = side(lambda t_in=t_in, d_up=d_up, ct=ct: ops.convt2x2_wgrad(t_in, d_up, ct.g_w))
             if self.ddp is not None:
-                self.ddp.segment_ready(self, ("dec", d))
+                self.ddp.segment_ready(self, ("dec", d), last_w[0])
         for l in reversed(range(5)):
             c1, c2 = self.encoder[l]
             e = pl.enc[l]
-            d_y = V(pl.d_y, e["y2"])
             d_a1 = V(pl.d_a1, e["a1"])
-            self._bn_bwd(c2, pl.d_skip[l], e["y2"], d_y)
-            ops.conv3x3_wgrad(d_y, e["a1"], None, c2.g_w)
-            ops.conv3x3_dgrad(d_y, c2.wd, d_a1)
-            self._bn_bwd(c1, d_a1, e["y1"], d_y)
+            iy, d_y = take(pl.d_y, free_dy, slot_y, e["y2"])
+            self._bn_apply_bwd(pl, c2, pl.d_skip[l], e["y2"], d_y)
+            ops.conv3x3_dgrad(d_y, c2.wd, d_a1, bn=ctx(pl, c1, e["y1"]))
+            free_dy[iy] = side(lambda d_y=d_y, e=e, c2=c2: ops.conv3x3_wgrad(d_y, e["a1"], None, c2.g_w))
+            iy, d_y = take(pl.d_y, free_dy, slot_y, e["y1"])
+            self._bn_apply_bwd(pl, c1, d_a1, e["y1"], d_y)
             if l == 0:
-                ops.first_conv_wgrad(pl.x, d_y, c1.g_w)
+                def first_wgrad(d_y=d_y, c1=c1):
+                    if self.n_channels <= 8 and FIRST_WGRAD_TC:
+                        ops.image_to_nhwc64(pl.x, pl.x64)
+                        ops.first_conv_wgrad_tc(pl.x64, d_y, pl.fc_scratch, c1.g_w)
+                    else:
+                        ops.first_conv_wgrad(pl.x, d_y, c1.g_w)
+                free_dy[iy] = side(first_wgrad)
             else:
                 src = pl.enc[l - 1]["p"]
                 d_p = V(pl.d_p, src)
-                ops.conv3x3_wgrad(d_y, src, None, c1.g_w)
                 ops.conv3x3_dgrad(d_y, c1.wd, d_p)
-                ops.maxpool_bwd(d_p, pl.enc[l - 1]["idx"], pl.d_skip[l - 1], accumulate=skip_written[l - 1])
+                # the skip gradient of level l-1 is complete after this accumulation
+                ops.maxpool_bwd(d_p, pl.enc[l - 1]["idx"], pl.d_skip[l - 1], accumulate=skip_written[l - 1],
+                                bn=ctx(pl, self.encoder[l - 1][1], pl.enc[l - 1]["y2"]))
                 skip_written[l - 1] = True
+                free_dy[iy] = side(lambda d_y=d_y, src=src, c1=c1: ops.conv3x3_wgrad(d_y, src, None, c1.g_w))
             if self.ddp is not None and l in (3, 0):
-                self.ddp.segment_ready(self, ("enc", l))
+                self.ddp.segment_ready(self, ("enc", l), last_w[0])
+        if last_w[0] is not None:
+            s0.wait_event(last_w[0])      # every weight gradient is in the staging buffer
         scale = 1.0
         if self.ddp is not None:
             scale = self.ddp.finish(self)

@@ -37,6 +37,10 @@ def _chk(t, dtype, name):
 _timing = None
 
 
+def timing_enabled():
+    return _timing is not None
+
+
 def enable_conv_timing():
     global _timing
     _timing = []
@@ -63,6 +67,18 @@ def _timed(flops, name, *args):
     _timing.append((flops, e0, e1))
 
 
+def bn_ctx(y, scale, shift, mean, invstd, sums):
+    """Host-side `unetk_bn_ctx` for the kernels that can fuse the BatchNorm-backward reduction."""
+    c = _lib.BnCtx(_p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums))
+    c._keep = (y, scale, shift, mean, invstd, sums)
+    return c
+
+
+def _bn(bn):
+    import ctypes
+    return ctypes.byref(bn) if bn is not None else None
+
+
 def zero_(t):
     _lib.call("unetk_memset_zero", _p(t), t.numel() * t.element_size(), _s())
     return t
@@ -85,7 +101,7 @@ def conv3x3_fwd(src1, src2, wf, y, stats=None, scale=None, shift=None, relu=Fals
     return y
 
 
-def conv3x3_dgrad(dy, wd, dx1, acc1=False, dx2=None, acc2=False, stats=None):
+def conv3x3_dgrad(dy, wd, dx1, acc1=False, dx2=None, acc2=False, stats=None, bn=None):
     _chk(dy, bf16, "dy"); _chk(wd, bf16, "wd"); _chk(dx1, bf16, "dx1")
     n, h, w, cout = dy.shape
     c1 = dx1.shape[3]
@@ -94,7 +110,7 @@ def conv3x3_dgrad(dy, wd, dx1, acc1=False, dx2=None, acc2=False, stats=None):
         _chk(dx2, bf16, "dx2")
         c2 = dx2.shape[3]
     _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "unetk_conv3x3_dgrad", _p(dy), cout, _p(wd), _p(dx1), c1, int(acc1), _p(dx2), c2,
-              int(acc2), _p(stats), n, h, w, _s())
+           int(acc2), _p(stats), _bn(bn), n, h, w, _s())
 
 
 def conv3x3_wgrad(dy, src1, src2, dw):
@@ -122,6 +138,22 @@ def first_conv_wgrad(x, dy, dw):
     _lib.call("unetk_first_conv_wgrad", _p(x), _p(dy), _p(dw), n, cin, h, ww, dy.shape[3], _s())
 
 
+def image_to_nhwc64(x, x64):
+    """channels [0, 8) of the zero-initialised NHWC bf16 buffer x64[n, h, w, 64] <- NCHW fp32 image."""
+    _chk(x, f32, "x"); _chk(x64, bf16, "x64")
+    n, cin, h, ww = x.shape
+    _lib.call("unetk_image_to_nhwc64", _p(x), _p(x64), n, cin, h, ww, _s())
+    return x64
+
+
+def first_conv_wgrad_tc(x64, dy, scratch, dw):
+    """dw (OIHW [64, cin, 3, 3], overwritten) through the tcgen05 weight-gradient kernel on the
+    channel-padded image; scratch: 64*9*64 floats."""
+    _chk(x64, bf16, "x64"); _chk(dy, bf16, "dy"); _chk(scratch, f32, "scratch"); _chk(dw, f32, "dw")
+    n, h, ww, _ = x64.shape
+    _lib.call("unetk_first_conv_wgrad_tc", _p(x64), _p(dy), _p(scratch), _p(dw), n, dw.shape[1], h, ww, dy.shape[3], _s())
+
+
 def convt2x2_fwd(a, wt, bias, up):
     _chk(a, bf16, "a"); _chk(wt, bf16, "wt"); _chk(up, bf16, "up")
     n, h, w, cin = a.shape
@@ -129,10 +161,10 @@ def convt2x2_fwd(a, wt, bias, up):
     return up
 
 
-def convt2x2_dgrad(dup, wtd, da, acc=False):
+def convt2x2_dgrad(dup, wtd, da, acc=False, bn=None):
     _chk(dup, bf16, "dup"); _chk(wtd, bf16, "wtd"); _chk(da, bf16, "da")
     n, h, w, cin = da.shape
-    _timed(2.0 * n * h * w * cin * 4 * dup.shape[3], "unetk_convt2x2_dgrad", _p(dup), dup.shape[3], _p(wtd), _p(da), cin, int(acc), n, h, w, _s())
+    _timed(2.0 * n * h * w * cin * 4 * dup.shape[3], "unetk_convt2x2_dgrad", _p(dup), dup.shape[3], _p(wtd), _p(da), cin, int(acc), _bn(bn), n, h, w, _s())
 
 
 def convt2x2_wgrad(a, dup, dw):
@@ -170,10 +202,10 @@ def bnrelu_pool(y, scale, shift, a, pooled, idx, apply=True):
               int(apply), _s())
 
 
-def maxpool_bwd(dpooled, idx, da, accumulate):
+def maxpool_bwd(dpooled, idx, da, accumulate, bn=None):
     _chk(dpooled, bf16, "dpooled"); _chk(da, bf16, "da")
     n, h, w, c = da.shape
-    _lib.call("unetk_maxpool_bwd", _p(dpooled), _p(idx), _p(da), n, h, w, c, int(accumulate), _s())
+    _lib.call("unetk_maxpool_bwd", _p(dpooled), _p(idx), _p(da), n, h, w, c, int(accumulate), _bn(bn), _s())
 
 
 def bn_bwd_reduce(da, y, scale, shift, mean, invstd, sums):
@@ -198,11 +230,11 @@ def head_fwd(a, w, b, out, sigmoid):
     return out
 
 
-def head_bwd(a, w, dout, out, da, dw, db, sigmoid):
+def head_bwd(a, w, dout, out, da, dw, db, sigmoid, bn=None):
     _chk(a, bf16, "a"); _chk(dout, f32, "dout"); _chk(da, bf16, "da")
     n, h, ww, c = a.shape
     _lib.call("unetk_head_bwd", _p(a), _p(w), _p(dout), _p(out), _p(da), _p(dw), _p(db), n, h, ww, c,
-              dout.shape[1], int(sigmoid), _s())
+              dout.shape[1], int(sigmoid), _bn(bn), _s())
 
 
 def combined_loss_workspace(device):

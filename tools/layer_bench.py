@@ -67,8 +67,14 @@ for name, lvl, c1, c2, cout, cnt in LAYERS:
     t_f = timeit(lambda: ops.conv3x3_fwd(s1, s2, wf, y, stats=stats))
     t_d = timeit(lambda: ops.conv3x3_dgrad(y, wd, dx1, False, dx2, False))
     t_w = timeit(lambda: ops.conv3x3_wgrad(y, s1, s2, dw))
+    extra = ""
+    if not c2:      # dgrad with the fused BatchNorm-backward reduction (single destination)
+        ones = torch.ones(c1, device=dev); zer = torch.zeros(c1, device=dev); sm = torch.zeros(2 * c1, device=dev)
+        ctx = ops.bn_ctx(s1, ones, zer, zer, ones, sm)
+        t_b = timeit(lambda: ops.conv3x3_dgrad(y, wd, dx1, False, bn=ctx))
+        extra = f" | dgrad+bnred {t_b:7.3f} ms"
     log(f"{name:8s} M={B*h*h:8d} N={cout:5d} K={9*cin:5d} x{cnt}  fwd {t_f:7.3f} ms {flop/t_f/1e9:7.1f} TF | "
-        f"dgrad {t_d:7.3f} ms {flop/t_d/1e9:7.1f} TF | wgrad {t_w:7.3f} ms {flop/t_w/1e9:7.1f} TF")
+        f"dgrad {t_d:7.3f} ms {flop/t_d/1e9:7.1f} TF | wgrad {t_w:7.3f} ms {flop/t_w/1e9:7.1f} TF" + extra)
     tot["fwd"] += t_f * cnt; tot["dgrad"] += t_d * cnt; tot["wgrad"] += t_w * cnt
     totf += flop * cnt
     del s1, s2, wf, wd, y, dx1, dx2, dw
@@ -89,7 +95,10 @@ for k, (lvl, cin) in enumerate([(4, 1024), (3, 512), (2, 256), (1, 128)]):
     t_f = timeit(lambda: ops.convt2x2_fwd(a, wt, bias, up))
     t_d = timeit(lambda: ops.convt2x2_dgrad(up, wt, da))
     t_w = timeit(lambda: ops.convt2x2_wgrad(a, up, dw))
-    log(f"up{k+1}.up  cin={cin:5d}  fwd {t_f:7.3f} ms {flop/t_f/1e9:7.1f} TF | dgrad {t_d:7.3f} ms {flop/t_d/1e9:7.1f} TF | wgrad {t_w:7.3f} ms {flop/t_w/1e9:7.1f} TF")
+    ones = torch.ones(cin, device=dev); zer = torch.zeros(cin, device=dev); sm = torch.zeros(2 * cin, device=dev)
+    ctx = ops.bn_ctx(a, ones, zer, zer, ones, sm)
+    t_b = timeit(lambda: ops.convt2x2_dgrad(up, wt, da, bn=ctx))
+    log(f"up{k+1}.up  cin={cin:5d}  fwd {t_f:7.3f} ms {flop/t_f/1e9:7.1f} TF | dgrad {t_d:7.3f} ms {flop/t_d/1e9:7.1f} TF | wgrad {t_w:7.3f} ms {flop/t_w/1e9:7.1f} TF | dgrad+bnred {t_b:7.3f} ms")
 
 log("# bandwidth kernels at full resolution (64 ch)")
 y = bf(B, H, H, 64)
@@ -123,6 +132,15 @@ log(f"head_fwd {t:.3f} ms  {nbytes/t/1e6:.0f} GB/s")
 dwh = torch.empty(3, 64, device=dev); dbh = torch.empty(3, device=dev)
 t = timeit(lambda: ops.head_bwd(y, hw, out, out, a, dwh, dbh, True))
 log(f"head_bwd {t:.3f} ms  {2*nbytes/t/1e6:.0f} GB/s")
+ctx = ops.bn_ctx(y, sc, sh, sh, sc, sums)
+t = timeit(lambda: ops.head_bwd(y, hw, out, out, a, dwh, dbh, True, bn=ctx))
+log(f"head_bwd+bnred {t:.3f} ms  {2*nbytes/t/1e6:.0f} GB/s")
+dp_ = bf(B, H // 2, H // 2, 64)
+idx8 = torch.randint(0, 4, (B, H // 2, H // 2, 64), dtype=torch.uint8, device=dev)
+t = timeit(lambda: ops.maxpool_bwd(dp_, idx8, a, accumulate=True))
+log(f"maxpool_bwd(acc) {t:.3f} ms")
+t = timeit(lambda: ops.maxpool_bwd(dp_, idx8, a, accumulate=True, bn=ctx))
+log(f"maxpool_bwd(acc)+bnred {t:.3f} ms")
 del y, a, dy, pooled, idx, x, out
 
 log("# whole training step (AnomalyUNet + CombinedLoss + fused Adam)")
