@@ -131,8 +131,10 @@ int unetk_bnrelu_apply(const void* y, const float* scale, const float* shift, vo
  * element, may be NULL) = position 0..3 of the first maximum. */
 int unetk_bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
                       void* idx, int n, int h, int w, int c, int apply, void* stream);
+/* da[2x2 window] (+)= scatter of dpooled by idx; accumulate != 0 adds to the existing da; extra (may be
+ * NULL, same shape as da) is a further gradient of the same activation added on the fly. */
 int unetk_maxpool_bwd(const void* dpooled, const void* idx, void* da, int n, int h, int w, int c,
-                      int accumulate, const unetk_bn_ctx* bn, void* stream);
+                      int accumulate, const void* extra, const unetk_bn_ctx* bn, void* stream);
 /* BatchNorm+ReLU backward in two passes: sums[2][C] (caller zeroes) then dy, dgamma, dbeta. */
 int unetk_bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
                         const float* mean, const float* invstd, float* sums, int64_t npix, int c,

@@ -283,6 +283,12 @@ def test_bn_relu_pool_roundtrip(cuda_device, n, h, w, c):
     ops.maxpool_bwd(dpb, idx, da2, accumulate=True)
     torch.cuda.synchronize()
     _close(da2.float(), base.float() + da.float(), 1e-2, "maxpool_bwd accumulate")
+    # a second gradient of the same activation added on the fly (parallel decoders)
+    extra = _nhwc(torch.randn(n, c, h, w, generator=g).to(dev))
+    da4 = base.clone()
+    ops.maxpool_bwd(dpb, idx, da4, accumulate=True, extra=extra)
+    torch.cuda.synchronize()
+    _close(da4.float(), base.float() + da.float() + extra.float(), 1.5e-2, "maxpool_bwd accumulate + extra")
     # fused first pass of the BatchNorm backward == the stand-alone reduction on the finished gradient
     da3 = base.clone()
     fused = torch.zeros(2 * c, device=dev)

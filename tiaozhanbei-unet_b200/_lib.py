@@ -34,7 +34,7 @@ SIGNATURES = {
     "unetk_bn_fold": (I, [P, P, P, P, P, P, I, F, P]),
     "unetk_bnrelu_apply": (I, [P, P, P, P, L, I, P]),
     "unetk_bnrelu_pool": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
-    "unetk_maxpool_bwd": (I, [P, P, P, I, I, I, I, I, P, P]),
+    "unetk_maxpool_bwd": (I, [P, P, P, I, I, I, I, I, P, P, P]),
     "unetk_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, L, I, P]),
     "unetk_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, L, I, P]),
     "unetk_head_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P]),

@@ -95,8 +95,8 @@ int unetk_bnrelu_pool(const void* y, const float* scale, const float* shift, voi
   return unetk::bnrelu_pool(y, scale, shift, a, pooled, idx, n, h, w, c, apply, S(stream));
 }
 int unetk_maxpool_bwd(const void* dpooled, const void* idx, void* da, int n, int h, int w, int c,
-                      int accumulate, const unetk_bn_ctx* bn, void* stream) {
-  return unetk::maxpool_bwd(dpooled, idx, da, n, h, w, c, accumulate, B(bn), S(stream));
+                      int accumulate, const void* extra, const unetk_bn_ctx* bn, void* stream) {
+  return unetk::maxpool_bwd(dpooled, idx, da, n, h, w, c, accumulate, extra, B(bn), S(stream));
 }
 int unetk_bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
                         const float* mean, const float* invstd, float* sums, int64_t npix, int c,

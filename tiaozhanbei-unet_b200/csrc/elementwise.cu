@@ -163,12 +163,13 @@ bnrelu_pool_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
   }
 }
 
-// dA[argmax position] (+)= dP, other positions (+)= 0.  When `bn_y` is given, dA is final after this
+// dA[argmax position] (+)= dP (+ extra), other positions (+)= 0 (+ extra).  When `bn_y` is given, dA is final after this
 // kernel and the first pass of the producing layer's BatchNorm+ReLU backward is fused in:
 // sums[0..C) += sum g, sums[C..2C) += sum g*xhat  (g = dA*[y*scale+shift > 0], xhat = (y-mean)*invstd).
 __global__ void __launch_bounds__(kEwThreads)
 maxpool_bwd_kernel(const uint4* __restrict__ dp, const uint2* __restrict__ idx, uint4* da, int N,
-                   int H, int W, int cgroups, int accumulate, const uint4* __restrict__ bn_y,
+                   int H, int W, int cgroups, int accumulate, const uint4* __restrict__ extra,
+                   const uint4* __restrict__ bn_y,
                    const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ mean, const float* __restrict__ invstd,
                    float* __restrict__ sums) {
@@ -219,6 +220,12 @@ maxpool_bwd_kernel(const uint4* __restrict__ dp, const uint2* __restrict__ idx, 
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      if (extra != nullptr) {       // a second gradient of the same activation (parallel decoder)
+        float e[8];
+        unpack8(ldg_nc_v4(extra + offs[k]), e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += e[j];
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += (bi[j] == static_cast<uint32_t>(k)) ? g[j] : 0.f;
@@ -427,7 +434,7 @@ int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, 
 }
 
 int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, int C, int accumulate,
-                const BnReduceCtx* bn, cudaStream_t s) {
+                const void* extra, const BnReduceCtx* bn, cudaStream_t s) {
   UNETK_CHECK_ARG(dp && idx && da, "maxpool_bwd: null pointer");
   UNETK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "maxpool_bwd: H and W must be even");
   if (int e = check_c(C, "maxpool_bwd")) return e;
@@ -439,7 +446,7 @@ int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, 
   if (fuse && grid > cap && (static_cast<long>(cap) * kEwThreads) % (C / 8) == 0) grid = cap;   // fewer global atomics
   maxpool_bwd_kernel<<<grid, kEwThreads, fuse ? 2 * C * sizeof(float) : 0, s>>>(
       static_cast<const uint4*>(dp), static_cast<const uint2*>(idx), static_cast<uint4*>(da), N, H, W, C / 8, accumulate,
-      fuse ? static_cast<const uint4*>(bn->y) : nullptr, fuse ? bn->scale : nullptr, fuse ? bn->shift : nullptr,
+      static_cast<const uint4*>(extra), fuse ? static_cast<const uint4*>(bn->y) : nullptr, fuse ? bn->scale : nullptr, fuse ? bn->shift : nullptr,
       fuse ? bn->mean : nullptr, fuse ? bn->invstd : nullptr, fuse ? bn->sums : nullptr);
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;

@@ -55,7 +55,7 @@ int bnrelu_apply(const void* y, const float* scale, const float* shift, void* a,
 int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
                 void* idx, int N, int H, int W, int C, int apply, cudaStream_t s);
 int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, int C, int accumulate,
-                const BnReduceCtx* bn, cudaStream_t s);
+                const void* extra, const BnReduceCtx* bn, cudaStream_t s);
 int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
                   const float* mean, const float* invstd, float* sums, long npix, int C,
                   cudaStream_t s);

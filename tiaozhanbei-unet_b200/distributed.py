@@ -70,8 +70,8 @@ class GradReducer:
         return self.segments
 
     def segment_ready(self, eng, tag, also_after=None):
-        """Reduce the bucket `tag` once the current stream (and the event `also_after`, recorded on the
-        engine's weight-gradient side stream) have finished writing it."""
+        """Reduce the bucket `tag` once the current stream (and the events `also_after`, recorded on the
+        engine's side streams) have finished writing it."""
         if self.world == 1:
             return
         a, b = self._segments(eng)[tag]
@@ -84,8 +84,8 @@ class GradReducer:
             ev.record(torch.cuda.current_stream(view.device))
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ev)
-                if also_after is not None:
-                    self.stream.wait_event(also_after)
+                for e in (also_after or ()):
+                    self.stream.wait_event(e)
                 self.works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         else:
             self.works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))

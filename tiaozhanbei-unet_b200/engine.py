@@ -39,6 +39,7 @@ FIRST_WGRAD_TC = os.environ.get("UNETK_FIRST_WGRAD_TC", "1") != "0"
 # so the tensor-bound wgrad kernel shares the SMs with the memory-bound BatchNorm-backward passes of the
 # next layer instead of queueing in front of them.
 OVERLAP_WGRAD = os.environ.get("UNETK_OVERLAP_WGRAD", "1") != "0"
+PARALLEL_DECODERS = os.environ.get("UNETK_PARALLEL_DECODERS", "1") != "0"
 ALIGN = 64  # elements; keeps every slice 256-byte aligned
 
 
@@ -102,6 +103,7 @@ class Plan:
                                "a2": act(lv, c)})
             self.dec.append(stages)
         self._act = act
+        self.n_dec = len(eng.decoders)
         self.grads_ready = False
         self.bnctx = {}
         self.fused = set()
@@ -111,12 +113,15 @@ class Plan:
             return
         act = self._act
         self.d_skip = [act(l, WIDTHS[l]) for l in range(5)]   # d(a2) of every encoder level
-        self.d_t = act(0, 64)       # running decoder gradient d(a2) of the current stage (max size)
-        self.d_a1 = act(0, 64)      # gradient wrt a DoubleConv's inner activation (max size)
-        # gradient wrt a raw conv output / an up-sampled tensor (max size).  Two slots each: the weight
-        # gradient that reads slot i runs on the side stream while the main stream already fills slot i^1
-        self.d_y = [act(0, 64), act(0, 64)]
-        self.d_up = [act(0, 64), act(0, 64)]
+        # skip gradients of the second, third... decoder when the decoders run on parallel streams
+        self.d_skipx = [[act(l, WIDTHS[l]) for l in range(4)] for _ in range(self.n_dec - 1)]
+        # scratch per backward chain (one per decoder; the encoder continues on chain 0), all of the
+        # largest (full resolution, 64 channel) size: d_t = running decoder gradient d(a2) of the current
+        # stage, d_a1 = gradient wrt a DoubleConv's inner activation, d_y = gradient wrt a raw conv output,
+        # d_up = gradient wrt an up-sampled tensor.  d_y / d_up have two slots each: the weight gradient
+        # that reads slot i runs on a side stream while the chain already fills slot i^1.
+        self.scratch = [{"d_t": act(0, 64), "d_a1": act(0, 64), "d_y": [act(0, 64), act(0, 64)],
+                         "d_up": [act(0, 64), act(0, 64)]} for _ in range(self.n_dec)]
         self.d_p = act(1, 64)       # gradient wrt a pooled tensor (max size)
         # first conv weight gradient on the tensor cores: channel-padded image (padding written once here)
         self.x64 = ops.zero_(act(0, 64))
@@ -126,6 +131,49 @@ class Plan:
     @staticmethod
     def view(buf, like):
         return buf.view(-1)[: like.numel()].view(like.shape)
+
+
+class _Chain:
+    """One backward chain (a decoder, then for chain 0 the encoder): its stream, the side stream of its
+    weight gradients and its scratch tensors."""
+
+    def __init__(self, stream, wstream, scratch):
+        self.stream, self.wstream = stream, wstream
+        self.d_t, self.d_a1 = scratch["d_t"], scratch["d_a1"]
+        self.d_y, self.d_up = scratch["d_y"], scratch["d_up"]
+        self.free_y, self.free_up = [None, None], [None, None]   # events after which a slot may be overwritten
+        self.slot_y = self.slot_up = 0
+        self.last_w = None                                       # last event recorded on the side stream
+
+    def side(self, fn):
+        """Run the weight-gradient launches of `fn` on the side stream, after everything enqueued on the
+        chain's stream so far (the data gradient of the same layer included)."""
+        if self.wstream is None:
+            fn()
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        self.wstream.wait_event(ev)
+        with torch.cuda.stream(self.wstream):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self.wstream)
+        self.last_w = done
+        return done
+
+    def _take(self, bufs, free, slot, like):
+        if free[slot] is not None:
+            self.stream.wait_event(free[slot])
+            free[slot] = None
+        return slot, Plan.view(bufs[slot], like)
+
+    def take_y(self, like):
+        self.slot_y ^= 1
+        return self._take(self.d_y, self.free_y, self.slot_y, like)
+
+    def take_up(self, like):
+        self.slot_up ^= 1
+        return self._take(self.d_up, self.free_up, self.slot_up, like)
 
 
 class Engine:
@@ -140,7 +188,8 @@ class Engine:
         self._sig = None
         self.ddp = None           # set by distributed.attach()
         self.fuse_check = []      # (layer, relative error) records of UNETK_FUSE_CHECK=1
-        self.wstream = None       # side stream of the weight gradients (OVERLAP_WGRAD)
+        self.wstreams = []        # side streams of the weight gradients, one per backward chain (OVERLAP_WGRAD)
+        self.dstreams = []        # side streams of the second, third... decoder (PARALLEL_DECODERS)
         self.weights_dirty = True
         self.fold_dirty = True
         m = module
@@ -392,23 +441,59 @@ class Engine:
             self._bn_train(c1, e["y1"], e["a1"], count)
             ops.conv3x3_fwd(e["a1"], None, c2.wf, e["y2"], stats=c2.stats)
             self._bn_train(c2, e["y2"], e["a2"], count, pool=(e["p"], e["idx"]) if l < 4 else None)
-        outs = []
-        for d, (stages, head) in enumerate(self.decoders):
-            t = pl.enc[4]["a2"]
-            for k, (ct, c1, c2) in enumerate(stages):
-                lv = 3 - k
-                s = pl.dec[d][k]
-                count = n * (pl.h >> lv) * (pl.w >> lv)
-                ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
-                ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["y1"], stats=c1.stats)
-                self._bn_train(c1, s["y1"], s["a1"], count)
-                ops.conv3x3_fwd(s["a1"], None, c2.wf, s["y2"], stats=c2.stats)
-                self._bn_train(c2, s["y2"], s["a2"], count)
-                t = s["a2"]
-            out = torch.empty(n, head.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device)
-            ops.head_fwd(t, head.w, head.b, out, head.sigmoid)
-            outs.append(out)
+        def stage(d, k):
+            ct, c1, c2 = self.decoders[d][0][k]
+            lv = 3 - k
+            s = pl.dec[d][k]
+            t = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
+            count = n * (pl.h >> lv) * (pl.w >> lv)
+            ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
+            ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["y1"], stats=c1.stats)
+            self._bn_train(c1, s["y1"], s["a1"], count)
+            ops.conv3x3_fwd(s["a1"], None, c2.wf, s["y2"], stats=c2.stats)
+            self._bn_train(c2, s["y2"], s["a2"], count)
+
+        return self._run_decoders(pl, x, stage)
+
+    def _run_decoders(self, pl, x, stage, parallel=True):
+        """Decoder stages + heads.  The decoders of an AnomalyUNet are independent given the encoder, so in
+        training they run on parallel streams, enqueued stage by stage: the memory-bound BatchNorm/ReLU
+        passes of one decoder share the SMs with the tensor-bound convolutions of the other (12.0 -> 11.0 ms
+        per step together with the backward chains).  Eval mode folds BatchNorm into the conv epilogue, is
+        tensor bound throughout and measured slower on two streams (2.90 -> 3.05 ms): one stream."""
+        n_dec = len(self.decoders)
+        outs = [torch.empty(pl.n, head.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device) for _, head in self.decoders]
+        streams = self._decoder_streams(n_dec if parallel else 1) * (1 if parallel else n_dec)
+        s0 = streams[0]
+        if n_dec > 1 and streams[1] is not s0:
+            ev = torch.cuda.Event()
+            ev.record(s0)
+            for st in streams[1:]:
+                st.wait_event(ev)
+        for k in range(5):
+            for d in range(n_dec):
+                with torch.cuda.stream(streams[d]):
+                    if k < 4:
+                        stage(d, k)
+                    else:
+                        head = self.decoders[d][1]
+                        ops.head_fwd(pl.dec[d][3]["a2"], head.w, head.b, outs[d], head.sigmoid)
+        for st in streams[1:]:
+            if st is not s0:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                s0.wait_event(ev)
         return outs
+
+    def _decoder_streams(self, n_dec):
+        """[current stream, side streams...]; all the current stream when parallel decoders are off or the
+        per-kernel timing instrumentation is on."""
+        s0 = torch.cuda.current_stream(self.device)
+        if n_dec == 1 or not PARALLEL_DECODERS or ops.timing_enabled():
+            return [s0] * n_dec
+        while len(self.dstreams) < n_dec - 1:
+            self.dstreams.append(torch.cuda.Stream(device=self.device))
+        return [s0] + self.dstreams[: n_dec - 1]
 
     def _fold(self):
         if self.fold_dirty:
@@ -429,20 +514,16 @@ class Engine:
             ops.conv3x3_fwd(e["a1"], None, c2.wf, e["a2"], scale=c2.scale, shift=c2.shift, relu=True)
             if l < 4:
                 ops.bnrelu_pool(e["a2"], None, None, None, e["p"], None, apply=False)
-        outs = []
-        for d, (stages, head) in enumerate(self.decoders):
-            t = pl.enc[4]["a2"]
-            for k, (ct, c1, c2) in enumerate(stages):
-                lv = 3 - k
-                s = pl.dec[d][k]
-                ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
-                ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["a1"], scale=c1.scale, shift=c1.shift, relu=True)
-                ops.conv3x3_fwd(s["a1"], None, c2.wf, s["a2"], scale=c2.scale, shift=c2.shift, relu=True)
-                t = s["a2"]
-            out = torch.empty(n, head.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device)
-            ops.head_fwd(t, head.w, head.b, out, head.sigmoid)
-            outs.append(out)
-        return outs
+        def stage(d, k):
+            ct, c1, c2 = self.decoders[d][0][k]
+            lv = 3 - k
+            s = pl.dec[d][k]
+            t = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
+            ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
+            ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["a1"], scale=c1.scale, shift=c1.shift, relu=True)
+            ops.conv3x3_fwd(s["a1"], None, c2.wf, s["a2"], scale=c2.scale, shift=c2.shift, relu=True)
+
+        return self._run_decoders(pl, x, stage, parallel=False)
 
     # ------------------------------------------------------------------------------------------
     # backward
@@ -481,99 +562,99 @@ class Engine:
         pl.alloc_grads()
         V = Plan.view
         ctx = self._ctx
-        s0 = torch.cuda.current_stream(self.device)
-        overlap = OVERLAP_WGRAD and not ops.timing_enabled()
-        if overlap and self.wstream is None:
-            self.wstream = torch.cuda.Stream(device=self.device)
-        sw = self.wstream if overlap else None
-        last_w = [None]                 # last event recorded on the side stream
-        free_dy = [None, None]          # event after which d_y[slot] / d_up[slot] may be overwritten
-        free_up = [None, None]
-        slot_y = [0]
-        slot_u = [0]
-
-        def side(fn):
-            """Run the weight-gradient launches of `fn` on the side stream, after everything enqueued on the
-            main stream so far (the data gradient of the same layer included)."""
-            if sw is None:
-                fn()
-                return None
-            ev = torch.cuda.Event()
-            ev.record(s0)
-            sw.wait_event(ev)
-            with torch.cuda.stream(sw):
-                fn()
-                done = torch.cuda.Event()
-                done.record(sw)
-            last_w[0] = done
-            return done
-
-        def take(bufs, free, slot, like):
-            """Next slot of a double-buffered scratch tensor, viewed like `like`."""
-            slot[0] ^= 1
-            i = slot[0]
-            if free[i] is not None:
-                s0.wait_event(free[i])
-                free[i] = None
-            return i, V(bufs[i], like)
-
-        ops.zero_(self.gstage)
-        ops.zero_(self.bn_sums_all)
-        skip_written = [False] * 5
         n_dec = len(self.decoders)
-        enc4 = self.encoder[4][1]
-        for d in reversed(range(n_dec)):
-            stages, head = self.decoders[d]
+        streams = self._decoder_streams(n_dec) if n_dec == 2 else [torch.cuda.current_stream(self.device)] * n_dec
+        s0 = streams[0]
+        parallel = n_dec == 2 and streams[1] is not s0
+        overlap = OVERLAP_WGRAD and not ops.timing_enabled()
+        while overlap and len(self.wstreams) < n_dec:
+            self.wstreams.append(torch.cuda.Stream(device=self.device))
+        chains = [_Chain(streams[d], self.wstreams[d if parallel else 0] if overlap else None, pl.scratch[d])
+                  for d in range(n_dec)]
+        grads = []
+        for d in range(n_dec):
             g = grad_outs[d]
-            last = pl.dec[d][3]
-            d_t = V(pl.d_t, last["a2"])
             if g is None:
                 g = ops.zero_(torch.empty_like(outs[d]))
-            g = g.contiguous().float()
-            ops.head_bwd(last["a2"], head.w, g, outs[d], d_t, head.g_w, head.g_b, head.sigmoid,
-                         bn=ctx(pl, stages[3][2], last["y2"], kind="head"))
-            for k in reversed(range(4)):
-                ct, c1, c2 = stages[k]
-                lv = 3 - k
-                s = pl.dec[d][k]
-                d_t = V(pl.d_t, s["a2"])
-                d_a1 = V(pl.d_a1, s["a1"])
-                skip = pl.enc[lv]["a2"]
-                # second conv of the DoubleConv
-                iy, d_y = take(pl.d_y, free_dy, slot_y, s["y2"])
-                self._bn_apply_bwd(pl, c2, d_t, s["y2"], d_y)
-                ops.conv3x3_dgrad(d_y, c2.wd, d_a1, bn=ctx(pl, c1, s["y1"]))
-                free_dy[iy] = side(lambda d_y=d_y, s=s, c2=c2: ops.conv3x3_wgrad(d_y, s["a1"], None, c2.g_w))
-                # first conv: two sources (skip, up)
-                iy, d_y = take(pl.d_y, free_dy, slot_y, s["y1"])
-                iu, d_up = take(pl.d_up, free_up, slot_u, s["up"])
-                self._bn_apply_bwd(pl, c1, d_a1, s["y1"], d_y)
-                ops.conv3x3_dgrad(d_y, c1.wd, pl.d_skip[lv], acc1=skip_written[lv], dx2=d_up, acc2=False,
-                                  stats=ct.g_bias)
+            grads.append(g.contiguous().float())
+        ops.zero_(self.gstage)
+        ops.zero_(self.bn_sums_all)
+        if parallel:
+            ev = torch.cuda.Event()
+            ev.record(s0)
+            streams[1].wait_event(ev)
+        enc4 = self.encoder[4][1]
+        bottleneck_done = None          # event: the previous decoder's contribution to d_skip[4] is stored
+        skip_written = [False] * 5
+
+        def decoder_stage(d, k, ch):
+            stages, head = self.decoders[d]
+            ct, c1, c2 = stages[k]
+            lv = 3 - k
+            s = pl.dec[d][k]
+            if k == 3:
+                ops.head_bwd(s["a2"], head.w, grads[d], outs[d], V(ch.d_t, s["a2"]), head.g_w, head.g_b, head.sigmoid,
+                             bn=ctx(pl, c2, s["y2"], kind="head"))
+            d_t = V(ch.d_t, s["a2"])
+            d_a1 = V(ch.d_a1, s["a1"])
+            skip = pl.enc[lv]["a2"]
+            # second conv of the DoubleConv
+            iy, d_y = ch.take_y(s["y2"])
+            self._bn_apply_bwd(pl, c2, d_t, s["y2"], d_y)
+            ops.conv3x3_dgrad(d_y, c2.wd, d_a1, bn=ctx(pl, c1, s["y1"]))
+            ch.free_y[iy] = ch.side(lambda: ops.conv3x3_wgrad(d_y, s["a1"], None, c2.g_w))
+            # first conv: two sources (skip, up)
+            iy, d_y1 = ch.take_y(s["y1"])
+            iu, d_up = ch.take_up(s["up"])
+            self._bn_apply_bwd(pl, c1, d_a1, s["y1"], d_y1)
+            if parallel and d > 0:      # own skip-gradient buffer: summed by the encoder's pool backward
+                ops.conv3x3_dgrad(d_y1, c1.wd, pl.d_skipx[d - 1][lv], acc1=False, dx2=d_up, acc2=False, stats=ct.g_bias)
+            else:
+                ops.conv3x3_dgrad(d_y1, c1.wd, pl.d_skip[lv], acc1=skip_written[lv], dx2=d_up, acc2=False, stats=ct.g_bias)
                 skip_written[lv] = True
-                free_dy[iy] = side(lambda d_y=d_y, s=s, c1=c1, skip=skip: ops.conv3x3_wgrad(d_y, skip, s["up"], c1.g_w))
-                # transposed conv
-                t_in = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
-                if k > 0:
-                    prev = stages[k - 1][2]
-                    ops.convt2x2_dgrad(d_up, ct.wd, V(pl.d_t, t_in), acc=False, bn=ctx(pl, prev, pl.dec[d][k - 1]["y2"]))
-                else:
-                    # the bottleneck gradient is complete after the LAST decoder processed (d == 0)
-                    ops.convt2x2_dgrad(d_up, ct.wd, pl.d_skip[4], acc=skip_written[4],
-                                       bn=ctx(pl, enc4, pl.enc[4]["y2"]) if d == 0 else None)
-                    skip_written[4] = True
-                free_up[iu] = side(lambda t_in=t_in, d_up=d_up, ct=ct: ops.convt2x2_wgrad(t_in, d_up, ct.g_w))
+            ch.free_y[iy] = ch.side(lambda: ops.conv3x3_wgrad(d_y1, skip, s["up"], c1.g_w))
+            # transposed conv
+            t_in = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
+            if k > 0:
+                prev = stages[k - 1][2]
+                ops.convt2x2_dgrad(d_up, ct.wd, V(ch.d_t, t_in), acc=False, bn=ctx(pl, prev, pl.dec[d][k - 1]["y2"]))
+            else:
+                # the bottleneck gradient is the sum over the decoders, complete after decoder 0 (processed last)
+                nonlocal bottleneck_done
+                if bottleneck_done is not None:
+                    ch.stream.wait_event(bottleneck_done)
+                ops.convt2x2_dgrad(d_up, ct.wd, pl.d_skip[4], acc=skip_written[4],
+                                   bn=ctx(pl, enc4, pl.enc[4]["y2"]) if d == 0 else None)
+                skip_written[4] = True
+                if parallel:
+                    bottleneck_done = torch.cuda.Event()
+                    bottleneck_done.record(ch.stream)
+            ch.free_up[iu] = ch.side(lambda: ops.convt2x2_wgrad(t_in, d_up, ct.g_w))
+
+        # decoders: enqueued stage by stage so that parallel chains advance together
+        for k in reversed(range(4)):
+            for d in reversed(range(n_dec)):
+                with torch.cuda.stream(chains[d].stream):
+                    decoder_stage(d, k, chains[d])
+        for d in reversed(range(n_dec)):
+            ch = chains[d]
+            done = None
+            if ch.stream is not s0:
+                done = torch.cuda.Event()
+                done.record(ch.stream)
+                s0.wait_event(done)
             if self.ddp is not None:
-                self.ddp.segment_ready(self, ("dec", d), last_w[0])
+                self.ddp.segment_ready(self, ("dec", d), [e for e in (done, ch.last_w) if e is not None])
+        ch = chains[0]
         for l in reversed(range(5)):
             c1, c2 = self.encoder[l]
             e = pl.enc[l]
-            d_a1 = V(pl.d_a1, e["a1"])
-            iy, d_y = take(pl.d_y, free_dy, slot_y, e["y2"])
+            d_a1 = V(ch.d_a1, e["a1"])
+            iy, d_y = ch.take_y(e["y2"])
             self._bn_apply_bwd(pl, c2, pl.d_skip[l], e["y2"], d_y)
             ops.conv3x3_dgrad(d_y, c2.wd, d_a1, bn=ctx(pl, c1, e["y1"]))
-            free_dy[iy] = side(lambda d_y=d_y, e=e, c2=c2: ops.conv3x3_wgrad(d_y, e["a1"], None, c2.g_w))
-            iy, d_y = take(pl.d_y, free_dy, slot_y, e["y1"])
+            ch.free_y[iy] = ch.side(lambda d_y=d_y, e=e, c2=c2: ops.conv3x3_wgrad(d_y, e["a1"], None, c2.g_w))
+            iy, d_y = ch.take_y(e["y1"])
             self._bn_apply_bwd(pl, c1, d_a1, e["y1"], d_y)
             if l == 0:
                 def first_wgrad(d_y=d_y, c1=c1):
@@ -582,20 +663,22 @@ class Engine:
                         ops.first_conv_wgrad_tc(pl.x64, d_y, pl.fc_scratch, c1.g_w)
                     else:
                         ops.first_conv_wgrad(pl.x, d_y, c1.g_w)
-                free_dy[iy] = side(first_wgrad)
+                ch.free_y[iy] = ch.side(first_wgrad)
             else:
                 src = pl.enc[l - 1]["p"]
                 d_p = V(pl.d_p, src)
                 ops.conv3x3_dgrad(d_y, c1.wd, d_p)
                 # the skip gradient of level l-1 is complete after this accumulation
                 ops.maxpool_bwd(d_p, pl.enc[l - 1]["idx"], pl.d_skip[l - 1], accumulate=skip_written[l - 1],
+                                extra=pl.d_skipx[0][l - 1] if parallel else None,
                                 bn=ctx(pl, self.encoder[l - 1][1], pl.enc[l - 1]["y2"]))
                 skip_written[l - 1] = True
-                free_dy[iy] = side(lambda d_y=d_y, src=src, c1=c1: ops.conv3x3_wgrad(d_y, src, None, c1.g_w))
+                ch.free_y[iy] = ch.side(lambda d_y=d_y, src=src, c1=c1: ops.conv3x3_wgrad(d_y, src, None, c1.g_w))
             if self.ddp is not None and l in (3, 0):
-                self.ddp.segment_ready(self, ("enc", l), last_w[0])
-        if last_w[0] is not None:
-            s0.wait_event(last_w[0])      # every weight gradient is in the staging buffer
+                self.ddp.segment_ready(self, ("enc", l), [ch.last_w] if ch.last_w is not None else [])
+        for c in chains:
+            if c.last_w is not None:
+                s0.wait_event(c.last_w)       # every weight gradient is in the staging buffer
         scale = 1.0
         if self.ddp is not None:
             scale = self.ddp.finish(self)

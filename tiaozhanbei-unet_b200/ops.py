@@ -202,10 +202,12 @@ def bnrelu_pool(y, scale, shift, a, pooled, idx, apply=True):
               int(apply), _s())
 
 
-def maxpool_bwd(dpooled, idx, da, accumulate, bn=None):
+def maxpool_bwd(dpooled, idx, da, accumulate, bn=None, extra=None):
     _chk(dpooled, bf16, "dpooled"); _chk(da, bf16, "da")
     n, h, w, c = da.shape
-    _lib.call("unetk_maxpool_bwd", _p(dpooled), _p(idx), _p(da), n, h, w, c, int(accumulate), _bn(bn), _s())
+    if extra is not None:
+        _chk(extra, bf16, "extra")
+    _lib.call("unetk_maxpool_bwd", _p(dpooled), _p(idx), _p(da), n, h, w, c, int(accumulate), _p(extra), _bn(bn), _s())
 
 
 def bn_bwd_reduce(da, y, scale, shift, mean, invstd, sums):

@@ -48,7 +48,10 @@ LAYERS = [("inc.3", 0, 64, 0, 64, 1), ("down1.0", 1, 64, 0, 128, 1), ("down1.3",
           ("up1.0", 3, 512, 512, 512, 2), ("up1.3", 3, 512, 0, 512, 2), ("up2.0", 2, 256, 256, 256, 2),
           ("up2.3", 2, 256, 0, 256, 2), ("up3.0", 1, 128, 128, 128, 2), ("up3.3", 1, 128, 0, 128, 2),
           ("up4.0", 0, 64, 64, 64, 2), ("up4.3", 0, 64, 0, 64, 2)]
-tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+ONLY_STEP = os.environ.get("ONLY_STEP", "0") == "1"
+if ONLY_STEP:
+    LAYERS = []
+tot = {"fwd": 1e-9, "dgrad": 1e-9, "wgrad": 1e-9}
 totf = 0.0
 log(f"# conv3x3 layers at B={B}, {H}x{H}: ms and TFLOP/s per pass")
 for name, lvl, c1, c2, cout, cnt in LAYERS:
@@ -82,7 +85,7 @@ log(f"sum conv3x3 (tcgen05 layers): fwd {tot['fwd']:.2f} ms, dgrad {tot['dgrad']
     f"{totf/1e12:.2f} TFLOP per pass -> fwd {totf/tot['fwd']/1e9:.0f} TF/s dgrad {totf/tot['dgrad']/1e9:.0f} wgrad {totf/tot['wgrad']/1e9:.0f}")
 
 log("# convT layers")
-for k, (lvl, cin) in enumerate([(4, 1024), (3, 512), (2, 256), (1, 128)]):
+for k, (lvl, cin) in enumerate([] if ONLY_STEP else [(4, 1024), (3, 512), (2, 256), (1, 128)]):
     h = H >> lvl
     cout = cin // 2
     a = bf(B, h, h, cin)
