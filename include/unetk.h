@@ -98,6 +98,9 @@ int unetk_first_conv_wgrad(const float* x, const void* dy, float* dw, int n, int
  * unetk_first_conv_wgrad_tc runs the 64->64 conv3x3 weight gradient on it (scratch: 64*9*64 floats,
  * zeroed by the call) and gathers dw in OIHW [64][cin][3][3] (overwritten). */
 int unetk_image_to_nhwc64(const float* x, void* x64, int n, int cin, int h, int w_, void* stream);
+/* The forward pass can take the same route: unetk_first_conv_pack writes the OIHW fp32 weight as
+ * Wf[64][9][64] bf16 (zero beyond cin), then unetk_conv3x3_fwd(x64, 64, NULL, 0, wf, ...) is the layer. */
+int unetk_first_conv_pack(const float* w, void* wf, int cin, void* stream);
 int unetk_first_conv_wgrad_tc(const void* x64, const void* dy, float* scratch, float* dw, int n,
                               int cin, int h, int w_, int cout, void* stream);
 

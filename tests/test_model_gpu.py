@@ -321,3 +321,53 @@ def test_full_size_config2_against_oracle(cuda_device):
     for i, (got, rf) in enumerate(zip(full, ref)):
         _check_out(got, rf, f"config-2 eval output {i}")
         _check_masks(got, rf, f"config-2 eval output {i}")
+
+
+def test_config4_inference_512_sharded(cuda_device):
+    """BASELINE config 4 shape class (UNet inference anomaly-map scoring at 512x512; 8 of the 64 images to
+    bound test time): sigmoid(UNet(x)) against the fp32 oracle, the src/test.py:88-96 scoring pattern, and
+    shard independence — contiguous image shards (what N ranks would each run) give bit-identical rows."""
+    from tiaozhanbei_unet_b200 import distributed as D, utils
+    dev = cuda_device
+    sd = O.synthetic_state_dict("unet", seed=9, device=dev)
+    m = _model("unet", {k: v.clone() for k, v in sd.items()}, dev).eval()
+    image, _ = _inputs(0, 8, 512, 512, dev)
+    with torch.no_grad():
+        amap = torch.sigmoid(m(image))
+        ref = torch.sigmoid(O.unet_forward({k: v.clone() for k, v in sd.items()}, image, training=False))
+    assert amap.shape == (8, 1, 512, 512) and amap.dtype == torch.float32
+    _check_out(amap, ref, "config-4 anomaly map")
+    _check_masks(amap, ref, "config-4 anomaly map")
+    # UNet branch of test_model: reconstruction = images, so the score map is identically zero
+    score = utils.compute_anomaly_score(image, image)
+    assert score.shape == (8, 512, 512) and float(score.abs().max()) == 0.0
+    world = 4
+    covered = 0
+    for rank in range(world):
+        b, e = D.shard_range(8, rank, world)
+        with torch.no_grad():
+            part = torch.sigmoid(m(image[b:e].contiguous()))
+        assert torch.equal(part, amap[b:e]), f"shard {rank} differs from the unsharded run"
+        covered += e - b
+    assert covered == 8
+
+
+def test_config5_strip_train_step(cuda_device):
+    """BASELINE config 5 shape class (UNet training on a 512x1408 KolektorSDD-shaped strip, one image per
+    GPU, grayscale replicated to RGB): loss and gradients of one step against the fp32 oracle."""
+    dev = cuda_device
+    sd = O.synthetic_state_dict("unet", seed=5, device=dev)
+    m = _model("unet", {k: v.clone() for k, v in sd.items()}, dev).train()
+    g = torch.Generator().manual_seed(0)
+    image = torch.randn(1, 1, 512, 1408, generator=g).expand(-1, 3, -1, -1).contiguous().to(dev)
+    mask = (torch.rand(1, 1, 512, 1408, generator=g) > 0.95).float().to(dev)
+    p = torch.sigmoid(m(image))
+    bce = torch.nn.functional.binary_cross_entropy(p, mask, reduction="none")
+    loss = torch.nn.functional.mse_loss(p, mask) + (0.25 * (1 - torch.exp(-bce)) ** 2 * bce).mean()
+    loss.backward()
+    ref_losses, ref_grads = O.train_step({k: v.clone() for k, v in sd.items()}, image, mask, arch="unet")
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref_losses["total_loss"]) <= LOSS_REL * abs(ref_losses["total_loss"]), (loss.item(), ref_losses)
+    worst = _check_grads(m.named_parameters(), ref_grads, "config-5 strip")
+    print(f"[parity] config-5 strip 1x512x1408: loss {loss.item():.6f} vs {ref_losses['total_loss']:.6f}; "
+          f"worst grad cosine {worst[0]:.3f}, worst head-side rel err {worst[1]:.3e}")

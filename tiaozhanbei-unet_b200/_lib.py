@@ -26,6 +26,7 @@ SIGNATURES = {
     "unetk_first_conv_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "unetk_first_conv_wgrad": (I, [P, P, P, I, I, I, I, I, P]),
     "unetk_image_to_nhwc64": (I, [P, P, I, I, I, I, P]),
+    "unetk_first_conv_pack": (I, [P, P, I, P]),
     "unetk_first_conv_wgrad_tc": (I, [P, P, P, P, I, I, I, I, I, P]),
     "unetk_convt2x2_fwd": (I, [P, I, P, P, P, I, I, I, I, P]),
     "unetk_convt2x2_dgrad": (I, [P, I, P, P, I, I, P, I, I, I, P]),

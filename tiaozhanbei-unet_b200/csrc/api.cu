@@ -53,6 +53,9 @@ int unetk_first_conv_fwd(const float* x, const float* w, void* y, float* stats, 
 int unetk_image_to_nhwc64(const float* x, void* x64, int n, int cin, int h, int w_, void* stream) {
   return unetk::image_to_nhwc64(x, x64, n, cin, h, w_, S(stream));
 }
+int unetk_first_conv_pack(const float* w, void* wf, int cin, void* stream) {
+  return unetk::first_conv_pack(w, wf, cin, S(stream));
+}
 int unetk_first_conv_wgrad_tc(const void* x64, const void* dy, float* scratch, float* dw, int n,
                               int cin, int h, int w_, int cout, void* stream) {
   return unetk::first_conv_wgrad_tc(x64, dy, scratch, dw, n, cin, h, w_, cout, S(stream));

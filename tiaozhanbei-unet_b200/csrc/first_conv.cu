@@ -207,6 +207,22 @@ __global__ void first_conv_gather_kernel(const float* __restrict__ scratch, floa
   dw[i] = scratch[(co * 9 + tap) * 64 + ci];
 }
 
+// OIHW fp32 [64][Cin][3][3] -> Wf[co][tap][64 ci] bf16, zero beyond Cin (B operand of the 64 -> 64 kernel)
+__global__ void first_conv_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, int Cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kFcCout * 9 * 64) return;
+  const int ci = i & 63, tap = (i >> 6) % 9, co = i / (9 * 64);
+  wf[i] = __float2bfloat16(ci < Cin ? w[(co * Cin + ci) * 9 + tap] : 0.f);
+}
+
+int first_conv_pack(const float* w, void* wf, int Cin, cudaStream_t s) {
+  UNETK_CHECK_ARG(w && wf, "first_conv_pack: null pointer");
+  UNETK_CHECK_ARG(Cin >= 1 && Cin <= 8, "first_conv_pack: 1..8 input channels supported (got %d)", Cin);
+  first_conv_pack_kernel<<<(kFcCout * 9 * 64 + 255) / 256, 256, 0, s>>>(w, static_cast<__nv_bfloat16*>(wf), Cin);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
 int image_to_nhwc64(const float* x, void* x64, int N, int Cin, int H, int W, cudaStream_t s) {
   UNETK_CHECK_ARG(x && x64, "image_to_nhwc64: null pointer");
   UNETK_CHECK_ARG(Cin >= 1 && Cin <= 8, "image_to_nhwc64: 1..8 input channels supported (got %d)", Cin);

@@ -39,6 +39,7 @@ int convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw,
 int first_conv_fwd(const float* x, const float* w, void* y, float* stats, int N, int Cin, int H, int W,
                    int cout, cudaStream_t s);
 int image_to_nhwc64(const float* x, void* x64, int N, int Cin, int H, int W, cudaStream_t s);
+int first_conv_pack(const float* w, void* wf, int Cin, cudaStream_t s);
 int first_conv_wgrad_tc(const void* x64, const void* dy, float* scratch, float* dw, int N, int Cin, int H, int W,
                         int cout, cudaStream_t s);
 int first_conv_wgrad(const float* x, const void* dy, float* dw, int N, int Cin, int H, int W, int cout,

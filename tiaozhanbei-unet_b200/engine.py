@@ -34,6 +34,9 @@ WIDTHS = [64, 128, 256, 512, 1024]
 FUSE_BN_REDUCE = os.environ.get("UNETK_FUSE_BN_REDUCE", "head")
 FUSE_CHECK = os.environ.get("UNETK_FUSE_CHECK", "0") == "1"
 FIRST_WGRAD_TC = os.environ.get("UNETK_FIRST_WGRAD_TC", "1") != "0"
+# The first conv (Cin = 3) as the 64 -> 64 tcgen05 layer on the channel-padded bf16 image (0.19 -> ~0.12 ms
+# at 16 x 256^2, and eval mode gets BatchNorm+ReLU in the epilogue); "0" = CUDA-core kernel on the fp32 image.
+FIRST_FWD_TC = os.environ.get("UNETK_FIRST_FWD_TC", "1") != "0"
 # Weight gradients are off the critical path of backward (nothing downstream reads them before the
 # optimizer): they run on a side stream, each one released only after the data gradient of the same layer,
 # so the tensor-bound wgrad kernel shares the SMs with the memory-bound BatchNorm-backward passes of the
@@ -104,6 +107,9 @@ class Plan:
             self.dec.append(stages)
         self._act = act
         self.n_dec = len(eng.decoders)
+        # the image as NHWC bf16 zero-padded to 64 channels (first conv on the tensor cores); the padding
+        # channels are written once, here
+        self.x64 = ops.zero_(act(0, 64)) if eng.n_channels <= 8 else None
         self.grads_ready = False
         self.bnctx = {}
         self.fused = set()
@@ -123,9 +129,7 @@ class Plan:
         self.scratch = [{"d_t": act(0, 64), "d_a1": act(0, 64), "d_y": [act(0, 64), act(0, 64)],
                          "d_up": [act(0, 64), act(0, 64)]} for _ in range(self.n_dec)]
         self.d_p = act(1, 64)       # gradient wrt a pooled tensor (max size)
-        # first conv weight gradient on the tensor cores: channel-padded image (padding written once here)
-        self.x64 = ops.zero_(act(0, 64))
-        self.fc_scratch = torch.empty(64 * 9 * 64, dtype=torch.float32, device=self.x64.device)
+        self.fc_scratch = torch.empty(64 * 9 * 64, dtype=torch.float32, device=self.d_p.device)   # first conv dW[co][tap][64]
         self.grads_ready = True
 
     @staticmethod
@@ -303,6 +307,7 @@ class Engine:
             if L.first:
                 L.g_w = self._slice(self.gstage, wk)            # written in OIHW directly
                 unpack.add(self.offsets[wk], self.offsets[wk], *packing.identity(n))
+                wplan.append((L, "wf0", walloc(64 * 9 * 64), 64 * 9 * 64))   # Wf[64][9][64], zero beyond Cin
             else:
                 L.g_w = self._slice(self.gstage, wk, (n,))      # [Cout][tap][Cin]
                 of, od = walloc(n), walloc(n)
@@ -366,7 +371,13 @@ class Engine:
         if self.weights_dirty:
             ops.pack_conv_weights(self.conv_pack_table, self.flat_p, self.wpack)     # conv3x3 layers (tiled)
             ops.permute_batched(self.pack_table, self.flat_p, self.wpack)            # transposed convs
+            first = self.encoder[0][0]
+            if self._first_tc():
+                ops.first_conv_pack(first.w, first.wf0)
             self.weights_dirty = False
+
+    def _first_tc(self):
+        return FIRST_FWD_TC and self.n_channels <= 8 and self.encoder[0][0].cout == 64
 
     def grad_views(self):
         """Fresh views of the flat gradient buffer, one per parameter (autograd takes ownership)."""
@@ -434,7 +445,10 @@ class Engine:
         for l, (c1, c2) in enumerate(self.encoder):
             e = pl.enc[l]
             count = n * (pl.h >> l) * (pl.w >> l)
-            if l == 0:
+            if l == 0 and self._first_tc():
+                ops.image_to_nhwc64(x, pl.x64)
+                ops.conv3x3_fwd(pl.x64, None, c1.wf0, e["y1"], stats=c1.stats, algo_cin=self.n_channels)
+            elif l == 0:
                 ops.first_conv_fwd(x, c1.w, e["y1"], c1.stats)
             else:
                 ops.conv3x3_fwd(pl.enc[l - 1]["p"], None, c1.wf, e["y1"], stats=c1.stats)
@@ -506,7 +520,11 @@ class Engine:
         n = pl.n
         for l, (c1, c2) in enumerate(self.encoder):
             e = pl.enc[l]
-            if l == 0:
+            if l == 0 and self._first_tc():
+                ops.image_to_nhwc64(x, pl.x64)
+                ops.conv3x3_fwd(pl.x64, None, c1.wf0, e["a1"], scale=c1.scale, shift=c1.shift, relu=True,
+                                algo_cin=self.n_channels)
+            elif l == 0:
                 ops.first_conv_fwd(x, c1.w, e["y1"], None)
                 ops.bnrelu_apply(e["y1"], c1.scale, c1.shift, e["a1"])
             else:
@@ -659,7 +677,8 @@ class Engine:
             if l == 0:
                 def first_wgrad(d_y=d_y, c1=c1):
                     if self.n_channels <= 8 and FIRST_WGRAD_TC:
-                        ops.image_to_nhwc64(pl.x, pl.x64)
+                        if not self._first_tc():                 # otherwise the forward pass already wrote x64
+                            ops.image_to_nhwc64(pl.x, pl.x64)
                         ops.first_conv_wgrad_tc(pl.x64, d_y, pl.fc_scratch, c1.g_w)
                     else:
                         ops.first_conv_wgrad(pl.x, d_y, c1.g_w)

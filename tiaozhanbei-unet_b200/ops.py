@@ -51,12 +51,30 @@ def collect_conv_timing(rec):
     """-> (algorithmic FLOPs, summed kernel milliseconds, launches); disables the instrumentation."""
     global _timing
     _timing = None
-    flops = sum(f for f, _, _ in rec)
-    ms = sum(a.elapsed_time(b) for _, a, b in rec)
+    flops = sum(r[0] for r in rec)
+    ms = sum(r[1].elapsed_time(r[2]) for r in rec)
     return flops, ms, len(rec)
 
 
-def _timed(flops, name, *args):
+def conv_timing_by_kernel(rec):
+    """{kernel variant: (algorithmic FLOPs, milliseconds, launches)} of an instrumentation record (call
+    before collect_conv_timing's result is discarded; events must have completed)."""
+    out = {}
+    for flops, e0, e1, tag in rec:
+        f, ms, n = out.get(tag, (0.0, 0.0, 0))
+        out[tag] = (f + flops, ms + e0.elapsed_time(e1), n + 1)
+    return out
+
+
+def _igemm_variant(ncols):
+    """Name of the igemm_kernel<BN, SUBS, CTAS> instantiation launch_igemm (csrc/igemm.cu) picks for a GEMM
+    with `ncols` output columns."""
+    if ncols % 256 == 0:
+        return "igemm_kernel<256,1,2>"
+    return "igemm_kernel<128,2,2>" if ncols % 128 == 0 else "igemm_kernel<64,2,2>"
+
+
+def _timed(flops, tag, name, *args):
     if _timing is None:
         _lib.call(name, *args)
         return
@@ -64,7 +82,7 @@ def _timed(flops, name, *args):
     e0.record()
     _lib.call(name, *args)
     e1.record()
-    _timing.append((flops, e0, e1))
+    _timing.append((flops, e0, e1, tag))
 
 
 def bn_ctx(y, scale, shift, mean, invstd, sums):
@@ -87,7 +105,13 @@ def zero_(t):
 # ---------------------------------------------------------------------------------------------
 # convolutions
 # ---------------------------------------------------------------------------------------------
-def conv3x3_fwd(src1, src2, wf, y, stats=None, scale=None, shift=None, relu=False):
+def first_conv_pack(w, wf):
+    """OIHW fp32 [64, cin, 3, 3] -> Wf[64][9][64] bf16, zero beyond cin."""
+    _chk(w, f32, "w"); _chk(wf, bf16, "wf")
+    _lib.call("unetk_first_conv_pack", _p(w), _p(wf), w.shape[1], _s())
+
+
+def conv3x3_fwd(src1, src2, wf, y, stats=None, scale=None, shift=None, relu=False, algo_cin=None):
     """y = conv3x3(cat(src1, src2)) with packed weights wf [Cout][9][Cin]."""
     _chk(src1, bf16, "src1"); _chk(wf, bf16, "wf"); _chk(y, bf16, "y")
     n, h, w, c1 = src1.shape
@@ -96,7 +120,8 @@ def conv3x3_fwd(src1, src2, wf, y, stats=None, scale=None, shift=None, relu=Fals
         _chk(src2, bf16, "src2")
         c2 = src2.shape[3]
     cout = y.shape[3]
-    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "unetk_conv3x3_fwd", _p(src1), c1, _p(src2), c2, _p(wf), _p(y), _p(stats), _p(scale),
+    # algo_cin: the layer's real input channels when src1 is zero-padded (first conv): only algorithmic FLOPs count
+    _timed(2.0 * n * h * w * cout * 9 * (algo_cin if algo_cin is not None else c1 + c2), _igemm_variant(cout), "unetk_conv3x3_fwd", _p(src1), c1, _p(src2), c2, _p(wf), _p(y), _p(stats), _p(scale),
               _p(shift), int(relu), n, h, w, cout, _s())
     return y
 
@@ -109,7 +134,7 @@ def conv3x3_dgrad(dy, wd, dx1, acc1=False, dx2=None, acc2=False, stats=None, bn=
     if dx2 is not None:
         _chk(dx2, bf16, "dx2")
         c2 = dx2.shape[3]
-    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "unetk_conv3x3_dgrad", _p(dy), cout, _p(wd), _p(dx1), c1, int(acc1), _p(dx2), c2,
+    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), _igemm_variant(c1 + c2), "unetk_conv3x3_dgrad", _p(dy), cout, _p(wd), _p(dx1), c1, int(acc1), _p(dx2), c2,
            int(acc2), _p(stats), _bn(bn), n, h, w, _s())
 
 
@@ -122,7 +147,7 @@ def conv3x3_wgrad(dy, src1, src2, dw):
     if src2 is not None:
         _chk(src2, bf16, "src2")
         c2 = src2.shape[3]
-    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "unetk_conv3x3_wgrad", _p(dy), _p(src1), c1, _p(src2), c2, _p(dw), n, h, w, cout, _s())
+    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "wgrad_kernel", "unetk_conv3x3_wgrad", _p(dy), _p(src1), c1, _p(src2), c2, _p(dw), n, h, w, cout, _s())
 
 
 def first_conv_fwd(x, w, y, stats=None):
@@ -157,20 +182,20 @@ def first_conv_wgrad_tc(x64, dy, scratch, dw):
 def convt2x2_fwd(a, wt, bias, up):
     _chk(a, bf16, "a"); _chk(wt, bf16, "wt"); _chk(up, bf16, "up")
     n, h, w, cin = a.shape
-    _timed(2.0 * n * h * w * cin * 4 * up.shape[3], "unetk_convt2x2_fwd", _p(a), cin, _p(wt), _p(bias), _p(up), n, h, w, up.shape[3], _s())
+    _timed(2.0 * n * h * w * cin * 4 * up.shape[3], _igemm_variant(4 * up.shape[3]), "unetk_convt2x2_fwd", _p(a), cin, _p(wt), _p(bias), _p(up), n, h, w, up.shape[3], _s())
     return up
 
 
 def convt2x2_dgrad(dup, wtd, da, acc=False, bn=None):
     _chk(dup, bf16, "dup"); _chk(wtd, bf16, "wtd"); _chk(da, bf16, "da")
     n, h, w, cin = da.shape
-    _timed(2.0 * n * h * w * cin * 4 * dup.shape[3], "unetk_convt2x2_dgrad", _p(dup), dup.shape[3], _p(wtd), _p(da), cin, int(acc), _bn(bn), n, h, w, _s())
+    _timed(2.0 * n * h * w * cin * 4 * dup.shape[3], _igemm_variant(cin), "unetk_convt2x2_dgrad", _p(dup), dup.shape[3], _p(wtd), _p(da), cin, int(acc), _bn(bn), n, h, w, _s())
 
 
 def convt2x2_wgrad(a, dup, dw):
     _chk(a, bf16, "a"); _chk(dup, bf16, "dup"); _chk(dw, f32, "dw")
     n, h, w, cin = a.shape
-    _timed(2.0 * n * h * w * cin * 4 * dup.shape[3], "unetk_convt2x2_wgrad", _p(a), cin, _p(dup), dup.shape[3], _p(dw), n, h, w, _s())
+    _timed(2.0 * n * h * w * cin * 4 * dup.shape[3], "wgrad_kernel", "unetk_convt2x2_wgrad", _p(a), cin, _p(dup), dup.shape[3], _p(dw), n, h, w, _s())
 
 
 # ---------------------------------------------------------------------------------------------
