@@ -168,6 +168,43 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # this build
 # ---------------------------------------------------------------------------------------------
+def measure_inference(torch, dist, world, rank, dev, timed):
+    """UNet eval: sigmoid(model(x)) + compute_anomaly_score on this rank's shard of 64 512x512 images."""
+    from tiaozhanbei_unet_b200 import distributed as D, utils
+    from tiaozhanbei_unet_b200.model import UNet
+    total = 64
+    b, e = D.shard_range(total, rank, world)
+    torch.manual_seed(42)
+    m = UNet(3, 1).to(dev).eval()
+    gen = torch.Generator().manual_seed(2000 + rank)
+    host = torch.randn(e - b, 3, 512, 512, generator=gen).pin_memory()
+    x = host.to(dev)
+
+    def run(img):
+        with torch.no_grad():
+            amap = torch.sigmoid(m(img))
+            score = utils.compute_anomaly_score(img, img)       # UNet branch: reconstruction = images
+        return amap, score
+
+    for _ in range(3):
+        run(x)
+    k = 5
+    ms = timed(lambda i: run(x), k)
+
+    def e2e(i):
+        amap, score = run(host.to(dev, non_blocking=True))
+        amap.cpu(); score.cpu()                                  # the caller's .cpu() of every map (src/test.py:99-106)
+    e2e(0)
+    ms_e2e = timed(e2e, k)
+    del m, x
+    torch.cuda.empty_cache()
+    return {"metric": "inference_images_per_sec_512x512", "value": total * k / (ms / 1e3), "unit": "img/s",
+            "e2e": total * k / (ms_e2e / 1e3), "ms_per_pass": ms / k,
+            "config": f"UNet(3,1) eval, sigmoid anomaly map + anomaly score, {total} images of 512x512 sharded {world}-way "
+                      f"({e - b} per GPU), no communication; e2e adds the H2D of the images and the D2H of both maps",
+            "gflop_per_image": 385.34}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -286,6 +323,12 @@ def run_ours(args):
                                         "by_kernel": {k: {"tflops": v[0] / (v[1] / 1e3) / 1e12, "ms_per_step": v[1] / k_inst,
                                                           "launches_per_step": v[2] // k_inst} for k, v in by_kernel.items()}}}
 
+    # ---- secondary figure: BASELINE configs[3], UNet inference anomaly-map scoring, 64 images of 512x512
+    # sharded contiguously over the ranks, no communication (src/test.py:88-96 pattern)
+    infer = None
+    if not args.no_inference:
+        infer = measure_inference(torch, dist, world, rank, dev, timed)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, threads, sample = cpu_reference_rate(steps=2, warmup=1, budget_s=25.0)
@@ -308,6 +351,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "inference": infer,
             "tensor_frac_whole_step": world and (TRAIN_GFLOP_PER_IMG * B * args.steps / (ms / 1e3) / 1e3) / read_peaks()["tflops_sustained"],
             "loss": criterion.last_values()[0],
         }
@@ -323,6 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

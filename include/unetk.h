@@ -58,6 +58,26 @@ typedef struct {
   float* sums;            /* [2][C] */
 } unetk_bn_ctx;
 
+/* Training-mode BatchNorm finalize folded into the kernel that applies it (HOST struct, read at launch):
+ * (scale, shift) are derived from the batch sums by every thread exactly as unetk_bn_finalize does; one
+ * block also stores scale / shift / mean / invstd and updates running_mean / running_var (momentum,
+ * unbiased variance) and num_batches_tracked (all three nullable). */
+typedef struct {
+  const float* stats;        /* [2][C] sum, sum of squares from the conv epilogue */
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  float* scale;              /* outputs, [C] each */
+  float* shift;
+  float* mean;
+  float* invstd;
+  float count;               /* N*H*W */
+  float eps;
+  float momentum;
+} unetk_bn_finalize_args;
+
 int unetk_version(void);
 const char* unetk_last_error(void);
 /* 0 when the current CUDA device is compute capability 10.x, UNETK_ERR_ARCH otherwise. */
@@ -132,6 +152,11 @@ int unetk_bnrelu_apply(const void* y, const float* scale, const float* shift, vo
 /* ---- nn.MaxPool2d(2): src/model.py:32, fused with the BatchNorm+ReLU that feeds it --------- */
 /* apply != 0: a = relu(y*scale+shift) is written too.  pooled = max over 2x2, idx (uint8 per
  * element, may be NULL) = position 0..3 of the first maximum. */
+/* The same two kernels with unetk_bn_finalize folded in (training forward: conv -> this). */
+int unetk_bnrelu_apply_fin(const void* y, const unetk_bn_finalize_args* fin, void* a, int64_t npix, int c,
+                           void* stream);
+int unetk_bnrelu_pool_fin(const void* y, const unetk_bn_finalize_args* fin, void* a, void* pooled, void* idx,
+                          int n, int h, int w, int c, void* stream);
 int unetk_bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
                       void* idx, int n, int h, int w, int c, int apply, void* stream);
 /* da[2x2 window] (+)= scatter of dpooled by idx; accumulate != 0 adds to the existing da; extra (may be

@@ -263,6 +263,23 @@ def test_bn_relu_pool_roundtrip(cuda_device, n, h, w, c):
     _close(_nchw(a), a_ref.detach(), 1e-2, "bnrelu (pool variant)")
     assert torch.equal(a, a2)
     _close(_nchw(pooled), p_ref.detach(), 1e-2, "pooled")
+    # the same with the finalize folded into the kernels: bit-identical outputs, constants and running stats
+    for pool_variant in (False, True):
+        rm2 = torch.zeros(c, device=dev); rv2 = torch.ones(c, device=dev); nbt2 = torch.zeros((), dtype=torch.int64, device=dev)
+        sc2 = torch.empty(c, device=dev); sh2 = torch.empty(c, device=dev); mu2 = torch.empty(c, device=dev); iv2 = torch.empty(c, device=dev)
+        fin = ops.bn_finalize_args(stats, gamma, beta, rm2, rv2, nbt2, sc2, sh2, mu2, iv2, n * h * w, 1e-5, 0.1)
+        a3 = torch.empty_like(yb)
+        if pool_variant:
+            pooled3 = torch.empty_like(pooled); idx3 = torch.empty_like(idx)
+            ops.bnrelu_pool_fin(yb, fin, a3, pooled3, idx3)
+        else:
+            ops.bnrelu_apply_fin(yb, fin, a3)
+        torch.cuda.synchronize()
+        assert torch.equal(a3, a) and int(nbt2.item()) == 1
+        for got, want in ((sc2, scale), (sh2, shift), (mu2, mean), (iv2, invstd), (rm2, rm), (rv2, rv)):
+            assert torch.equal(got, want)
+        if pool_variant:
+            assert torch.equal(pooled3, pooled) and torch.equal(idx3, idx)
     # backward: upstream gradient on the pooled tensor
     dp = torch.randn(n, c, h // 2, w // 2, generator=g).to(dev)
     dpb = _nhwc(dp)

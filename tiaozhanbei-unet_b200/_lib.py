@@ -35,6 +35,8 @@ SIGNATURES = {
     "unetk_bn_fold": (I, [P, P, P, P, P, P, I, F, P]),
     "unetk_bnrelu_apply": (I, [P, P, P, P, L, I, P]),
     "unetk_bnrelu_pool": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
+    "unetk_bnrelu_apply_fin": (I, [P, P, P, L, I, P]),
+    "unetk_bnrelu_pool_fin": (I, [P, P, P, P, P, I, I, I, I, P]),
     "unetk_maxpool_bwd": (I, [P, P, P, I, I, I, I, I, P, P, P]),
     "unetk_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, L, I, P]),
     "unetk_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, L, I, P]),
@@ -65,6 +67,14 @@ class BnCtx(ctypes.Structure):
     """Mirror of `unetk_bn_ctx` (include/unetk.h): fused BatchNorm-backward first pass."""
     _fields_ = [("y", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("mean", c_void_p), ("invstd", c_void_p),
                 ("sums", c_void_p)]
+
+
+class BnFinalizeArgs(ctypes.Structure):
+    """Mirror of `unetk_bn_finalize_args` (include/unetk.h)."""
+    _fields_ = [("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p),
+                ("running_var", c_void_p), ("num_batches_tracked", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
+                ("mean", c_void_p), ("invstd", c_void_p), ("count", ctypes.c_float), ("eps", ctypes.c_float),
+                ("momentum", ctypes.c_float)]
 
 
 _lib = None

@@ -93,6 +93,15 @@ int unetk_bnrelu_apply(const void* y, const float* scale, const float* shift, vo
                        int c, void* stream) {
   return unetk::bnrelu_apply(y, scale, shift, a, static_cast<long>(npix), c, S(stream));
 }
+static const unetk::BnFinalizeArgs* F(const unetk_bn_finalize_args* f) { return reinterpret_cast<const unetk::BnFinalizeArgs*>(f); }
+static_assert(sizeof(unetk_bn_finalize_args) == sizeof(unetk::BnFinalizeArgs), "unetk_bn_finalize_args mirrors BnFinalizeArgs");
+int unetk_bnrelu_apply_fin(const void* y, const unetk_bn_finalize_args* fin, void* a, int64_t npix, int c, void* stream) {
+  return unetk::bnrelu_apply_fin(y, F(fin), a, static_cast<long>(npix), c, S(stream));
+}
+int unetk_bnrelu_pool_fin(const void* y, const unetk_bn_finalize_args* fin, void* a, void* pooled, void* idx, int n,
+                          int h, int w, int c, void* stream) {
+  return unetk::bnrelu_pool_fin(y, F(fin), a, pooled, idx, n, h, w, c, S(stream));
+}
 int unetk_bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
                       void* idx, int n, int h, int w, int c, int apply, void* stream) {
   return unetk::bnrelu_pool(y, scale, shift, a, pooled, idx, n, h, w, c, apply, S(stream));

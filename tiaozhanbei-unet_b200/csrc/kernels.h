@@ -18,6 +18,24 @@ struct BnReduceCtx {
   float* sums;
 };
 
+// Training-mode BatchNorm finalize folded into the kernel that applies it (same layout as
+// unetk_bn_finalize_args in unetk.h).
+struct BnFinalizeArgs {
+  const float* stats;        // [2][C] sum, sum of squares (conv epilogue)
+  const float* gamma;
+  const float* beta;
+  float* running_mean;       // nullable pair
+  float* running_var;
+  long long* num_batches_tracked;   // nullable
+  float* scale;              // outputs [C] each, kept for the backward pass
+  float* shift;
+  float* mean;
+  float* invstd;
+  float count;               // N*H*W
+  float eps;
+  float momentum;
+};
+
 // igemm.cu — K-major implicit GEMMs (tcgen05)
 int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
                 float* stats, const float* scale, const float* shift, int relu, int n, int h, int w,
@@ -53,6 +71,9 @@ int bn_fold(const float* gamma, const float* beta, const float* rm, const float*
             float* shift, int C, float eps, cudaStream_t s);
 int bnrelu_apply(const void* y, const float* scale, const float* shift, void* a, long npix, int C,
                  cudaStream_t s);
+int bnrelu_apply_fin(const void* y, const BnFinalizeArgs* fin, void* a, long npix, int C, cudaStream_t s);
+int bnrelu_pool_fin(const void* y, const BnFinalizeArgs* fin, void* a, void* pooled, void* idx, int N, int H, int W,
+                    int C, cudaStream_t s);
 int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, void* pooled,
                 void* idx, int N, int H, int W, int C, int apply, cudaStream_t s);
 int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, int C, int accumulate,

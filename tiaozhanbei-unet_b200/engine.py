@@ -37,6 +37,10 @@ FIRST_WGRAD_TC = os.environ.get("UNETK_FIRST_WGRAD_TC", "1") != "0"
 # The first conv (Cin = 3) as the 64 -> 64 tcgen05 layer on the channel-padded bf16 image (0.19 -> ~0.12 ms
 # at 16 x 256^2, and eval mode gets BatchNorm+ReLU in the epilogue); "0" = CUDA-core kernel on the fp32 image.
 FIRST_FWD_TC = os.environ.get("UNETK_FIRST_FWD_TC", "1") != "0"
+# Training forward: the BatchNorm finalize (batch sums -> scale/shift, running statistics) is folded into the
+# BN+ReLU(+pool) kernel instead of a separate dependent launch per layer.
+FUSE_BN_FINALIZE = os.environ.get("UNETK_FUSE_BN_FINALIZE", "1") != "0"
+SPLIT_PACK = os.environ.get("UNETK_SPLIT_PACK", "1") != "0"
 # Weight gradients are off the critical path of backward (nothing downstream reads them before the
 # optimizer): they run on a side stream, each one released only after the data gradient of the same layer,
 # so the tensor-bound wgrad kernel shares the SMs with the memory-bound BatchNorm-backward passes of the
@@ -194,6 +198,8 @@ class Engine:
         self.fuse_check = []      # (layer, relative error) records of UNETK_FUSE_CHECK=1
         self.wstreams = []        # side streams of the weight gradients, one per backward chain (OVERLAP_WGRAD)
         self.dstreams = []        # side streams of the second, third... decoder (PARALLEL_DECODERS)
+        self.pstream = None       # side stream packing the decoders' weights (SPLIT_PACK)
+        self.pack_done = None
         self.weights_dirty = True
         self.fold_dirty = True
         m = module
@@ -267,7 +273,11 @@ class Engine:
         chunk = _lib.get().unetk_permute_chunk_elems()
         pack = packing.PermuteTable(chunk)
         unpack = packing.PermuteTable(chunk)
-        conv_pack = packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32))
+        # conv3x3 weight packing in two groups: the encoder's (needed first, packed on the caller's stream) and
+        # the decoders' (packed on a side stream under the encoder's forward pass)
+        n_enc_layers = 2 * len(self.encoder)
+        conv_pack_enc = packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32))
+        conv_pack_dec = packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32))
         conv_unpack = packing.ConvTable(lambda cout, cin: cout)
         pdict = dict(zip(self.param_names, self.params))
         wsize = 0
@@ -286,8 +296,9 @@ class Engine:
         co = 0
         wplan = []
         handled = set()
-        for L in self.convbn:
+        for li, L in enumerate(self.convbn):
             c = L.cout
+            conv_pack = conv_pack_enc if li < n_enc_layers else conv_pack_dec
             L.stats = self.bn_stats_all[2 * co: 2 * co + 2 * c]
             L.sums = self.bn_sums_all[2 * co: 2 * co + 2 * c]
             L.scale = self.bn_aux[4 * co: 4 * co + c]
@@ -349,7 +360,7 @@ class Engine:
             setattr(obj, attr, self.wpack[off: off + n])
         self.pack_table = pack.finalize(device)
         self.unpack_table = unpack.finalize(device)
-        self.conv_pack_table = conv_pack.finalize(device)
+        self.conv_pack_tables = (conv_pack_enc.finalize(device), conv_pack_dec.finalize(device))
         self.conv_unpack_table = conv_unpack.finalize(device)
 
     def mark_weights_dirty(self):
@@ -368,13 +379,34 @@ class Engine:
         return v
 
     def _pack_weights(self):
-        if self.weights_dirty:
-            ops.pack_conv_weights(self.conv_pack_table, self.flat_p, self.wpack)     # conv3x3 layers (tiled)
+        """fp32 master weights -> bf16 kernel layouts.  The encoder's on the caller's stream; the decoders'
+        (2/3 of the bytes) on a side stream that the decoder chains wait for (self.pack_done)."""
+        self.pack_done = None
+        if not self.weights_dirty:
+            return
+        first = self.encoder[0][0]
+        if self._first_tc():
+            ops.first_conv_pack(first.w, first.wf0)
+        ops.pack_conv_weights(self.conv_pack_tables[0], self.flat_p, self.wpack)     # encoder conv3x3 layers (tiled)
+
+        def decoders():
+            ops.pack_conv_weights(self.conv_pack_tables[1], self.flat_p, self.wpack)
             ops.permute_batched(self.pack_table, self.flat_p, self.wpack)            # transposed convs
-            first = self.encoder[0][0]
-            if self._first_tc():
-                ops.first_conv_pack(first.w, first.wf0)
-            self.weights_dirty = False
+
+        if SPLIT_PACK and not ops.timing_enabled():
+            s0 = torch.cuda.current_stream(self.device)
+            if self.pstream is None:
+                self.pstream = torch.cuda.Stream(device=self.device)
+            ev = torch.cuda.Event()
+            ev.record(s0)                       # the optimizer's parameter update is on the caller's stream
+            self.pstream.wait_event(ev)
+            with torch.cuda.stream(self.pstream):
+                decoders()
+                self.pack_done = torch.cuda.Event()
+                self.pack_done.record(self.pstream)
+        else:
+            decoders()
+        self.weights_dirty = False
 
     def _first_tc(self):
         return FIRST_FWD_TC and self.n_channels <= 8 and self.encoder[0][0].cout == 64
@@ -432,8 +464,21 @@ class Engine:
         return outs, pl, pl.generation
 
     def _bn_train(self, L, y, a, count, pool=None):
+        mom = L.bn.momentum if L.bn.momentum is not None else 0.1
+        if FUSE_BN_FINALIZE:
+            key = (count, L.bn.eps, mom, L.rm.data_ptr(), L.rv.data_ptr(), L.stats.data_ptr(), L.gamma.data_ptr())
+            fin = L.__dict__.get("_fin")
+            if fin is None or fin[0] != key:
+                fin = (key, ops.bn_finalize_args(L.stats, L.gamma, L.beta, L.rm, L.rv, L.nbt, L.scale, L.shift, L.mean,
+                                                 L.invstd, count, L.bn.eps, mom))
+                L._fin = fin
+            if pool is None:
+                ops.bnrelu_apply_fin(y, fin[1], a)
+            else:
+                ops.bnrelu_pool_fin(y, fin[1], a, pool[0], pool[1])
+            return
         ops.bn_finalize(L.stats, L.gamma, L.beta, L.rm, L.rv, L.nbt, L.scale, L.shift, L.mean, L.invstd,
-                        count, L.bn.eps, L.bn.momentum if L.bn.momentum is not None else 0.1)
+                        count, L.bn.eps, mom)
         if pool is None:
             ops.bnrelu_apply(y, L.scale, L.shift, a)
         else:
@@ -479,6 +524,9 @@ class Engine:
         outs = [torch.empty(pl.n, head.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device) for _, head in self.decoders]
         streams = self._decoder_streams(n_dec if parallel else 1) * (1 if parallel else n_dec)
         s0 = streams[0]
+        if self.pack_done is not None:          # decoder weights are packed on a side stream
+            s0.wait_event(self.pack_done)
+            self.pack_done = None
         if n_dec > 1 and streams[1] is not s0:
             ev = torch.cuda.Event()
             ev.record(s0)

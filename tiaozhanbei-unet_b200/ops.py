@@ -220,6 +220,29 @@ def bnrelu_apply(y, scale, shift, a):
     return a
 
 
+def bn_finalize_args(stats, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd, count, eps, momentum):
+    """Host-side `unetk_bn_finalize_args` for bnrelu_apply_fin / bnrelu_pool_fin."""
+    f = _lib.BnFinalizeArgs(_p(stats), _p(gamma), _p(beta), _p(rm), _p(rv), _p(nbt), _p(scale), _p(shift), _p(mean),
+                            _p(invstd), float(count), float(eps), float(momentum))
+    f._keep = (stats, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd)
+    return f
+
+
+def bnrelu_apply_fin(y, fin, a):
+    """a = relu(BatchNorm_train(y)) with the statistics finalize folded in (see bn_finalize_args)."""
+    import ctypes
+    _chk(y, bf16, "y"); _chk(a, bf16, "a")
+    c = y.shape[-1]
+    _lib.call("unetk_bnrelu_apply_fin", _p(y), ctypes.byref(fin), _p(a), y.numel() // c, c, _s())
+
+
+def bnrelu_pool_fin(y, fin, a, pooled, idx):
+    import ctypes
+    _chk(y, bf16, "y"); _chk(a, bf16, "a"); _chk(pooled, bf16, "pooled")
+    n, h, w, c = y.shape
+    _lib.call("unetk_bnrelu_pool_fin", _p(y), ctypes.byref(fin), _p(a), _p(pooled), _p(idx), n, h, w, c, _s())
+
+
 def bnrelu_pool(y, scale, shift, a, pooled, idx, apply=True):
     _chk(y, bf16, "y"); _chk(pooled, bf16, "pooled")
     n, h, w, c = y.shape
