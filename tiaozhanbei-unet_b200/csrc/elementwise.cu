@@ -310,11 +310,12 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
   const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
   const int cg = static_cast<int>(tid % cgroups);
-  float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+  // The kernel is issue bound, not bandwidth bound (3.9 TB/s with ~9 instructions per element), so the
+  // inner loop accumulates sum g and sum g*y only (5 instructions per element) and the affine map to
+  // sum g*xhat = invstd * (sum g*y - mean * sum g) is applied once per thread.
+  float sc[8], sh[8], s1[8], s2[8];
   load8(scale + cg * 8, sc);
   load8(shift + cg * 8, sh);
-  load8(mean + cg * 8, mu);
-  load8(invstd + cg * 8, is);
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   for (long i = tid; i < nvec; i += nthreads) {
@@ -325,13 +326,32 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
     for (int j = 0; j < 8; ++j) {
       const float gg = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
       s1[j] += gg;
-      s2[j] = fmaf(gg, (v[j] - mu[j]) * is[j], s2[j]);
+      s2[j] = fmaf(gg, v[j], s2[j]);
     }
   }
+  {
+    float mu[8], is[8];
+    load8(mean + cg * 8, mu);
+    load8(invstd + cg * 8, is);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sacc[cg * 8 + j], s1[j]);
-    atomicAdd(&sacc[C + cg * 8 + j], s2[j]);
+    for (int j = 0; j < 8; ++j) s2[j] = is[j] * (s2[j] - mu[j] * s1[j]);
+  }
+  // lanes that share a channel group fold through shuffles first (when cgroups is a power of two < 32,
+  // lanes l and l ^ o hold the same channels for every o >= cgroups)
+  const bool fold = cgroups < 32 && (cgroups & (cgroups - 1)) == 0;
+  for (int o = 16; fold && o >= cgroups; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+    }
+  }
+  if (!fold || (threadIdx.x & 31) < cgroups) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sacc[cg * 8 + j], s1[j]);
+      atomicAdd(&sacc[C + cg * 8 + j], s2[j]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, sacc[i]);
@@ -355,17 +375,22 @@ bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
   const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
   const int cg = static_cast<int>(tid % cgroups);
-  float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
-  load8(scale + cg * 8, sc);
-  load8(shift + cg * 8, sh);
-  load8(mean + cg * 8, mu);
-  load8(invstd + cg * 8, is);
-  load8(sums + cg * 8, m1);
-  load8(sums + C + cg * 8, m2);
+  // dY = scale*(g - m1 - xhat*m2) = scale*g + A*y + B with A = -scale*m2*invstd, B = -scale*m1 - A*mean:
+  // 5 instructions per element instead of 9 (the kernel is issue bound like the reduction)
+  float sc[8], sh[8], ca[8], cb[8];
+  {
+    float mu[8], is[8], m1[8], m2[8];
+    load8(scale + cg * 8, sc);
+    load8(shift + cg * 8, sh);
+    load8(mean + cg * 8, mu);
+    load8(invstd + cg * 8, is);
+    load8(sums + cg * 8, m1);
+    load8(sums + C + cg * 8, m2);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    m1[j] *= inv_count;
-    m2[j] *= inv_count;
+    for (int j = 0; j < 8; ++j) {
+      ca[j] = -sc[j] * (m2[j] * inv_count) * is[j];
+      cb[j] = -sc[j] * (m1[j] * inv_count) - ca[j] * mu[j];
+    }
   }
   for (long i = tid; i < nvec; i += nthreads) {
     float g[8], v[8];
@@ -374,8 +399,7 @@ bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float gg = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
-      const float xh = (v[j] - mu[j]) * is[j];
-      v[j] = sc[j] * (gg - m1[j] - xh * m2[j]);
+      v[j] = fmaf(sc[j], gg, fmaf(ca[j], v[j], cb[j]));
     }
     dy[i] = pack8(v);
   }

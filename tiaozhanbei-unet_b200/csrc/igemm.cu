@@ -64,12 +64,13 @@ struct IgemmParams {
   const float* bn_invstd;
 };
 
-// warps: 0 TMA, 1 MMA, 2.. epilogue.  One epilogue warp per TMEM lane quarter: two per quarter (8 warps,
-// 320 threads, 168-register cap) measured SLOWER on the K=576 layers (fwd 0.107 -> 0.113 ms, dgrad
-// 0.086 -> 0.099 ms at 64 ch x 256^2 x 16), so the epilogue is not what limits them.
-constexpr int kEpiWarps = 4;
-constexpr int kEpiPerQuarter = kEpiWarps / 4;
-constexpr int kIgemmThreads = 64 + 32 * kEpiWarps;
+// warps: 0 TMA, 1 MMA, 2.. epilogue (EPW of them).  One epilogue warp per TMEM lane quarter by default: two
+// per quarter (8 warps, 320 threads, 168-register cap) measured SLOWER on the K=576 conv layers (fwd
+// 0.107 -> 0.113 ms, dgrad 0.086 -> 0.099 ms at 64 ch x 256^2 x 16), whose limit is the operand fetch.  The
+// transposed-conv forward is different: K = Cin is short (8..64 MMAs per tile) and its pixel-shuffle
+// epilogue moves 256 columns per tile, so it is epilogue bound (ncu: 9 % tensor pipe, 21 % DRAM at
+// Cin = 128) and takes EPW = 8.
+constexpr int igemm_threads(int epw) { return 64 + 32 * epw; }
 constexpr int kRegionH = 16;                  // CTA tile: (8*SUBS) x 16 output pixels
 constexpr int kSubW = 8;                      // sub-tile: 8 wide x 16 tall = 128 GEMM rows
 
@@ -99,8 +100,8 @@ struct IgemmCfg {
 
 // BNRED: the epilogue also runs the first pass of the BatchNorm+ReLU backward of the layer that produced
 //        the activation whose gradient this kernel completes (IgemmParams::bn_*), see unetk_bn_ctx.
-template <int BN, int SUBS, int CTAS, bool BNRED>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+template <int BN, int SUBS, int CTAS, bool BNRED, int EPW>
+__global__ void __launch_bounds__(igemm_threads(EPW), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
   using Cfg = IgemmCfg<BN, SUBS, CTAS>;
@@ -141,7 +142,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&tempty[i], EPW * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
   }
@@ -301,7 +302,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     int cur_nb = -1;
     // add this warp's partial column sums of column block `nbk` to the global statistics
     auto flush_stats = [&](int nbk) {
-      for (int c = half; c < BN / 32; c += kEpiPerQuarter) {
+      for (int c = half; c < BN / 32; c += EPW / 4) {
         const int i = c * 32 + lane;
         const int col = nbk * BN + i;
         if (col >= p.stats_from) {
@@ -347,7 +348,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       tc_fence_after();
       if (live) {
 #pragma unroll 1
-        for (int ch = half; ch < BN / 32; ch += kEpiPerQuarter) {
+        for (int ch = half; ch < BN / 32; ch += EPW / 4) {
           const int col = col0 + ch * 32;
           // BNRED: fetch the producing layer's raw conv output under the TMEM load latency
           uint4 yv[BNRED ? SUBS : 1][4];
@@ -434,8 +435,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               dst = p.out1 + opix * p.cout_t + co;
               accum = false;
               if (p.bias != nullptr) {
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + co);   // co is a multiple of 32
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co + j);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = __ldg(b4 + j);
+                  v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                }
               }
             }
             uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -577,16 +582,16 @@ struct IgemmLaunch {
   IgemmParams p;
 };
 
-template <int BN, int SUBS, int CTAS, bool BNRED>
+template <int BN, int SUBS, int CTAS, bool BNRED, int EPW = 4>
 static int launch_cfg(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB, const IgemmParams& p,
                       int grid, size_t colbytes, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, SUBS, CTAS>;
   const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;
-  auto kern = igemm_kernel<BN, SUBS, CTAS, BNRED>;
+  auto kern = igemm_kernel<BN, SUBS, CTAS, BNRED, EPW>;
   UNETK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kIgemmThreads);
+  cfg.blockDim = dim3(igemm_threads(EPW));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -652,6 +657,8 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
 #define UNETK_IGEMM_LAUNCH(BN_, SUBS_, CTAS_)                                                             \
   (red ? launch_cfg<BN_, SUBS_, CTAS_, true>(tmA1, tmA2, tmB, p, grid, colbytes, stream)                 \
        : launch_cfg<BN_, SUBS_, CTAS_, false>(tmA1, tmA2, tmB, p, grid, colbytes, stream))
+  if (bn == 256 && p.epi_mode == 1 && !red)      // transposed-conv forward: epilogue bound, eight epilogue warps
+    return launch_cfg<256, 1, 2, false, 8>(tmA1, tmA2, tmB, p, grid, colbytes, stream);
   if (bn == 256) return UNETK_IGEMM_LAUNCH(256, 1, 2);
   if (ctas == 2) return bn == 128 ? UNETK_IGEMM_LAUNCH(128, 2, 2) : UNETK_IGEMM_LAUNCH(64, 2, 2);
   return bn == 128 ? UNETK_IGEMM_LAUNCH(128, 2, 1) : UNETK_IGEMM_LAUNCH(64, 2, 1);
