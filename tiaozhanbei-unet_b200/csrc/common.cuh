@@ -46,6 +46,10 @@ void set_last_error(const char* fmt, ...);
 
 int check_device_sm100();  // 0 if the current device is compute capability 10.x
 int num_sms();
+// Programmatic dependent launch (UNETK_PDL=1 turns it on, see pdl_enabled() in runtime.cu): a kernel launched through launch_pdl may
+// start while the previous kernel of the stream drains; it MUST call pdl_wait() before it touches
+// global memory.  Kernels call pdl_trigger() first thing so that their successor is released early.
+bool pdl_enabled();
 
 // TMA tensor-map encoding through the driver entry point (resolved at run time; the library does
 // not link libcuda so that it loads on a machine without a driver).
@@ -54,9 +58,31 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
 
 #ifdef __CUDACC__
+// Launch `kernel` with the programmatic-stream-serialization attribute (see pdl_enabled()).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: release the next kernel of the stream / wait for the previous one
+// (completed and its memory visible).  Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

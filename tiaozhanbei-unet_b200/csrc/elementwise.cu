@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(kEwThreads)
 bnrelu_apply_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
                     const float* __restrict__ shift, uint4* __restrict__ a, long nvec, int cgroups,
                     const BnFinalizeArgs fin) {
+  pdl_trigger();
+  pdl_wait();
   const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long nthreads = static_cast<long>(gridDim.x) * blockDim.x;
   const int cg = static_cast<int>(tid % cgroups);
@@ -152,6 +154,8 @@ bnrelu_pool_kernel(const uint4* __restrict__ y, const float* __restrict__ scale,
                    const float* __restrict__ shift, uint4* __restrict__ a,
                    uint4* __restrict__ pooled, uint2* __restrict__ idx, int N, int H, int W,
                    int cgroups, int apply, const BnFinalizeArgs fin) {
+  pdl_trigger();
+  pdl_wait();
   const int Hp = H / 2, Wp = W / 2;
   const long nvec = static_cast<long>(N) * Hp * Wp * cgroups;
   const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -212,6 +216,8 @@ maxpool_bwd_kernel(const uint4* __restrict__ dp, const uint2* __restrict__ idx, 
                    const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ mean, const float* __restrict__ invstd,
                    float* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sacc[];  // [2][C] when bn_y != nullptr
   const int C = cgroups * 8;
   const bool bn = bn_y != nullptr;
@@ -303,6 +309,8 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ invstd,
                      float* __restrict__ sums, long nvec, int cgroups) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sacc[];  // [2][C]
   const int C = cgroups * 8;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
@@ -365,6 +373,8 @@ bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
                     const float* __restrict__ sums, uint4* __restrict__ dy,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, long nvec, int cgroups,
                     float inv_count) {
+  pdl_trigger();
+  pdl_wait();
   const int C = cgroups * 8;
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
@@ -476,8 +486,8 @@ int bnrelu_apply(const void* y, const float* scale, const float* shift, void* a,
   UNETK_CHECK_ARG(y && scale && shift && a, "bnrelu_apply: null pointer");
   if (int e = check_c(C, "bnrelu_apply")) return e;
   const long nvec = npix * (C / 8);
-  bnrelu_apply_kernel<false><<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(static_cast<const uint4*>(y), scale, shift,
-                                                                         static_cast<uint4*>(a), nvec, C / 8, BnFinalizeArgs{});
+  UNETK_CUDA(launch_pdl(bnrelu_apply_kernel<false>, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s, static_cast<const uint4*>(y), scale, shift,
+                                                                         static_cast<uint4*>(a), nvec, C / 8, BnFinalizeArgs{}));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -496,8 +506,8 @@ int bnrelu_apply_fin(const void* y, const BnFinalizeArgs* fin, void* a, long npi
   if (int e = check_c(C, "bnrelu_apply_fin")) return e;
   if (int e = check_fin(fin, C, "bnrelu_apply_fin")) return e;
   const long nvec = npix * (C / 8);
-  bnrelu_apply_kernel<true><<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(static_cast<const uint4*>(y), nullptr, nullptr,
-                                                                        static_cast<uint4*>(a), nvec, C / 8, *fin);
+  UNETK_CUDA(launch_pdl(bnrelu_apply_kernel<true>, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s, static_cast<const uint4*>(y), nullptr, nullptr,
+                                                                        static_cast<uint4*>(a), nvec, C / 8, *fin));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -509,9 +519,9 @@ int bnrelu_pool_fin(const void* y, const BnFinalizeArgs* fin, void* a, void* poo
   if (int e = check_c(C, "bnrelu_pool_fin")) return e;
   if (int e = check_fin(fin, C, "bnrelu_pool_fin")) return e;
   const long nvec = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
-  bnrelu_pool_kernel<true><<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(static_cast<const uint4*>(y), nullptr, nullptr,
+  UNETK_CUDA(launch_pdl(bnrelu_pool_kernel<true>, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s, static_cast<const uint4*>(y), nullptr, nullptr,
                                                                        static_cast<uint4*>(a), static_cast<uint4*>(pooled),
-                                                                       static_cast<uint2*>(idx), N, H, W, C / 8, 1, *fin);
+                                                                       static_cast<uint2*>(idx), N, H, W, C / 8, 1, *fin));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -523,9 +533,9 @@ int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, 
   UNETK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "bnrelu_pool: H and W must be even (got %dx%d)", H, W);
   if (int e = check_c(C, "bnrelu_pool")) return e;
   const long nvec = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
-  bnrelu_pool_kernel<false><<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(static_cast<const uint4*>(y), scale, shift,
+  UNETK_CUDA(launch_pdl(bnrelu_pool_kernel<false>, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s, static_cast<const uint4*>(y), scale, shift,
                                                                         static_cast<uint4*>(a), static_cast<uint4*>(pooled),
-                                                                        static_cast<uint2*>(idx), N, H, W, C / 8, apply, BnFinalizeArgs{});
+                                                                        static_cast<uint2*>(idx), N, H, W, C / 8, apply, BnFinalizeArgs{}));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -541,10 +551,10 @@ int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, 
   int grid = ew_grid(nvec, C / 8);
   const int cap = num_sms() * 4;
   if (fuse && grid > cap && (static_cast<long>(cap) * kEwThreads) % (C / 8) == 0) grid = cap;   // fewer global atomics
-  maxpool_bwd_kernel<<<grid, kEwThreads, fuse ? 2 * C * sizeof(float) : 0, s>>>(
+  UNETK_CUDA(launch_pdl(maxpool_bwd_kernel, dim3(grid), dim3(kEwThreads), fuse ? 2 * C * sizeof(float) : 0, s,
       static_cast<const uint4*>(dp), static_cast<const uint2*>(idx), static_cast<uint4*>(da), N, H, W, C / 8, accumulate,
       static_cast<const uint4*>(extra), fuse ? static_cast<const uint4*>(bn->y) : nullptr, fuse ? bn->scale : nullptr, fuse ? bn->shift : nullptr,
-      fuse ? bn->mean : nullptr, fuse ? bn->invstd : nullptr, fuse ? bn->sums : nullptr);
+      fuse ? bn->mean : nullptr, fuse ? bn->invstd : nullptr, fuse ? bn->sums : nullptr));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -558,8 +568,8 @@ int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float
   // full grid (8 blocks per SM): at 4 per SM the two read streams ran at 3.9 TB/s, latency bound; an
   // unrolled variant with four loads in flight per thread was slower still (3.2 TB/s)
   const int grid = ew_grid(nvec, C / 8);
-  bn_bwd_reduce_kernel<<<grid, kEwThreads, 2 * C * sizeof(float), s>>>(static_cast<const uint4*>(da), static_cast<const uint4*>(y),
-                                                                      scale, shift, mean, invstd, sums, nvec, C / 8);
+  UNETK_CUDA(launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), s, static_cast<const uint4*>(da), static_cast<const uint4*>(y),
+                                                                      scale, shift, mean, invstd, sums, nvec, C / 8));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -570,9 +580,9 @@ int bn_bwd_apply(const void* da, const void* y, const float* scale, const float*
   UNETK_CHECK_ARG(da && y && scale && shift && mean && invstd && sums && dy && dgamma && dbeta, "bn_bwd_apply: null pointer");
   if (int e = check_c(C, "bn_bwd_apply")) return e;
   const long nvec = npix * (C / 8);
-  bn_bwd_apply_kernel<<<ew_grid(nvec, C / 8), kEwThreads, 0, s>>>(
+  UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s,
       static_cast<const uint4*>(da), static_cast<const uint4*>(y), scale, shift, mean, invstd, sums,
-      static_cast<uint4*>(dy), dgamma, dbeta, nvec, C / 8, 1.0f / static_cast<float>(npix));
+      static_cast<uint4*>(dy), dgamma, dbeta, nvec, C / 8, 1.0f / static_cast<float>(npix)));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }

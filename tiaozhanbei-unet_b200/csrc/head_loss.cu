@@ -23,6 +23,8 @@ head_fwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const 
                 float* __restrict__ out, long npix_total, long hw, int n_out, int sigmoid) {
   __shared__ float sw[kHeadMaxOut * kHeadC];
   __shared__ float sb[kHeadMaxOut];
+  pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x; i < n_out * kHeadC; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < n_out) sb[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
@@ -72,6 +74,8 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
   __shared__ float sdw[NOUT * kHeadC];
   __shared__ float sdb[NOUT];
   __shared__ float sbn[2 * kHeadC];
+  pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x; i < NOUT * kHeadC; i += blockDim.x) sdw[i] = 0.f;
   if (threadIdx.x < NOUT) sdb[threadIdx.x] = 0.f;
   if (threadIdx.x < 2 * kHeadC) sbn[threadIdx.x] = 0.f;
@@ -527,7 +531,7 @@ int head_fwd(const void* a, const float* w, const float* b, float* out, int N, i
   UNETK_CHECK_ARG(C == kHeadC, "head_fwd: input channels must be 64 (got %d)", C);
   UNETK_CHECK_ARG(n_out >= 1 && n_out <= kHeadMaxOut, "head_fwd: 1..4 output channels supported (got %d)", n_out);
   const long hw = static_cast<long>(H) * W, np = hw * N;
-  head_fwd_kernel<<<ew_blocks(np, 256), 256, 0, s>>>(static_cast<const uint4*>(a), w, b, out, np, hw, n_out, sigmoid);
+  UNETK_CUDA(launch_pdl(head_fwd_kernel, dim3(ew_blocks(np, 256)), dim3(256), 0, s, static_cast<const uint4*>(a), w, b, out, np, hw, n_out, sigmoid));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -553,10 +557,10 @@ int head_bwd(const void* a, const float* w, const float* dout, const float* out,
   const float* b3 = fuse ? bn->mean : nullptr;  const float* b4 = fuse ? bn->invstd : nullptr;
   float* b5 = fuse ? bn->sums : nullptr;
   switch (n_out) {
-    case 1: head_bwd_kernel<1><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5); break;
-    case 2: head_bwd_kernel<2><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5); break;
-    case 3: head_bwd_kernel<3><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5); break;
-    default: head_bwd_kernel<4><<<blocks, 256, 0, s>>>(a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5); break;
+    case 1: UNETK_CUDA(launch_pdl(head_bwd_kernel<1>, dim3(blocks), dim3(256), 0, s, a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5)); break;
+    case 2: UNETK_CUDA(launch_pdl(head_bwd_kernel<2>, dim3(blocks), dim3(256), 0, s, a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5)); break;
+    case 3: UNETK_CUDA(launch_pdl(head_bwd_kernel<3>, dim3(blocks), dim3(256), 0, s, a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5)); break;
+    default: UNETK_CUDA(launch_pdl(head_bwd_kernel<4>, dim3(blocks), dim3(256), 0, s, a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5)); break;
   }
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;

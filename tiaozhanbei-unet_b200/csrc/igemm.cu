@@ -128,6 +128,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  pdl_trigger();       // the next kernel of the stream may set itself up while this one runs
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmA2);
@@ -151,6 +152,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     if (CTAS == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
     else tmem_alloc(tmem_slot, Cfg::kTmemCols);
   }
+  // everything above (barriers, tensor-map prefetch, TMEM allocation) overlapped the previous kernel of the
+  // stream; from here on global memory is touched
+  pdl_wait();
   if (p.scale != nullptr) {          // [2][Ntot]: scale, shift
     for (int i = threadIdx.x; i < 2 * p.Ntot; i += blockDim.x)
       colbuf[i] = (i < p.Ntot) ? p.scale[i] : p.shift[i - p.Ntot];
@@ -594,13 +598,15 @@ static int launch_cfg(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CU
   cfg.blockDim = dim3(igemm_threads(EPW));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   UNETK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA1, tmA2, tmB, p));
   return UNETK_OK;
 }

@@ -96,6 +96,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
   const int total_k = p.tiles_x * p.tiles_y * p.tiles_n;
   const int k_begin = static_cast<int>(static_cast<long>(total_k) * blockIdx.y / p.ksplit);
   const int k_end = static_cast<int>(static_cast<long>(total_k) * (blockIdx.y + 1) / p.ksplit);
+  pdl_trigger();
   if (k_end <= k_begin) return;  // uniform for the whole CTA
 
   if (warp == 0 && lane == 0) {
@@ -118,6 +119,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ C
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // set-up above overlapped the previous kernel of the stream; global memory from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -298,13 +300,15 @@ static int launch_wgrad_t(const CUtensorMap& x1, const CUtensorMap& x2, const CU
   cfg.blockDim = dim3(kWgThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   UNETK_CUDA(cudaLaunchKernelEx(&cfg, kern, x1, x2, dy, p));
   return UNETK_OK;
 }
