@@ -199,6 +199,32 @@ int unetk_ssim_bwd(const float* img1, const float* img2, const float* maps, cons
                    float* grad, int n, int c, int h, int w, int window_size, int which,
                    int per_image, void* stream);
 
+/* ---- SegmentationUNet pipeline ---------------------------------------- */
+/* CombinedSegmentationLoss.forward (src/metrics.py:285-335): logits NCHW fp32 [n,c,h,w] (c <= 8), target
+ * int64 [n,h,w], class_w [c] or NULL.  out4 = {total, ce, dice, focal} with
+ *   ce    = F.cross_entropy(logits, target, weight=class_w, ignore_index)        (weighted mean)
+ *   dice  = 1 - mean_{n,c} (2 I + 1e-8) / (U + 1e-8) on softmax(logits) vs one-hot(target)  (:233-261)
+ *   focal = mean over ALL pixels of alpha (1 - pt)^gamma ce                       (:264-282)
+ *   total = sum of the terms whose weight is > 0, like the reference.
+ * Targets outside [0, c) belong to no class (dice) and are skipped by ce / focal like ignore_index.
+ * is_prob != 0: `logits` already holds probabilities (stand-alone dice_loss); only dice is meaningful.
+ * work: unetk_seg_loss_workspace_bytes(n, c) bytes, written by _fwd and read by _bwd.
+ * _bwd: dlogits = (*gout, or 1 when gout is NULL) * d total / d logits. */
+size_t unetk_seg_loss_workspace_bytes(int n, int c);
+int unetk_seg_loss_fwd(const float* logits, const int64_t* target, const float* class_w, float* out4,
+                       void* work, size_t work_bytes, int n, int c, int h, int w, int64_t ignore_index,
+                       float ce_w, float dice_w, float focal_w, float focal_alpha, float focal_gamma,
+                       int is_prob, void* stream);
+int unetk_seg_loss_bwd(const float* logits, const int64_t* target, const float* class_w, const void* work,
+                       const float* gout, float* dlogits, int n, int c, int h, int w, int64_t ignore_index,
+                       float ce_w, float dice_w, float focal_w, float focal_alpha, float focal_gamma,
+                       int is_prob, void* stream);
+/* nn.Dropout2d applied in place to an NHWC bf16 activation: x[n,h,w,c] *= mask[n,c] (src/model.py:130,146;
+ * the caller draws mask = bernoulli(1-p)/(1-p)). */
+int unetk_channel_scale(void* x, const float* mask, int n, int h, int w, int c, void* stream);
+/* torch.argmax(logits, dim=1): NCHW fp32 -> int64 [n,h,w], first maximum wins (test.py:98). */
+int unetk_argmax_channels(const float* logits, int64_t* out, int n, int c, int h, int w, void* stream);
+
 /* ---- compute_anomaly_score: src/utils.py:205-215 (method 0 = 'mse'/'ssim', 1 = 'l1') ------- */
 int unetk_anomaly_score(const float* recon, const float* orig, float* out, int n, int c, int h,
                         int w, int method, void* stream);

@@ -185,6 +185,16 @@ def unet_forward(sd, x, training=False, storage="fp32"):
     return _decoder(sd, _encoder(sd, x, training, r), "", training, r)
 
 
+def segmentation_unet_forward(sd, x, training=False, dropout=0.1, storage="fp32"):
+    """SegmentationUNet.forward -> logits: the UNet graph with nn.Dropout2d(dropout) on the bottleneck
+    (src/model.py:111-153; dropout draws from torch's global generator like the module does)."""
+    r = _rounder(storage)
+    feats = _encoder(sd, x, training, r)
+    if dropout > 0:
+        feats[4] = r(F.dropout2d(feats[4], dropout, training))
+    return _decoder(sd, feats, "", training, r)
+
+
 def anomaly_unet_forward(sd, x, training=False, storage="fp32"):
     """AnomalyUNet.forward -> (sigmoid reconstruction, sigmoid anomaly map).  src/model.py:188-210."""
     r = _rounder(storage)
@@ -192,6 +202,47 @@ def anomaly_unet_forward(sd, x, training=False, storage="fp32"):
     recon = torch.sigmoid(_decoder(sd, feats, "_recon", training, r))
     amap = torch.sigmoid(_decoder(sd, feats, "_seg", training, r))
     return recon, amap
+
+
+# ---------------------------------------------------------------------------------------------
+# segmentation losses (Gear / KolektorSDD pipelines) — src/metrics.py:233-335
+# ---------------------------------------------------------------------------------------------
+def seg_dice_loss(pred, target, smooth=1e-8):
+    """src/metrics.py:233-261: pred = probabilities (N, C, H, W), target = labels (N, H, W)."""
+    c = pred.size(1)
+    onehot = F.one_hot(target, c).permute(0, 3, 1, 2).float()
+    p = pred.reshape(pred.size(0), c, -1)
+    y = onehot.reshape(onehot.size(0), c, -1)
+    inter = (p * y).sum(dim=2)
+    union = p.sum(dim=2) + y.sum(dim=2)
+    return 1 - ((2 * inter + smooth) / (union + smooth)).mean()
+
+
+def seg_focal_loss(pred, target, alpha=1, gamma=2, ignore_index=-100):
+    """src/metrics.py:264-282 (ignore_index must be an int: the reference's None default is rejected by
+    F.cross_entropy)."""
+    ce = F.cross_entropy(pred, target, ignore_index=ignore_index, reduction="none")
+    pt = torch.exp(-ce)
+    return (alpha * (1 - pt) ** gamma * ce).mean()
+
+
+def combined_segmentation_loss(pred, target, ce_weight=1.0, dice_weight=1.0, focal_weight=0.0, ignore_index=None,
+                               class_weights=None):
+    """CombinedSegmentationLoss.forward (src/metrics.py:285-335) -> (total, {term: value})."""
+    terms = {}
+    total = 0
+    if ce_weight > 0:
+        w = None if class_weights is None else torch.as_tensor(class_weights, dtype=torch.float32, device=pred.device)
+        kw = {} if ignore_index is None else {"ignore_index": ignore_index}
+        terms["ce"] = F.cross_entropy(pred, target, weight=w, **kw)
+        total = total + ce_weight * terms["ce"]
+    if dice_weight > 0:
+        terms["dice"] = seg_dice_loss(F.softmax(pred, dim=1), target)
+        total = total + dice_weight * terms["dice"]
+    if focal_weight > 0:
+        terms["focal"] = seg_focal_loss(pred, target, ignore_index=ignore_index)
+        total = total + focal_weight * terms["focal"]
+    return total, terms
 
 
 # ---------------------------------------------------------------------------------------------

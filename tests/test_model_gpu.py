@@ -18,7 +18,7 @@ tests/test_ops_gpu.py).  Hence, against the fp32 reference numbers:
     (heads and the last BatchNorm), which see no accumulated noise, within 3e-2 relative L2
   * threshold masks: bit-exact wherever the reference margin |p - 0.5| exceeds 1.5e-1, and fewer than
     0.2 % flips outside a 5e-2 margin
-  * loss curve over 20 Adam steps within 1 %
+  * loss curve over 100 Adam steps within 1 %
 """
 import os
 import sys
@@ -209,7 +209,8 @@ def test_loss_kernels_match_reference_golden(cuda_device):
 
 
 def test_loss_curve_tracks_oracle(cuda_device):
-    """20 Adam steps from identical weights on fresh seeded batches: loss curves within 1 %."""
+    """100 Adam steps from identical weights on fresh seeded batches: loss curves within 1 % (the bound
+    BASELINE.json's north star states)."""
     from tiaozhanbei_unet_b200 import train_utils
     dev = cuda_device
     arch = "anomaly_unet"
@@ -221,7 +222,7 @@ def test_loss_curve_tracks_oracle(cuda_device):
     opt_state = {}
     g = torch.Generator().manual_seed(0)
     ours, refs = [], []
-    for step in range(1, 21):
+    for step in range(1, 101):
         image = torch.randn(4, 3, 32, 32, generator=g).to(dev)
         mask = (torch.rand(4, 1, 32, 32, generator=g) > 0.95).float().to(dev)
         r, a = m(image)

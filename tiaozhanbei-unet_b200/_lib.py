@@ -49,6 +49,11 @@ SIGNATURES = {
     "unetk_ssim_finalize": (I, [P, P, I, I, I, I, I, P]),
     "unetk_ssim_bwd": (I, [P, P, P, P, P, I, I, I, I, I, I, I, P]),
     "unetk_anomaly_score": (I, [P, P, P, I, I, I, I, I, P]),
+    "unetk_seg_loss_workspace_bytes": (Z, [I, I]),
+    "unetk_seg_loss_fwd": (I, [P, P, P, P, P, Z, I, I, I, I, L, F, F, F, F, F, I, P]),
+    "unetk_seg_loss_bwd": (I, [P, P, P, P, P, P, I, I, I, I, L, F, F, F, F, F, I, P]),
+    "unetk_channel_scale": (I, [P, P, I, I, I, I, P]),
+    "unetk_argmax_channels": (I, [P, P, I, I, I, I, P]),
     "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),
     "unetk_permute_batched": (I, [P, I, I, P, P, I, F, P]),
     "unetk_permute_chunk_elems": (I, []),

@@ -155,6 +155,27 @@ int unetk_ssim_bwd(const float* img1, const float* img2, const float* maps, cons
                    int per_image, void* stream) {
   return unetk::ssim_bwd(img1, img2, maps, gout, grad, n, c, h, w, window_size, which, per_image, S(stream));
 }
+size_t unetk_seg_loss_workspace_bytes(int n, int c) { return unetk::seg_loss_workspace_bytes(n, c); }
+int unetk_seg_loss_fwd(const float* logits, const int64_t* target, const float* class_w, float* out4,
+                       void* work, size_t work_bytes, int n, int c, int h, int w, int64_t ignore_index,
+                       float ce_w, float dice_w, float focal_w, float focal_alpha, float focal_gamma,
+                       int is_prob, void* stream) {
+  return unetk::seg_loss_fwd(logits, reinterpret_cast<const long long*>(target), class_w, out4, work, work_bytes, n, c, h, w,
+                             ignore_index, ce_w, dice_w, focal_w, focal_alpha, focal_gamma, is_prob, S(stream));
+}
+int unetk_seg_loss_bwd(const float* logits, const int64_t* target, const float* class_w, const void* work,
+                       const float* gout, float* dlogits, int n, int c, int h, int w, int64_t ignore_index,
+                       float ce_w, float dice_w, float focal_w, float focal_alpha, float focal_gamma,
+                       int is_prob, void* stream) {
+  return unetk::seg_loss_bwd(logits, reinterpret_cast<const long long*>(target), class_w, work, gout, dlogits, n, c, h, w,
+                             ignore_index, ce_w, dice_w, focal_w, focal_alpha, focal_gamma, is_prob, S(stream));
+}
+int unetk_channel_scale(void* x, const float* mask, int n, int h, int w, int c, void* stream) {
+  return unetk::channel_scale(x, mask, n, h, w, c, S(stream));
+}
+int unetk_argmax_channels(const float* logits, int64_t* out, int n, int c, int h, int w, void* stream) {
+  return unetk::argmax_channels(logits, reinterpret_cast<long long*>(out), n, c, h, w, S(stream));
+}
 int unetk_anomaly_score(const float* recon, const float* orig, float* out, int n, int c, int h,
                         int w, int method, void* stream) {
   return unetk::anomaly_score(recon, orig, out, n, c, h, w, method, S(stream));

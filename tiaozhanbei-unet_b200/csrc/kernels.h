@@ -98,6 +98,16 @@ int combined_loss(const float* recon, const float* amap, const float* image, con
                   long n_recon, long n_seg, float rw, float sw, float alpha, float gamma,
                   cudaStream_t s);
 int scale_by_scalar(float* y, const float* s, long n, cudaStream_t st);
+// seg_loss.cu — SegmentationUNet pipeline extras
+size_t seg_loss_workspace_bytes(int N, int C);
+int seg_loss_fwd(const float* logits, const long long* target, const float* class_w, float* out4, void* work,
+                 size_t work_bytes, int N, int C, int H, int W, long long ignore_index, float ce_w, float dice_w,
+                 float focal_w, float focal_alpha, float focal_gamma, int is_prob, cudaStream_t s);
+int seg_loss_bwd(const float* logits, const long long* target, const float* class_w, const void* work, const float* gout,
+                 float* dlogits, int N, int C, int H, int W, long long ignore_index, float ce_w, float dice_w,
+                 float focal_w, float focal_alpha, float focal_gamma, int is_prob, cudaStream_t s);
+int channel_scale(void* x, const float* mask, int N, int H, int W, int C, cudaStream_t s);
+int argmax_channels(const float* logits, long long* out, int N, int C, int H, int W, cudaStream_t s);
 int anomaly_score(const float* recon, const float* orig, float* out, int N, int C, int H, int W,
                   int method, cudaStream_t s);
 int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int N, int C, int H,

@@ -117,6 +117,7 @@ class Plan:
         self.grads_ready = False
         self.bnctx = {}
         self.fused = set()
+        self.drop_mask = None
 
     def alloc_grads(self):
         if self.grads_ready:
@@ -199,6 +200,7 @@ class Engine:
         self.wstreams = []        # side streams of the weight gradients, one per backward chain (OVERLAP_WGRAD)
         self.dstreams = []        # side streams of the second, third... decoder (PARALLEL_DECODERS)
         self.pstream = None       # side stream packing the decoders' weights (SPLIT_PACK)
+        self.bottleneck_dropout = 0.0   # SegmentationUNet: nn.Dropout2d(p) on the bottleneck (src/model.py:130,146)
         self.pack_done = None
         self.weights_dirty = True
         self.fold_dirty = True
@@ -500,6 +502,16 @@ class Engine:
             self._bn_train(c1, e["y1"], e["a1"], count)
             ops.conv3x3_fwd(e["a1"], None, c2.wf, e["y2"], stats=c2.stats)
             self._bn_train(c2, e["y2"], e["a2"], count, pool=(e["p"], e["idx"]) if l < 4 else None)
+        pl.drop_mask = None
+        if self.bottleneck_dropout > 0.0:
+            # F.dropout2d(x5, p, training=True): one Bernoulli(1-p)/(1-p) factor per (image, channel), drawn from
+            # torch's generator exactly as ATen's feature_dropout does (same stream as the reference on this
+            # device); applied in place -- the bottleneck's ReLU mask in backward comes from y2, not from a2
+            x5 = pl.enc[4]["a2"]
+            keep = 1.0 - self.bottleneck_dropout
+            pl.drop_mask = torch.empty(x5.shape[0], x5.shape[3], 1, 1, dtype=torch.float32, device=x5.device).bernoulli_(keep).div_(keep)
+            ops.channel_scale(x5, pl.drop_mask)
+
         def stage(d, k):
             ct, c1, c2 = self.decoders[d][0][k]
             lv = 3 - k
@@ -690,7 +702,7 @@ class Engine:
                 if bottleneck_done is not None:
                     ch.stream.wait_event(bottleneck_done)
                 ops.convt2x2_dgrad(d_up, ct.wd, pl.d_skip[4], acc=skip_written[4],
-                                   bn=ctx(pl, enc4, pl.enc[4]["y2"]) if d == 0 else None)
+                                   bn=ctx(pl, enc4, pl.enc[4]["y2"]) if d == 0 and pl.drop_mask is None else None)
                 skip_written[4] = True
                 if parallel:
                     bottleneck_done = torch.cuda.Event()
@@ -712,6 +724,8 @@ class Engine:
             if self.ddp is not None:
                 self.ddp.segment_ready(self, ("dec", d), [e for e in (done, ch.last_w) if e is not None])
         ch = chains[0]
+        if pl.drop_mask is not None:            # Dropout2d backward: the same per-(image, channel) factors
+            ops.channel_scale(pl.d_skip[4], pl.drop_mask)
         for l in reversed(range(5)):
             c1, c2 = self.encoder[l]
             e = pl.enc[l]

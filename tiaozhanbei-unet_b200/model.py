@@ -268,10 +268,40 @@ class AnomalyUNet(_EngineModule):
         return reconstruction, anomaly_map
 
 
-class SegmentationUNet(nn.Module):
-    """src/model.py:111-153 — Gear / KolektorSDD pipelines; outside this version's hot-path scope."""
+class SegmentationUNet(_EngineModule):
+    """src/model.py:111-153 — UNet for multi-class segmentation (Gear / KolektorSDD pipelines): the UNet graph
+    with nn.Dropout2d on the bottleneck and an n_classes-channel head; forward returns logits.  The state_dict
+    is the UNet's (Dropout2d has no parameters)."""
+    _arch = "unet"
 
-    def __init__(self, *args, **kwargs):
+    def __init__(self, n_channels=3, n_classes=4, bilinear=False, dropout=0.1):
         super().__init__()
-        raise NotImplementedError("SegmentationUNet belongs to the Gear/KolektorSDD pipelines, which are out of scope "
-                                  "of this version (SURVEY.md §8(f) rank 1)")
+        if n_classes > 4:
+            raise NotImplementedError("the head kernels support up to 4 output channels")
+        self.n_channels = n_channels
+        self.n_classes = n_classes
+        self.bilinear = bilinear
+        self.inc = DoubleConv(n_channels, 64)
+        self.down1 = Down(64, 128)
+        self.down2 = Down(128, 256)
+        self.down3 = Down(256, 512)
+        factor = 2 if bilinear else 1
+        self.down4 = Down(512, 1024 // factor)
+        # like the reference: a Dropout2d module (or Identity) that holds p; the engine applies it
+        self.dropout = nn.Dropout2d(dropout) if dropout > 0 else nn.Identity()
+        self.up1 = Up(1024, 512 // factor, bilinear)
+        self.up2 = Up(512, 256 // factor, bilinear)
+        self.up3 = Up(256, 128 // factor, bilinear)
+        self.up4 = Up(128, 64, bilinear)
+        self.outc = OutConv(64, n_classes)
+
+    def _head_specs(self):
+        return [("", self.n_classes, False)]
+
+    def _engine(self):
+        eng = super()._engine()
+        eng.bottleneck_dropout = float(self.dropout.p) if isinstance(self.dropout, nn.Dropout2d) else 0.0
+        return eng
+
+    def forward(self, x):
+        return self._run(x)[0]

@@ -287,6 +287,41 @@ def head_bwd(a, w, dout, out, da, dw, db, sigmoid, bn=None):
               dout.shape[1], int(sigmoid), _bn(bn), _s())
 
 
+def channel_scale(x, mask):
+    """x[n, h, w, c] *= mask[n, c] in place (Dropout2d on an NHWC bf16 activation)."""
+    _chk(x, bf16, "x"); _chk(mask, f32, "mask")
+    n, h, w, c = x.shape
+    if mask.numel() != n * c:
+        raise _lib.UnetkError(f"mask: expected {n * c} elements, got {mask.numel()}")
+    _lib.call("unetk_channel_scale", _p(x), _p(mask), n, h, w, c, _s())
+    return x
+
+
+def seg_loss_workspace(n, c, device):
+    return torch.empty(_lib.get().unetk_seg_loss_workspace_bytes(n, c) // 4, dtype=f32, device=device)
+
+
+def seg_loss_fwd(logits, target, class_w, out4, work, ignore_index, ce_w, dice_w, focal_w, alpha, gamma, is_prob=False):
+    _chk(logits, f32, "logits"); _chk(target, torch.int64, "target"); _chk(out4, f32, "out4")
+    n, c, h, w = logits.shape
+    _lib.call("unetk_seg_loss_fwd", _p(logits), _p(target), _p(class_w), _p(out4), _p(work), work.numel() * 4, n, c, h, w,
+              int(ignore_index), float(ce_w), float(dice_w), float(focal_w), float(alpha), float(gamma), int(is_prob), _s())
+
+
+def seg_loss_bwd(logits, target, class_w, work, gout, dlogits, ignore_index, ce_w, dice_w, focal_w, alpha, gamma, is_prob=False):
+    _chk(logits, f32, "logits"); _chk(target, torch.int64, "target"); _chk(dlogits, f32, "dlogits")
+    n, c, h, w = logits.shape
+    _lib.call("unetk_seg_loss_bwd", _p(logits), _p(target), _p(class_w), _p(work), _p(gout), _p(dlogits), n, c, h, w,
+              int(ignore_index), float(ce_w), float(dice_w), float(focal_w), float(alpha), float(gamma), int(is_prob), _s())
+
+
+def argmax_channels(logits, out):
+    _chk(logits, f32, "logits"); _chk(out, torch.int64, "out")
+    n, c, h, w = logits.shape
+    _lib.call("unetk_argmax_channels", _p(logits), _p(out), n, c, h, w, _s())
+    return out
+
+
 def combined_loss_workspace(device):
     nbytes = _lib.get().unetk_combined_loss_workspace_bytes()
     return torch.zeros(nbytes, dtype=torch.uint8, device=device)

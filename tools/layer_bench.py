@@ -180,5 +180,33 @@ m.eval()
 with torch.no_grad():
     t = timeit(lambda: m(image), iters=8, warm=3)
 log(f"eval forward {t:.3f} ms -> {B/t*1e3:.1f} img/s")
+log("# SegmentationUNet(3, 4) + CombinedSegmentationLoss(ce + dice) + fused Adam, B=8 @512x512 (Gear pipeline shape)")
+from tiaozhanbei_unet_b200.model import SegmentationUNet  # noqa: E402
+from tiaozhanbei_unet_b200 import metrics  # noqa: E402
+del m, opt
+torch.cuda.empty_cache()
+torch.manual_seed(42)
+ms_ = SegmentationUNet(3, 4).to(dev).train()
+crit_s = metrics.CombinedSegmentationLoss(1.0, 1.0)
+opt_s = train_utils.get_optimizer(ms_)
+xs = torch.randn(8, 3, 512, 512, generator=g).to(dev)
+ts = torch.randint(0, 4, (8, 512, 512), generator=g).to(dev)
+
+
+def seg_step():
+    loss = crit_s(ms_(xs), ts)
+    opt_s.zero_grad()
+    loss.backward()
+    opt_s.step()
+
+
+t = timeit(seg_step, iters=8, warm=3)
+log(f"segmentation train step {t:.3f} ms -> {8/t*1e3:.1f} img/s @512x512 ({8*288.78*4/t:.0f} TFLOP/s); loss terms {crit_s.last_terms()}")
+zl = torch.randn(8, 4, 512, 512, device=dev, requires_grad=True)
+t_f = timeit(lambda: crit_s(zl, ts))
+lv = crit_s(zl, ts)
+t_b = timeit(lambda: lv.backward(retain_graph=True))
+nb = zl.numel() * 4 + ts.numel() * 8
+log(f"seg loss fwd {t_f:.3f} ms ({nb/t_f/1e6:.0f} GB/s of logits+labels), bwd {t_b:.3f} ms ({(nb + zl.numel()*4)/t_b/1e6:.0f} GB/s)")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 open(os.path.join(ROOT, "gpurun_out", "layer_bench.txt"), "w").write("\n".join(lines) + "\n")
