@@ -125,6 +125,13 @@ def call(name: str, *args) -> None:
         raise UnetkError(f"{name} failed with code {rc}: {last_error()}")
 
 
+def add_replayed(calls: int, kernels: int) -> None:
+    """A CUDA-graph replay launched `kernels` of our kernels (`calls` C-ABI calls were captured)."""
+    global _launches, _kernel_launches
+    _launches += calls
+    _kernel_launches += kernels
+
+
 def launch_count() -> int:
     return _launches
 

@@ -41,6 +41,13 @@ FIRST_FWD_TC = os.environ.get("UNETK_FIRST_FWD_TC", "1") != "0"
 # BN+ReLU(+pool) kernel instead of a separate dependent launch per layer.
 FUSE_BN_FINALIZE = os.environ.get("UNETK_FUSE_BN_FINALIZE", "1") != "0"
 SPLIT_PACK = os.environ.get("UNETK_SPLIT_PACK", "1") != "0"
+# CUDA graphs: the plan is static (same kernels, same buffers every step), so after one eager warm-up call
+# the whole forward (and backward) launch sequence, side streams included, is captured once per input shape
+# and replayed with ONE call: Python enqueue drops from 6.5-10 ms per step (host dependent) to the copies in
+# and out of the static buffers.  "0" = always eager.  Under data parallelism only the forward pass is
+# captured unless UNETK_GRAPH_DDP=1 (the backward contains the NCCL all-reduces).
+USE_GRAPHS = os.environ.get("UNETK_GRAPHS", "1") != "0"
+GRAPH_DDP = os.environ.get("UNETK_GRAPH_DDP", "0") == "1"
 # Weight gradients are off the critical path of backward (nothing downstream reads them before the
 # optimizer): they run on a side stream, each one released only after the data gradient of the same layer,
 # so the tensor-bound wgrad kernel shares the SMs with the memory-bound BatchNorm-backward passes of the
@@ -118,6 +125,10 @@ class Plan:
         self.bnctx = {}
         self.fused = set()
         self.drop_mask = None
+        self.static_outs = None   # outputs owned by the forward graph (backward reads them)
+        self.graphs = {}          # "train" / "eval" / "bwd" -> _GraphState
+        self.x_in = None          # static copy of the input image (graph replays read it)
+        self.g_in = None          # static copies of the output gradients
 
     def alloc_grads(self):
         if self.grads_ready:
@@ -140,6 +151,44 @@ class Plan:
     @staticmethod
     def view(buf, like):
         return buf.view(-1)[: like.numel()].view(like.shape)
+
+
+class _GraphState:
+    """Capture state of one launch sequence of a plan: call 1 runs eagerly (warm-up), call 2 captures,
+    later calls replay."""
+
+    def __init__(self):
+        self.calls = 0
+        self.graph = None
+        self.result = None
+        self.failed = False
+        self.n_calls = self.n_kernels = 0      # C-ABI calls / kernel launches one replay stands for
+
+    def run(self, body, after=None):
+        """body() enqueues the sequence on the current stream (and side streams that rejoin it) and
+        returns tensors that live as long as the graph.  Returns (result, replayed)."""
+        self.calls += 1
+        if self.graph is not None:
+            self.graph.replay()
+            _lib.add_replayed(self.n_calls, self.n_kernels)
+            return self.result, True
+        if self.calls >= 2 and not self.failed:
+            g = torch.cuda.CUDAGraph()
+            c0, k0 = _lib.launch_count(), _lib.kernel_launch_count()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    result = body()
+            except Exception as e:      # stay on the eager path: same kernels, launched one by one
+                self.failed = True
+                torch.cuda.synchronize()
+                import warnings
+                warnings.warn(f"unetk: CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly")
+                return body(), False
+            self.graph, self.result = g, result
+            self.n_calls, self.n_kernels = _lib.launch_count() - c0, _lib.kernel_launch_count() - k0
+            g.replay()                  # capture does not execute (the calls above were counted once already)
+            return result, True
+        return body(), False
 
 
 class _Chain:
@@ -380,7 +429,7 @@ class Engine:
             v += L.rm._version + L.rv._version
         return v
 
-    def _pack_weights(self):
+    def _pack_weights(self, split=True):
         """fp32 master weights -> bf16 kernel layouts.  The encoder's on the caller's stream; the decoders'
         (2/3 of the bytes) on a side stream that the decoder chains wait for (self.pack_done)."""
         self.pack_done = None
@@ -395,7 +444,7 @@ class Engine:
             ops.pack_conv_weights(self.conv_pack_tables[1], self.flat_p, self.wpack)
             ops.permute_batched(self.pack_table, self.flat_p, self.wpack)            # transposed convs
 
-        if SPLIT_PACK and not ops.timing_enabled():
+        if split and SPLIT_PACK and not ops.timing_enabled():
             s0 = torch.cuda.current_stream(self.device)
             if self.pstream is None:
                 self.pstream = torch.cuda.Stream(device=self.device)
@@ -446,6 +495,9 @@ class Engine:
             x = x.float()
         return x.contiguous()
 
+    def _graphs_ok(self):
+        return USE_GRAPHS and not ops.timing_enabled() and self.bottleneck_dropout == 0.0 and not FUSE_CHECK
+
     def forward(self, x, training):
         x = self._check_input(x)
         self.ensure(x.device)
@@ -456,14 +508,43 @@ class Engine:
         if training or sig != getattr(self, "_vsig", None):
             self.mark_weights_dirty()
             self._vsig = sig
-        self._pack_weights()
-        if training:
-            outs = self._forward_train(pl, x)
-            self.fold_dirty = True   # running statistics moved
+        if self._graphs_ok():
+            outs = self._forward_graphed(pl, x, training)
         else:
-            outs = self._forward_eval(pl, x)
-        pl.x = x
+            self._pack_weights()
+            outs = self._forward_train(pl, x) if training else self._forward_eval(pl, x)
+            pl.x = x
+            pl.static_outs = None
+        if training:
+            self.fold_dirty = True   # running statistics moved
         return outs, pl, pl.generation
+
+    def _forward_graphed(self, pl, x, training):
+        """Forward through a captured graph (see USE_GRAPHS): the image is copied into the plan's static
+        input, the outputs are clones of the graph's static outputs."""
+        if pl.x_in is None:
+            pl.x_in = torch.empty_like(x)
+        pl.x_in.copy_(x)
+        pl.x = pl.x_in
+        key = "train" if training else "eval"
+        st = pl.graphs.get(key)
+        if st is None:
+            st = pl.graphs[key] = _GraphState()
+        if training:
+            def body():
+                self.weights_dirty = True       # the optimizer moved the weights: re-pack inside the graph
+                self._pack_weights()
+                return self._forward_train(pl, pl.x_in)
+        else:
+            self._pack_weights(split=False)     # only when something changed the weights; not part of the graph
+            self._fold()
+
+            def body():
+                return self._forward_eval(pl, pl.x_in, fold=False)
+        outs, replayed = st.run(body)
+        self.weights_dirty = False
+        pl.static_outs = outs if replayed else None
+        return [o.clone() for o in outs] if replayed else outs
 
     def _bn_train(self, L, y, a, count, pool=None):
         mom = L.bn.momentum if L.bn.momentum is not None else 0.1
@@ -575,8 +656,9 @@ class Engine:
                 ops.bn_fold(L.gamma, L.beta, L.rm, L.rv, L.scale, L.shift, L.bn.eps)
             self.fold_dirty = False
 
-    def _forward_eval(self, pl, x):
-        self._fold()
+    def _forward_eval(self, pl, x, fold=True):
+        if fold:
+            self._fold()
         n = pl.n
         for l, (c1, c2) in enumerate(self.encoder):
             e = pl.enc[l]
@@ -638,6 +720,31 @@ class Engine:
             raise RuntimeError("backward() after another forward() through the same model and input shape: the saved "
                                "activations of this graph were overwritten (only one live graph per shape is supported)")
         pl.alloc_grads()
+        graphed = (self._graphs_ok() and pl.static_outs is not None and (self.ddp is None or GRAPH_DDP))
+        if not graphed:
+            grads = []
+            for d in range(len(self.decoders)):
+                g = grad_outs[d]
+                if g is None:
+                    g = ops.zero_(torch.empty_like(outs[d]))
+                grads.append(g.contiguous().float())
+            return self._backward_body(pl, grads, outs)
+        # graph replay: output gradients go through static buffers, the heads read the forward graph's outputs
+        if pl.g_in is None:
+            pl.g_in = [torch.empty_like(o) for o in pl.static_outs]
+        for d, g in enumerate(grad_outs):
+            if g is None:
+                ops.zero_(pl.g_in[d])
+            else:
+                pl.g_in[d].copy_(g)
+        st = pl.graphs.get("bwd")
+        if st is None:
+            st = pl.graphs["bwd"] = _GraphState()
+        static_outs = pl.static_outs
+        st.run(lambda: self._backward_body(pl, pl.g_in, static_outs))
+        return self.grad_views()
+
+    def _backward_body(self, pl, grads, outs):
         V = Plan.view
         ctx = self._ctx
         n_dec = len(self.decoders)
@@ -649,12 +756,6 @@ class Engine:
             self.wstreams.append(torch.cuda.Stream(device=self.device))
         chains = [_Chain(streams[d], self.wstreams[d if parallel else 0] if overlap else None, pl.scratch[d])
                   for d in range(n_dec)]
-        grads = []
-        for d in range(n_dec):
-            g = grad_outs[d]
-            if g is None:
-                g = ops.zero_(torch.empty_like(outs[d]))
-            grads.append(g.contiguous().float())
         ops.zero_(self.gstage)
         ops.zero_(self.bn_sums_all)
         if parallel:
