@@ -8,7 +8,7 @@ import sys
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import unet_oracle as O  # noqa: E402
 from tiaozhanbei_unet_b200 import distributed as D, train_utils  # noqa: E402

@@ -9,7 +9,7 @@ os.environ["UNETK_FUSE_BN_REDUCE"] = "all"
 os.environ["UNETK_FUSE_CHECK"] = "1"
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import unet_oracle as O  # noqa: E402
 from tiaozhanbei_unet_b200 import train_utils  # noqa: E402

@@ -3,7 +3,7 @@ vectors recorded from the reference, on identical seeded inputs and weights.
 
 Tolerances.  The build stores activations and their gradients in bf16 (fp32 accumulation).  The
 noise floor of that storage contract was measured on the reference algorithm itself
-(oracle storage="bf16" vs storage="fp32", tools/parity_report.py, profiles/parity_r01.txt): on the
+(oracle storage="bf16" vs storage="fp32", tests/checks/parity_report.py, profiles/parity_r01.txt): on the
 He-scaled synthetic weights used here, sigmoid outputs deviate by mean 3e-3 / p99.9 6e-2 / max 1e-1,
 and deep-layer gradients by 50-60 % in relative L2 (cosine ~0.85) although their norms agree to a few
 percent and loss curves agree to 3e-3 — the deviation between two bf16 evaluations of the SAME

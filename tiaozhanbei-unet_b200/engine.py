@@ -43,9 +43,10 @@ FUSE_BN_FINALIZE = os.environ.get("UNETK_FUSE_BN_FINALIZE", "1") != "0"
 SPLIT_PACK = os.environ.get("UNETK_SPLIT_PACK", "1") != "0"
 # CUDA graphs: the plan is static (same kernels, same buffers every step), so after one eager warm-up call
 # the whole forward (and backward) launch sequence, side streams included, is captured once per input shape
-# and replayed with ONE call: Python enqueue drops from 6.5-10 ms per step (host dependent) to the copies in
-# and out of the static buffers.  "0" = always eager.  Under data parallelism only the forward pass is
-# captured unless UNETK_GRAPH_DDP=1 (the backward contains the NCCL all-reduces).
+# and replayed with ONE call: Python enqueue drops from 6.5-10 ms per step (host dependent) to 2.8 ms (loss,
+# optimizer, copies in and out of the static buffers).  "0" = always eager.  Under data parallelism only the
+# forward pass is captured: UNETK_GRAPH_DDP=1 also captures the backward with its NCCL all-reduces, which
+# ran correctly on 2 B200s (tests/checks/ddp_check.py) but hung in destroy_process_group() at exit.
 USE_GRAPHS = os.environ.get("UNETK_GRAPHS", "1") != "0"
 GRAPH_DDP = os.environ.get("UNETK_GRAPH_DDP", "0") == "1"
 # Weight gradients are off the critical path of backward (nothing downstream reads them before the
