@@ -90,21 +90,24 @@ int unetk_memset_zero(void* ptr, size_t bytes, void* stream);
  * GEMM).  src2/c2 fold torch.cat([x2, x1], dim=1) of src/model.py:65 into the K loop (c2 = 0: none).
  * stats != NULL: adds per-channel sum / sum of squares of the fp32 accumulators into stats[2][Cout]
  * (training BatchNorm, src/model.py:15,18).  scale/shift != NULL: y = relu?(acc*scale+shift)
- * (eval-mode BatchNorm + ReLU folded in).  stats and scale are mutually exclusive. */
+ * (eval-mode BatchNorm + ReLU folded in).  stats and scale are mutually exclusive.
+ * h2, w2 (0 = h, w): extent of src2 [n,h2,w2,c2], aligned at the origin of the h x w grid and read as zero
+ * beyond -- F.pad of the up-sampled tensor to the skip's size (src/model.py:57-61) for inputs whose
+ * size is not a multiple of 16; the same pair on dgrad bounds dx2, on wgrad it is src2's extent. */
 int unetk_conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wf, void* y,
                       float* stats, const float* scale, const float* shift, int relu, int n, int h,
-                      int w, int cout, void* stream);
+                      int w, int cout, int h2, int w2, void* stream);
 /* autograd of the above w.r.t. its input: dx = conv(dy, flipped W^T).  Columns [0,c1) go to dx1,
  * [c1,c1+c2) to dx2 (the two concat sources); accK != 0 accumulates into dxK (skip connections
  * receive several gradients).  stats != NULL: stats[c2] += sum over pixels of dx2 (the bias
  * gradient of the ConvTranspose2d that produced src2; the caller zeroes it). */
 int unetk_conv3x3_dgrad(const void* dy, int cout, const void* wd, void* dx1, int c1, int acc1,
                         void* dx2, int c2, int acc2, float* stats, const unetk_bn_ctx* bn, int n, int h,
-                        int w, void* stream);
+                        int w, int h2, int w2, void* stream);
 /* autograd w.r.t. the weight: dw[co][tap][ci] += sum_pix dy * x  (split-K, fp32 atomics; the
  * caller zeroes dw). */
 int unetk_conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2,
-                        float* dw, int n, int h, int w, int cout, void* stream);
+                        float* dw, int n, int h, int w, int cout, int h2, int w2, void* stream);
 
 /* First encoder conv, Conv2d(n_channels<=4, 64, 3, padding=1, bias=False) on the caller's NCHW
  * fp32 image (src/model.py:86 / :168 -> :14); w is the reference OIHW fp32 weight; dw is written

@@ -372,3 +372,37 @@ def test_config5_strip_train_step(cuda_device):
     worst = _check_grads(m.named_parameters(), ref_grads, "config-5 strip")
     print(f"[parity] config-5 strip 1x512x1408: loss {loss.item():.6f} vs {ref_losses['total_loss']:.6f}; "
           f"worst grad cosine {worst[0]:.3f}, worst head-side rel err {worst[1]:.3e}")
+
+
+def test_odd_sizes_take_the_pad_path(cuda_device):
+    """Input sizes that are not multiples of 16 (100x100, 52x76, 37x90): the reference zero-pads the
+    up-sampled tensor to the skip's size (src/model.py:57-61); here the consumer kernels read it as zero
+    beyond its extent.  Eval outputs against golden vectors of the reference, one training step (loss and
+    gradients, floor pooling and its backward included) against the oracle."""
+    from tiaozhanbei_unet_b200 import train_utils
+    dev = cuda_device
+    gold = torch.load(os.path.join(os.path.dirname(GOLDEN), "odd_golden.pt"), weights_only=False)
+    for case in gold["cases"]:
+        arch = case["arch"]
+        sd = O.synthetic_state_dict(arch, seed=case["weights_seed"], device=dev)
+        m = _model(arch, {k: v.clone() for k, v in sd.items()}, dev).eval()
+        g = torch.Generator().manual_seed(case["input_seed"])
+        x = torch.randn(*case["shape"], generator=g).to(dev)
+        with torch.no_grad():
+            y = m(x)
+        outs = [y] if arch == "unet" else list(y)
+        for i, (got, want) in enumerate(zip(outs, case["outputs"])):
+            assert got.shape == want.shape
+            _check_out(got, want.to(dev), f"{arch} {tuple(case['shape'])} output {i}")
+    for arch, (n, h, w) in (("anomaly_unet", (2, 52, 76)), ("unet", (2, 100, 100))):
+        sd = O.synthetic_state_dict(arch, seed=41, device=dev)
+        m = _model(arch, {k: v.clone() for k, v in sd.items()}, dev).train()
+        image, mask = _inputs(7, n, h, w, dev)
+        crit = train_utils.CombinedLoss()
+        outs, losses = _train_step_ours(m, arch, image, mask, crit)
+        ref_losses, ref_grads = O.train_step({k: v.clone() for k, v in sd.items()}, image, mask, arch=arch)
+        torch.cuda.synchronize()
+        assert abs(losses["total_loss"] - ref_losses["total_loss"]) <= LOSS_REL * abs(ref_losses["total_loss"])
+        worst = _check_grads(m.named_parameters(), ref_grads, f"{arch} {n}x{h}x{w}")
+        print(f"[parity] {arch} {n}x{h}x{w} (pad path): loss {losses['total_loss']:.6f} vs {ref_losses['total_loss']:.6f}; "
+              f"worst grad cosine {worst[0]:.3f}, worst head-side rel err {worst[1]:.3e}")

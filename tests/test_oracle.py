@@ -125,3 +125,17 @@ def test_oracle_matches_live_reference():
     for k, v in model.state_dict().items():
         if O.is_buffer(k):
             torch.testing.assert_close(sd[k], v, rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_matches_reference_on_odd_sizes():
+    """Sizes that are not multiples of 16 (F.pad path, src/model.py:57-61): golden vectors of the reference."""
+    gold = torch.load(os.path.join(os.path.dirname(GOLDEN), "odd_golden.pt"), weights_only=False)
+    for case in gold["cases"]:
+        sd = O.synthetic_state_dict(case["arch"], seed=case["weights_seed"])
+        g = torch.Generator().manual_seed(case["input_seed"])
+        x = torch.randn(*case["shape"], generator=g)
+        with torch.no_grad():
+            y = O.unet_forward(sd, x) if case["arch"] == "unet" else O.anomaly_unet_forward(sd, x)
+        outs = [y] if case["arch"] == "unet" else list(y)
+        for got, want in zip(outs, case["outputs"]):
+            torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)

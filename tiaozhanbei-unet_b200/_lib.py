@@ -20,9 +20,9 @@ SIGNATURES = {
     "unetk_last_error": (c_char_p, []),
     "unetk_check_device": (I, []),
     "unetk_memset_zero": (I, [P, Z, P]),
-    "unetk_conv3x3_fwd": (I, [P, I, P, I, P, P, P, P, P, I, I, I, I, I, P]),
-    "unetk_conv3x3_dgrad": (I, [P, I, P, P, I, I, P, I, I, P, P, I, I, I, P]),
-    "unetk_conv3x3_wgrad": (I, [P, P, I, P, I, P, I, I, I, I, P]),
+    "unetk_conv3x3_fwd": (I, [P, I, P, I, P, P, P, P, P, I, I, I, I, I, I, I, P]),
+    "unetk_conv3x3_dgrad": (I, [P, I, P, P, I, I, P, I, I, P, P, I, I, I, I, I, P]),
+    "unetk_conv3x3_wgrad": (I, [P, P, I, P, I, P, I, I, I, I, I, I, P]),
     "unetk_first_conv_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "unetk_first_conv_wgrad": (I, [P, P, P, I, I, I, I, I, P]),
     "unetk_image_to_nhwc64": (I, [P, P, I, I, I, I, P]),

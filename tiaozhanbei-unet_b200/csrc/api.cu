@@ -31,20 +31,20 @@ int unetk_memset_zero(void* ptr, size_t bytes, void* stream) {
 
 int unetk_conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wf, void* y,
                       float* stats, const float* scale, const float* shift, int relu, int n, int h,
-                      int w, int cout, void* stream) {
-  return unetk::conv3x3_fwd(src1, c1, src2, c2, wf, y, stats, scale, shift, relu, n, h, w, cout, S(stream));
+                      int w, int cout, int h2, int w2, void* stream) {
+  return unetk::conv3x3_fwd(src1, c1, src2, c2, wf, y, stats, scale, shift, relu, n, h, w, cout, h2, w2, S(stream));
 }
 static const unetk::BnReduceCtx* B(const unetk_bn_ctx* bn) { return reinterpret_cast<const unetk::BnReduceCtx*>(bn); }
 static_assert(sizeof(unetk_bn_ctx) == sizeof(unetk::BnReduceCtx), "unetk_bn_ctx mirrors BnReduceCtx");
 
 int unetk_conv3x3_dgrad(const void* dy, int cout, const void* wd, void* dx1, int c1, int acc1,
                         void* dx2, int c2, int acc2, float* stats, const unetk_bn_ctx* bn, int n, int h, int w,
-                        void* stream) {
-  return unetk::conv3x3_dgrad(dy, cout, wd, dx1, c1, acc1, dx2, c2, acc2, stats, B(bn), n, h, w, S(stream));
+                        int h2, int w2, void* stream) {
+  return unetk::conv3x3_dgrad(dy, cout, wd, dx1, c1, acc1, dx2, c2, acc2, stats, B(bn), n, h, w, h2, w2, S(stream));
 }
 int unetk_conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2,
-                        float* dw, int n, int h, int w, int cout, void* stream) {
-  return unetk::conv3x3_wgrad(dy, src1, c1, src2, c2, dw, n, h, w, cout, S(stream));
+                        float* dw, int n, int h, int w, int cout, int h2, int w2, void* stream) {
+  return unetk::conv3x3_wgrad(dy, src1, c1, src2, c2, dw, n, h, w, cout, h2, w2, S(stream));
 }
 int unetk_first_conv_fwd(const float* x, const float* w, void* y, float* stats, int n, int cin,
                          int h, int w_, int cout, void* stream) {

@@ -530,7 +530,10 @@ int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, 
                 void* idx, int N, int H, int W, int C, int apply, cudaStream_t s) {
   UNETK_CHECK_ARG(y && pooled, "bnrelu_pool: null pointer");
   UNETK_CHECK_ARG(!apply || (scale && shift && a), "bnrelu_pool: apply needs scale, shift and a");
-  UNETK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "bnrelu_pool: H and W must be even (got %dx%d)", H, W);
+  // odd sizes pool with floor semantics (nn.MaxPool2d(2)); the last row / column is then outside every
+  // window, so the fused BatchNorm+ReLU variant, which writes `a` window by window, needs even sizes
+  UNETK_CHECK_ARG(!apply || (H % 2 == 0 && W % 2 == 0), "bnrelu_pool: the fused apply needs even H and W (got %dx%d): apply first, then pool", H, W);
+  UNETK_CHECK_ARG(H >= 2 && W >= 2, "bnrelu_pool: input smaller than the 2x2 window");
   if (int e = check_c(C, "bnrelu_pool")) return e;
   const long nvec = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
   UNETK_CUDA(launch_pdl(bnrelu_pool_kernel<false>, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s, static_cast<const uint4*>(y), scale, shift,
@@ -543,7 +546,10 @@ int bnrelu_pool(const void* y, const float* scale, const float* shift, void* a, 
 int maxpool_bwd(const void* dp, const void* idx, void* da, int N, int H, int W, int C, int accumulate,
                 const void* extra, const BnReduceCtx* bn, cudaStream_t s) {
   UNETK_CHECK_ARG(dp && idx && da, "maxpool_bwd: null pointer");
-  UNETK_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "maxpool_bwd: H and W must be even");
+  // odd sizes: the last row / column lies outside every window and keeps what it holds, which is only
+  // right when the kernel accumulates into an existing gradient and adds no second tensor
+  UNETK_CHECK_ARG((H % 2 == 0 && W % 2 == 0) || (accumulate && extra == nullptr),
+                  "maxpool_bwd: odd H or W (%dx%d) needs accumulate != 0 and no extra tensor", H, W);
   if (int e = check_c(C, "maxpool_bwd")) return e;
   const long nvec = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
   const bool fuse = bn != nullptr && bn->y != nullptr;

@@ -241,7 +241,7 @@ int first_conv_wgrad_tc(const void* x64, const void* dy, float* scratch, float* 
   UNETK_CHECK_ARG(Cin >= 1 && Cin <= 8, "first_conv_wgrad_tc: 1..8 input channels supported (got %d)", Cin);
   UNETK_CHECK_ARG(cout == kFcCout, "first_conv_wgrad_tc: 64 output channels required (got %d)", cout);
   UNETK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * kFcCout * 9 * 64, s));
-  if (int e = conv3x3_wgrad(dy, x64, 64, nullptr, 0, scratch, N, H, W, cout, s)) return e;
+  if (int e = conv3x3_wgrad(dy, x64, 64, nullptr, 0, scratch, N, H, W, cout, 0, 0, s)) return e;
   const int n = kFcCout * Cin * 9;
   first_conv_gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(scratch, dw, Cin);
   UNETK_CUDA(cudaGetLastError());

@@ -33,6 +33,8 @@ namespace unetk {
 
 struct IgemmParams {
   int n_img, H, W;      // GEMM pixel grid (rows of D)
+  int H2, W2;           // extent of the second source / destination inside that grid (origin-aligned; the
+                        // reference zero-pads the up-sampled tensor to the skip's size, src/model.py:57-61)
   int regions_x, regions_y;
   int n_blocks;         // Ntot / BN
   int Ntot;             // columns of D
@@ -342,11 +344,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       }
       const int col0 = nb * BN;
       int xs[SUBS];
-      bool valids[SUBS];
+      bool valids[SUBS], valids2[SUBS];      // inside the pixel grid / inside the second destination
 #pragma unroll
       for (int sub = 0; sub < SUBS; ++sub) {
         xs[sub] = rx * kRegionW + sub * kSubW + sx;
         valids[sub] = live && (xs[sub] < p.W) && (y < p.H);
+        valids2[sub] = valids[sub] && (xs[sub] < p.W2) && (y < p.H2);
       }
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
@@ -374,10 +377,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             // the sub-tiles share the columns: add them first, then ONE transposing butterfly each
             // for the sum and the sum of squares; per-quarter smem slots (no shared-memory atomics)
             float s[32];
+            const bool second = col >= p.split;      // columns of the second destination: its own extent
+            const bool ok0 = second ? valids2[0] : valids[0];
+            const bool ok1 = second ? valids2[SUBS - 1] : valids[SUBS - 1];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float a = valids[0] ? v2[0][j] : 0.f;
-              if (SUBS == 2) a += valids[SUBS - 1] ? v2[SUBS - 1][j] : 0.f;
+              float a = ok0 ? v2[0][j] : 0.f;
+              if (SUBS == 2) a += ok1 ? v2[SUBS - 1][j] : 0.f;
               s[j] = a;
             }
             const float cs = warp_colsum32(s);
@@ -385,10 +391,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             if (p.stats_sq != nullptr) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float a = valids[0] ? v2[0][j] : 0.f;
+                const float a = ok0 ? v2[0][j] : 0.f;
                 float sq = a * a;
                 if (SUBS == 2) {
-                  const float b = valids[SUBS - 1] ? v2[SUBS - 1][j] : 0.f;
+                  const float b = ok1 ? v2[SUBS - 1][j] : 0.f;
                   sq = fmaf(b, b, sq);
                 }
                 s[j] = sq;
@@ -428,7 +434,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                 dst = p.out1 + pix * p.ldc1 + col;
                 accum = p.acc1 != 0;
               } else {
-                dst = p.out2 + pix * p.ldc2 + (col - p.split);
+                if (!valids2[sub]) continue;
+                const size_t pix2 = (static_cast<size_t>(n) * p.H2 + y) * p.W2 + x;
+                dst = p.out2 + pix2 * p.ldc2 + (col - p.split);
                 accum = p.acc2 != 0;
               }
             } else {
@@ -619,6 +627,8 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
   UNETK_CHECK_ARG((reinterpret_cast<uintptr_t>(L.a1) & 15) == 0 && (reinterpret_cast<uintptr_t>(L.b) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(p.out1) & 15) == 0, "igemm: pointers must be 16-byte aligned");
   if (int e = check_device_sm100()) return e;
+  if (p.H2 <= 0 || p.W2 <= 0) { p.H2 = p.H; p.W2 = p.W; }
+  UNETK_CHECK_ARG(p.H2 <= p.H && p.W2 <= p.W, "igemm: the second tensor (%dx%d) must fit inside the pixel grid (%dx%d)", p.H2, p.W2, p.H, p.W);
   p.halo = (p.num_taps == 9) ? 1 : 0;
   p.c1_chunks = L.c1 / 64;
   p.c2_chunks = L.c2 / 64;
@@ -642,7 +652,7 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
   if (p.a_mode == 0) {
     if ((e = make_act_tmap(&tmA1, L.a1, p.n_img, p.H, p.W, L.c1, box_w, box_h, 1))) return e;
     if (L.c2 > 0) {
-      if ((e = make_act_tmap(&tmA2, L.a2, p.n_img, p.H, p.W, L.c2, box_w, box_h, 1))) return e;
+      if ((e = make_act_tmap(&tmA2, L.a2, p.n_img, p.H2, p.W2, L.c2, box_w, box_h, 1))) return e;
     } else {
       tmA2 = tmA1;
     }
@@ -673,13 +683,13 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
 
 int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
                 float* stats, const float* scale, const float* shift, int relu, int n, int h, int w,
-                int cout, cudaStream_t stream) {
+                int cout, int h2, int w2, cudaStream_t stream) {
   UNETK_CHECK_ARG(src1 && wpk && y, "conv3x3_fwd: null pointer");
   UNETK_CHECK_ARG(c2 == 0 || src2 != nullptr, "conv3x3_fwd: second source missing");
   IgemmLaunch L{};
   L.a1 = src1; L.c1 = c1; L.a2 = src2; L.c2 = c2; L.b = wpk;
   IgemmParams& p = L.p;
-  p.n_img = n; p.H = h; p.W = w; p.Ntot = cout; p.num_taps = 9; p.a_mode = 0; p.epi_mode = 0;
+  p.n_img = n; p.H = h; p.W = w; p.H2 = h2; p.W2 = w2; p.Ntot = cout; p.num_taps = 9; p.a_mode = 0; p.epi_mode = 0;
   p.split = cout; p.out1 = static_cast<__nv_bfloat16*>(y); p.out2 = nullptr; p.ldc1 = cout; p.ldc2 = 0;
   p.stats = stats; p.stats_sq = stats ? stats + cout : nullptr; p.stats_from = 0;
   p.scale = scale; p.shift = shift; p.relu = relu;
@@ -697,14 +707,15 @@ static int apply_bn_ctx(IgemmParams& p, const BnReduceCtx* bn, const char* who) 
 }
 
 int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1, int acc1, void* dx2,
-                  int c2, int acc2, float* stats, const BnReduceCtx* bn, int n, int h, int w, cudaStream_t stream) {
+                  int c2, int acc2, float* stats, const BnReduceCtx* bn, int n, int h, int w, int h2, int w2,
+                  cudaStream_t stream) {
   UNETK_CHECK_ARG(dy && wdpk && dx1, "conv3x3_dgrad: null pointer");
   UNETK_CHECK_ARG(c2 == 0 || dx2 != nullptr, "conv3x3_dgrad: second destination missing");
   UNETK_CHECK_ARG(stats == nullptr || c2 > 0, "conv3x3_dgrad: stats requested without a second destination");
   IgemmLaunch L{};
   L.a1 = dy; L.c1 = cout; L.a2 = nullptr; L.c2 = 0; L.b = wdpk;
   IgemmParams& p = L.p;
-  p.n_img = n; p.H = h; p.W = w; p.Ntot = c1 + c2; p.num_taps = 9; p.a_mode = 0; p.epi_mode = 0;
+  p.n_img = n; p.H = h; p.W = w; p.H2 = h2; p.W2 = w2; p.Ntot = c1 + c2; p.num_taps = 9; p.a_mode = 0; p.epi_mode = 0;
   p.split = c1; p.out1 = static_cast<__nv_bfloat16*>(dx1); p.out2 = static_cast<__nv_bfloat16*>(dx2);
   p.ldc1 = c1; p.ldc2 = c2; p.acc1 = acc1; p.acc2 = acc2;
   // bias gradient of the ConvTranspose2d that produced the second concat source: sum over pixels of dx2

@@ -39,9 +39,10 @@ struct BnFinalizeArgs {
 // igemm.cu — K-major implicit GEMMs (tcgen05)
 int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
                 float* stats, const float* scale, const float* shift, int relu, int n, int h, int w,
-                int cout, cudaStream_t stream);
+                int cout, int h2, int w2, cudaStream_t stream);
 int conv3x3_dgrad(const void* dy, int cout, const void* wdpk, void* dx1, int c1, int acc1, void* dx2,
-                  int c2, int acc2, float* stats, const BnReduceCtx* bn, int n, int h, int w, cudaStream_t stream);
+                  int c2, int acc2, float* stats, const BnReduceCtx* bn, int n, int h, int w, int h2, int w2,
+                  cudaStream_t stream);
 int convt2x2_fwd(const void* a, int cin, const void* wpk, const float* bias, void* up, int n, int h,
                  int w, int cout, cudaStream_t stream);
 int convt2x2_dgrad(const void* dup, int cout, const void* wdpk, void* da, int cin, int acc,
@@ -49,7 +50,7 @@ int convt2x2_dgrad(const void* dup, int cout, const void* wdpk, void* da, int ci
 
 // wgrad.cu — MN-major split-K GEMMs (tcgen05)
 int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2, float* dw,
-                  int n, int h, int w, int cout, cudaStream_t stream);
+                  int n, int h, int w, int cout, int h2, int w2, cudaStream_t stream);
 int convt2x2_wgrad(const void* a, int cin, const void* dup, int cout, float* dw, int n, int h, int w,
                    cudaStream_t stream);
 

@@ -341,7 +341,9 @@ static int choose_ksplit(int work_tiles, int total_k, double us_per_ktile, doubl
 }
 
 int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, int c2, float* dw,
-                  int n, int h, int w, int cout, cudaStream_t stream) {
+                  int n, int h, int w, int cout, int h2, int w2, cudaStream_t stream) {
+  if (h2 <= 0 || w2 <= 0) { h2 = h; w2 = w; }      // extent of src2 inside the pixel grid (zero beyond: src/model.py:57-61)
+  UNETK_CHECK_ARG(h2 <= h && w2 <= w, "conv3x3_wgrad: the second source (%dx%d) must fit inside the pixel grid (%dx%d)", h2, w2, h, w);
   UNETK_CHECK_ARG(dy && src1 && dw, "conv3x3_wgrad: null pointer");
   UNETK_CHECK_ARG(c2 == 0 || src2 != nullptr, "conv3x3_wgrad: second source missing");
   const int cin = c1 + c2;
@@ -363,7 +365,7 @@ int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, in
     CUtensorMap x1, x2, tdy;
     int e;
     if ((e = make_act_tmap(&x1, src1, n, h, w, c1, 10, 10, 1))) return e;
-    if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h, w, c2, 10, 10, 1))) return e; } else x2 = x1;
+    if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h2, w2, c2, 10, 10, 1))) return e; } else x2 = x1;
     if ((e = make_act_tmap(&tdy, dy, n, h, w, cout, 8, 8, 1))) return e;
     return launch_wgrad_t<2, 64, true>(x1, x2, tdy, p, dim3(work, p.ksplit), stream);
   }
@@ -382,7 +384,7 @@ int conv3x3_wgrad(const void* dy, const void* src1, int c1, const void* src2, in
   CUtensorMap x1, x2, tdy;
   int e;
   if ((e = make_act_tmap(&x1, src1, n, h, w, c1, 10, 8, 1))) return e;
-  if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h, w, c2, 10, 8, 1))) return e; } else x2 = x1;
+  if (c2 > 0) { if ((e = make_act_tmap(&x2, src2, n, h2, w2, c2, 10, 8, 1))) return e; } else x2 = x1;
   if ((e = make_act_tmap(&tdy, dy, n, h, w, cout, 8, 8, 1))) return e;
   dim3 grid(work, p.ksplit);
   if (ctas == 2) return m64 ? launch_wgrad_t<0, 128, true, 2>(x1, x2, tdy, p, grid, stream)

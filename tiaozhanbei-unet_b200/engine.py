@@ -114,10 +114,15 @@ class Plan:
             for k in range(1, 5):
                 lv = 4 - k
                 c = WIDTHS[lv]
-                stages.append({"up": act(lv, c), "y1": act(lv, c), "a1": act(lv, c), "y2": act(lv, c),
+                # the transposed conv doubles the level below: up to one row / column short of the skip when
+                # the input size is not a multiple of 16 (the reference zero-pads it, src/model.py:57-61: the
+                # consumer kernels read it as zero beyond its extent instead)
+                up = torch.empty(n, 2 * (h >> (lv + 1)), 2 * (w >> (lv + 1)), c, dtype=bf, device=device)
+                stages.append({"up": up, "y1": act(lv, c), "a1": act(lv, c), "y2": act(lv, c),
                                "a2": act(lv, c)})
             self.dec.append(stages)
         self._act = act
+        self.all_even = all((h >> l) % 2 == 0 and (w >> l) % 2 == 0 for l in range(4))
         self.n_dec = len(eng.decoders)
         # the image as NHWC bf16 zero-padded to 64 channels (first conv on the tensor cores); the padding
         # channels are written once, here
@@ -475,9 +480,8 @@ class Engine:
         key = (n, h, w)
         pl = self.plans.get(key)
         if pl is None:
-            if h % 16 or w % 16:
-                raise ValueError(f"input size {h}x{w} is not a multiple of 16: the F.pad path of the reference "
-                                 "(src/model.py:57-61) is not implemented in this version")
+            if h < 16 or w < 16:
+                raise ValueError(f"input size {h}x{w} is too small: four 2x2 poolings need at least 16x16")
             if len(self.plans) >= 3:      # e.g. train batch, last ragged batch, validation batch
                 self.plans.pop(next(iter(self.plans)))
             pl = Plan(self, n, h, w, self.device)
@@ -558,6 +562,9 @@ class Engine:
                 L._fin = fin
             if pool is None:
                 ops.bnrelu_apply_fin(y, fin[1], a)
+            elif y.shape[1] % 2 or y.shape[2] % 2:    # floor pooling leaves the last row / column outside every window
+                ops.bnrelu_apply_fin(y, fin[1], a)
+                ops.bnrelu_pool(a, None, None, None, pool[0], pool[1], apply=False)
             else:
                 ops.bnrelu_pool_fin(y, fin[1], a, pool[0], pool[1])
             return
@@ -565,6 +572,9 @@ class Engine:
                         count, L.bn.eps, mom)
         if pool is None:
             ops.bnrelu_apply(y, L.scale, L.shift, a)
+        elif y.shape[1] % 2 or y.shape[2] % 2:
+            ops.bnrelu_apply(y, L.scale, L.shift, a)
+            ops.bnrelu_pool(a, None, None, None, pool[0], pool[1], apply=False)
         else:
             ops.bnrelu_pool(y, L.scale, L.shift, a, pool[0], pool[1], apply=True)
 
@@ -749,7 +759,9 @@ class Engine:
         V = Plan.view
         ctx = self._ctx
         n_dec = len(self.decoders)
-        streams = self._decoder_streams(n_dec) if n_dec == 2 else [torch.cuda.current_stream(self.device)] * n_dec
+        # (odd sizes: the pool backward cannot add the second decoder's skip gradient to the last row / column)
+        streams = (self._decoder_streams(n_dec) if n_dec == 2 and pl.all_even
+                   else [torch.cuda.current_stream(self.device)] * n_dec)
         s0 = streams[0]
         parallel = n_dec == 2 and streams[1] is not s0
         overlap = OVERLAP_WGRAD and not ops.timing_enabled()

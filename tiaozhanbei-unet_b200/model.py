@@ -6,9 +6,9 @@ checkpoints round-trip with the reference.  The modules only HOLD parameters; `f
 whole network to engine.Engine, which launches the sm_100a kernels of include/unetk.h.  There is
 no PyTorch-operator or CPU fallback: on anything but a CUDA sm_100 device forward raises.
 
-Not implemented in this version (raise at construction / call time):
-`bilinear=True` decoders (src/model.py:47-49), input sizes that are not multiples of 16
-(the F.pad path, src/model.py:57-61), SegmentationUNet (src/model.py:111-153).
+Not implemented in this version (raises at construction): `bilinear=True` decoders
+(src/model.py:47-49).  Input sizes that are not multiples of 16 take the reference's F.pad path
+(src/model.py:57-61) inside the kernels: the up-sampled tensor is read as zero beyond its extent.
 """
 from __future__ import annotations
 

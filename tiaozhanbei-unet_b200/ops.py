@@ -115,14 +115,14 @@ def conv3x3_fwd(src1, src2, wf, y, stats=None, scale=None, shift=None, relu=Fals
     """y = conv3x3(cat(src1, src2)) with packed weights wf [Cout][9][Cin]."""
     _chk(src1, bf16, "src1"); _chk(wf, bf16, "wf"); _chk(y, bf16, "y")
     n, h, w, c1 = src1.shape
-    c2 = 0
+    c2 = h2 = w2 = 0
     if src2 is not None:
         _chk(src2, bf16, "src2")
-        c2 = src2.shape[3]
+        _, h2, w2, c2 = src2.shape       # may be up to one row / column short of src1 (F.pad path, src/model.py:57-61)
     cout = y.shape[3]
     # algo_cin: the layer's real input channels when src1 is zero-padded (first conv): only algorithmic FLOPs count
     _timed(2.0 * n * h * w * cout * 9 * (algo_cin if algo_cin is not None else c1 + c2), _igemm_variant(cout), "unetk_conv3x3_fwd", _p(src1), c1, _p(src2), c2, _p(wf), _p(y), _p(stats), _p(scale),
-              _p(shift), int(relu), n, h, w, cout, _s())
+              _p(shift), int(relu), n, h, w, cout, h2, w2, _s())
     return y
 
 
@@ -130,12 +130,12 @@ def conv3x3_dgrad(dy, wd, dx1, acc1=False, dx2=None, acc2=False, stats=None, bn=
     _chk(dy, bf16, "dy"); _chk(wd, bf16, "wd"); _chk(dx1, bf16, "dx1")
     n, h, w, cout = dy.shape
     c1 = dx1.shape[3]
-    c2 = 0
+    c2 = h2 = w2 = 0
     if dx2 is not None:
         _chk(dx2, bf16, "dx2")
-        c2 = dx2.shape[3]
+        _, h2, w2, c2 = dx2.shape
     _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), _igemm_variant(c1 + c2), "unetk_conv3x3_dgrad", _p(dy), cout, _p(wd), _p(dx1), c1, int(acc1), _p(dx2), c2,
-           int(acc2), _p(stats), _bn(bn), n, h, w, _s())
+           int(acc2), _p(stats), _bn(bn), n, h, w, h2, w2, _s())
 
 
 def conv3x3_wgrad(dy, src1, src2, dw):
@@ -143,11 +143,12 @@ def conv3x3_wgrad(dy, src1, src2, dw):
     _chk(dy, bf16, "dy"); _chk(src1, bf16, "src1"); _chk(dw, f32, "dw")
     n, h, w, cout = dy.shape
     c1 = src1.shape[3]
-    c2 = 0
+    c2 = h2 = w2 = 0
     if src2 is not None:
         _chk(src2, bf16, "src2")
-        c2 = src2.shape[3]
-    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "wgrad_kernel", "unetk_conv3x3_wgrad", _p(dy), _p(src1), c1, _p(src2), c2, _p(dw), n, h, w, cout, _s())
+        _, h2, w2, c2 = src2.shape
+    _timed(2.0 * n * h * w * cout * 9 * (c1 + c2), "wgrad_kernel", "unetk_conv3x3_wgrad", _p(dy), _p(src1), c1, _p(src2), c2, _p(dw), n, h, w, cout,
+           h2, w2, _s())
 
 
 def first_conv_fwd(x, w, y, stats=None):
