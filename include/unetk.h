@@ -225,6 +225,10 @@ int unetk_seg_loss_bwd(const float* logits, const int64_t* target, const float* 
 /* nn.Dropout2d applied in place to an NHWC bf16 activation: x[n,h,w,c] *= mask[n,c] (src/model.py:130,146;
  * the caller draws mask = bernoulli(1-p)/(1-p)). */
 int unetk_channel_scale(void* x, const float* mask, int n, int h, int w, int c, void* stream);
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of the bilinear=True decoders
+ * (src/model.py:47-49), NHWC bf16: out[n,2h,2w,c] from x[n,h,w,c]; _bwd: dx (+)= gradient w.r.t. x. */
+int unetk_upsample2x_fwd(const void* x, void* out, int n, int h, int w, int c, void* stream);
+int unetk_upsample2x_bwd(const void* dout, void* dx, int n, int h, int w, int c, int accumulate, void* stream);
 /* torch.argmax(logits, dim=1): NCHW fp32 -> int64 [n,h,w], first maximum wins (test.py:98). */
 int unetk_argmax_channels(const float* logits, int64_t* out, int n, int c, int h, int w, void* stream);
 

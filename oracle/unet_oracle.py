@@ -40,27 +40,33 @@ WIDTHS = [64, 128, 256, 512, 1024]
 # ---------------------------------------------------------------------------------------------
 # parameter tables
 # ---------------------------------------------------------------------------------------------
-def state_dict_spec(arch: str = "anomaly_unet", n_channels: int = 3, n_classes: int = 1):
-    """Ordered {key: (shape, dtype)} exactly as the reference's state_dict() (transpose-conv decoder).
-    src/model.py:78-95 (UNet), :161-186 (AnomalyUNet)."""
+def state_dict_spec(arch: str = "anomaly_unet", n_channels: int = 3, n_classes: int = 1, bilinear: bool = False):
+    """Ordered {key: (shape, dtype)} exactly as the reference's state_dict().  src/model.py:78-95 (UNet),
+    :161-186 (AnomalyUNet); bilinear=True: parameter-free up-sampling, DoubleConv(in, out, in // 2) and a
+    512-channel bottleneck (src/model.py:47-49, 90-95)."""
     spec = OrderedDict()
+    factor = 2 if bilinear else 1
 
-    def double_conv(prefix, cin, cout):
-        for ci, (i_conv, i_bn) in zip((cin, cout), ((0, 1), (3, 4))):
-            spec[f"{prefix}.double_conv.{i_conv}.weight"] = ((cout, ci, 3, 3), torch.float32)
-            spec[f"{prefix}.double_conv.{i_bn}.weight"] = ((cout,), torch.float32)
-            spec[f"{prefix}.double_conv.{i_bn}.bias"] = ((cout,), torch.float32)
-            spec[f"{prefix}.double_conv.{i_bn}.running_mean"] = ((cout,), torch.float32)
-            spec[f"{prefix}.double_conv.{i_bn}.running_var"] = ((cout,), torch.float32)
+    def double_conv(prefix, cin, cout, mid=None):
+        mid = mid or cout
+        for ci, co, (i_conv, i_bn) in zip((cin, mid), (mid, cout), ((0, 1), (3, 4))):
+            spec[f"{prefix}.double_conv.{i_conv}.weight"] = ((co, ci, 3, 3), torch.float32)
+            spec[f"{prefix}.double_conv.{i_bn}.weight"] = ((co,), torch.float32)
+            spec[f"{prefix}.double_conv.{i_bn}.bias"] = ((co,), torch.float32)
+            spec[f"{prefix}.double_conv.{i_bn}.running_mean"] = ((co,), torch.float32)
+            spec[f"{prefix}.double_conv.{i_bn}.running_var"] = ((co,), torch.float32)
             spec[f"{prefix}.double_conv.{i_bn}.num_batches_tracked"] = ((), torch.int64)
 
     double_conv("inc", n_channels, 64)
     for k in range(1, 5):
-        double_conv(f"down{k}.maxpool_conv.1", WIDTHS[k - 1], WIDTHS[k])
+        double_conv(f"down{k}.maxpool_conv.1", WIDTHS[k - 1], WIDTHS[k] // (factor if k == 4 else 1))
 
     def decoder(suffix, n_out):
         for k in range(1, 5):
             cin = WIDTHS[5 - k]
+            if bilinear:
+                double_conv(f"up{k}{suffix}.conv", cin, (cin // 2) // (factor if k < 4 else 1), cin // 2)
+                continue
             spec[f"up{k}{suffix}.up.weight"] = ((cin, cin // 2, 2, 2), torch.float32)
             spec[f"up{k}{suffix}.up.bias"] = ((cin // 2,), torch.float32)
             double_conv(f"up{k}{suffix}.conv", cin, cin // 2)
@@ -81,12 +87,12 @@ def is_buffer(key: str) -> bool:
     return key.endswith(("running_mean", "running_var", "num_batches_tracked"))
 
 
-def synthetic_state_dict(arch="anomaly_unet", seed=0, n_channels=3, n_classes=1, device="cpu"):
+def synthetic_state_dict(arch="anomaly_unet", seed=0, n_channels=3, n_classes=1, device="cpu", bilinear=False):
     """Deterministic non-trivial weights (NOT the reference initialiser): every tensor is drawn
     from a CPU generator in key order, so the same seed reproduces the same state_dict anywhere."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     sd = OrderedDict()
-    for key, (shape, dtype) in state_dict_spec(arch, n_channels, n_classes).items():
+    for key, (shape, dtype) in state_dict_spec(arch, n_channels, n_classes, bilinear).items():
         if key.endswith("num_batches_tracked"):
             t = torch.zeros((), dtype=torch.int64)
         elif key.endswith("running_var"):
@@ -156,7 +162,10 @@ def _double_conv(sd, prefix, x, training, r, first=False):
 def _up(sd, prefix, x1, x2, training, r):
     # ConvTranspose2d(k2, s2) -> pad to the skip's size -> cat([skip, up]) -> DoubleConv
     #                                                                   src/model.py:51,54-66
-    x1 = r(F.conv_transpose2d(x1, r(sd[prefix + ".up.weight"]), sd[prefix + ".up.bias"], stride=2))
+    if prefix + ".up.weight" in sd:
+        x1 = r(F.conv_transpose2d(x1, r(sd[prefix + ".up.weight"]), sd[prefix + ".up.bias"], stride=2))
+    else:      # bilinear=True: nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)   src/model.py:47-49
+        x1 = r(F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True))
     dy = x2.size(2) - x1.size(2)
     dx = x2.size(3) - x1.size(3)
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])

@@ -101,8 +101,7 @@ def test_no_cpu_fallback():
     assert "CUDA" in str(e.value) or "cuda" in str(e.value)
     with pytest.raises(RuntimeError):
         train_utils.CombinedLoss()(torch.rand(1, 3, 8, 8), torch.rand(1, 1, 8, 8), torch.rand(1, 3, 8, 8), torch.rand(1, 1, 8, 8))
-    with pytest.raises(NotImplementedError):
-        Up(128, 64, bilinear=True)
+    assert isinstance(Up(128, 64, bilinear=True).up, torch.nn.Upsample)      # parameter-free up-sampling branch
 
 
 def test_optimizer_state_dict_is_torch_shaped():

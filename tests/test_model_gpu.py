@@ -406,3 +406,60 @@ def test_odd_sizes_take_the_pad_path(cuda_device):
         worst = _check_grads(m.named_parameters(), ref_grads, f"{arch} {n}x{h}x{w}")
         print(f"[parity] {arch} {n}x{h}x{w} (pad path): loss {losses['total_loss']:.6f} vs {ref_losses['total_loss']:.6f}; "
               f"worst grad cosine {worst[0]:.3f}, worst head-side rel err {worst[1]:.3e}")
+
+
+def test_bilinear_decoders(cuda_device):
+    """bilinear=True (src/model.py:47-49): the x2 bilinear up-sampling kernels against F.interpolate, eval
+    outputs against golden vectors of the reference (incl. an odd size), one training step against the oracle."""
+    import torch.nn.functional as F
+    from tiaozhanbei_unet_b200 import ops, train_utils
+    from tiaozhanbei_unet_b200.model import AnomalyUNet, UNet
+    dev = cuda_device
+    g = torch.Generator().manual_seed(1)
+    for n, h, w, c in ((2, 5, 7, 64), (1, 16, 16, 128), (1, 1, 3, 8)):
+        x = torch.randn(n, c, h, w, generator=g).to(dev).to(torch.bfloat16)
+        xb = x.permute(0, 2, 3, 1).contiguous()
+        out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=dev)
+        ops.upsample2x_fwd(xb, out)
+        xr = x.float().requires_grad_(True)
+        ref = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True)
+        torch.cuda.synchronize()
+        d = (out.permute(0, 3, 1, 2).float() - ref.detach()).abs().max().item()
+        assert d <= 2e-2 * ref.abs().max().item(), (n, h, w, c, d)
+        go = torch.randn(n, c, 2 * h, 2 * w, generator=g).to(dev).to(torch.bfloat16)
+        ref.backward(go.float())
+        dx = torch.empty_like(xb)
+        ops.upsample2x_bwd(go.permute(0, 2, 3, 1).contiguous(), dx)
+        base = dx.clone()
+        ops.upsample2x_bwd(go.permute(0, 2, 3, 1).contiguous(), dx, accumulate=True)
+        torch.cuda.synchronize()
+        want = xr.grad
+        assert (base.permute(0, 3, 1, 2).float() - want).abs().max().item() <= 2e-2 * want.abs().max().item()
+        assert (dx.permute(0, 3, 1, 2).float() - 2 * want).abs().max().item() <= 4e-2 * want.abs().max().item()
+    gold = torch.load(os.path.join(os.path.dirname(GOLDEN), "bilinear_golden.pt"), weights_only=False)
+    for case in gold["cases"]:
+        arch = case["arch"]
+        m = UNet(3, 1, bilinear=True) if arch == "unet" else AnomalyUNet(3, bilinear=True)
+        m.load_state_dict(O.synthetic_state_dict(arch, seed=case["weights_seed"], bilinear=True))
+        m = m.to(dev).eval()
+        gi = torch.Generator().manual_seed(case["input_seed"])
+        x = torch.randn(*case["shape"], generator=gi).to(dev)
+        with torch.no_grad():
+            y = m(x)
+        outs = [y] if arch == "unet" else list(y)
+        for i, (got, want) in enumerate(zip(outs, case["outputs"])):
+            _check_out(got, want.to(dev), f"bilinear {arch} {tuple(case['shape'])} output {i}")
+    arch = "anomaly_unet"
+    sd = O.synthetic_state_dict(arch, seed=61, device=dev, bilinear=True)
+    m = AnomalyUNet(3, bilinear=True)
+    m.load_state_dict({k: v.clone() for k, v in sd.items()})
+    m = m.to(dev).train()
+    image, mask = _inputs(9, 2, 64, 48, dev)
+    crit = train_utils.CombinedLoss()
+    outs, losses = _train_step_ours(m, arch, image, mask, crit)
+    ref_losses, ref_grads = O.train_step({k: v.clone() for k, v in sd.items()}, image, mask, arch=arch)
+    torch.cuda.synchronize()
+    assert abs(losses["total_loss"] - ref_losses["total_loss"]) <= LOSS_REL * abs(ref_losses["total_loss"])
+    worst = _check_grads(m.named_parameters(), ref_grads, "bilinear anomaly_unet 2x64x48")
+    print(f"[parity] bilinear anomaly_unet 2x64x48: loss {losses['total_loss']:.6f} vs {ref_losses['total_loss']:.6f}; "
+          f"worst grad cosine {worst[0]:.3f}, worst head-side rel err {worst[1]:.3e}")

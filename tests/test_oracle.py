@@ -139,3 +139,30 @@ def test_oracle_matches_reference_on_odd_sizes():
         outs = [y] if case["arch"] == "unet" else list(y)
         for got, want in zip(outs, case["outputs"]):
             torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_matches_reference_bilinear():
+    """bilinear=True decoders (src/model.py:47-49): golden vectors of the reference, incl. the known answer
+    of SURVEY.md section 4 (UNet(3, 1, bilinear=True) has 17,262,977 parameters)."""
+    gold = torch.load(os.path.join(os.path.dirname(GOLDEN), "bilinear_golden.pt"), weights_only=False)
+    assert gold["cases"][0]["n_params"] == 17_262_977
+    for case in gold["cases"]:
+        sd = O.synthetic_state_dict(case["arch"], seed=case["weights_seed"], bilinear=True)
+        assert list(sd.keys()) == case["keys"]
+        assert sum(v.numel() for k, v in sd.items() if not O.is_buffer(k)) == case["n_params"]
+        g = torch.Generator().manual_seed(case["input_seed"])
+        x = torch.randn(*case["shape"], generator=g)
+        with torch.no_grad():
+            y = O.unet_forward(sd, x) if case["arch"] == "unet" else O.anomaly_unet_forward(sd, x)
+        outs = [y] if case["arch"] == "unet" else list(y)
+        for got, want in zip(outs, case["outputs"]):
+            torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_bilinear_modules_have_the_reference_layout():
+    from tiaozhanbei_unet_b200.model import AnomalyUNet, UNet
+    for arch, m in (("unet", UNet(3, 1, bilinear=True)), ("anomaly_unet", AnomalyUNet(3, bilinear=True))):
+        spec = O.state_dict_spec(arch, 3, 1, bilinear=True)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(spec.keys())
+        assert all(tuple(sd[k].shape) == tuple(spec[k][0]) for k in spec)

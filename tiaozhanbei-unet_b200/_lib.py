@@ -54,6 +54,8 @@ SIGNATURES = {
     "unetk_seg_loss_bwd": (I, [P, P, P, P, P, P, I, I, I, I, L, F, F, F, F, F, I, P]),
     "unetk_channel_scale": (I, [P, P, I, I, I, I, P]),
     "unetk_argmax_channels": (I, [P, P, I, I, I, I, P]),
+    "unetk_upsample2x_fwd": (I, [P, P, I, I, I, I, P]),
+    "unetk_upsample2x_bwd": (I, [P, P, I, I, I, I, I, P]),
     "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),
     "unetk_permute_batched": (I, [P, I, I, P, P, I, F, P]),
     "unetk_permute_chunk_elems": (I, []),

@@ -173,6 +173,12 @@ int unetk_seg_loss_bwd(const float* logits, const int64_t* target, const float* 
 int unetk_channel_scale(void* x, const float* mask, int n, int h, int w, int c, void* stream) {
   return unetk::channel_scale(x, mask, n, h, w, c, S(stream));
 }
+int unetk_upsample2x_fwd(const void* x, void* out, int n, int h, int w, int c, void* stream) {
+  return unetk::upsample2x_fwd(x, out, n, h, w, c, S(stream));
+}
+int unetk_upsample2x_bwd(const void* dout, void* dx, int n, int h, int w, int c, int accumulate, void* stream) {
+  return unetk::upsample2x_bwd(dout, dx, n, h, w, c, accumulate, S(stream));
+}
 int unetk_argmax_channels(const float* logits, int64_t* out, int n, int c, int h, int w, void* stream) {
   return unetk::argmax_channels(logits, reinterpret_cast<long long*>(out), n, c, h, w, S(stream));
 }

@@ -109,6 +109,8 @@ int seg_loss_bwd(const float* logits, const long long* target, const float* clas
                  float focal_w, float focal_alpha, float focal_gamma, int is_prob, cudaStream_t s);
 int channel_scale(void* x, const float* mask, int N, int H, int W, int C, cudaStream_t s);
 int argmax_channels(const float* logits, long long* out, int N, int C, int H, int W, cudaStream_t s);
+int upsample2x_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s);
+int upsample2x_bwd(const void* dout, void* dx, int N, int H, int W, int C, int accumulate, cudaStream_t s);
 int anomaly_score(const float* recon, const float* orig, float* out, int N, int C, int H, int W,
                   int method, cudaStream_t s);
 int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int N, int C, int H,

@@ -232,6 +232,126 @@ argmax_channels_kernel(const float* __restrict__ z, long long* __restrict__ out,
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of the bilinear=True decoders
+// (src/model.py:47-49) on NHWC bf16: out[n, 2h, 2w, c].  Source coordinate o * (in - 1) / (out - 1), the
+// four taps blended in fp32 exactly as ATen's upsample_bilinear2d does.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up2_src(int o, int in, int out, int& i0, int& i1, float& l1) {
+  const float r = out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+  const float f = r * o;
+  i0 = static_cast<int>(f);
+  i1 = i0 + ((i0 < in - 1) ? 1 : 0);
+  l1 = f - i0;
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W, int cgroups, long nvec) {
+  const int OH = 2 * H, OW = 2 * W;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cgroups);
+    long pp = i / cgroups;
+    const int ox = static_cast<int>(pp % OW);
+    pp /= OW;
+    const int oy = static_cast<int>(pp % OH);
+    const long n = pp / OH;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    up2_src(oy, H, OH, y0, y1, ly);
+    up2_src(ox, W, OW, x0, x1, lx);
+    const uint4* b = x + n * H * W * cgroups + cg;
+    const uint4 q00 = ldg_nc_v4(b + (static_cast<long>(y0) * W + x0) * cgroups), q01 = ldg_nc_v4(b + (static_cast<long>(y0) * W + x1) * cgroups);
+    const uint4 q10 = ldg_nc_v4(b + (static_cast<long>(y1) * W + x0) * cgroups), q11 = ldg_nc_v4(b + (static_cast<long>(y1) * W + x1) * cgroups);
+    const uint32_t* a = &q00.x; const uint32_t* bb = &q01.x; const uint32_t* c = &q10.x; const uint32_t* d = &q11.x;
+    uint4 o;
+    uint32_t* po = &o.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 v00 = unpack_bf16x2(a[k]), v01 = unpack_bf16x2(bb[k]), v10 = unpack_bf16x2(c[k]), v11 = unpack_bf16x2(d[k]);
+      const float r0 = (1.f - ly) * ((1.f - lx) * v00.x + lx * v01.x) + ly * ((1.f - lx) * v10.x + lx * v11.x);
+      const float r1 = (1.f - ly) * ((1.f - lx) * v00.y + lx * v01.y) + ly * ((1.f - lx) * v10.y + lx * v11.y);
+      po[k] = pack_bf16x2(r0, r1);
+    }
+    out[i] = o;
+  }
+}
+
+// gradient w.r.t. the input, gathered per input pixel from the (at most 4 x 4) output pixels that read it
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const uint4* __restrict__ dout, uint4* dx, int H, int W, int cgroups, long nvec, int accumulate) {
+  const int OH = 2 * H, OW = 2 * W;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cgroups);
+    long pp = i / cgroups;
+    const int ix = static_cast<int>(pp % W);
+    pp /= W;
+    const int iy = static_cast<int>(pp % H);
+    const long n = pp / H;
+    float acc[8];
+    if (accumulate) {
+      const uint4 o = dx[i];
+      const float2 a = unpack_bf16x2(o.x), b = unpack_bf16x2(o.y), c = unpack_bf16x2(o.z), d = unpack_bf16x2(o.w);
+      acc[0] = a.x; acc[1] = a.y; acc[2] = b.x; acc[3] = b.y; acc[4] = c.x; acc[5] = c.y; acc[6] = d.x; acc[7] = d.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    }
+    const uint4* b = dout + n * OH * OW * cgroups + cg;
+    const int oy_lo = max(0, 2 * iy - 3), oy_hi = min(OH - 1, 2 * iy + 3);
+    const int ox_lo = max(0, 2 * ix - 3), ox_hi = min(OW - 1, 2 * ix + 3);
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1;
+      float ly;
+      up2_src(oy, H, OH, y0, y1, ly);
+      const float wy = (y0 == iy ? 1.f - ly : 0.f) + (y1 == iy ? ly : 0.f) - ((y0 == iy && y1 == iy) ? 0.f : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        int x0, x1;
+        float lx;
+        up2_src(ox, W, OW, x0, x1, lx);
+        const float wx = (x0 == ix ? 1.f - lx : 0.f) + (x1 == ix ? lx : 0.f);
+        if (wx == 0.f) continue;
+        const float wgt = wy * wx;
+        const uint4 g = ldg_nc_v4(b + (static_cast<long>(oy) * OW + ox) * cgroups);
+        const float2 a = unpack_bf16x2(g.x), bb = unpack_bf16x2(g.y), c = unpack_bf16x2(g.z), d = unpack_bf16x2(g.w);
+        acc[0] = fmaf(wgt, a.x, acc[0]); acc[1] = fmaf(wgt, a.y, acc[1]); acc[2] = fmaf(wgt, bb.x, acc[2]); acc[3] = fmaf(wgt, bb.y, acc[3]);
+        acc[4] = fmaf(wgt, c.x, acc[4]); acc[5] = fmaf(wgt, c.y, acc[5]); acc[6] = fmaf(wgt, d.x, acc[6]); acc[7] = fmaf(wgt, d.y, acc[7]);
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    dx[i] = o;
+  }
+}
+
+static int ew_blocks256(long nvec) {
+  long blocks = (nvec + 255) / 256;
+  const long cap = static_cast<long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  return static_cast<int>(blocks < 1 ? 1 : blocks);
+}
+
+int upsample2x_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s) {
+  UNETK_CHECK_ARG(x && out, "upsample2x_fwd: null pointer");
+  UNETK_CHECK_ARG(C > 0 && C % 8 == 0, "upsample2x_fwd: channel count must be a multiple of 8 (got %d)", C);
+  const long nvec = static_cast<long>(N) * 4 * H * W * (C / 8);
+  upsample2x_fwd_kernel<<<ew_blocks256(nvec), 256, 0, s>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), H, W, C / 8, nvec);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int upsample2x_bwd(const void* dout, void* dx, int N, int H, int W, int C, int accumulate, cudaStream_t s) {
+  UNETK_CHECK_ARG(dout && dx, "upsample2x_bwd: null pointer");
+  UNETK_CHECK_ARG(C > 0 && C % 8 == 0, "upsample2x_bwd: channel count must be a multiple of 8 (got %d)", C);
+  const long nvec = static_cast<long>(N) * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<ew_blocks256(nvec), 256, 0, s>>>(static_cast<const uint4*>(dout), static_cast<uint4*>(dx), H, W, C / 8, nvec, accumulate);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
 static int seg_grid_x(long hw, int N) {
   long b = (hw + kSegThreads - 1) / kSegThreads;
   const long cap = (static_cast<long>(num_sms()) * 8 + N - 1) / N;

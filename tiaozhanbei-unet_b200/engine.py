@@ -101,25 +101,26 @@ class Plan:
             return torch.empty(n, h >> lvl, w >> lvl, c, dtype=bf, device=device)
 
         self.enc = []
+        self.enc_c = [c2.cout for _, c2 in eng.encoder]       # 64..1024 (512 at the bottom for bilinear decoders)
         for l in range(5):
-            c = WIDTHS[l]
+            c = self.enc_c[l]
             d = {"y1": act(l, c), "a1": act(l, c), "y2": act(l, c), "a2": act(l, c)}
             if l < 4:
                 d["p"] = act(l + 1, c)
                 d["idx"] = torch.empty(n, h >> (l + 1), w >> (l + 1), c, dtype=torch.uint8, device=device)
             self.enc.append(d)
         self.dec = []
-        for _ in eng.decoders:
+        for dec_stages, _ in eng.decoders:
             stages = []
             for k in range(1, 5):
                 lv = 4 - k
-                c = WIDTHS[lv]
+                ct, c1, c2 = dec_stages[k - 1]
                 # the transposed conv doubles the level below: up to one row / column short of the skip when
                 # the input size is not a multiple of 16 (the reference zero-pads it, src/model.py:57-61: the
                 # consumer kernels read it as zero beyond its extent instead)
-                up = torch.empty(n, 2 * (h >> (lv + 1)), 2 * (w >> (lv + 1)), c, dtype=bf, device=device)
-                stages.append({"up": up, "y1": act(lv, c), "a1": act(lv, c), "y2": act(lv, c),
-                               "a2": act(lv, c)})
+                up = torch.empty(n, 2 * (h >> (lv + 1)), 2 * (w >> (lv + 1)), c1.cin2, dtype=bf, device=device)
+                stages.append({"up": up, "y1": act(lv, c1.cout), "a1": act(lv, c1.cout), "y2": act(lv, c2.cout),
+                               "a2": act(lv, c2.cout)})
             self.dec.append(stages)
         self._act = act
         self.all_even = all((h >> l) % 2 == 0 and (w >> l) % 2 == 0 for l in range(4))
@@ -140,9 +141,9 @@ class Plan:
         if self.grads_ready:
             return
         act = self._act
-        self.d_skip = [act(l, WIDTHS[l]) for l in range(5)]   # d(a2) of every encoder level
+        self.d_skip = [act(l, self.enc_c[l]) for l in range(5)]   # d(a2) of every encoder level
         # skip gradients of the second, third... decoder when the decoders run on parallel streams
-        self.d_skipx = [[act(l, WIDTHS[l]) for l in range(4)] for _ in range(self.n_dec - 1)]
+        self.d_skipx = [[act(l, self.enc_c[l]) for l in range(4)] for _ in range(self.n_dec - 1)]
         # scratch per backward chain (one per decoder; the encoder continues on chain 0), all of the
         # largest (full resolution, 64 channel) size: d_t = running decoder gradient d(a2) of the current
         # stage, d_a1 = gradient wrt a DoubleConv's inner activation, d_y = gradient wrt a raw conv output,
@@ -264,24 +265,31 @@ class Engine:
         self.encoder = []
         dcs = [("inc", m.inc)] + [(f"down{k}.maxpool_conv.1", getattr(m, f"down{k}").maxpool_conv[1]) for k in range(1, 5)]
         for l, (name, dc) in enumerate(dcs):
-            cin = n_channels if l == 0 else WIDTHS[l - 1]
-            c1 = _ConvBN(f"{name}.double_conv.0", dc.double_conv[0], dc.double_conv[1], cin, 0, WIDTHS[l], first=(l == 0))
-            c2 = _ConvBN(f"{name}.double_conv.3", dc.double_conv[3], dc.double_conv[4], WIDTHS[l], 0, WIDTHS[l])
+            k1, k2 = dc.double_conv[0], dc.double_conv[3]
+            c1 = _ConvBN(f"{name}.double_conv.0", k1, dc.double_conv[1], k1.in_channels, 0, k1.out_channels, first=(l == 0))
+            c2 = _ConvBN(f"{name}.double_conv.3", k2, dc.double_conv[4], k2.in_channels, 0, k2.out_channels)
             self.encoder.append((c1, c2))
             self.convbn += [c1, c2]
         self.decoders = []
         for suffix, n_out, sigmoid in head_specs:
             stages = []
+            t_c = self.encoder[4][1].cout            # channels of the tensor entering the stage
             for k in range(1, 5):
                 up = getattr(m, f"up{k}{suffix}")
-                cin = WIDTHS[5 - k]
-                ct = _ConvT(f"up{k}{suffix}.up", up.up, cin, cin // 2)
-                c1 = _ConvBN(f"up{k}{suffix}.conv.double_conv.0", up.conv.double_conv[0], up.conv.double_conv[1],
-                             cin // 2, cin // 2, cin // 2)
-                c2 = _ConvBN(f"up{k}{suffix}.conv.double_conv.3", up.conv.double_conv[3], up.conv.double_conv[4],
-                             cin // 2, 0, cin // 2)
+                skip_c = self.encoder[4 - k][1].cout
+                k1, k2 = up.conv.double_conv[0], up.conv.double_conv[3]
+                if getattr(up, "bilinear", False):
+                    # nn.Upsample(x2, bilinear, align_corners=True) keeps the channels; DoubleConv(in, out, in // 2)
+                    ct, up_c = None, t_c
+                else:
+                    ct, up_c = _ConvT(f"up{k}{suffix}.up", up.up, t_c, t_c // 2), t_c // 2
+                if k1.in_channels != skip_c + up_c:
+                    raise _lib.UnetkError(f"up{k}{suffix}: conv expects {k1.in_channels} channels, the graph provides {skip_c} + {up_c}")
+                c1 = _ConvBN(f"up{k}{suffix}.conv.double_conv.0", k1, up.conv.double_conv[1], skip_c, up_c, k1.out_channels)
+                c2 = _ConvBN(f"up{k}{suffix}.conv.double_conv.3", k2, up.conv.double_conv[4], k2.in_channels, 0, k2.out_channels)
                 stages.append((ct, c1, c2))
                 self.convbn += [c1, c2]
+                t_c = k2.out_channels
             head = _Head(f"outc{suffix}.conv", getattr(m, f"outc{suffix}").conv, n_out, sigmoid)
             self.decoders.append((stages, head))
 
@@ -388,6 +396,8 @@ class Engine:
             handled.update((wk, gk, bk))
         for stages, head in self.decoders:
             for ct, _, _ in stages:
+                if ct is None:                # bilinear stage: no parameters
+                    continue
                 wk, bk = ct.name + ".weight", ct.name + ".bias"
                 n = pdict[wk].numel()
                 ct.bias = self._slice(self.flat_p, bk)
@@ -610,7 +620,10 @@ class Engine:
             s = pl.dec[d][k]
             t = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
             count = n * (pl.h >> lv) * (pl.w >> lv)
-            ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
+            if ct is None:
+                ops.upsample2x_fwd(t, s["up"])
+            else:
+                ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
             ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["y1"], stats=c1.stats)
             self._bn_train(c1, s["y1"], s["a1"], count)
             ops.conv3x3_fwd(s["a1"], None, c2.wf, s["y2"], stats=c2.stats)
@@ -690,7 +703,10 @@ class Engine:
             lv = 3 - k
             s = pl.dec[d][k]
             t = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
-            ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
+            if ct is None:
+                ops.upsample2x_fwd(t, s["up"])
+            else:
+                ops.convt2x2_fwd(t, ct.wf, ct.bias, s["up"])
             ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["a1"], scale=c1.scale, shift=c1.shift, relu=True)
             ops.conv3x3_fwd(s["a1"], None, c2.wf, s["a2"], scale=c2.scale, shift=c2.shift, relu=True)
 
@@ -780,6 +796,7 @@ class Engine:
         skip_written = [False] * 5
 
         def decoder_stage(d, k, ch):
+            nonlocal bottleneck_done
             stages, head = self.decoders[d]
             ct, c1, c2 = stages[k]
             lv = 3 - k
@@ -799,20 +816,32 @@ class Engine:
             iy, d_y1 = ch.take_y(s["y1"])
             iu, d_up = ch.take_up(s["up"])
             self._bn_apply_bwd(pl, c1, d_a1, s["y1"], d_y1)
+            bias_grad = ct.g_bias if ct is not None else None     # transposed-conv bias gradient = column sums of d_up
             if parallel and d > 0:      # own skip-gradient buffer: summed by the encoder's pool backward
-                ops.conv3x3_dgrad(d_y1, c1.wd, pl.d_skipx[d - 1][lv], acc1=False, dx2=d_up, acc2=False, stats=ct.g_bias)
+                ops.conv3x3_dgrad(d_y1, c1.wd, pl.d_skipx[d - 1][lv], acc1=False, dx2=d_up, acc2=False, stats=bias_grad)
             else:
-                ops.conv3x3_dgrad(d_y1, c1.wd, pl.d_skip[lv], acc1=skip_written[lv], dx2=d_up, acc2=False, stats=ct.g_bias)
+                ops.conv3x3_dgrad(d_y1, c1.wd, pl.d_skip[lv], acc1=skip_written[lv], dx2=d_up, acc2=False, stats=bias_grad)
                 skip_written[lv] = True
             ch.free_y[iy] = ch.side(lambda: ops.conv3x3_wgrad(d_y1, skip, s["up"], c1.g_w))
             # transposed conv
             t_in = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
+            if ct is None:              # bilinear up-sampling: no parameters, gather backward
+                if k > 0:
+                    ops.upsample2x_bwd(d_up, V(ch.d_t, t_in), accumulate=False)
+                else:
+                    if bottleneck_done is not None:
+                        ch.stream.wait_event(bottleneck_done)
+                    ops.upsample2x_bwd(d_up, pl.d_skip[4], accumulate=skip_written[4])
+                    skip_written[4] = True
+                    if parallel:
+                        bottleneck_done = torch.cuda.Event()
+                        bottleneck_done.record(ch.stream)
+                return
             if k > 0:
                 prev = stages[k - 1][2]
                 ops.convt2x2_dgrad(d_up, ct.wd, V(ch.d_t, t_in), acc=False, bn=ctx(pl, prev, pl.dec[d][k - 1]["y2"]))
             else:
                 # the bottleneck gradient is the sum over the decoders, complete after decoder 0 (processed last)
-                nonlocal bottleneck_done
                 if bottleneck_done is not None:
                     ch.stream.wait_event(bottleneck_done)
                 ops.convt2x2_dgrad(d_up, ct.wd, pl.d_skip[4], acc=skip_written[4],

@@ -6,8 +6,8 @@ checkpoints round-trip with the reference.  The modules only HOLD parameters; `f
 whole network to engine.Engine, which launches the sm_100a kernels of include/unetk.h.  There is
 no PyTorch-operator or CPU fallback: on anything but a CUDA sm_100 device forward raises.
 
-Not implemented in this version (raises at construction): `bilinear=True` decoders
-(src/model.py:47-49).  Input sizes that are not multiples of 16 take the reference's F.pad path
+`bilinear=True` decoders (src/model.py:47-49) use the bilinear x2 up-sampling kernels instead of the
+transposed conv.  Input sizes that are not multiples of 16 take the reference's F.pad path
 (src/model.py:57-61) inside the kernels: the up-sampled tensor is read as zero beyond its extent.
 """
 from __future__ import annotations
@@ -134,11 +134,13 @@ class Up(nn.Module):
 
     def __init__(self, in_channels, out_channels, bilinear=True):
         super().__init__()
-        if bilinear:
-            raise NotImplementedError("bilinear=True decoders (src/model.py:47-49) are not implemented in this "
-                                      "version; use the reference default bilinear=False")
-        self.up = _ConvTranspose2dParams(in_channels, in_channels // 2)
-        self.conv = DoubleConv(in_channels, out_channels)
+        self.bilinear = bool(bilinear)
+        if bilinear:      # src/model.py:47-49: parameter-free up-sampling, the DoubleConv narrows through in // 2
+            self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+            self.conv = DoubleConv(in_channels, out_channels, in_channels // 2)
+        else:
+            self.up = _ConvTranspose2dParams(in_channels, in_channels // 2)
+            self.conv = DoubleConv(in_channels, out_channels)
 
     def forward(self, x1, x2):
         _no_standalone("Up")

@@ -316,6 +316,24 @@ def seg_loss_bwd(logits, target, class_w, work, gout, dlogits, ignore_index, ce_
               int(ignore_index), float(ce_w), float(dice_w), float(focal_w), float(alpha), float(gamma), int(is_prob), _s())
 
 
+def upsample2x_fwd(x, out):
+    """out[n, 2h, 2w, c] = bilinear x2 (align_corners=True) of x[n, h, w, c], NHWC bf16."""
+    _chk(x, bf16, "x"); _chk(out, bf16, "out")
+    n, h, w, c = x.shape
+    if tuple(out.shape) != (n, 2 * h, 2 * w, c):
+        raise _lib.UnetkError(f"out: expected shape {(n, 2 * h, 2 * w, c)}, got {tuple(out.shape)}")
+    _lib.call("unetk_upsample2x_fwd", _p(x), _p(out), n, h, w, c, _s())
+    return out
+
+
+def upsample2x_bwd(dout, dx, accumulate=False):
+    _chk(dout, bf16, "dout"); _chk(dx, bf16, "dx")
+    n, h, w, c = dx.shape
+    if tuple(dout.shape) != (n, 2 * h, 2 * w, c):
+        raise _lib.UnetkError(f"dout: expected shape {(n, 2 * h, 2 * w, c)}, got {tuple(dout.shape)}")
+    _lib.call("unetk_upsample2x_bwd", _p(dout), _p(dx), n, h, w, c, int(accumulate), _s())
+
+
 def argmax_channels(logits, out):
     _chk(logits, f32, "logits"); _chk(out, torch.int64, "out")
     n, c, h, w = logits.shape
@@ -373,11 +391,15 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, mode=
 
 def permute_batched(table, src, dst, scale=1.0):
     """table: packing.PermuteTable (device descriptor array)."""
+    if table.n_desc == 0:          # e.g. bilinear decoders: no transposed-conv weights to re-lay-out
+        return
     _lib.call("unetk_permute_batched", _p(table.device_descs), table.n_desc, table.n_chunks, _p(src), _p(dst),
               int(dst.dtype == bf16), scale, _s())
 
 
 def pack_conv_weights(table, flat_p, wpack):
+    if table.n_desc == 0:
+        return
     _lib.call("unetk_pack_conv_weights", _p(table.device_descs), table.n_desc, table.n_blocks, _p(flat_p), _p(wpack), _s())
 
 
