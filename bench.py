@@ -48,14 +48,14 @@ def read_peaks():
             "source": "B200_PROFILING.md fallback (of fallback)"}
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` summary of this round
-    (profiles/ncu_traffic.json, written by tools/ncu_summarise.py), or None."""
+def ncu_traffic(kernel, key="dram_bytes_per_launch"):
+    """DRAM bytes per launch (or another recorded figure) of `kernel` from the committed `ncu --set full`
+    summary of this round (profiles/ncu_traffic.json, written by tools/ncu_summarise.py), or None."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
-        return t.get(kernel.split(" ")[0], {}).get("dram_bytes_per_launch")
+        return t.get(kernel.split(" ")[0], {}).get(key)
     except Exception:
         return None
 
@@ -314,6 +314,7 @@ def run_ours(args):
                                                    "launches with >= 256 output columns)",
                 "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tflops_sustained"], "traffic": ncu_traffic(top),
+                "tensor_pipe_active_pct_ncu": ncu_traffic(top, "tensor_pipe_active_pct_time_weighted"),
                 "traffic_unit": "bytes per launch (dram read + write, ncu --set full, mean over one step's launches)",
                 "flop_per_launch": tf / n_top, "launches_per_step": n_top // k_inst, "kernel_ms_per_step": tms_top / k_inst,
                 "share_of_step": (tms_top / k_inst) / (ms / args.steps), "peak_source": peaks["source"],

@@ -463,3 +463,34 @@ def test_bilinear_decoders(cuda_device):
     worst = _check_grads(m.named_parameters(), ref_grads, "bilinear anomaly_unet 2x64x48")
     print(f"[parity] bilinear anomaly_unet 2x64x48: loss {losses['total_loss']:.6f} vs {ref_losses['total_loss']:.6f}; "
           f"worst grad cosine {worst[0]:.3f}, worst head-side rel err {worst[1]:.3e}")
+
+
+@pytest.mark.parametrize("arch,n,h,w,n_classes", [("unet", 1, 16, 16, 1), ("unet", 3, 17, 31, 2), ("anomaly_unet", 1, 16, 48, 1),
+                                                  ("unet", 2, 24, 40, 4)])
+def test_minimum_and_unusual_shapes(cuda_device, arch, n, h, w, n_classes):
+    """Edge shapes: the smallest legal input (16x16: a 1x1 bottleneck), odd sizes just above it, batch 1,
+    2- and 4-class heads.  Eval outputs against the fp32 oracle; one training step must give finite
+    gradients of the reference's shapes."""
+    from tiaozhanbei_unet_b200.model import AnomalyUNet, UNet
+    dev = cuda_device
+    sd = O.synthetic_state_dict(arch, seed=71, n_classes=n_classes, device=dev)
+    m = UNet(3, n_classes) if arch == "unet" else AnomalyUNet(3)
+    m.load_state_dict({k: v.clone() for k, v in sd.items()})
+    m = m.to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, 3, h, w, generator=g).to(dev)
+    with torch.no_grad():
+        y = m(x)
+        ref = O.unet_forward({k: v.clone() for k, v in sd.items()}, x) if arch == "unet" else \
+            O.anomaly_unet_forward({k: v.clone() for k, v in sd.items()}, x)
+    outs, refs = ([y], [ref]) if arch == "unet" else (list(y), list(ref))
+    for i, (got, want) in enumerate(zip(outs, refs)):
+        assert got.shape == want.shape
+        _check_out(got, want, f"{arch} {n}x{h}x{w} output {i}")
+    m.train()
+    out = m(x)
+    loss = out.square().mean() if arch == "unet" else (out[0].square().mean() + out[1].mean())
+    loss.backward()
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape and torch.isfinite(p.grad).all(), k
