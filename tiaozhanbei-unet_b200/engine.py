@@ -25,7 +25,6 @@ from . import _lib, ops, packing
 
 import os
 
-WIDTHS = [64, 128, 256, 512, 1024]
 # Which producers of an activation gradient also run the first pass (per-channel sums) of the BatchNorm
 # backward of the layer below them: "head" (default: the 1x1 head backward already holds the activation in
 # registers, +0.01 ms instead of a 0.07 ms pass), "all" (+ conv / transposed-conv dgrad epilogues and the
