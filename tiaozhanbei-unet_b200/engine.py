@@ -255,6 +255,7 @@ class Engine:
         self.wstreams = []        # side streams of the weight gradients, one per backward chain (OVERLAP_WGRAD)
         self.dstreams = []        # side streams of the second, third... decoder (PARALLEL_DECODERS)
         self.pstream = None       # side stream packing the decoders' weights (SPLIT_PACK)
+        self.ustream = None       # side stream un-packing the decoders' gradients during the encoder's backward
         self.bottleneck_dropout = 0.0   # SegmentationUNet: nn.Dropout2d(p) on the bottleneck (src/model.py:130,146)
         self.pack_done = None
         self.weights_dirty = True
@@ -336,13 +337,14 @@ class Engine:
     def _build_views(self, device):
         chunk = _lib.get().unetk_permute_chunk_elems()
         pack = packing.PermuteTable(chunk)
-        unpack = packing.PermuteTable(chunk)
+        unpack_enc, unpack_dec = packing.PermuteTable(chunk), packing.PermuteTable(chunk)
         # conv3x3 weight packing in two groups: the encoder's (needed first, packed on the caller's stream) and
         # the decoders' (packed on a side stream under the encoder's forward pass)
         n_enc_layers = 2 * len(self.encoder)
         conv_pack_enc = packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32))
         conv_pack_dec = packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32))
-        conv_unpack = packing.ConvTable(lambda cout, cin: cout)
+        conv_unpack_enc = packing.ConvTable(lambda cout, cin: cout)
+        conv_unpack_dec = packing.ConvTable(lambda cout, cin: cout)
         pdict = dict(zip(self.param_names, self.params))
         wsize = 0
 
@@ -363,6 +365,8 @@ class Engine:
         for li, L in enumerate(self.convbn):
             c = L.cout
             conv_pack = conv_pack_enc if li < n_enc_layers else conv_pack_dec
+            unpack = unpack_enc if li < n_enc_layers else unpack_dec
+            conv_unpack = conv_unpack_enc if li < n_enc_layers else conv_unpack_dec
             L.stats = self.bn_stats_all[2 * co: 2 * co + 2 * c]
             L.sums = self.bn_sums_all[2 * co: 2 * co + 2 * c]
             L.scale = self.bn_aux[4 * co: 4 * co + c]
@@ -393,6 +397,7 @@ class Engine:
             for k in (gk, bk):
                 unpack.add(self.offsets[k], self.offsets[k], *packing.identity(pdict[k].numel()))
             handled.update((wk, gk, bk))
+        unpack = unpack_dec
         for stages, head in self.decoders:
             for ct, _, _ in stages:
                 if ct is None:                # bilinear stage: no parameters
@@ -425,9 +430,9 @@ class Engine:
         for obj, attr, off, n in wplan:
             setattr(obj, attr, self.wpack[off: off + n])
         self.pack_table = pack.finalize(device)
-        self.unpack_table = unpack.finalize(device)
+        self.unpack_tables = (unpack_enc.finalize(device), unpack_dec.finalize(device))
         self.conv_pack_tables = (conv_pack_enc.finalize(device), conv_pack_dec.finalize(device))
-        self.conv_unpack_table = conv_unpack.finalize(device)
+        self.conv_unpack_tables = (conv_unpack_enc.finalize(device), conv_unpack_dec.finalize(device))
 
     def mark_weights_dirty(self):
         self.weights_dirty = True
@@ -865,6 +870,22 @@ class Engine:
                 s0.wait_event(done)
             if self.ddp is not None:
                 self.ddp.segment_ready(self, ("dec", d), [e for e in (done, ch.last_w) if e is not None])
+        # the decoders' gradients are final: re-lay them out on a side stream under the encoder's backward
+        # (without data parallelism; with it the buckets are still being all-reduced)
+        early_unpack = None
+        if self.ddp is None and overlap:
+            if self.ustream is None:
+                self.ustream = torch.cuda.Stream(device=self.device)
+            ev = torch.cuda.Event()
+            ev.record(s0)
+            self.ustream.wait_event(ev)
+            for c in chains:
+                if c.last_w is not None:
+                    self.ustream.wait_event(c.last_w)
+            with torch.cuda.stream(self.ustream):
+                self._unpack(1, 1.0)
+                early_unpack = torch.cuda.Event()
+                early_unpack.record(self.ustream)
         ch = chains[0]
         if pl.drop_mask is not None:            # Dropout2d backward: the same per-(image, channel) factors
             ops.channel_scale(pl.d_skip[4], pl.drop_mask)
@@ -905,6 +926,15 @@ class Engine:
         scale = 1.0
         if self.ddp is not None:
             scale = self.ddp.finish(self)
-        ops.unpack_conv_grads(self.conv_unpack_table, self.gstage, self.flat_g, scale)
-        ops.permute_batched(self.unpack_table, self.gstage, self.flat_g, scale)
+        if early_unpack is not None:
+            s0.wait_event(early_unpack)       # the decoders' gradients were re-laid-out under the encoder's backward
+        else:
+            self._unpack(1, scale)
+        self._unpack(0, scale)
         return self.grad_views()
+
+    def _unpack(self, part, scale):
+        """Staged gradients ([Cout][tap][Cin] conv weights, ...) -> `.grad` in the reference layouts, for the
+        encoder's (part 0) or the decoders' (part 1) parameters."""
+        ops.unpack_conv_grads(self.conv_unpack_tables[part], self.gstage, self.flat_g, scale)
+        ops.permute_batched(self.unpack_tables[part], self.gstage, self.flat_g, scale)
