@@ -4,6 +4,7 @@
 # command exited 0 without ncu.  Reports are exported to CSV on the box (gpurun_out/ is capped at 64 MiB);
 # one single-launch report with source is kept.  Numbers printed under ncu are never bench values.
 mkdir -p gpurun_out
+export UNETK_GRAPHS=0     # ncu cannot profile launches recorded during stream capture: eager launches for profiling
 R=${1:-r01b}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 timeout 600 $CMD > gpurun_out/ncu_plain.log 2>&1 || { echo "plain bench run failed"; tail -n 20 gpurun_out/ncu_plain.log; exit 1; }
