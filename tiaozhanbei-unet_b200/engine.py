@@ -46,7 +46,9 @@ SPLIT_PACK = os.environ.get("UNETK_SPLIT_PACK", "1") != "0"
 # optimizer, copies in and out of the static buffers).  "0" = always eager.  Under data parallelism only the
 # forward pass is captured: UNETK_GRAPH_DDP=1 also captures the backward with its NCCL all-reduces, which
 # ran correctly on 2 B200s (tests/checks/ddp_check.py) but hung in destroy_process_group() at exit.
-USE_GRAPHS = os.environ.get("UNETK_GRAPHS", "1") != "0"
+# Profilers that inject into the process (Nsight Compute / Systems set CUDA_INJECTION64_PATH) serialise and
+# replay kernel launches and cannot handle launches recorded during stream capture: stay eager under them.
+USE_GRAPHS = os.environ.get("UNETK_GRAPHS", "1") != "0" and not os.environ.get("CUDA_INJECTION64_PATH")
 GRAPH_DDP = os.environ.get("UNETK_GRAPH_DDP", "0") == "1"
 # Weight gradients are off the critical path of backward (nothing downstream reads them before the
 # optimizer): they run on a side stream, each one released only after the data gradient of the same layer,
