@@ -170,9 +170,12 @@ int unetk_maxpool_bwd(const void* dpooled, const void* idx, void* da, int n, int
 int unetk_bn_bwd_reduce(const void* da, const void* y, const float* scale, const float* shift,
                         const float* mean, const float* invstd, float* sums, int64_t npix, int c,
                         void* stream);
+/* param_sums (NULL = sums): the sums that become dgamma / dbeta -- under synchronised BatchNorm `sums` holds
+ * the cross-rank MEAN of the per-rank sums (dy then uses the global statistics) while the parameter
+ * gradients stay this rank's own sums, to be averaged with all other gradients. */
 int unetk_bn_bwd_apply(const void* da, const void* y, const float* scale, const float* shift,
-                       const float* mean, const float* invstd, const float* sums, void* dy,
-                       float* dgamma, float* dbeta, int64_t npix, int c, void* stream);
+                       const float* mean, const float* invstd, const float* sums, const float* param_sums,
+                       void* dy, float* dgamma, float* dbeta, int64_t npix, int c, void* stream);
 
 /* ---- OutConv = nn.Conv2d(64, n_out, 1) (+ torch.sigmoid): src/model.py:69-75,201,208 ------- */
 int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, int n, int h, int w_,

@@ -27,15 +27,18 @@ m = AnomalyUNet(3)
 m.load_state_dict(sd)
 m = m.to(dev).train()
 D.broadcast_parameters(m)
-red = D.attach(m)
+SYNC_BN = "--sync-bn" in sys.argv       # exact global-batch semantics instead of per-shard BatchNorm
+red = D.attach(m, sync_bn=SYNC_BN)
 crit = train_utils.CombinedLoss()
 opt = train_utils.get_optimizer(m)
 n, h, w = 4, 64, 64
 
 
 def shard(r):
+    # shards with different statistics (scale / offset per rank), so that per-shard and global-batch
+    # BatchNorm are clearly different models
     g = torch.Generator().manual_seed(500 + r)
-    return torch.randn(n, 3, h, w, generator=g), (torch.rand(n, 1, h, w, generator=g) > 0.95).float()
+    return torch.randn(n, 3, h, w, generator=g) * (1.0 + 0.5 * r) + 0.3 * r, (torch.rand(n, 1, h, w, generator=g) > 0.95).float()
 
 
 image, mask = (t.to(dev) for t in shard(rank))
@@ -53,12 +56,17 @@ same = all(torch.equal(allc[0], c) for c in allc)
 ok = same
 msg = f"identical across ranks: {same}; reduced {red.bytes_reduced / 1e6:.1f} MB in buckets"
 if rank == 0:
-    ref = None
-    for r in range(world):
-        im, mk = (t.to(dev) for t in shard(r))
-        _, g = O.train_step({k: v.to(dev).clone() for k, v in sd.items()}, im, mk, arch="anomaly_unet")
-        ref = g if ref is None else {k: ref[k] + g[k] for k in g}
-    ref = {k: v / world for k, v in ref.items()}
+    if SYNC_BN:      # the reference on the concatenated global batch (mean loss over all images)
+        im = torch.cat([shard(r)[0] for r in range(world)]).to(dev)
+        mk = torch.cat([shard(r)[1] for r in range(world)]).to(dev)
+        _, ref = O.train_step({k: v.to(dev).clone() for k, v in sd.items()}, im, mk, arch="anomaly_unet")
+    else:
+        ref = None
+        for r in range(world):
+            im, mk = (t.to(dev) for t in shard(r))
+            _, g = O.train_step({k: v.to(dev).clone() for k, v in sd.items()}, im, mk, arch="anomaly_unet")
+            ref = g if ref is None else {k: ref[k] + g[k] for k in g}
+        ref = {k: v / world for k, v in ref.items()}
     worst_cos, head = 1.0, 0.0
     for k, p in m.named_parameters():
         g, gr = p.grad, ref[k]
@@ -69,7 +77,24 @@ if rank == 0:
         nr = abs(g.norm().item() - gr.norm().item()) / gr.norm().item()
         ok = ok and cos > 0.6 and nr < 0.2
     ok = ok and head < 3e-2
-    msg += f"; vs mean of per-shard oracle grads: worst cosine {worst_cos:.3f}, head rel err {head:.2e}"
+    msg += (f"; vs {'the oracle on the global batch (SyncBN)' if SYNC_BN else 'mean of per-shard oracle grads'}: "
+            f"worst cosine {worst_cos:.3f}, head rel err {head:.2e}")
+    if SYNC_BN:      # control: the per-shard-BatchNorm model must NOT match (the check discriminates the two semantics)
+        alt = None
+        for r in range(world):
+            ims, mks = (t.to(dev) for t in shard(r))
+            _, g = O.train_step({k: v.to(dev).clone() for k, v in sd.items()}, ims, mks, arch="anomaly_unet")
+            alt = g if alt is None else {k: alt[k] + g[k] for k in g}
+        ctrl = max(((p.grad - alt[k] / world).norm() / (alt[k].norm() / world)).item() for k, p in m.named_parameters() if k.startswith("outc"))
+        ok = ok and ctrl > 2 * max(head, 1e-2)
+        msg += f" (control vs per-shard BatchNorm: {ctrl:.2e})"
+    if SYNC_BN:      # running statistics are those of the global batch
+        msd, rsd = m.state_dict(), {k: v.to(dev).clone() for k, v in sd.items()}
+        O.anomaly_unet_forward(rsd, im, training=True)
+        dev_rs = max(((msd[k] - rsd[k]).abs().max() / (rsd[k].abs().max() + 1e-3)).item() for k in rsd
+                     if k.endswith(("running_mean", "running_var")))
+        ok = ok and dev_rs < 5e-2
+        msg += f", running-stat rel dev {dev_rs:.2e}"
 opt.step()
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -39,7 +39,7 @@ SIGNATURES = {
     "unetk_bnrelu_pool_fin": (I, [P, P, P, P, P, I, I, I, I, P]),
     "unetk_maxpool_bwd": (I, [P, P, P, I, I, I, I, I, P, P, P]),
     "unetk_bn_bwd_reduce": (I, [P, P, P, P, P, P, P, L, I, P]),
-    "unetk_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, L, I, P]),
+    "unetk_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, P]),
     "unetk_head_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "unetk_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, I, P, P]),
     "unetk_combined_loss_workspace_bytes": (Z, []),

@@ -116,10 +116,10 @@ int unetk_bn_bwd_reduce(const void* da, const void* y, const float* scale, const
   return unetk::bn_bwd_reduce(da, y, scale, shift, mean, invstd, sums, static_cast<long>(npix), c, S(stream));
 }
 int unetk_bn_bwd_apply(const void* da, const void* y, const float* scale, const float* shift,
-                       const float* mean, const float* invstd, const float* sums, void* dy,
-                       float* dgamma, float* dbeta, int64_t npix, int c, void* stream) {
-  return unetk::bn_bwd_apply(da, y, scale, shift, mean, invstd, sums, dy, dgamma, dbeta, static_cast<long>(npix), c,
-                             S(stream));
+                       const float* mean, const float* invstd, const float* sums, const float* param_sums,
+                       void* dy, float* dgamma, float* dbeta, int64_t npix, int c, void* stream) {
+  return unetk::bn_bwd_apply(da, y, scale, shift, mean, invstd, sums, param_sums, dy, dgamma, dbeta,
+                             static_cast<long>(npix), c, S(stream));
 }
 int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, int n, int h, int w_,
                    int c, int n_out, int sigmoid, void* stream) {

@@ -370,16 +370,16 @@ __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const uint4* __restrict__ da, const uint4* __restrict__ y,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ sums, uint4* __restrict__ dy,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta, long nvec, int cgroups,
-                    float inv_count) {
+                    const float* __restrict__ sums, const float* __restrict__ param_sums,
+                    uint4* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, long nvec,
+                    int cgroups, float inv_count) {
   pdl_trigger();
   pdl_wait();
   const int C = cgroups * 8;
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0) {      // parameter gradients: this rank's sums (`sums` are the cross-rank means under SyncBN)
     for (int i = threadIdx.x; i < C; i += blockDim.x) {
-      dbeta[i] = sums[i];
-      dgamma[i] = sums[C + i];
+      dbeta[i] = param_sums[i];
+      dgamma[i] = param_sums[C + i];
     }
   }
   const long tid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -581,14 +581,15 @@ int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float
 }
 
 int bn_bwd_apply(const void* da, const void* y, const float* scale, const float* shift,
-                 const float* mean, const float* invstd, const float* sums, void* dy, float* dgamma,
-                 float* dbeta, long npix, int C, cudaStream_t s) {
+                 const float* mean, const float* invstd, const float* sums, const float* param_sums, void* dy,
+                 float* dgamma, float* dbeta, long npix, int C, cudaStream_t s) {
   UNETK_CHECK_ARG(da && y && scale && shift && mean && invstd && sums && dy && dgamma && dbeta, "bn_bwd_apply: null pointer");
   if (int e = check_c(C, "bn_bwd_apply")) return e;
   const long nvec = npix * (C / 8);
   UNETK_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s,
       static_cast<const uint4*>(da), static_cast<const uint4*>(y), scale, shift, mean, invstd, sums,
-      static_cast<uint4*>(dy), dgamma, dbeta, nvec, C / 8, 1.0f / static_cast<float>(npix)));
+      param_sums != nullptr ? param_sums : sums, static_cast<uint4*>(dy), dgamma, dbeta, nvec, C / 8,
+      1.0f / static_cast<float>(npix)));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }

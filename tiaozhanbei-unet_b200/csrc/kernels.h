@@ -83,8 +83,8 @@ int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float
                   const float* mean, const float* invstd, float* sums, long npix, int C,
                   cudaStream_t s);
 int bn_bwd_apply(const void* da, const void* y, const float* scale, const float* shift,
-                 const float* mean, const float* invstd, const float* sums, void* dy, float* dgamma,
-                 float* dbeta, long npix, int C, cudaStream_t s);
+                 const float* mean, const float* invstd, const float* sums, const float* param_sums, void* dy,
+                 float* dgamma, float* dbeta, long npix, int C, cudaStream_t s);
 int nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, cudaStream_t s);
 int nhwc_to_nchw(const void* in, float* out, int N, int C, int H, int W, cudaStream_t s);
 

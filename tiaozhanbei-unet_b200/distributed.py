@@ -6,8 +6,9 @@ staged by the backward kernels in ONE flat fp32 buffer laid out in parameter ord
 a contiguous range of it: the two decoders and two halves of the encoder, reduced on a side stream as
 soon as the backward pass has finished writing them (reverse layer order) and overlapped with the
 remaining backward kernels.  The 1/world_size average is folded into the single un-packing launch
-that produces `.grad`.  BatchNorm statistics stay local per rank (DDP semantics): parity oracle =
-the reference run per shard with gradients averaged.
+that produces `.grad`.  BatchNorm statistics stay local per rank by default (DDP semantics): parity
+oracle = the reference run per shard with gradients averaged; attach(sync_bn=True)
+synchronises them (parity oracle = the reference on the concatenated global batch).
 
 Inference shards images contiguously across ranks with no communication.
 """
@@ -98,10 +99,14 @@ class GradReducer:
         return 1.0 / self.world
 
 
-def attach(model, group=None):
-    """Enable gradient averaging across the process group for a UNet / AnomalyUNet of this package."""
+def attach(model, group=None, sync_bn=False):
+    """Enable gradient averaging across the process group for a UNet / AnomalyUNet of this package.
+    sync_bn=True also synchronises the BatchNorm batch statistics (two small all-reduces per BatchNorm
+    layer and step): training then equals the single-process reference on the concatenated global batch
+    instead of per-shard BatchNorm (the default, = DistributedDataParallel semantics)."""
     eng = model._engine()
     eng.ddp = GradReducer(group)
+    eng.sync_bn = (group, dist.get_world_size(group)) if sync_bn and dist.get_world_size(group) > 1 else None
     return eng.ddp
 
 

@@ -258,6 +258,7 @@ class Engine:
         self.dstreams = []        # side streams of the second, third... decoder (PARALLEL_DECODERS)
         self.pstream = None       # side stream packing the decoders' weights (SPLIT_PACK)
         self.ustream = None       # side stream un-packing the decoders' gradients during the encoder's backward
+        self.sync_bn = None       # process group for synchronised BatchNorm statistics (distributed.attach(sync_bn=True))
         self.bottleneck_dropout = 0.0   # SegmentationUNet: nn.Dropout2d(p) on the bottleneck (src/model.py:130,146)
         self.pack_done = None
         self.weights_dirty = True
@@ -517,7 +518,8 @@ class Engine:
         return x.contiguous()
 
     def _graphs_ok(self):
-        return USE_GRAPHS and not ops.timing_enabled() and self.bottleneck_dropout == 0.0 and not FUSE_CHECK
+        return (USE_GRAPHS and not ops.timing_enabled() and self.bottleneck_dropout == 0.0 and not FUSE_CHECK
+                and self.sync_bn is None)        # synchronised BatchNorm puts NCCL calls into the forward pass
 
     def forward(self, x, training):
         x = self._check_input(x)
@@ -569,6 +571,12 @@ class Engine:
 
     def _bn_train(self, L, y, a, count, pool=None):
         mom = L.bn.momentum if L.bn.momentum is not None else 0.1
+        if self.sync_bn is not None:
+            # synchronised BatchNorm: statistics over the GLOBAL batch (sum of the per-rank sums, global count),
+            # i.e. exactly the single-process reference on the concatenated batch
+            import torch.distributed as dist
+            dist.all_reduce(L.stats, op=dist.ReduceOp.SUM, group=self.sync_bn[0])
+            count = count * self.sync_bn[1]
         if FUSE_BN_FINALIZE:
             key = (count, L.bn.eps, mom, L.rm.data_ptr(), L.rv.data_ptr(), L.stats.data_ptr(), L.gamma.data_ptr())
             fin = L.__dict__.get("_fin")
@@ -733,7 +741,15 @@ class Engine:
                 self.fuse_check.append((L.name, err))
         else:
             ops.bn_bwd_reduce(d_a, y, L.scale, L.shift, L.mean, L.invstd, L.sums)
-        ops.bn_bwd_apply(d_a, y, L.scale, L.shift, L.mean, L.invstd, L.sums, d_y, L.g_gamma, L.g_beta)
+        local = None
+        if self.sync_bn is not None:
+            # like torch's SyncBatchNorm: dy uses the sums over all ranks (AVG of the per-rank sums with the
+            # per-rank pixel count = global sums / global count); dgamma / dbeta stay this rank's own sums and
+            # are averaged with every other gradient
+            import torch.distributed as dist
+            local = L.sums.clone()
+            dist.all_reduce(L.sums, op=dist.ReduceOp.AVG, group=self.sync_bn[0])
+        ops.bn_bwd_apply(d_a, y, L.scale, L.shift, L.mean, L.invstd, L.sums, d_y, L.g_gamma, L.g_beta, param_sums=local)
 
     @staticmethod
     def _ctx(pl, L, y, kind="igemm"):

@@ -265,9 +265,9 @@ def bn_bwd_reduce(da, y, scale, shift, mean, invstd, sums):
               y.numel() // c, c, _s())
 
 
-def bn_bwd_apply(da, y, scale, shift, mean, invstd, sums, dy, dgamma, dbeta):
+def bn_bwd_apply(da, y, scale, shift, mean, invstd, sums, dy, dgamma, dbeta, param_sums=None):
     c = y.shape[-1]
-    _lib.call("unetk_bn_bwd_apply", _p(da), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums),
+    _lib.call("unetk_bn_bwd_apply", _p(da), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums), _p(param_sums),
               _p(dy), _p(dgamma), _p(dbeta), y.numel() // c, c, _s())
 
 
