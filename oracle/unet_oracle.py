@@ -7,6 +7,9 @@ U-Net hot path, written from the reference's behaviour:
     CombinedLoss (MSE + focal) and SSIMLoss                   /root/reference/src/train_utils.py:10-104
     compute_anomaly_score                                     /root/reference/src/utils.py:205-215
     Adam step built by get_optimizer                          /root/reference/src/train_utils.py:263-272
+    SegmentationUNet (Dropout2d on the bottleneck)            /root/reference/src/model.py:111-153
+    dice_loss / focal_loss / CombinedSegmentationLoss         /root/reference/src/metrics.py:233-335
+    bilinear=True decoders, F.pad path for odd sizes          /root/reference/src/model.py:47-49, 57-61
 
 The arithmetic underneath the reference lives in PyTorch (third party, `torch>=2.0.0` in the
 reference's requirements.txt; this image has torch 2.11.0), so the restatement calls the same
@@ -15,9 +18,10 @@ bench.py's cpu_baseline / --impl reference legs may import this file, and only a
 
 Parity pinning: the reference ships no tests or golden vectors for this path, so
 the oracle is pinned against outputs of the reference itself:
-  * tests/golden/*.pt were produced by tests/golden/make_golden.py, which imports the unmodified
-    reference from /root/reference/src and records its outputs, losses and gradient summaries on
-    seeded inputs; tests/test_oracle.py checks this oracle against them (CPU, -m "not gpu");
+  * tests/golden/*.pt were produced by tests/golden/make_golden*.py (U-Net / AnomalyUNet path, segmentation
+    pipeline, odd sizes, bilinear decoders), which import the unmodified reference from /root/reference/src
+    and record its outputs, losses and gradients on seeded inputs; tests/test_oracle.py and
+    tests/test_seg_oracle.py check this oracle against them (CPU, -m "not gpu");
   * where /root/reference is present (the build container), tests/test_oracle.py also runs the
     live reference side by side with the oracle.
 Weights are addressed by the reference's own state_dict keys.
