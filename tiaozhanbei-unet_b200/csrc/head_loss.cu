@@ -297,13 +297,29 @@ combined_loss_kernel(const float* __restrict__ recon, const float* __restrict__ 
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
+  __shared__ double fold[2][256];
+  if (is_last) {
+    // the last block folds the per-block partials: every thread a strided slice, then a fixed-order tree
+    // (deterministic; a single thread walking 1024 partials cost ~40 us on the forward->backward critical path)
     __threadfence();
     double a = 0.0, b = 0.0;
-    for (unsigned int i = 0; i < gridDim.x; ++i) {
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
       a += reinterpret_cast<volatile double*>(work->partial)[2 * i];
       b += reinterpret_cast<volatile double*>(work->partial)[2 * i + 1];
     }
+    fold[0][threadIdx.x] = a;
+    fold[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        fold[0][threadIdx.x] += fold[0][threadIdx.x + o];
+        fold[1][threadIdx.x] += fold[1][threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+  }
+  if (is_last && threadIdx.x == 0) {
+    const double a = fold[0][0], b = fold[1][0];
     const float rl = static_cast<float>(a / static_cast<double>(n_recon));
     const float sl = static_cast<float>(b / static_cast<double>(n_seg));
     out3[0] = rw * rl + sw * sl;

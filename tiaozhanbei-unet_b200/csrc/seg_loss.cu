@@ -26,6 +26,12 @@ constexpr int kSegThreads = 256;
 // then per (n, c): A, B (backward coefficients of the dice term)
 __host__ __device__ inline size_t seg_ws_floats(int N, int C) { return 4 + static_cast<size_t>(N) * C * 5; }
 
+// (1 - pt)^gamma and gamma (1 - pt)^(gamma - 1): gamma = 2 (the reference's default everywhere) avoids powf
+__device__ __forceinline__ float seg_pow(float om, float gamma) { return gamma == 2.f ? om * om : powf(om, gamma); }
+__device__ __forceinline__ float seg_dpow(float om, float gamma) {
+  return gamma == 2.f ? 2.f * om : (om > 0.f ? gamma * powf(om, gamma - 1.f) : 0.f);
+}
+
 struct SegPixel {
   float p[kSegMaxC];   // probabilities
   float ce;            // -log p_t (0 when the target is not a class)
@@ -86,7 +92,7 @@ seg_loss_fwd_kernel(const float* __restrict__ z, const long long* __restrict__ t
       acc[0] = fmaf(w, s.ce, acc[0]);
       acc[1] += w;
       const float pt = expf(-s.ce);
-      acc[2] += focal_alpha * powf(fmaxf(1.f - pt, 0.f), focal_gamma) * s.ce;
+      acc[2] += focal_alpha * seg_pow(fmaxf(1.f - pt, 0.f), focal_gamma) * s.ce;
     }
 #pragma unroll
     for (int c = 0; c < kSegMaxC; ++c) {
@@ -170,7 +176,7 @@ seg_loss_bwd_kernel(const float* __restrict__ z, const long long* __restrict__ t
       const float w = class_w != nullptr ? __ldg(class_w + s.t) : 1.f;
       const float pt = expf(-s.ce);
       const float om = fmaxf(1.f - pt, 0.f);
-      const float dfdce = focal_alpha * (powf(om, focal_gamma) + (om > 0.f ? focal_gamma * powf(om, focal_gamma - 1.f) * pt * s.ce : 0.f));
+      const float dfdce = focal_alpha * (seg_pow(om, focal_gamma) + seg_dpow(om, focal_gamma) * pt * s.ce);
       k_lin = k_ce * w + k_focal * dfdce;
     }
     // dice: G_c = dL/dp_c = B - y_c A; through the softmax: dz_k = p_k (G_k - sum_c G_c p_c)
