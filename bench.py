@@ -74,7 +74,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
