@@ -120,3 +120,55 @@ def test_optimizer_state_dict_is_torch_shaped():
     sch = train_utils.get_scheduler(ours, "cosine", 10)
     assert isinstance(sch, torch.optim.lr_scheduler.CosineAnnealingLR)
     assert train_utils.get_scheduler(ours, "none") is None
+
+
+def test_graph_state_protocol(monkeypatch):
+    """engine._GraphState (CUDA-graph capture of a static launch sequence): call 1 runs eagerly, call 2
+    captures and replays, later calls only replay; a failed capture falls back to eager launches for good.
+    torch.cuda's graph objects are replaced by recorders (no GPU here)."""
+    from tiaozhanbei_unet_b200 import engine
+
+    log = []
+
+    class FakeGraph:
+        def replay(self):
+            log.append("replay")
+
+    class FakeCapture:
+        def __init__(self, g, capture_error_mode=None):
+            assert capture_error_mode == "thread_local"
+
+        def __enter__(self):
+            log.append("capture-begin")
+
+        def __exit__(self, *exc):
+            log.append("capture-end")
+            return False
+
+    monkeypatch.setattr(engine.torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(engine.torch.cuda, "graph", FakeCapture)
+    monkeypatch.setattr(engine.torch.cuda, "synchronize", lambda: log.append("sync"))
+    calls = []
+
+    def body():
+        calls.append(len(calls))
+        return ["out%d" % len(calls)]
+
+    st = engine._GraphState()
+    assert st.run(body) == (["out1"], False) and log == []                      # warm-up: eager
+    res, replayed = st.run(body)                                                # capture, then one replay
+    assert replayed and res == ["out2"] and log == ["capture-begin", "capture-end", "replay"]
+    res, replayed = st.run(body)                                                # replay only: body not called again
+    assert replayed and res == ["out2"] and len(calls) == 2 and log[-1] == "replay" and log.count("replay") == 2
+
+    def bad():
+        if log and log[-1] == "capture-begin":
+            raise RuntimeError("operation not permitted when stream is capturing")
+        return ["eager"]
+
+    st2 = engine._GraphState()
+    st2.run(bad)
+    with pytest.warns(UserWarning):
+        res, replayed = st2.run(bad)
+    assert res == ["eager"] and not replayed and st2.failed and st2.graph is None
+    assert st2.run(bad) == (["eager"], False)                                   # stays eager
