@@ -58,3 +58,65 @@ def test_reference_train_script_runs_on_top_of_this_package(tmp_path, monkeypatc
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+REF_SEG_TRAIN = "/root/reference/train.py"
+
+
+def _make_gear_tree(root, n=4, size=48):
+    """images/<split>/*.png + labels/<split>/*.txt, one normalised polygon per line (src/gear_dataset.py:66-150)."""
+    from PIL import Image
+    rng = np.random.default_rng(1)
+    for split in ("train", "val", "test"):
+        os.makedirs(os.path.join(root, "images", split), exist_ok=True)
+        os.makedirs(os.path.join(root, "labels", split), exist_ok=True)
+        for i in range(n):
+            Image.fromarray(rng.integers(0, 255, (size, size, 3), dtype=np.uint8)).save(
+                os.path.join(root, "images", split, f"{i:03d}.png"))
+            with open(os.path.join(root, "labels", split, f"{i:03d}.txt"), "w") as f:
+                f.write("0 0.1 0.1 0.5 0.1 0.5 0.5 0.1 0.5\n")      # pitting
+                f.write("1 0.4 0.4 0.9 0.4 0.9 0.9\n")              # spalling (overlaps: priority resolution)
+                f.write("2 0.6 0.1 0.9 0.1 0.9 0.3 0.6 0.3\n")      # scrape
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SEG_TRAIN), reason="reference sources only exist in the build container")
+def test_reference_segmentation_train_script_runs_on_top_of_this_package(tmp_path, monkeypatch):
+    """Root train.py (Gear pipeline, train.py:20-23 imports src.model / src.metrics): dataset, 4-class
+    SegmentationUNet, CombinedSegmentationLoss and Adam are built from OUR modules, then the first step stops
+    at the loud no-CPU-path error."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU wiring test")
+    pytest.importorskip("torchvision")
+    pytest.importorskip("sklearn")
+    from tiaozhanbei_unet_b200 import _lib
+    from tiaozhanbei_unet_b200.dropin import launch
+    data = str(tmp_path / "Gear")
+    _make_gear_tree(data)
+    names = ("model", "train_utils", "matplotlib", "seaborn", "src", "src.model", "src.metrics", "src.utils",
+             "src.gear_dataset")
+    saved_modules = {k: sys.modules.get(k) for k in names}
+    saved_argv, saved_path = list(sys.argv), list(sys.path)
+    monkeypatch.chdir(os.path.dirname(REF_SEG_TRAIN))
+    try:
+        with pytest.raises((_lib.UnetkError, RuntimeError)) as e:
+            launch.run(REF_SEG_TRAIN, ["--data_root", data, "--image_size", "32", "--epochs", "1", "--batch_size", "2",
+                                       "--num_workers", "0", "--model", "seg_unet", "--focal_weight", "0.5",
+                                       "--class_weights", "0.5,1,1,2", "--save_dir", str(tmp_path / "out"),
+                                       "--device", "cpu"])
+        assert "CUDA" in str(e.value) or "CPU" in str(e.value)
+        import src.metrics as sm
+        import src.model as smodel
+        assert smodel.SegmentationUNet.__module__ == "tiaozhanbei_unet_b200.model"
+        assert sm.CombinedSegmentationLoss.__module__ == "tiaozhanbei_unet_b200.metrics"
+        assert sm.dice_loss.__module__ == "tiaozhanbei_unet_b200.metrics"
+        assert sm.SegmentationMetrics.__module__ == "src.metrics"      # reporting half stays the reference's
+        assert os.path.isdir(str(tmp_path / "out"))
+    finally:
+        sys.argv[:] = saved_argv
+        sys.path[:] = saved_path
+        for k, v in saved_modules.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

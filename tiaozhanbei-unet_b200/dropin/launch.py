@@ -1,11 +1,18 @@
-"""Run an UNMODIFIED reference script (src/train.py, src/test.py) on top of this package.
+"""Run an UNMODIFIED reference script on top of this package.
 
     python -m tiaozhanbei_unet_b200.dropin.launch /path/to/reference/src/train.py --category bottle ...
+    python -m tiaozhanbei_unet_b200.dropin.launch /path/to/reference/train.py --data_root datasets/Gear ...
 
 What it does: (a) registers empty stand-ins for matplotlib / seaborn when they are
 not installed (src/utils.py:6-8 imports them at top level; they only draw plots), (b) registers
 this package's `model` and `train_utils` under the flat names the reference imports, (c) runs the
 script with runpy as __main__ from its own directory, so its `utils` and `dataset` stay its own.
+
+The repository-root scripts of the segmentation pipelines (train.py, test.py, train_kolektorsdd.py ...)
+import `src.model` / `src.metrics` instead (train.py:20-23): for them `src.model` is this package's
+model module and `src.metrics` is the reference's own file (confusion matrix, reports) with its three
+loss entry points (src/metrics.py:233-335) replaced by this package's kernels; `src.utils` and the
+dataset modules stay the reference's.
 """
 from __future__ import annotations
 
@@ -57,10 +64,26 @@ def install(stub_plotting: bool = True):
     sys.modules["train_utils"] = _train_utils
 
 
+def install_src_package(root: str):
+    """`src.model` / `src.metrics` for the scripts that sit next to the reference's src/ directory."""
+    import importlib.util
+    from tiaozhanbei_unet_b200 import metrics as _metrics, model as _model
+    sys.modules["src.model"] = _model
+    spec = importlib.util.spec_from_file_location("src.metrics", os.path.join(root, "src", "metrics.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)       # the reference's SegmentationMetrics etc., unmodified
+    for name in ("dice_loss", "focal_loss", "CombinedSegmentationLoss"):
+        setattr(mod, name, getattr(_metrics, name))
+    sys.modules["src.metrics"] = mod
+
+
 def run(script: str, argv):
     script = os.path.abspath(script)
     install()
-    sys.path.insert(0, os.path.dirname(script))
+    here = os.path.dirname(script)
+    if os.path.isfile(os.path.join(here, "src", "metrics.py")) and os.path.isfile(os.path.join(here, "src", "model.py")):
+        install_src_package(here)
+    sys.path.insert(0, here)
     sys.argv = [script] + list(argv)
     runpy.run_path(script, run_name="__main__")
 
