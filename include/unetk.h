@@ -239,6 +239,22 @@ int unetk_argmax_channels(const float* logits, int64_t* out, int n, int c, int h
 int unetk_anomaly_score(const float* recon, const float* orig, float* out, int n, int c, int h,
                         int w, int method, void* stream);
 
+/* ---- evaluation reductions of validate_epoch / calculate_pixel_metrics on the device ----------
+ * src/train_utils.py:232-246 and src/utils.py:97-108: for every threshold t (1..8 of them, a HOST array),
+ * counts[t*4 + {0 tn, 1 fp, 2 fn, 3 tp}] += number of pixels by (truth > truth_threshold, pred > thresholds[t]),
+ * sklearn's confusion_matrix(y_true, y_pred).ravel() order, over the images i with include[i] != 0 (all images
+ * when include is NULL; the reference keeps the anomalous images only).  pred / truth: fp32 [n, elems_per_image];
+ * counts: int64 [n_thresholds, 4] on the device, ACCUMULATED into (zero it before the first batch). */
+int unetk_pixel_confusion(const float* pred, const float* truth, const uint8_t* include, const float* thresholds,
+                          int n_thresholds, float truth_threshold, int64_t* counts, int n, int64_t elems_per_image,
+                          void* stream);
+/* Exact order statistics of an fp32 device array (NaN orders last, as in numpy): out2[0] = k-th smallest
+ * (0-based), out2[1] = (k+1)-th smallest (= out2[0] when k = n-1) — the two neighbours
+ * np.percentile(all_scores, 95) interpolates between (src/train_utils.py:213).  x is not modified. */
+size_t unetk_select_workspace_bytes(void);
+int unetk_select_kth(const float* x, int64_t n, int64_t k, float* out2, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 /* ---- get_optimizer -> torch.optim.{Adam,AdamW,SGD}: src/train_utils.py:263-272 ------------- */
 /* mode 0 Adam (L2 decay in the gradient), 1 AdamW, 2 SGD+momentum (beta1 = momentum, v unused). */
 int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

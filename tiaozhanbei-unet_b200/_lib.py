@@ -56,6 +56,9 @@ SIGNATURES = {
     "unetk_argmax_channels": (I, [P, P, I, I, I, I, P]),
     "unetk_upsample2x_fwd": (I, [P, P, I, I, I, I, P]),
     "unetk_upsample2x_bwd": (I, [P, P, I, I, I, I, I, P]),
+    "unetk_pixel_confusion": (I, [P, P, P, P, I, F, P, I, L, P]),
+    "unetk_select_workspace_bytes": (Z, []),
+    "unetk_select_kth": (I, [P, L, L, P, P, Z, P]),
     "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),
     "unetk_permute_batched": (I, [P, I, I, P, P, I, F, P]),
     "unetk_permute_chunk_elems": (I, []),

@@ -186,6 +186,17 @@ int unetk_anomaly_score(const float* recon, const float* orig, float* out, int n
                         int w, int method, void* stream) {
   return unetk::anomaly_score(recon, orig, out, n, c, h, w, method, S(stream));
 }
+int unetk_pixel_confusion(const float* pred, const float* truth, const uint8_t* include, const float* thresholds,
+                          int n_thresholds, float truth_threshold, int64_t* counts, int n, int64_t elems_per_image,
+                          void* stream) {
+  return unetk::pixel_confusion(pred, truth, include, thresholds, n_thresholds, truth_threshold,
+                                reinterpret_cast<long long*>(counts), n, static_cast<long>(elems_per_image), S(stream));
+}
+size_t unetk_select_workspace_bytes(void) { return unetk::select_workspace_bytes(); }
+int unetk_select_kth(const float* x, int64_t n, int64_t k, float* out2, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  return unetk::select_kth(x, static_cast<long>(n), static_cast<long>(k), out2, workspace, workspace_bytes, S(stream));
+}
 int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                     int mode, void* stream) {

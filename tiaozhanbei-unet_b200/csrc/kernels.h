@@ -111,6 +111,11 @@ int channel_scale(void* x, const float* mask, int N, int H, int W, int C, cudaSt
 int argmax_channels(const float* logits, long long* out, int N, int C, int H, int W, cudaStream_t s);
 int upsample2x_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s);
 int upsample2x_bwd(const void* dout, void* dx, int N, int H, int W, int C, int accumulate, cudaStream_t s);
+int pixel_confusion(const float* pred, const float* truth, const unsigned char* include, const float* thresholds,
+                    int n_thresholds, float truth_threshold, long long* counts, int n, long elems_per_image,
+                    cudaStream_t s);
+size_t select_workspace_bytes();
+int select_kth(const float* x, long n, long k, float* out2, void* workspace, size_t workspace_bytes, cudaStream_t s);
 int anomaly_score(const float* recon, const float* orig, float* out, int N, int C, int H, int W,
                   int method, cudaStream_t s);
 int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int N, int C, int H,

@@ -381,6 +381,40 @@ def anomaly_score(recon, orig, out, method=0):
     return out
 
 
+def pixel_confusion(pred, truth, include, thresholds, counts, truth_threshold=0.5):
+    """counts[t] += (tn, fp, fn, tp) of (truth > truth_threshold, pred > thresholds[t]) over the images with
+    include[i] != 0 (all images when include is None).  pred / truth: fp32 [n, ...] of equal shape."""
+    import ctypes
+    _chk(pred, f32, "pred"); _chk(truth, f32, "truth"); _chk(counts, torch.int64, "counts")
+    if pred.shape != truth.shape:
+        raise ValueError(f"pixel_confusion: shapes differ: {tuple(pred.shape)} vs {tuple(truth.shape)}")
+    n = pred.shape[0] if pred.dim() > 0 else 0
+    per = pred.numel() // n if n else 0
+    nt = len(thresholds)
+    if counts.numel() != nt * 4:
+        raise ValueError(f"pixel_confusion: counts must hold {nt} x 4 values")
+    if include is not None:
+        _chk(include, torch.uint8, "include")
+        if include.numel() != n:
+            raise ValueError("pixel_confusion: one include flag per image")
+    thr = (ctypes.c_float * max(nt, 1))(*[float(t) for t in thresholds])
+    _lib.call("unetk_pixel_confusion", _p(pred), _p(truth), _p(include) if include is not None else None,
+              ctypes.cast(thr, ctypes.c_void_p), nt, float(truth_threshold), _p(counts), n, per, _s())
+    return counts
+
+
+def select_kth(x, k, out2=None, work=None):
+    """(k-th, (k+1)-th) smallest values of the fp32 tensor x (0-based rank, NaN last) -> fp32 [2] on the device."""
+    _chk(x, f32, "x")
+    nbytes = _lib.get().unetk_select_workspace_bytes()
+    if work is None:
+        work = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=x.device)
+    if out2 is None:
+        out2 = torch.empty(2, dtype=f32, device=x.device)
+    _lib.call("unetk_select_kth", _p(x), x.numel(), int(k), _p(out2), _p(work), work.numel() * 8, _s())
+    return out2
+
+
 # ---------------------------------------------------------------------------------------------
 # optimizer / layout
 # ---------------------------------------------------------------------------------------------

@@ -6,6 +6,8 @@ get_optimizer, get_scheduler, train_epoch, validate_epoch); the losses are CUDA 
 """
 from __future__ import annotations
 
+from collections.abc import Mapping
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -13,7 +15,8 @@ from torch.autograd.function import once_differentiable
 
 from . import ops
 from .optim import FusedOptimizer
-from .utils import AverageMeter, calculate_metrics, compute_anomaly_score
+from .utils import (AverageMeter, calculate_metrics, compute_anomaly_score, metrics_from_confusion, percentile,
+                    pixel_confusion_counts)
 
 try:  # progress bars are cosmetic; the reference uses tqdm (src/train_utils.py:5)
     from tqdm import tqdm
@@ -210,11 +213,47 @@ def train_epoch(model, train_loader, criterion, optimizer, device, epoch):
     return {"total_loss": losses.avg, "recon_loss": recon_losses.avg, "seg_loss": seg_losses.avg}
 
 
+class _Predictions(Mapping):
+    """`validate_epoch(...)['predictions']`: the reference's four host arrays (src/train_utils.py:255-260), copied
+    from the device the first time one of them is read.  The reference's own caller never reads them
+    (src/train.py:241-265), so an epoch of validation no longer moves every map over PCIe."""
+
+    _KEYS = ("labels", "scores", "masks_true", "masks_pred")
+
+    def __init__(self, labels, scores, masks_true, masks_pred):
+        self._host = {"labels": labels}
+        self._dev = {"scores": scores, "masks_true": masks_true, "masks_pred": masks_pred}
+
+    def __getitem__(self, key):
+        if key not in self._host:
+            if key not in self._dev:
+                raise KeyError(key)
+            parts = self._dev.pop(key)
+            # np.array(list of per-image arrays), as the reference builds it
+            self._host[key] = (torch.cat(parts).cpu().numpy() if parts else np.array([]))
+        return self._host[key]
+
+    def __iter__(self):
+        return iter(self._KEYS)
+
+    def __len__(self):
+        return len(self._KEYS)
+
+
+_PIXEL_THRESHOLDS = (0.3, 0.5, 0.7)     # src/train_utils.py:235
+
+
 def validate_epoch(model, val_loader, criterion, device):
-    """Validate for one epoch (same flow, keys and thresholds as src/train_utils.py:155-260)."""
+    """Validate for one epoch: same flow, keys, thresholds and values as src/train_utils.py:155-260.
+
+    The per-pixel reductions run on the device while the maps are still there: the confusion counts behind
+    `pixel_f1_@t` (anomalous images only) are accumulated batch by batch by `unetk_pixel_confusion`, the 95th
+    percentile of the score maps by `unetk_select_kth`; `predictions` is materialised on the host only when read.
+    """
     model.eval()
     losses, recon_losses, seg_losses = AverageMeter(), AverageMeter(), AverageMeter()
-    all_labels, all_scores, all_masks_true, all_masks_pred = [], [], [], []
+    all_labels, dev_scores, dev_true, dev_pred = [], [], [], []
+    counts = None
     with torch.no_grad():
         pbar = tqdm(val_loader, desc="Validation")
         for batch in pbar:
@@ -228,39 +267,37 @@ def validate_epoch(model, val_loader, criterion, device):
             losses.update(t, batch_size)
             recon_losses.update(r, batch_size)
             seg_losses.update(s, batch_size)
-            anomaly_scores = compute_anomaly_score(reconstruction, images).cpu().numpy()
             all_labels.extend(labels)
-            all_scores.extend(anomaly_scores)
-            all_masks_true.extend(masks.cpu().numpy())
-            all_masks_pred.extend(anomaly_map.cpu().numpy())
+            dev_scores.append(compute_anomaly_score(reconstruction, images))
+            dev_true.append(masks)
+            dev_pred.append(anomaly_map)
+            if np.any(labels == 1):
+                counts = pixel_confusion_counts(anomaly_map, masks, _PIXEL_THRESHOLDS, include=(labels == 1),
+                                                counts=counts)
             if hasattr(pbar, "set_postfix"):
                 pbar.set_postfix({"Loss": f"{losses.avg:.4f}", "Recon": f"{recon_losses.avg:.4f}",
                                   "Seg": f"{seg_losses.avg:.4f}"})
     all_labels = np.array(all_labels)
-    all_scores = np.array(all_scores)
-    all_masks_true = np.array(all_masks_true)
-    all_masks_pred = np.array(all_masks_pred)
+    predictions = _Predictions(all_labels, dev_scores, dev_true, dev_pred)
     if len(np.unique(all_labels)) > 1:
-        threshold = np.percentile(all_scores, 95)
-        predictions = (all_scores > threshold).astype(int)
-        image_metrics = calculate_metrics(all_labels, predictions, all_scores)
+        # (the reference compares the [N] labels with the [N, H, W] thresholded score maps here and sklearn
+        # rejects the lengths: same call, same ValueError)
+        threshold = percentile(torch.cat([x.reshape(-1) for x in dev_scores]), 95)
+        all_scores = predictions["scores"]
+        image_metrics = calculate_metrics(all_labels, (all_scores > threshold).astype(int), all_scores)
     else:
         normal = all_labels[0] == 0
         image_metrics = {"accuracy": 1.0 if normal else 0.0, "precision": 0.0, "recall": 0.0,
                          "specificity": 1.0 if normal else 0.0, "f1_score": 0.0, "auroc": 0.0, "auprc": 0.0}
     pixel_metrics = {}
-    anomaly_indices = all_labels == 1
-    if np.sum(anomaly_indices) > 0:
-        for threshold in [0.3, 0.5, 0.7]:
-            pred_flat = (all_masks_pred[anomaly_indices] > threshold).astype(np.uint8).flatten()
-            true_flat = (all_masks_true[anomaly_indices] > 0.5).astype(np.uint8).flatten()
-            if len(np.unique(true_flat)) > 1:
-                pixel_metrics[f"pixel_f1_@{threshold}"] = calculate_metrics(true_flat, pred_flat)["f1_score"]
+    if counts is not None:
+        for threshold, (tn, fp, fn, tp) in zip(_PIXEL_THRESHOLDS, counts.cpu().numpy()):
+            if tp + fn > 0 and tn + fp > 0:        # len(np.unique(true_flat)) > 1
+                pixel_metrics[f"pixel_f1_@{threshold}"] = metrics_from_confusion(tn, fp, fn, tp)["f1_score"]
     return {
         "total_loss": losses.avg, "recon_loss": recon_losses.avg, "seg_loss": seg_losses.avg,
         "image_metrics": image_metrics, "pixel_metrics": pixel_metrics,
-        "predictions": {"labels": all_labels, "scores": all_scores, "masks_true": all_masks_true,
-                        "masks_pred": all_masks_pred},
+        "predictions": predictions,
     }
 
 
