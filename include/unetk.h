@@ -255,6 +255,23 @@ size_t unetk_select_workspace_bytes(void);
 int unetk_select_kth(const float* x, int64_t n, int64_t k, float* out2, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* ---- evaluation-time input transform on the device: src/dataset.py:141-152 --------------------
+ * transforms.Resize((S, S)) -> ToTensor() -> Normalize(mean, std) of a PIL image, i.e. Pillow's separable,
+ * antialiased bilinear resampling in 8-bit fixed point (22 fractional bits, the horizontal pass rounded to a
+ * byte before the vertical one), then (v / 255 - mean[c]) / std[c] in fp32.  Bit-exact against
+ * Pillow + torchvision.
+ * unetk_resize_ksize / unetk_resize_coeffs are HOST functions (no device needed): the tap table of one axis,
+ * bounds int32 [out, 2] = (first source index, tap count), coeffs int32 [out, ksize].
+ * unetk_resize_u8: src u8 [n, h, w, c] (c = 3 RGB or 1 mask) -> tmp u8 [n, h, ow, c] -> out_u8 [n, oh, ow, c]
+ * and / or out_f32 [n, c, oh, ow] (either may be NULL); the tap tables are DEVICE copies; mean / std are HOST
+ * arrays of c floats (NULL: 0 / 1, i.e. ToTensor only, the mask transform). */
+int unetk_resize_ksize(int in_size, int out_size);
+int unetk_resize_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* coeffs);
+int unetk_resize_u8(const uint8_t* src, uint8_t* tmp, uint8_t* out_u8, float* out_f32, int n, int h, int w, int c,
+                    int oh, int ow, const int32_t* hbounds, const int32_t* hcoeffs, int hksize,
+                    const int32_t* vbounds, const int32_t* vcoeffs, int vksize, const float* mean, const float* std,
+                    void* stream);
+
 /* ---- get_optimizer -> torch.optim.{Adam,AdamW,SGD}: src/train_utils.py:263-272 ------------- */
 /* mode 0 Adam (L2 decay in the gradient), 1 AdamW, 2 SGD+momentum (beta1 = momentum, v unused). */
 int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

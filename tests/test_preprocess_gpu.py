@@ -1,0 +1,97 @@
+"""Evaluation-time input transform on the device (deterministic half) through the C ABI:
+bit-exact against torchvision + Pillow (the libraries src/dataset.py:141-152 calls) and the numpy oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import preprocess_oracle as P  # noqa: E402
+from test_preprocess_oracle import SIZES, images, reference_transforms  # noqa: E402
+
+
+@pytest.mark.parametrize("h,w,size", SIZES)
+def test_eval_transforms_are_bit_exact(cuda_device, h, w, size):
+    pytest.importorskip("torchvision")
+    from PIL import Image
+    from tiaozhanbei_unet_b200 import transforms as T
+    batch = [images(h * 1000 + w + i, h, w) for i in range(3)]
+    imgs = np.stack([b[0] for b in batch])
+    masks = np.stack([b[1] for b in batch])
+    it, mt = reference_transforms(size)
+    want_i = torch.stack([it(Image.fromarray(b[0])) for b in batch])
+    want_m = torch.stack([mt(Image.fromarray(b[1])) for b in batch])
+    got_i = T.eval_image_transform(torch.from_numpy(imgs).to(cuda_device), size)
+    got_m = T.eval_mask_transform(torch.from_numpy(masks).to(cuda_device), size)
+    assert got_i.is_cuda and got_i.dtype == torch.float32 and got_i.shape == (3, 3, size, size)
+    assert got_m.shape == (3, 1, size, size)
+    assert torch.equal(got_i.cpu(), want_i), (got_i.cpu() - want_i).abs().max()
+    assert torch.equal(got_m.cpu(), want_m)
+    # the resized bytes themselves, against Pillow and the oracle
+    u8 = T.resize_u8(torch.from_numpy(imgs).to(cuda_device), size).cpu().numpy()
+    for i, b in enumerate(batch):
+        np.testing.assert_array_equal(u8[i], np.asarray(Image.fromarray(b[0]).resize((size, size), Image.BILINEAR)))
+    np.testing.assert_array_equal(u8[0], P.resize(imgs[0], size, size))
+    m8 = T.resize_u8(torch.from_numpy(masks).to(cuda_device), size).cpu().numpy()
+    np.testing.assert_array_equal(m8[1], P.resize(masks[1], size, size))
+
+
+def test_single_pil_image_and_get_transforms(cuda_device):
+    from PIL import Image
+    from tiaozhanbei_unet_b200 import transforms as T
+    img, mask = images(11, 90, 120)
+    it, mt = reference_transforms(64)
+    image_transform, mask_transform = T.get_transforms(64, is_train=False)
+    got_i, got_m = image_transform(Image.fromarray(img)), mask_transform(Image.fromarray(mask))
+    assert got_i.shape == (3, 64, 64) and got_m.shape == (1, 64, 64) and got_i.is_cuda
+    assert torch.equal(got_i.cpu(), it(Image.fromarray(img)))
+    assert torch.equal(got_m.cpu(), mt(Image.fromarray(mask)))
+    # non-square target, bytes only
+    out = T.resize_u8(img, (32, 48)).cpu().numpy()
+    np.testing.assert_array_equal(out, np.asarray(Image.fromarray(img).resize((48, 32), Image.BILINEAR)))
+    with pytest.raises(NotImplementedError):
+        T.get_transforms(64, is_train=True)
+    with pytest.raises(TypeError):
+        T.eval_image_transform(torch.zeros(2, 8, 8, 3, device=cuda_device), 4)
+    with pytest.raises(ValueError):
+        T.eval_image_transform(torch.zeros(2, 8, 8, 4, dtype=torch.uint8, device=cuda_device), 4)
+
+
+def test_transformed_batch_feeds_the_model(cuda_device):
+    """uint8 MVTec-sized images -> device transform -> UNet eval -> sigmoid map: the transform's output is what the
+    model takes (NCHW fp32), and equals the model on the torchvision-transformed batch bit for bit."""
+    from PIL import Image
+    from tiaozhanbei_unet_b200 import transforms as T
+    from tiaozhanbei_unet_b200.model import UNet
+    torch.manual_seed(0)
+    model = UNet(3, 1).to(cuda_device).eval()
+    batch = [images(50 + i, 300, 300)[0] for i in range(2)]
+    it, _ = reference_transforms(64)
+    x_ref = torch.stack([it(Image.fromarray(b)) for b in batch]).to(cuda_device)
+    x_dev = T.eval_image_transform(np.stack(batch), 64, device=cuda_device)
+    assert torch.equal(x_ref, x_dev)
+    with torch.no_grad():
+        assert torch.equal(torch.sigmoid(model(x_dev)), torch.sigmoid(model(x_ref)))
+
+
+def test_transform_throughput(cuda_device):
+    """Printed for the log (HBM-bound byte work): 16 MVTec-sized images (1024 x 1024 RGB) -> 256 x 256 normalised."""
+    from tiaozhanbei_unet_b200 import transforms as T
+    x = torch.randint(0, 256, (16, 1024, 1024, 3), dtype=torch.uint8, device=cuda_device)
+    T.eval_image_transform(x, 256)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        T.eval_image_transform(x, 256)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    moved = x.numel() + 2 * 16 * 1024 * 256 * 3 + 16 * 3 * 256 * 256 * 4
+    print(f"\neval_image_transform 16 x 1024^2 -> 256^2: {ms:.3f} ms, {16 / ms * 1e3:.0f} img/s, {moved / ms / 1e6:.0f} GB/s")
+    assert 16 / ms * 1e3 > 5000

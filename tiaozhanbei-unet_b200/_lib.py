@@ -59,6 +59,9 @@ SIGNATURES = {
     "unetk_pixel_confusion": (I, [P, P, P, P, I, F, P, I, L, P]),
     "unetk_select_workspace_bytes": (Z, []),
     "unetk_select_kth": (I, [P, L, L, P, P, Z, P]),
+    "unetk_resize_ksize": (I, [I, I]),
+    "unetk_resize_coeffs": (I, [I, I, P, P]),
+    "unetk_resize_u8": (I, [P, P, P, P, I, I, I, I, I, I, P, P, I, P, P, I, P, P, P]),
     "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),
     "unetk_permute_batched": (I, [P, I, I, P, P, I, F, P]),
     "unetk_permute_chunk_elems": (I, []),
@@ -126,6 +129,13 @@ def call(name: str, *args) -> None:
     _launches += 1
     if name != "unetk_memset_zero":
         _kernel_launches += 1
+    if rc != 0:
+        raise UnetkError(f"{name} failed with code {rc}: {last_error()}")
+
+
+def call_host(name: str, *args) -> None:
+    """Call a host-only entry point (no kernel launch, works without a device)."""
+    rc = getattr(get(), name)(*args)
     if rc != 0:
         raise UnetkError(f"{name} failed with code {rc}: {last_error()}")
 

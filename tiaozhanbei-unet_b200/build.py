@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(BUILD, "libunetk.so")
 SOURCES = ["runtime.cu", "igemm.cu", "wgrad.cu", "elementwise.cu", "head_loss.cu", "first_conv.cu", "seg_loss.cu",
-           "eval_metrics.cu", "optim.cu", "api.cu"]
+           "eval_metrics.cu", "preprocess.cu", "optim.cu", "api.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "unetk.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -197,6 +197,17 @@ int unetk_select_kth(const float* x, int64_t n, int64_t k, float* out2, void* wo
                      void* stream) {
   return unetk::select_kth(x, static_cast<long>(n), static_cast<long>(k), out2, workspace, workspace_bytes, S(stream));
 }
+int unetk_resize_ksize(int in_size, int out_size) { return unetk::resize_ksize(in_size, out_size); }
+int unetk_resize_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* coeffs) {
+  return unetk::resize_coeffs(in_size, out_size, bounds, coeffs);
+}
+int unetk_resize_u8(const uint8_t* src, uint8_t* tmp, uint8_t* out_u8, float* out_f32, int n, int h, int w, int c,
+                    int oh, int ow, const int32_t* hbounds, const int32_t* hcoeffs, int hksize,
+                    const int32_t* vbounds, const int32_t* vcoeffs, int vksize, const float* mean, const float* std,
+                    void* stream) {
+  return unetk::resize_u8(src, tmp, out_u8, out_f32, n, h, w, c, oh, ow, hbounds, hcoeffs, hksize, vbounds, vcoeffs,
+                          vksize, mean, std, S(stream));
+}
 int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                     int mode, void* stream) {

@@ -116,6 +116,11 @@ int pixel_confusion(const float* pred, const float* truth, const unsigned char* 
                     cudaStream_t s);
 size_t select_workspace_bytes();
 int select_kth(const float* x, long n, long k, float* out2, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int resize_ksize(int in_size, int out_size);
+int resize_coeffs(int in_size, int out_size, int* bounds, int* coeffs);
+int resize_u8(const unsigned char* src, unsigned char* tmp, unsigned char* out_u8, float* out_f32, int n, int h,
+              int w, int c, int oh, int ow, const int* hbounds, const int* hcoeffs, int hksize, const int* vbounds,
+              const int* vcoeffs, int vksize, const float* mean, const float* stdv, cudaStream_t s);
 int anomaly_score(const float* recon, const float* orig, float* out, int N, int C, int H, int W,
                   int method, cudaStream_t s);
 int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int N, int C, int H,

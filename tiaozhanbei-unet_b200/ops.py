@@ -415,6 +415,48 @@ def select_kth(x, k, out2=None, work=None):
     return out2
 
 
+def resize_coeffs(in_size, out_size):
+    """HOST: Pillow's bilinear tap table of one axis -> (bounds int32 [out, 2], coeffs int32 [out, ksize])."""
+    import numpy as np
+    lib = _lib.get()
+    ksize = lib.unetk_resize_ksize(int(in_size), int(out_size))
+    if ksize <= 0:
+        raise ValueError(f"resize_coeffs: bad sizes {in_size} -> {out_size}")
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    coeffs = np.zeros((out_size, ksize), dtype=np.int32)
+    _lib.call_host("unetk_resize_coeffs", int(in_size), int(out_size), bounds.ctypes.data, coeffs.ctypes.data)
+    return bounds, coeffs
+
+
+def resize_u8(src, tmp, out_u8, out_f32, hplan, vplan, mean=None, std=None):
+    """src u8 [n, h, w, c] -> out_u8 [n, oh, ow, c] / out_f32 [n, c, oh, ow]; hplan / vplan: device (bounds, coeffs)."""
+    import ctypes
+    u8 = torch.uint8
+    _chk(src, u8, "src"); _chk(tmp, u8, "tmp")
+    n, h, w, c = src.shape
+    (hb, hk), (vb, vk) = hplan, vplan
+    for t, nm in ((hb, "hbounds"), (hk, "hcoeffs"), (vb, "vbounds"), (vk, "vcoeffs")):
+        _chk(t, torch.int32, nm)
+    ow, oh = hb.shape[0], vb.shape[0]
+    if tmp.numel() < n * h * ow * c:
+        raise ValueError("resize_u8: tmp too small")
+    if out_u8 is not None:
+        _chk(out_u8, u8, "out_u8")
+        if tuple(out_u8.shape) != (n, oh, ow, c):
+            raise ValueError(f"resize_u8: out_u8 must be {(n, oh, ow, c)}")
+    if out_f32 is not None:
+        _chk(out_f32, f32, "out_f32")
+        if tuple(out_f32.shape) != (n, c, oh, ow):
+            raise ValueError(f"resize_u8: out_f32 must be {(n, c, oh, ow)}")
+    m = (ctypes.c_float * c)(*[float(v) for v in mean]) if mean is not None else None
+    sd = (ctypes.c_float * c)(*[float(v) for v in std]) if std is not None else None
+    _lib.call("unetk_resize_u8", _p(src), _p(tmp), _p(out_u8), _p(out_f32), n, h, w, c, oh, ow, _p(hb), _p(hk),
+              hk.shape[1], _p(vb), _p(vk), vk.shape[1],
+              ctypes.cast(m, ctypes.c_void_p) if m is not None else None,
+              ctypes.cast(sd, ctypes.c_void_p) if sd is not None else None, _s())
+    return out_f32 if out_f32 is not None else out_u8
+
+
 # ---------------------------------------------------------------------------------------------
 # optimizer / layout
 # ---------------------------------------------------------------------------------------------
