@@ -34,7 +34,7 @@ def _as_u8_batch(x, channels, device):
     """PIL image / HWC uint8 array / uint8 tensor ([H, W, C], [N, H, W, C]; masks [H, W], [N, H, W]) -> CUDA
     uint8 [N, H, W, C]."""
     if not isinstance(x, torch.Tensor):
-        x = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+        x = torch.from_numpy(np.array(x))      # (a copy: PIL hands out read-only buffers)
     if x.dtype != torch.uint8:
         raise TypeError(f"expected decoded uint8 pixels, got {x.dtype}")
     single = False
