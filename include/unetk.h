@@ -272,6 +272,25 @@ int unetk_resize_u8(const uint8_t* src, uint8_t* tmp, uint8_t* out_u8, float* ou
                     const int32_t* vbounds, const int32_t* vcoeffs, int vksize, const float* mean, const float* std,
                     void* stream);
 
+/* ---- training augmentations on the device: src/dataset.py:131-138 -----------------------------
+ * RandomHorizontalFlip -> RandomRotation -> ColorJitter of the resized uint8 image with HOST-drawn parameters
+ * (torchvision's draws from torch's generator), restated from torchvision 0.26 + Pillow 12.2; bit-exact.
+ * geom: DEVICE int32 [n, 8] = (mode, flip, a0, a1, a2, a3, a4, a5): mode 0 identity, 1 Pillow's affine_fixed
+ * nearest-neighbour rotation (16.16 fixed point: source x = (a2 + a1 y + a0 x) >> 16, source y =
+ * (a5 + a4 y + a3 x) >> 16, outside the image -> 0), 2 / 3 / 4 the exact 180 / 90 / 270 degree transposes;
+ * the flip is applied to the source before the rotation.  src != dst, u8 [n, h, w, c]. */
+int unetk_flip_rotate_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int c, const int32_t* geom,
+                         void* stream);
+/* ColorJitter in place on u8 [n, h, w, 3]: four stages, ops DEVICE int32 [n, 4] per stage 0 brightness,
+ * 1 contrast, 2 saturation (Image.blend of the black / mean-luma / luma image with the image, factors[n, stage]
+ * = alpha), 3 hue (RGB -> HSV -> RGB, factors = the uint8 amount added to H), other values skip the stage.
+ * gray_sums: DEVICE workspace of 4 * n uint64. */
+int unetk_color_jitter_u8(uint8_t* img, int n, int h, int w, const int32_t* ops, const float* factors,
+                          uint64_t* gray_sums, void* stream);
+/* ToTensor + Normalize: u8 [n, h, w, c] -> fp32 [n, c, h, w] = (v / 255 - mean[c]) / std[c] (HOST arrays or NULL). */
+int unetk_u8_to_tensor(const uint8_t* hwc, float* chw, int n, int h, int w, int c, const float* mean,
+                       const float* std, void* stream);
+
 /* ---- get_optimizer -> torch.optim.{Adam,AdamW,SGD}: src/train_utils.py:263-272 ------------- */
 /* mode 0 Adam (L2 decay in the gradient), 1 AdamW, 2 SGD+momentum (beta1 = momentum, v unused). */
 int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

@@ -54,8 +54,6 @@ def test_single_pil_image_and_get_transforms(cuda_device):
     # non-square target, bytes only
     out = T.resize_u8(img, (32, 48)).cpu().numpy()
     np.testing.assert_array_equal(out, np.asarray(Image.fromarray(img).resize((48, 32), Image.BILINEAR)))
-    with pytest.raises(NotImplementedError):
-        T.get_transforms(64, is_train=True)
     with pytest.raises(TypeError):
         T.eval_image_transform(torch.zeros(2, 8, 8, 3, device=cuda_device), 4)
     with pytest.raises(ValueError):
@@ -95,3 +93,97 @@ def test_transform_throughput(cuda_device):
     moved = x.numel() + 2 * 16 * 1024 * 256 * 3 + 16 * 3 * 256 * 256 * 4
     print(f"\neval_image_transform 16 x 1024^2 -> 256^2: {ms:.3f} ms, {16 / ms * 1e3:.0f} img/s, {moved / ms / 1e6:.0f} GB/s")
     assert 16 / ms * 1e3 > 5000
+
+
+# ---------------------------------------------------------------------------------------------
+# training augmentations (src/dataset.py:131-138)
+# ---------------------------------------------------------------------------------------------
+def test_flip_rotate_is_bit_exact(cuda_device):
+    from tiaozhanbei_unet_b200 import ops, transforms as T
+    rng = np.random.default_rng(2)
+    for h, w in ((64, 64), (33, 47), (256, 256)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        cases = [(f, a) for f in (False, True) for a in list(rng.uniform(-10, 10, 4)) + [0.0, 180.0, 90.0, 270.0, 45.0, -123.4]]
+        src = torch.from_numpy(np.stack([img] * len(cases))).to(cuda_device)
+        geom = torch.tensor([T._geometry(f, a, w, h) for f, a in cases], dtype=torch.int32, device=cuda_device)
+        out = ops.flip_rotate_u8(src, torch.empty_like(src), geom).cpu().numpy()
+        for i, (f, a) in enumerate(cases):
+            want = P.rotate_nearest(img[:, ::-1].copy() if f else img, a)
+            np.testing.assert_array_equal(out[i], want, err_msg=f"{h}x{w} flip {f} angle {a}")
+
+
+def test_colour_jitter_stages_are_bit_exact(cuda_device):
+    from test_preprocess_oracle import colour_cube
+    from tiaozhanbei_unet_b200 import ops
+    dev = cuda_device
+    # hue over all 2^24 colours (RGB -> HSV -> +delta -> RGB), two deltas
+    cube = colour_cube()
+    for delta in (0, 37, 243):
+        x = torch.from_numpy(cube)[None].to(dev).clone()
+        ops.color_jitter_u8(x, torch.tensor([[3, -1, -1, -1]], dtype=torch.int32, device=dev),
+                            torch.tensor([[float(delta), 0, 0, 0]], dtype=torch.float32, device=dev))
+        hsv = P.rgb_to_hsv(cube)
+        hsv[..., 0] = (hsv[..., 0].astype(np.int32) + delta).astype(np.uint8)
+        np.testing.assert_array_equal(x[0].cpu().numpy(), P.hsv_to_rgb(hsv), err_msg=f"hue delta {delta}")
+    # the three blends, interpolating and extrapolating factors, each alone
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (96, 80, 3), dtype=np.uint8)
+    img[:20] = (img[:20] // 16)              # dark rows: extrapolation clamps at 0 / truncation matters
+    factors = [0.0, 1.0, 0.9, 1.1, 0.3, 1.7, 0.9999999, 1.0000001, float(np.float32(0.95))]
+    for op in (0, 1, 2):
+        x = torch.from_numpy(np.stack([img] * len(factors))).to(dev)
+        ops.color_jitter_u8(x, torch.tensor([[op, -1, -1, -1]] * len(factors), dtype=torch.int32, device=dev),
+                            torch.tensor([[f, 0, 0, 0] for f in factors], dtype=torch.float32, device=dev))
+        for i, f in enumerate(factors):
+            want = P.color_jitter(img, [op], (f, f, f, 0.0))
+            np.testing.assert_array_equal(x[i].cpu().numpy(), want, err_msg=f"op {op} factor {f}")
+    # all 24 orders on one image
+    import itertools
+    orders = list(itertools.permutations(range(4)))
+    fac = (0.93, 1.08, 1.04, -0.031)
+    x = torch.from_numpy(np.stack([img] * 24)).to(dev)
+    per_op = {0: fac[0], 1: fac[1], 2: fac[2], 3: float(P.hue_delta(fac[3]))}
+    ops.color_jitter_u8(x, torch.tensor(orders, dtype=torch.int32, device=dev),
+                        torch.tensor([[per_op[o] for o in order] for order in orders], dtype=torch.float32, device=dev))
+    for i, order in enumerate(orders):
+        np.testing.assert_array_equal(x[i].cpu().numpy(), P.color_jitter(img, list(order), fac), err_msg=str(order))
+
+
+@pytest.mark.parametrize("h,w,size", [(300, 300, 64), (100, 130, 128), (900, 900, 256)])
+def test_train_transform_is_torchvisions(cuda_device, h, w, size):
+    """Same seed -> the batch the reference's single-process loader would produce, bit for bit."""
+    pytest.importorskip("torchvision")
+    from PIL import Image
+    from test_preprocess_oracle import reference_train_transform
+    from tiaozhanbei_unet_b200 import transforms as T
+    tf = reference_train_transform(size)
+    batch = [images(h + i, h, w)[0] for i in range(6)]
+    for seed in range(3):
+        torch.manual_seed(seed)
+        want = torch.stack([tf(Image.fromarray(b)) for b in batch])
+        torch.manual_seed(seed)
+        got = T.train_image_transform(torch.from_numpy(np.stack(batch)).to(cuda_device), size)
+        assert got.shape == want.shape and got.dtype == torch.float32
+        assert torch.equal(got.cpu(), want), (seed, (got.cpu() != want).sum().item())
+    image_transform, mask_transform = T.get_transforms(size, is_train=True)
+    torch.manual_seed(5)
+    one = image_transform(Image.fromarray(batch[0]))
+    torch.manual_seed(5)
+    assert torch.equal(one.cpu(), tf(Image.fromarray(batch[0])))
+
+
+def test_train_transform_throughput(cuda_device):
+    from tiaozhanbei_unet_b200 import transforms as T
+    x = torch.randint(0, 256, (16, 1024, 1024, 3), dtype=torch.uint8, device=cuda_device)
+    params = T.draw_train_params(16)
+    T.train_image_transform(x, 256, params)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        T.train_image_transform(x, 256, params)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 10
+    print(f"\ntrain_image_transform 16 x 1024^2 -> 256^2 (flip, rotate, 4 jitter stages): {ms:.3f} ms, {16 / ms * 1e3:.0f} img/s")
+    assert 16 / ms * 1e3 > 2000

@@ -79,7 +79,82 @@ def test_transforms_have_no_cpu_path():
     from tiaozhanbei_unet_b200 import transforms as T
     with pytest.raises(Exception):
         T.eval_image_transform(np.zeros((8, 8, 3), np.uint8), 4)
-    with pytest.raises(NotImplementedError):
-        T.get_transforms(256, is_train=True)
     with pytest.raises(TypeError):
         T.eval_image_transform(np.zeros((8, 8, 3), np.float32), 4)
+
+
+# ---------------------------------------------------------------------------------------------
+# training augmentations (src/dataset.py:131-138)
+# ---------------------------------------------------------------------------------------------
+def reference_train_transform(size):
+    """get_transforms(image_size, is_train=True)[0] as written in src/dataset.py:131-139."""
+    import torchvision.transforms as transforms
+    return transforms.Compose([
+        transforms.Resize((size, size)),
+        transforms.RandomHorizontalFlip(p=0.5),
+        transforms.RandomRotation(degrees=10),
+        transforms.ColorJitter(brightness=0.1, contrast=0.1, saturation=0.1, hue=0.05),
+        transforms.ToTensor(),
+        transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225]),
+    ])
+
+
+def colour_cube():
+    """All 2^24 RGB (or HSV) triples as a 4096 x 4096 image."""
+    c = np.arange(256, dtype=np.uint8)
+    return np.stack(np.meshgrid(c, c, c, indexing="ij"), -1).reshape(4096, 4096, 3)
+
+
+def test_colour_conversions_are_pillows_over_all_colours():
+    from PIL import Image
+    cube = colour_cube()
+    np.testing.assert_array_equal(P.luma(cube), np.asarray(Image.fromarray(cube).convert("L")))
+    np.testing.assert_array_equal(P.rgb_to_hsv(cube), np.asarray(Image.fromarray(cube).convert("HSV")))
+    np.testing.assert_array_equal(P.hsv_to_rgb(cube), np.asarray(Image.fromarray(cube, "HSV").convert("RGB")))
+
+
+def test_blend_and_rotation_are_pillows():
+    from PIL import Image
+    a = np.repeat(np.arange(256, dtype=np.uint8)[:, None], 256, 1)
+    b = np.ascontiguousarray(a.T)
+    rng = np.random.default_rng(0)
+    for alpha in list(rng.uniform(0.0, 2.0, 40)) + [0.0, 1.0, 0.9, 1.1, 0.5, 1.0000001, 0.9999999]:
+        np.testing.assert_array_equal(P.blend(a, b, alpha), np.asarray(Image.blend(Image.fromarray(a), Image.fromarray(b), alpha)))
+    for h, w in ((64, 64), (33, 47), (256, 256)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for angle in list(rng.uniform(-10, 10, 12)) + [10.0, -10.0, 1e-3, 45.0, 90.0, 180.0, 270.0, 360.0, 123.4]:
+            want = np.asarray(Image.fromarray(img).rotate(angle, Image.NEAREST, False, None, fillcolor=(0, 0, 0)))
+            np.testing.assert_array_equal(P.rotate_nearest(img, angle), want, err_msg=f"{h}x{w} angle {angle}")
+
+
+@pytest.mark.parametrize("h,w,size", [(300, 300, 64), (100, 130, 128), (40, 40, 32)])
+def test_train_transform_oracle_is_torchvisions(h, w, size):
+    """Same seed, same draws, same pixels: the whole is_train=True pipeline against torchvision on PIL images."""
+    pytest.importorskip("torchvision")
+    from PIL import Image
+    tf = reference_train_transform(size)
+    batch = [images(h + i, h, w)[0] for i in range(5)]
+    for seed in range(3):
+        torch.manual_seed(seed)
+        want = [tf(Image.fromarray(b)).numpy() for b in batch]
+        torch.manual_seed(seed)
+        params = P.draw_train_params(len(batch))
+        for b, p, wnt in zip(batch, params, want):
+            np.testing.assert_array_equal(P.train_image_transform(b, size, p), wnt)
+        assert len({tuple(p["order"]) for p in params}) > 1 or seed      # the op order really varies
+
+
+def test_product_host_parameters_are_the_oracles():
+    """transforms.draw_train_params / _geometry (product host code) against the oracle's restatement."""
+    from tiaozhanbei_unet_b200 import transforms as T
+    torch.manual_seed(11)
+    a = T.draw_train_params(8)
+    torch.manual_seed(11)
+    assert a == P.draw_train_params(8)
+    for p in a:
+        g = T._geometry(p["flip"], p["angle"], 256, 192)
+        assert g[0] == 1 and g[1] == int(p["flip"])
+        assert tuple(g[2:]) == P.affine_fixed_coeffs(P.rotate_matrix(p["angle"] % 360.0, 256, 192))
+    assert T._geometry(False, 180.0, 8, 8)[0] == 2 and T._geometry(False, 90.0, 8, 8)[0] == 3
+    assert T._geometry(True, 270.0, 8, 8)[:2] == [4, 1] and T._geometry(False, 360.0, 8, 8)[0] == 0
+    assert T._geometry(False, 90.0, 8, 6)[0] == 1          # 90 degrees on a non-square image is a real affine

@@ -62,6 +62,9 @@ SIGNATURES = {
     "unetk_resize_ksize": (I, [I, I]),
     "unetk_resize_coeffs": (I, [I, I, P, P]),
     "unetk_resize_u8": (I, [P, P, P, P, I, I, I, I, I, I, P, P, I, P, P, I, P, P, P]),
+    "unetk_flip_rotate_u8": (I, [P, P, I, I, I, I, P, P]),
+    "unetk_color_jitter_u8": (I, [P, I, I, I, P, P, P, P]),
+    "unetk_u8_to_tensor": (I, [P, P, I, I, I, I, P, P, P]),
     "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),
     "unetk_permute_batched": (I, [P, I, I, P, P, I, F, P]),
     "unetk_permute_chunk_elems": (I, []),

@@ -208,6 +208,19 @@ int unetk_resize_u8(const uint8_t* src, uint8_t* tmp, uint8_t* out_u8, float* ou
   return unetk::resize_u8(src, tmp, out_u8, out_f32, n, h, w, c, oh, ow, hbounds, hcoeffs, hksize, vbounds, vcoeffs,
                           vksize, mean, std, S(stream));
 }
+int unetk_flip_rotate_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int c, const int32_t* geom,
+                         void* stream) {
+  return unetk::flip_rotate_u8(src, dst, n, h, w, c, geom, S(stream));
+}
+int unetk_color_jitter_u8(uint8_t* img, int n, int h, int w, const int32_t* ops, const float* factors,
+                          uint64_t* gray_sums, void* stream) {
+  return unetk::color_jitter_u8(img, n, h, w, ops, factors, reinterpret_cast<unsigned long long*>(gray_sums),
+                                S(stream));
+}
+int unetk_u8_to_tensor(const uint8_t* hwc, float* chw, int n, int h, int w, int c, const float* mean,
+                       const float* std, void* stream) {
+  return unetk::u8_to_tensor(hwc, chw, n, h, w, c, mean, std, S(stream));
+}
 int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                     int mode, void* stream) {

@@ -121,6 +121,12 @@ int resize_coeffs(int in_size, int out_size, int* bounds, int* coeffs);
 int resize_u8(const unsigned char* src, unsigned char* tmp, unsigned char* out_u8, float* out_f32, int n, int h,
               int w, int c, int oh, int ow, const int* hbounds, const int* hcoeffs, int hksize, const int* vbounds,
               const int* vcoeffs, int vksize, const float* mean, const float* stdv, cudaStream_t s);
+int flip_rotate_u8(const unsigned char* src, unsigned char* dst, int n, int h, int w, int c, const int* geom,
+                   cudaStream_t s);
+int color_jitter_u8(unsigned char* img, int n, int h, int w, const int* ops, const float* factors,
+                    unsigned long long* gray_sums, cudaStream_t s);
+int u8_to_tensor(const unsigned char* hwc, float* chw, int n, int h, int w, int c, const float* mean,
+                 const float* stdv, cudaStream_t s);
 int anomaly_score(const float* recon, const float* orig, float* out, int N, int C, int H, int W,
                   int method, cudaStream_t s);
 int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int N, int C, int H,

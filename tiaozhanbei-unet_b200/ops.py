@@ -457,6 +457,43 @@ def resize_u8(src, tmp, out_u8, out_f32, hplan, vplan, mean=None, std=None):
     return out_f32 if out_f32 is not None else out_u8
 
 
+def flip_rotate_u8(src, dst, geom):
+    """dst = rotate(flip(src)) per image; geom int32 [n, 8] on the device (see include/unetk.h)."""
+    _chk(src, torch.uint8, "src"); _chk(dst, torch.uint8, "dst"); _chk(geom, torch.int32, "geom")
+    n, h, w, c = src.shape
+    if dst.shape != src.shape or geom.numel() != n * 8:
+        raise ValueError("flip_rotate_u8: dst must have src's shape and geom 8 ints per image")
+    _lib.call("unetk_flip_rotate_u8", _p(src), _p(dst), n, h, w, c, _p(geom), _s())
+    return dst
+
+
+def color_jitter_u8(img, stage_ops, factors, work=None):
+    """ColorJitter's four adjustments in place on u8 [n, h, w, 3]; stage_ops int32 [n, 4], factors fp32 [n, 4]."""
+    _chk(img, torch.uint8, "img"); _chk(stage_ops, torch.int32, "ops"); _chk(factors, f32, "factors")
+    n, h, w, c = img.shape
+    if c != 3 or stage_ops.numel() != n * 4 or factors.numel() != n * 4:
+        raise ValueError("color_jitter_u8: RGB images, 4 ops and 4 factors per image")
+    if work is None:
+        work = torch.empty(4 * n, dtype=torch.int64, device=img.device)
+    _lib.call("unetk_color_jitter_u8", _p(img), n, h, w, _p(stage_ops), _p(factors), _p(work), _s())
+    return img
+
+
+def u8_to_tensor(hwc, out, mean=None, std=None):
+    """ToTensor + Normalize: u8 [n, h, w, c] -> fp32 [n, c, h, w]."""
+    import ctypes
+    _chk(hwc, torch.uint8, "hwc"); _chk(out, f32, "out")
+    n, h, w, c = hwc.shape
+    if tuple(out.shape) != (n, c, h, w):
+        raise ValueError(f"u8_to_tensor: out must be {(n, c, h, w)}")
+    m = (ctypes.c_float * c)(*[float(v) for v in mean]) if mean is not None else None
+    sd = (ctypes.c_float * c)(*[float(v) for v in std]) if std is not None else None
+    _lib.call("unetk_u8_to_tensor", _p(hwc), _p(out), n, h, w, c,
+              ctypes.cast(m, ctypes.c_void_p) if m is not None else None,
+              ctypes.cast(sd, ctypes.c_void_p) if sd is not None else None, _s())
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # optimizer / layout
 # ---------------------------------------------------------------------------------------------
