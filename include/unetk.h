@@ -291,6 +291,15 @@ int unetk_color_jitter_u8(uint8_t* img, int n, int h, int w, const int32_t* ops,
 int unetk_u8_to_tensor(const uint8_t* hwc, float* chw, int n, int h, int w, int c, const float* mean,
                        const float* std, void* stream);
 
+/* Label masks of the segmentation datasets: transforms.Resize(size, interpolation=NEAREST) -> MaskToTensor
+ * (src/gear_dataset.py:255-258, src/kolektorsdd_dataset.py:156-159), i.e. Pillow's nearest-neighbour resize.
+ * unetk_resize_nearest_table is a HOST function: the source index of every output index of one axis (int32
+ * [out]).  unetk_resize_nearest_u8: src u8 [n, h, w] -> out_i64 [n, oh, ow] (the .long() label map) and / or
+ * out_u8 (either may be NULL); xtab [ow] / ytab [oh] are DEVICE copies of the tables. */
+int unetk_resize_nearest_table(int in_size, int out_size, int32_t* table);
+int unetk_resize_nearest_u8(const uint8_t* src, int64_t* out_i64, uint8_t* out_u8, int n, int h, int w, int oh, int ow,
+                            const int32_t* xtab, const int32_t* ytab, void* stream);
+
 /* ---- get_optimizer -> torch.optim.{Adam,AdamW,SGD}: src/train_utils.py:263-272 ------------- */
 /* mode 0 Adam (L2 decay in the gradient), 1 AdamW, 2 SGD+momentum (beta1 = momentum, v unused). */
 int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

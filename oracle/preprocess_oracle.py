@@ -263,3 +263,22 @@ def train_image_transform(img_u8, size, params, mean=(0.485, 0.456, 0.406), std=
     x = rotate_nearest(x, params["angle"])
     x = color_jitter(x, params["order"], params["factors"])
     return normalize(to_tensor(x), mean, std)
+
+
+def nearest_table(in_size, out_size):
+    """Image.resize(NEAREST) (Geometry.c ImagingScaleAffine): source index per output index; the sampling
+    position starts at scale / 2 and is accumulated in double."""
+    step = in_size / out_size
+    pos = 0.0 + step * 0.5
+    t = np.zeros(out_size, np.int32)
+    for x in range(out_size):
+        xin = -1 if pos < 0.0 else int(pos)
+        t[x] = xin if 0 <= xin < in_size else -1
+        pos += step
+    return t
+
+
+def label_mask_transform(mask_u8, oh, ow):
+    """src/gear_dataset.py:255-258: Resize(NEAREST) -> int64 class indices."""
+    m = np.asarray(mask_u8, dtype=np.uint8)
+    return m[nearest_table(m.shape[0], oh)][:, nearest_table(m.shape[1], ow)].astype(np.int64)

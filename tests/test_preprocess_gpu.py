@@ -187,3 +187,37 @@ def test_train_transform_throughput(cuda_device):
     ms = a.elapsed_time(b) / 10
     print(f"\ntrain_image_transform 16 x 1024^2 -> 256^2 (flip, rotate, 4 jitter stages): {ms:.3f} ms, {16 / ms * 1e3:.0f} img/s")
     assert 16 / ms * 1e3 > 2000
+
+
+def test_label_mask_transform_is_bit_exact(cuda_device):
+    from test_preprocess_oracle import NEAREST_SIZES
+    from tiaozhanbei_unet_b200 import transforms as T
+    for h, w, oh, ow in NEAREST_SIZES:
+        masks = np.random.default_rng(h * w).integers(0, 4, (3, h, w), dtype=np.uint8)
+        got = T.label_mask_transform(torch.from_numpy(masks).to(cuda_device), (oh, ow))
+        assert got.dtype == torch.int64 and got.shape == (3, oh, ow)
+        for i in range(3):
+            np.testing.assert_array_equal(got[i].cpu().numpy(), P.label_mask_transform(masks[i], oh, ow))
+    one = T.label_mask_transform(masks[0], (oh, ow), device=cuda_device)
+    assert one.shape == (oh, ow)
+
+
+def test_gear_train_transform_settings(cuda_device):
+    """The Gear pipeline's ranges (src/gear_dataset.py:236-243) on a non-square target, against torchvision."""
+    pytest.importorskip("torchvision")
+    import torchvision.transforms as transforms
+    from PIL import Image
+    from tiaozhanbei_unet_b200 import transforms as T
+    size = (96, 128)
+    tf = transforms.Compose([
+        transforms.Resize(size), transforms.RandomHorizontalFlip(p=0.5), transforms.RandomRotation(10),
+        transforms.ColorJitter(brightness=0.2, contrast=0.2, saturation=0.2, hue=0.1), transforms.ToTensor(),
+        transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    batch = [images(70 + i, 200, 310)[0] for i in range(5)]
+    for seed in (0, 1):
+        torch.manual_seed(seed)
+        want = torch.stack([tf(Image.fromarray(b)) for b in batch])
+        torch.manual_seed(seed)
+        got = T.train_image_transform(torch.from_numpy(np.stack(batch)).to(cuda_device), size, degrees=10,
+                                      brightness=0.2, contrast=0.2, saturation=0.2, hue=0.1)
+        assert torch.equal(got.cpu(), want), (seed, (got.cpu() != want).sum().item())

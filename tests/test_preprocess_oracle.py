@@ -158,3 +158,22 @@ def test_product_host_parameters_are_the_oracles():
     assert T._geometry(False, 180.0, 8, 8)[0] == 2 and T._geometry(False, 90.0, 8, 8)[0] == 3
     assert T._geometry(True, 270.0, 8, 8)[:2] == [4, 1] and T._geometry(False, 360.0, 8, 8)[0] == 0
     assert T._geometry(False, 90.0, 8, 6)[0] == 1          # 90 degrees on a non-square image is a real affine
+
+
+NEAREST_SIZES = [(900, 900, 512, 512), (1024, 1024, 256, 256), (100, 130, 256, 256), (500, 1240, 512, 1408),
+                 (704, 256, 512, 512), (33, 47, 64, 16), (5, 5, 9, 3), (777, 1333, 511, 313)]
+
+
+@pytest.mark.parametrize("h,w,oh,ow", NEAREST_SIZES)
+def test_label_mask_transform_is_torchvisions(h, w, oh, ow):
+    """src/gear_dataset.py:255-258 target transform: oracle vs torchvision, library host tables vs oracle."""
+    pytest.importorskip("torchvision")
+    import torchvision.transforms as transforms
+    from PIL import Image
+    from tiaozhanbei_unet_b200 import ops
+    mask = np.random.default_rng(h + w).integers(0, 4, (h, w), dtype=np.uint8)
+    tf = transforms.Compose([transforms.Resize((oh, ow), interpolation=Image.NEAREST)])
+    want = torch.from_numpy(np.array(tf(Image.fromarray(mask, mode="L")))).long().numpy()
+    np.testing.assert_array_equal(P.label_mask_transform(mask, oh, ow), want)
+    np.testing.assert_array_equal(ops.resize_nearest_table(w, ow), P.nearest_table(w, ow))
+    np.testing.assert_array_equal(ops.resize_nearest_table(h, oh), P.nearest_table(h, oh))

@@ -65,6 +65,8 @@ SIGNATURES = {
     "unetk_flip_rotate_u8": (I, [P, P, I, I, I, I, P, P]),
     "unetk_color_jitter_u8": (I, [P, I, I, I, P, P, P, P]),
     "unetk_u8_to_tensor": (I, [P, P, I, I, I, I, P, P, P]),
+    "unetk_resize_nearest_table": (I, [I, I, P]),
+    "unetk_resize_nearest_u8": (I, [P, P, P, I, I, I, I, I, P, P, P]),
     "unetk_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, L, F, I, P]),
     "unetk_permute_batched": (I, [P, I, I, P, P, I, F, P]),
     "unetk_permute_chunk_elems": (I, []),

@@ -221,6 +221,14 @@ int unetk_u8_to_tensor(const uint8_t* hwc, float* chw, int n, int h, int w, int 
                        const float* std, void* stream) {
   return unetk::u8_to_tensor(hwc, chw, n, h, w, c, mean, std, S(stream));
 }
+int unetk_resize_nearest_table(int in_size, int out_size, int32_t* table) {
+  return unetk::resize_nearest_table(in_size, out_size, table);
+}
+int unetk_resize_nearest_u8(const uint8_t* src, int64_t* out_i64, uint8_t* out_u8, int n, int h, int w, int oh, int ow,
+                            const int32_t* xtab, const int32_t* ytab, void* stream) {
+  return unetk::resize_nearest_u8(src, reinterpret_cast<long long*>(out_i64), out_u8, n, h, w, oh, ow, xtab, ytab,
+                                  S(stream));
+}
 int unetk_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                     int mode, void* stream) {

@@ -127,6 +127,9 @@ int color_jitter_u8(unsigned char* img, int n, int h, int w, const int* ops, con
                     unsigned long long* gray_sums, cudaStream_t s);
 int u8_to_tensor(const unsigned char* hwc, float* chw, int n, int h, int w, int c, const float* mean,
                  const float* stdv, cudaStream_t s);
+int resize_nearest_table(int in_size, int out_size, int* table);
+int resize_nearest_u8(const unsigned char* src, long long* out_i64, unsigned char* out_u8, int n, int h, int w,
+                      int oh, int ow, const int* xtab, const int* ytab, cudaStream_t s);
 int anomaly_score(const float* recon, const float* orig, float* out, int N, int C, int H, int W,
                   int method, cudaStream_t s);
 int ssim_fwd(const float* img1, const float* img2, float* sums, float* maps, int N, int C, int H,

@@ -275,6 +275,25 @@ u8_to_tensor_kernel(const unsigned char* __restrict__ src, float* __restrict__ o
   }
 }
 
+// Image.resize(size, NEAREST) of a label mask (src/gear_dataset.py:255-258): a gather through the per-axis source
+// index tables of Pillow's ImagingScaleAffine (resize_nearest_table); u8 [n, h, w] -> int64 [n, oh, ow]
+// (MaskToTensor's .long()) and / or u8.
+__global__ void __launch_bounds__(256)
+resize_nearest_kernel(const unsigned char* __restrict__ src, long long* __restrict__ out_i64,
+                      unsigned char* __restrict__ out_u8, int n, int h, int w, int oh, int ow,
+                      const int* __restrict__ xtab, const int* __restrict__ ytab) {
+  const long plane = static_cast<long>(oh) * ow, total = plane * n;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long img = i / plane, r = i - img * plane;
+    const int oy = static_cast<int>(r / ow), ox = static_cast<int>(r - static_cast<long>(oy) * ow);
+    const int sx = __ldg(xtab + ox), sy = __ldg(ytab + oy);
+    const unsigned char v = (sx >= 0 && sy >= 0) ? __ldg(src + (img * h + sy) * w + sx) : 0;
+    if (out_i64 != nullptr) out_i64[i] = v;
+    if (out_u8 != nullptr) out_u8[i] = v;
+  }
+}
+
 inline double triangle(double x) {
   if (x < 0.0) x = -x;
   return x < 1.0 ? 1.0 - x : 0.0;
@@ -415,6 +434,30 @@ int u8_to_tensor(const unsigned char* hwc, float* chw, int n, int h, int w, int 
     u8_to_tensor_kernel<3><<<grid_for(total), 256, 0, s>>>(hwc, chw, plane, total, norm);
   else
     u8_to_tensor_kernel<1><<<grid_for(total), 256, 0, s>>>(hwc, chw, plane, total, norm);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+// HOST: source index per output index of one axis for Image.resize(NEAREST) (Geometry.c ImagingScaleAffine:
+// the sampling position starts at scale / 2 and is ACCUMULATED in double, one addition per output index)
+int resize_nearest_table(int in_size, int out_size, int* table) {
+  UNETK_CHECK_ARG(in_size >= 1 && out_size >= 1 && table, "resize_nearest_table: bad arguments");
+  const double step = static_cast<double>(in_size) / out_size;
+  double pos = 0.0 + step * 0.5;
+  for (int x = 0; x < out_size; ++x) {
+    const int xin = pos < 0.0 ? -1 : static_cast<int>(pos);
+    table[x] = (xin >= 0 && xin < in_size) ? xin : -1;
+    pos += step;
+  }
+  return UNETK_OK;
+}
+
+int resize_nearest_u8(const unsigned char* src, long long* out_i64, unsigned char* out_u8, int n, int h, int w,
+                      int oh, int ow, const int* xtab, const int* ytab, cudaStream_t s) {
+  UNETK_CHECK_ARG(src && (out_i64 || out_u8) && xtab && ytab, "resize_nearest_u8: null pointer");
+  UNETK_CHECK_ARG(n >= 1 && h >= 1 && w >= 1 && oh >= 1 && ow >= 1, "resize_nearest_u8: bad sizes");
+  resize_nearest_kernel<<<grid_for(static_cast<long>(n) * oh * ow), 256, 0, s>>>(src, out_i64, out_u8, n, h, w, oh,
+                                                                                ow, xtab, ytab);
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }

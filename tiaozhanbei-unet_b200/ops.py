@@ -457,6 +457,28 @@ def resize_u8(src, tmp, out_u8, out_f32, hplan, vplan, mean=None, std=None):
     return out_f32 if out_f32 is not None else out_u8
 
 
+def resize_nearest_table(in_size, out_size):
+    """HOST: Pillow's nearest-neighbour source index per output index of one axis (int32 [out])."""
+    import numpy as np
+    table = np.zeros(out_size, dtype=np.int32)
+    _lib.call_host("unetk_resize_nearest_table", int(in_size), int(out_size), table.ctypes.data)
+    return table
+
+
+def resize_nearest_u8(src, out_i64, out_u8, xtab, ytab):
+    """u8 [n, h, w] -> int64 / u8 [n, oh, ow] through the device copies of the two index tables."""
+    _chk(src, torch.uint8, "src"); _chk(xtab, torch.int32, "xtab"); _chk(ytab, torch.int32, "ytab")
+    n, h, w = src.shape
+    oh, ow = ytab.numel(), xtab.numel()
+    for t, dt, nm in ((out_i64, torch.int64, "out_i64"), (out_u8, torch.uint8, "out_u8")):
+        if t is not None:
+            _chk(t, dt, nm)
+            if tuple(t.shape) != (n, oh, ow):
+                raise ValueError(f"resize_nearest_u8: {nm} must be {(n, oh, ow)}")
+    _lib.call("unetk_resize_nearest_u8", _p(src), _p(out_i64), _p(out_u8), n, h, w, oh, ow, _p(xtab), _p(ytab), _s())
+    return out_i64 if out_i64 is not None else out_u8
+
+
 def flip_rotate_u8(src, dst, geom):
     """dst = rotate(flip(src)) per image; geom int32 [n, 8] on the device (see include/unetk.h)."""
     _chk(src, torch.uint8, "src"); _chk(dst, torch.uint8, "dst"); _chk(geom, torch.int32, "geom")

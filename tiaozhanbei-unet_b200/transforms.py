@@ -97,6 +97,28 @@ def eval_mask_transform(masks, image_size=256, device=None):
     return out[0] if single else out
 
 
+_tables = {}
+
+
+def label_mask_transform(masks, image_size=(512, 512), device=None):
+    """The target transform of the segmentation datasets (src/gear_dataset.py:255-258,
+    src/kolektorsdd_dataset.py:156-159): Resize(size, NEAREST) -> MaskToTensor -> int64 [N, H', W'] class indices
+    ([H', W'] for one mask)."""
+    x, single = _as_u8_batch(masks, 1, device)
+    x = x[..., 0].contiguous()
+    oh, ow = (image_size, image_size) if isinstance(image_size, int) else image_size
+    n, h, w = x.shape
+    tabs = []
+    for a, b in ((w, ow), (h, oh)):
+        key = (a, b, str(x.device))
+        if key not in _tables:
+            _tables[key] = torch.from_numpy(ops.resize_nearest_table(a, b)).to(x.device)
+        tabs.append(_tables[key])
+    out = torch.empty(n, oh, ow, dtype=torch.int64, device=x.device)
+    ops.resize_nearest_u8(x, out, None, tabs[0], tabs[1])
+    return out[0] if single else out
+
+
 # ---------------------------------------------------------------------------------------------
 # training augmentations: parameters on the host (torchvision's draws), pixels on the device
 # ---------------------------------------------------------------------------------------------
@@ -145,13 +167,16 @@ def _geometry(flip, angle, w, h):
             _fix16(m[3]), _fix16(m[4]), _fix16(m[5] + m[3] * 0.5 + m[4] * 0.5)]
 
 
-def train_image_transform(images, image_size=256, params=None, mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None):
+def train_image_transform(images, image_size=256, params=None, mean=IMAGENET_MEAN, std=IMAGENET_STD, device=None,
+                          **ranges):
     """The `is_train=True` image transform (src/dataset.py:131-139) on a uint8 batch -> fp32 [N, 3, S, S].
-    `params`: the output of `draw_train_params` (drawn here when None)."""
+    `params`: the output of `draw_train_params` (drawn here when None, with `ranges` = its keyword arguments:
+    the Gear pipeline uses degrees=10, brightness=contrast=saturation=0.2, hue=0.1, src/gear_dataset.py:236-243;
+    KolektorSDD degrees=5, src/kolektorsdd_dataset.py:140-147)."""
     x, single = _as_u8_batch(images, 3, device)
     n = x.shape[0]
     if params is None:
-        params = draw_train_params(n)
+        params = draw_train_params(n, **ranges)
     if len(params) != n:
         raise ValueError(f"{len(params)} parameter sets for {n} images")
     oh, ow = (image_size, image_size) if isinstance(image_size, int) else image_size
