@@ -286,16 +286,23 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public API with host batches
-    def e2e_step(i):
-        hi, hm = host[i % n_host]
-        image = hi.to(dev, non_blocking=True)
-        mask = hm.to(dev, non_blocking=True)
-        step(image, mask)
-        criterion.last_values()                 # D2H read of (total, recon, seg)
-    for i in range(2):
-        e2e_step(i)
-    ms_e2e = timed(e2e_step, args.steps)
+    # ---- end to end through the public API with host batches: train_utils.train_epoch (the call src/train.py:232
+    # makes) over a loader of pinned host batches in the dataset's dict form; every step copies its batch to the
+    # device (train_epoch issues the next batch's copy on a side stream) and reads the three loss scalars back
+    class HostLoader:
+        def __init__(self, k):
+            self.k = k
+
+        def __len__(self):
+            return self.k
+
+        def __iter__(self):
+            for i in range(self.k):
+                hi, hm = host[i % n_host]
+                yield {"image": hi, "mask": hm}
+
+    train_utils.train_epoch(model, HostLoader(2), criterion, optimizer, dev, 0)
+    ms_e2e = timed(lambda _: train_utils.train_epoch(model, HostLoader(args.steps), criterion, optimizer, dev, 0), 1)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = (B * 3 * H * W + B * H * W) * 4
     d2h = 12

@@ -494,3 +494,49 @@ def test_minimum_and_unusual_shapes(cuda_device, arch, n, h, w, n_classes):
     torch.cuda.synchronize()
     for k, p in m.named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape and torch.isfinite(p.grad).all(), k
+
+
+def test_train_epoch_prefetch_matches_the_step_loop(cuda_device):
+    """train_epoch (src/train_utils.py:107-153) over pinned host batches — the next batch's copy runs on a side
+    stream during the current step — gives the averages of the plain forward / loss / backward / step loop,
+    a ragged last batch and the per-batch weighting of AverageMeter included.  The learning rate is tiny so that
+    the comparison is about which batch reached which step, not about Adam amplifying the last-bit differences of
+    two runs (atomics) in noise-level gradients."""
+    from tiaozhanbei_unet_b200 import train_utils
+    dev = cuda_device
+    arch = "anomaly_unet"
+    sd = O.synthetic_state_dict(arch, seed=7, device=dev)
+    g = torch.Generator().manual_seed(3)
+    batches = []
+    for i, n in enumerate((4, 4, 4, 4, 2)):      # every batch on its own scale: a stale or swapped batch shows
+        batches.append({"image": (torch.randn(n, 3, 32, 32, generator=g) * (1.0 + 0.5 * i)).pin_memory(),
+                        "mask": (torch.rand(n, 1, 32, 32, generator=g) > 0.9).float().pin_memory()})
+
+    m1 = _model(arch, {k: v.clone() for k, v in sd.items()}, dev)
+    c1 = train_utils.CombinedLoss()
+    o1 = train_utils.get_optimizer(m1, "adam", 1e-7, 0.0)
+    got = train_utils.train_epoch(m1, batches, c1, o1, dev, 1)
+
+    m2 = _model(arch, {k: v.clone() for k, v in sd.items()}, dev).train()
+    c2 = train_utils.CombinedLoss()
+    o2 = train_utils.get_optimizer(m2, "adam", 1e-7, 0.0)
+    tot = [0.0, 0.0, 0.0]
+    count = 0
+    for b in batches:
+        image, mask = b["image"].to(dev), b["mask"].to(dev)
+        r, a = m2(image)
+        ld = c2(r, a, image, mask)
+        o2.zero_grad()
+        ld["total_loss"].backward()
+        o2.step()
+        n = image.size(0)
+        for i, v in enumerate(c2.last_values()):
+            tot[i] += v * n
+        count += n
+    for key, want in zip(("total_loss", "recon_loss", "seg_loss"), tot):
+        want /= count
+        assert abs(got[key] - want) <= 1e-3 * abs(want), (key, got[key], want)
+    # every batch is different, so a wrong / stale batch in any step would show: the five per-step losses differ
+    assert len({round(float(((b["image"] ** 2).mean())), 6) for b in batches}) == len(batches)
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.allclose(p1, p2, rtol=0, atol=2e-6), k

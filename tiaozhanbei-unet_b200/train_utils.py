@@ -80,6 +80,7 @@ class CombinedLoss(nn.Module):
         self.focal_gamma = focal_gamma
         self._work = None
         self._last = None
+        self._pinned = None
 
     def _workspace(self, device):
         if self._work is None or self._work.device != device:
@@ -100,6 +101,24 @@ class CombinedLoss(nn.Module):
         """(total, recon, seg) of the most recent forward as python floats: ONE device->host copy
         instead of the three `.item()` syncs of src/train_utils.py:137-139."""
         return tuple(self._last.tolist())
+
+    def last_values_async(self):
+        """Start the device->host copy of (total, recon, seg) into pinned memory and return a callable that waits
+        for it and gives the three floats: train_epoch reads a step's losses while the next step is already
+        enqueued, so the GPU never idles on the `.item()` round trip of src/train_utils.py:137-139."""
+        if self._pinned is None:
+            self._pinned = [torch.empty(3, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._turn = 0
+        host = self._pinned[self._turn]
+        self._turn ^= 1
+        host.copy_(self._last, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+
+        def wait():
+            done.synchronize()
+            return tuple(host.tolist())
+        return wait
 
 
 class _FocalOnlyFn(torch.autograd.Function):
@@ -188,28 +207,100 @@ def _loss_values(criterion, loss_dict):
     return (loss_dict["total_loss"].item(), loss_dict["recon_loss"].item(), loss_dict["seg_loss"].item())
 
 
+def _loss_values_later(criterion, loss_dict):
+    """A callable giving the three loss floats of this step (resolved one step later by train_epoch)."""
+    if isinstance(criterion, CombinedLoss) and loss_dict["total_loss"].is_cuda:
+        return criterion.last_values_async()
+    values = _loss_values(criterion, loss_dict)
+    return lambda: values
+
+
+_prefetch = {}      # device -> {"stream": side stream, "bufs": {(name, slot, shape, dtype): device tensor}}
+
+
+def _device_batches(loader, device):
+    """Iterate `loader`, yielding (batch, images, masks) with the tensors on `device` (src/train_utils.py:118-119).
+    On a CUDA device the host->device copy of the NEXT batch is issued on a side stream before the current step
+    is enqueued, so it overlaps the step instead of preceding it (pinned loader memory makes it asynchronous).
+    The copies land in two alternating, persistent device buffers per batch shape: nothing is allocated per step,
+    and a buffer is overwritten only after the step that read it has been enqueued completely (event).  The
+    yielded tensors are therefore valid for ONE step."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        for batch in loader:
+            yield batch, batch["image"].to(device), batch["mask"].to(device)
+        return
+    state = _prefetch.get(device)
+    if state is None:
+        state = _prefetch[device] = {"stream": torch.cuda.Stream(device), "bufs": {}}
+    side, bufs = state["stream"], state["bufs"]
+    it = iter(loader)
+    released = [None, None]        # per slot: event after the last step that used the slot's buffers
+    start = torch.cuda.Event()
+    start.record(torch.cuda.current_stream(device))      # buffers may still feed work enqueued before this epoch
+
+    def load(slot):
+        try:
+            batch = next(it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(side):
+            side.wait_event(released[slot] if released[slot] is not None else start)
+            out = []
+            for name in ("image", "mask"):
+                src = batch[name]
+                key = (name, slot, tuple(src.shape), src.dtype)
+                buf = bufs.get(key)
+                if buf is None:
+                    buf = bufs[key] = torch.empty(src.shape, dtype=src.dtype, device=device)
+                buf.copy_(src, non_blocking=True)
+                out.append(buf)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        return batch, out[0], out[1], ready
+
+    k = 0
+    nxt = load(0)
+    while nxt is not None:
+        batch, images, masks, ready = nxt
+        torch.cuda.current_stream(device).wait_event(ready)
+        nxt = load((k + 1) % 2)
+        yield batch, images, masks
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(device))
+        released[k % 2] = done
+        k += 1
+
+
 def train_epoch(model, train_loader, criterion, optimizer, device, epoch):
     """Train for one epoch; returns the same dict of three running averages as the reference."""
     model.train()
     losses, recon_losses, seg_losses = AverageMeter(), AverageMeter(), AverageMeter()
     pbar = tqdm(train_loader, desc=f"Epoch {epoch}")
-    for batch_idx, batch in enumerate(pbar):
-        images = batch["image"].to(device, non_blocking=True)
-        masks = batch["mask"].to(device, non_blocking=True)
-        reconstruction, anomaly_map = model(images)
-        loss_dict = criterion(reconstruction, anomaly_map, images, masks)
-        total_loss = loss_dict["total_loss"]
-        optimizer.zero_grad()
-        total_loss.backward()
-        optimizer.step()
-        batch_size = images.size(0)
-        t, r, s = _loss_values(criterion, loss_dict)
+    def account(pending):
+        values, batch_size = pending
+        t, r, s = values()
         losses.update(t, batch_size)
         recon_losses.update(r, batch_size)
         seg_losses.update(s, batch_size)
         if hasattr(pbar, "set_postfix"):
             pbar.set_postfix({"Loss": f"{losses.avg:.4f}", "Recon": f"{recon_losses.avg:.4f}",
                               "Seg": f"{seg_losses.avg:.4f}"})
+
+    pending = None
+    for batch, images, masks in _device_batches(pbar, device):
+        reconstruction, anomaly_map = model(images)
+        loss_dict = criterion(reconstruction, anomaly_map, images, masks)
+        total_loss = loss_dict["total_loss"]
+        optimizer.zero_grad()
+        total_loss.backward()
+        optimizer.step()
+        current = (_loss_values_later(criterion, loss_dict), images.size(0))
+        if pending is not None:
+            account(pending)        # the previous step's losses: its copy finished while this step was enqueued
+        pending = current
+    if pending is not None:
+        account(pending)
     return {"total_loss": losses.avg, "recon_loss": recon_losses.avg, "seg_loss": seg_losses.avg}
 
 
