@@ -172,3 +172,41 @@ def test_graph_state_protocol(monkeypatch):
         res, replayed = st2.run(bad)
     assert res == ["eager"] and not replayed and st2.failed and st2.graph is None
     assert st2.run(bad) == (["eager"], False)                                   # stays eager
+
+
+def test_train_epoch_host_logic_on_cpu_stand_ins():
+    """The loop of train_epoch itself (src/train_utils.py:107-153) with CPU stand-ins for model / criterion /
+    optimizer: every batch is stepped once and in order, the three averages are weighted by the batch size
+    (ragged last batch), and a step's losses are accounted even though they are read one step late."""
+    import torch
+    from tiaozhanbei_unet_b200 import train_utils as T
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(1))
+            self.seen = []
+
+        def forward(self, x):
+            self.seen.append(float(x.mean()))
+            return x * self.w, x[:, :1] * self.w
+
+    class Criterion:
+        def __call__(self, recon, amap, image, mask):
+            r, s = (recon ** 2).mean(), (amap - mask).abs().mean()
+            return {"total_loss": r + s, "recon_loss": r.detach(), "seg_loss": s.detach()}
+
+    sizes = (4, 4, 3)
+    batches = [{"image": torch.full((n, 3, 4, 4), float(i + 1)), "mask": torch.zeros(n, 1, 4, 4)} for i, n in enumerate(sizes)]
+    model = Model()
+    opt = torch.optim.SGD(model.parameters(), lr=0.0)
+    out = T.train_epoch(model, batches, Criterion(), opt, torch.device("cpu"), 3)
+    assert model.seen == [1.0, 2.0, 3.0] and model.training
+    n = sum(sizes)
+    want_r = sum(s * float(i + 1) ** 2 for i, s in enumerate(sizes)) / n
+    want_s = sum(s * float(i + 1) for i, s in enumerate(sizes)) / n
+    assert abs(out["recon_loss"] - want_r) < 1e-6 and abs(out["seg_loss"] - want_s) < 1e-6
+    assert abs(out["total_loss"] - (want_r + want_s)) < 1e-6
+    assert set(out) == {"total_loss", "recon_loss", "seg_loss"}
+    # an empty loader returns the reference's zero averages
+    assert T.train_epoch(model, [], Criterion(), opt, torch.device("cpu"), 4) == {"total_loss": 0, "recon_loss": 0, "seg_loss": 0}
