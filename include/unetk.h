@@ -248,6 +248,15 @@ int unetk_anomaly_score(const float* recon, const float* orig, float* out, int n
 int unetk_pixel_confusion(const float* pred, const float* truth, const uint8_t* include, const float* thresholds,
                           int n_thresholds, float truth_threshold, int64_t* counts, int n, int64_t elems_per_image,
                           void* stream);
+/* SegmentationMetrics.update (src/metrics.py:22-45): cm[t * c + p] += 1 (int64 [c, c] on the device, ACCUMULATED)
+ * over the pixels with label t and prediction p both in [0, c) — sklearn's
+ * confusion_matrix(target, pred, labels=range(c)) — where p = argmax over the class axis of NCHW fp32 `logits`
+ * (first maximum wins), or `preds` int64 [n, elems] when logits is NULL (exactly one of the two).  With
+ * has_ignore the pixels whose label equals ignore_index are dropped first; *kept (device int64, accumulated)
+ * counts the remaining pixels (total_samples).  c <= 8. */
+int unetk_class_confusion(const float* logits, const int64_t* preds, const int64_t* target, int n, int c,
+                          int64_t elems_per_image, int64_t ignore_index, int has_ignore, int64_t* cm, int64_t* kept,
+                          void* stream);
 /* Exact order statistics of an fp32 device array (NaN orders last, as in numpy): out2[0] = k-th smallest
  * (0-based), out2[1] = (k+1)-th smallest (= out2[0] when k = n-1) — the two neighbours
  * np.percentile(all_scores, 95) interpolates between (src/train_utils.py:213).  x is not modified. */

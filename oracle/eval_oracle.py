@@ -65,3 +65,21 @@ def kth_pair(values, k):
     """The two order statistics the linear percentile interpolates: (k-th, (k+1)-th) smallest, NaN last."""
     s = np.sort(np.asarray(values, dtype=np.float32).reshape(-1))
     return s[k], s[min(k + 1, s.size - 1)]
+
+
+def class_confusion(pred, target, num_classes, ignore_index=None):
+    """SegmentationMetrics.update (src/metrics.py:22-45) for numpy inputs: (counts int64 [C, C], total_samples).
+    pred (N, C, H, W) scores -> argmax over axis 1 (first maximum) or (N, H, W) indices; pixels with the ignored
+    label are removed, then sklearn's confusion_matrix(target, pred, labels=range(C)) counts the pairs whose label
+    and prediction are both one of the C classes."""
+    pred = np.asarray(pred)
+    if pred.ndim == 4:
+        pred = np.argmax(pred, axis=1)
+    pred = pred.reshape(-1).astype(np.int64)
+    target = np.asarray(target).reshape(-1).astype(np.int64)
+    if ignore_index is not None:
+        keep = target != ignore_index
+        pred, target = pred[keep], target[keep]
+    ok = (target >= 0) & (target < num_classes) & (pred >= 0) & (pred < num_classes)
+    cm = np.bincount(target[ok] * num_classes + pred[ok], minlength=num_classes * num_classes)
+    return cm.reshape(num_classes, num_classes).astype(np.int64), int(target.size)

@@ -110,7 +110,12 @@ def test_reference_segmentation_train_script_runs_on_top_of_this_package(tmp_pat
         assert smodel.SegmentationUNet.__module__ == "tiaozhanbei_unet_b200.model"
         assert sm.CombinedSegmentationLoss.__module__ == "tiaozhanbei_unet_b200.metrics"
         assert sm.dice_loss.__module__ == "tiaozhanbei_unet_b200.metrics"
-        assert sm.SegmentationMetrics.__module__ == "src.metrics"      # reporting half stays the reference's
+        assert sm.SegmentationMetrics.__module__ == "src.metrics"      # reporting half stays the reference's ...
+        from tiaozhanbei_unet_b200.metrics import DeviceConfusion
+        calc = sm.SegmentationMetrics(4)
+        assert isinstance(calc, DeviceConfusion)                        # ... over the device-side confusion counts
+        assert type(calc).compute_all_metrics.__module__ == "src.metrics" and type(calc).update is DeviceConfusion.update
+        assert calc.confusion_matrix.shape == (4, 4) and calc.compute_all_metrics()["mean_iou"] == 0.0
         assert os.path.isdir(str(tmp_path / "out"))
     finally:
         sys.argv[:] = saved_argv

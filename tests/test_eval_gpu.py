@@ -189,3 +189,38 @@ def test_confusion_and_select_bandwidth(cuda_device):
     assert gb_conf / t_conf > 500 and gb_sel / t_sel > 100
     want = torch.sort(scores).values[k:k + 2]
     assert torch.equal(out2, want)
+
+
+SEG_CASES = [dict(), dict(ignore=255), dict(stray=True), dict(c=1), dict(c=8, ignore=7), dict(c=3, h=33, w=47),
+             dict(n=4, c=4, h=512, w=512, ignore=255)]
+
+
+@pytest.mark.parametrize("kw", SEG_CASES, ids=[str(i) for i in range(len(SEG_CASES))])
+def test_segmentation_metrics_update_is_bit_exact(cuda_device, kw):
+    """SegmentationMetrics.update (src/metrics.py:22-45) on the device: logits and index input, accumulation over
+    updates, ignored and out-of-range labels, ties and NaN in the argmax, reads between updates."""
+    from test_eval_oracle import seg_case
+    from tiaozhanbei_unet_b200 import metrics as M
+    dev = cuda_device
+    logits, target = seg_case(20 + len(kw), **kw)
+    logits[0, 0, 0, :5] = float("nan")                       # torch.argmax: a NaN is the maximum
+    c, ignore = logits.shape[1], kw.get("ignore")
+    cm, total = E.class_confusion(logits.numpy(), target.numpy(), c, ignore)
+    np.testing.assert_array_equal(torch.argmax(logits, dim=1).numpy(), np.argmax(logits.numpy(), axis=1))
+    m = M.SegmentationMetrics(c, ignore_index=ignore)
+    m.update(logits[:2].to(dev), target[:2].to(dev))                               # (N, C, H, W) scores
+    m.update(torch.argmax(logits[2:], dim=1).to(dev), target[2:].to(dev))          # (N, H, W) indices
+    np.testing.assert_array_equal(m.confusion_matrix, cm)
+    assert m.total_samples == total and m.confusion_matrix.dtype == np.int64
+    m.update(logits.to(dev), target.to(dev))                                       # counting goes on after a read
+    m.update(logits[:0].to(dev), target[:0].to(dev))                               # an empty batch adds nothing
+    np.testing.assert_array_equal(m.confusion_matrix, 2 * cm)
+    assert m.total_samples == 2 * total
+    got = m.compute_all_metrics()
+    tp, rows, cols = np.diag(2 * cm), (2 * cm).sum(1), (2 * cm).sum(0)
+    np.testing.assert_array_equal(got["iou_per_class"], tp / np.maximum(rows + cols - tp, 1e-8))
+    assert got["pixel_accuracy"] == tp.sum() / max((2 * cm).sum(), 1e-8)
+    m.reset()
+    assert m.total_samples == 0 and not m.confusion_matrix.any()
+    full = M.compute_metrics_from_predictions(logits.to(dev), target.to(dev), c)
+    np.testing.assert_array_equal(full["confusion_matrix"], E.class_confusion(logits.numpy(), target.numpy(), c)[0])

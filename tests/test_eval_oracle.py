@@ -94,3 +94,88 @@ def test_lazy_predictions_mapping():
     np.testing.assert_array_equal(p["masks_true"], torch.cat(true).numpy())
     with pytest.raises(KeyError):
         p["nope"]
+
+
+# ---------------------------------------------------------------------------------------------
+# SegmentationMetrics (src/metrics.py:9-133)
+# ---------------------------------------------------------------------------------------------
+REF_METRICS = "/root/reference/src/metrics.py"
+
+
+def seg_case(seed, n=3, c=4, h=20, w=24, ignore=None, stray=False):
+    """Seeded logits / labels: a dominant background, exact ties between channels, optional ignored / stray labels."""
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(n, c, h, w, generator=g)
+    logits[:, 0] += 1.0
+    if c > 1:
+        logits[:, 1, ::3] = logits[:, 0, ::3]              # ties: the first maximum wins
+    target = torch.randint(0, c, (n, h, w), generator=g)
+    target[torch.rand(n, h, w, generator=g) < 0.5] = 0
+    if ignore is not None:
+        target[torch.rand(n, h, w, generator=g) < 0.1] = ignore
+    if stray:
+        target[torch.rand(n, h, w, generator=g) < 0.05] = 255      # a label outside range(C) that is NOT ignored
+    return logits, target
+
+
+def _reference_metrics_module():
+    import importlib.util
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    spec = importlib.util.spec_from_file_location("_ref_metrics", REF_METRICS)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_class_confusion_oracle_is_sklearns():
+    from sklearn.metrics import confusion_matrix
+    for seed, kw in enumerate([dict(), dict(ignore=255), dict(stray=True), dict(c=1), dict(c=8, ignore=7)]):
+        logits, target = seg_case(seed, **kw)
+        c = logits.shape[1]
+        ignore = kw.get("ignore")
+        cm, total = E.class_confusion(logits.numpy(), target.numpy(), c, ignore)
+        pred = torch.argmax(logits, dim=1).numpy().reshape(-1)
+        t = target.numpy().reshape(-1)
+        if ignore is not None:
+            pred, t = pred[t != ignore], t[t != ignore]
+        np.testing.assert_array_equal(cm, confusion_matrix(t, pred, labels=range(c)))
+        assert total == t.size
+        cm2, _ = E.class_confusion(torch.argmax(logits, dim=1).numpy(), target.numpy(), c, ignore)
+        np.testing.assert_array_equal(cm, cm2)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_METRICS), reason="reference sources only exist in the build container")
+def test_segmentation_metrics_match_the_live_reference():
+    """Oracle counts == the reference's SegmentationMetrics.update; this package's compute_* formulas == the
+    reference's on those counts (every key of compute_all_metrics, exactly)."""
+    from tiaozhanbei_unet_b200 import metrics as M
+    ref = _reference_metrics_module()
+    for seed, kw in enumerate([dict(), dict(ignore=255), dict(stray=True), dict(c=8, ignore=7)]):
+        logits, target = seg_case(10 + seed, **kw)
+        c = logits.shape[1]
+        r = ref.SegmentationMetrics(c, ignore_index=kw.get("ignore"))
+        r.update(logits[:2], target[:2])
+        r.update(torch.argmax(logits[2:], dim=1), target[2:])
+        cm, total = E.class_confusion(logits.numpy(), target.numpy(), c, kw.get("ignore"))
+        np.testing.assert_array_equal(cm, r.confusion_matrix)
+        assert total == r.total_samples
+        ours = M.SegmentationMetrics(c, ignore_index=kw.get("ignore"))
+        ours.confusion_matrix = cm
+        ours.total_samples = total
+        want, got = r.compute_all_metrics(), ours.compute_all_metrics()
+        assert set(want) == set(got)
+        for k in want:
+            np.testing.assert_array_equal(np.asarray(got[k]), np.asarray(want[k]), err_msg=k)
+        assert ours.compute_iou(per_class=False) == r.compute_iou(per_class=False)
+        assert ours.compute_dice(per_class=False) == r.compute_dice(per_class=False)
+        assert ours.compute_precision_recall_f1(per_class=False) == r.compute_precision_recall_f1(per_class=False)
+    empty = M.SegmentationMetrics(3)
+    assert empty.compute_all_metrics()["mean_iou"] == ref.SegmentationMetrics(3).compute_all_metrics()["mean_iou"] == 0.0
+    with pytest.raises(NotImplementedError):
+        M.SegmentationMetrics(9)
+    with pytest.raises(RuntimeError):
+        M.SegmentationMetrics(4).update(torch.zeros(1, 4, 2, 2), torch.zeros(1, 2, 2, dtype=torch.long))

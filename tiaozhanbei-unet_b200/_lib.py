@@ -57,6 +57,7 @@ SIGNATURES = {
     "unetk_upsample2x_fwd": (I, [P, P, I, I, I, I, P]),
     "unetk_upsample2x_bwd": (I, [P, P, I, I, I, I, I, P]),
     "unetk_pixel_confusion": (I, [P, P, P, P, I, F, P, I, L, P]),
+    "unetk_class_confusion": (I, [P, P, P, I, I, L, L, I, P, P, P]),
     "unetk_select_workspace_bytes": (Z, []),
     "unetk_select_kth": (I, [P, L, L, P, P, Z, P]),
     "unetk_resize_ksize": (I, [I, I]),

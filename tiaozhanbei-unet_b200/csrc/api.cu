@@ -192,6 +192,14 @@ int unetk_pixel_confusion(const float* pred, const float* truth, const uint8_t* 
   return unetk::pixel_confusion(pred, truth, include, thresholds, n_thresholds, truth_threshold,
                                 reinterpret_cast<long long*>(counts), n, static_cast<long>(elems_per_image), S(stream));
 }
+int unetk_class_confusion(const float* logits, const int64_t* preds, const int64_t* target, int n, int c,
+                          int64_t elems_per_image, int64_t ignore_index, int has_ignore, int64_t* cm, int64_t* kept,
+                          void* stream) {
+  return unetk::class_confusion(logits, reinterpret_cast<const long long*>(preds),
+                                reinterpret_cast<const long long*>(target), n, c, static_cast<long>(elems_per_image),
+                                static_cast<long long>(ignore_index), has_ignore, reinterpret_cast<long long*>(cm),
+                                reinterpret_cast<long long*>(kept), S(stream));
+}
 size_t unetk_select_workspace_bytes(void) { return unetk::select_workspace_bytes(); }
 int unetk_select_kth(const float* x, int64_t n, int64_t k, float* out2, void* workspace, size_t workspace_bytes,
                      void* stream) {

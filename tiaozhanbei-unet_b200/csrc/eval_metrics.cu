@@ -108,6 +108,65 @@ pixel_confusion_kernel(const float* __restrict__ pred, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// SegmentationMetrics.update (src/metrics.py:22-45): torch.argmax over the class axis fused with
+// sklearn's confusion_matrix(target, pred, labels=range(C)): cm[t, p] += 1 for the pixels whose label and
+// prediction are both in [0, C); pixels with target == ignore_index are dropped first and `kept` counts the
+// rest (total_samples).  Integer work, bit-exact.  One pass over the logits (or the predicted indices) and
+// the labels; equal (t, p) pairs of a warp are combined before the shared-memory histogram (the background
+// class dominates).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxClasses = 8;
+
+template <bool LOGITS>
+__global__ void __launch_bounds__(256)
+class_confusion_kernel(const float* __restrict__ logits, const long long* __restrict__ preds,
+                       const long long* __restrict__ target, int C, long hw, long total, long long ignore_index,
+                       int has_ignore, unsigned long long* __restrict__ cm, unsigned long long* __restrict__ kept) {
+  __shared__ unsigned h[kMaxClasses * kMaxClasses + 1];
+  for (int i = threadIdx.x; i <= kMaxClasses * kMaxClasses; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long rounded = (total + 31) & ~31L;      // whole warps stay in the loop together (warp-wide votes below)
+  for (long p = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; p < rounded;
+       p += static_cast<long>(gridDim.x) * blockDim.x) {
+    int bin = -1;
+    bool keep = false;
+    if (p < total) {
+      const long long t = target[p];
+      if (!(has_ignore && t == ignore_index)) {
+        keep = true;
+        long long pr;
+        if (LOGITS) {
+          const long n = p / hw, r = p - n * hw;
+          const float* b = logits + n * C * hw + r;
+          float best = __ldg(b);
+          int bi = 0;
+          for (int c = 1; c < C; ++c) {
+            const float v = __ldg(b + c * hw);
+            if (v > best || (v != v && best == best)) {   // first maximum wins, NaN counts as the maximum (ATen)
+              best = v;
+              bi = c;
+            }
+          }
+          pr = bi;
+        } else {
+          pr = preds[p];
+        }
+        if (t >= 0 && t < C && pr >= 0 && pr < C) bin = static_cast<int>(t) * C + static_cast<int>(pr);
+      }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&h[bin], static_cast<unsigned>(__popc(peers)));
+    const unsigned kept_lanes = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0 && kept_lanes) atomicAdd(&h[kMaxClasses * kMaxClasses], static_cast<unsigned>(__popc(kept_lanes)));
+  }
+  __syncthreads();
+  if (threadIdx.x < C * C && h[threadIdx.x]) atomicAdd(cm + threadIdx.x, static_cast<unsigned long long>(h[threadIdx.x]));
+  if (threadIdx.x == kMaxClasses * kMaxClasses && h[threadIdx.x])
+    atomicAdd(kept, static_cast<unsigned long long>(h[threadIdx.x]));
+}
+
+// ---------------------------------------------------------------------------------------------
 // radix selection on the order-preserving 32-bit key of an fp32 value (NaN orders last, like numpy)
 // ---------------------------------------------------------------------------------------------
 struct SelectState {
@@ -282,6 +341,25 @@ int select_kth(const float* x, long n, long k, float* out2, void* workspace, siz
       select_next_kernel<false><<<blocks, 256, 0, s>>>(x, n, st);
   }
   select_finish_kernel<<<1, 1, 0, s>>>(st, out2, has_next);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int class_confusion(const float* logits, const long long* preds, const long long* target, int n, int c, long hw,
+                    long long ignore_index, int has_ignore, long long* cm, long long* kept, cudaStream_t s) {
+  UNETK_CHECK_ARG((logits != nullptr) != (preds != nullptr), "class_confusion: exactly one of logits / preds");
+  UNETK_CHECK_ARG(target && cm && kept, "class_confusion: null pointer");
+  UNETK_CHECK_ARG(c >= 1 && c <= kMaxClasses, "class_confusion: 1..%d classes, got %d", kMaxClasses, c);
+  UNETK_CHECK_ARG(n >= 0 && hw >= 0, "class_confusion: bad sizes");
+  const long total = static_cast<long>(n) * hw;
+  if (total == 0) return UNETK_OK;
+  const int blocks = capped_blocks(total, 8);
+  auto* m = reinterpret_cast<unsigned long long*>(cm);
+  auto* k = reinterpret_cast<unsigned long long*>(kept);
+  if (logits != nullptr)
+    class_confusion_kernel<true><<<blocks, 256, 0, s>>>(logits, nullptr, target, c, hw, total, ignore_index, has_ignore, m, k);
+  else
+    class_confusion_kernel<false><<<blocks, 256, 0, s>>>(nullptr, preds, target, c, hw, total, ignore_index, has_ignore, m, k);
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }

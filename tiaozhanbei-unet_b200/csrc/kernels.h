@@ -114,6 +114,8 @@ int upsample2x_bwd(const void* dout, void* dx, int N, int H, int W, int C, int a
 int pixel_confusion(const float* pred, const float* truth, const unsigned char* include, const float* thresholds,
                     int n_thresholds, float truth_threshold, long long* counts, int n, long elems_per_image,
                     cudaStream_t s);
+int class_confusion(const float* logits, const long long* preds, const long long* target, int n, int c, long hw,
+                    long long ignore_index, int has_ignore, long long* cm, long long* kept, cudaStream_t s);
 size_t select_workspace_bytes();
 int select_kth(const float* x, long n, long k, float* out2, void* workspace, size_t workspace_bytes, cudaStream_t s);
 int resize_ksize(int in_size, int out_size);

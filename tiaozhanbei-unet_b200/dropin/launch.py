@@ -10,8 +10,9 @@ script with runpy as __main__ from its own directory, so its `utils` and `datase
 
 The repository-root scripts of the segmentation pipelines (train.py, test.py, train_kolektorsdd.py ...)
 import `src.model` / `src.metrics` instead (train.py:20-23): for them `src.model` is this package's
-model module and `src.metrics` is the reference's own file (confusion matrix, reports) with its three
-loss entry points (src/metrics.py:233-335) replaced by this package's kernels; `src.utils` and the
+model module and `src.metrics` is the reference's own file (reports, plots) with its three loss entry points
+(src/metrics.py:233-335) replaced by this package's kernels and `SegmentationMetrics` re-based on the
+device-side confusion counts (its `compute_*` / `print_metrics` / `plot_confusion_matrix` stay the reference's); `src.utils` and the
 dataset modules stay the reference's.
 """
 from __future__ import annotations
@@ -74,6 +75,11 @@ def install_src_package(root: str):
     spec.loader.exec_module(mod)       # the reference's SegmentationMetrics etc., unmodified
     for name in ("dice_loss", "focal_loss", "CombinedSegmentationLoss"):
         setattr(mod, name, getattr(_metrics, name))
+    # SegmentationMetrics: the reference's own class (compute_* / print / plot unmodified) over the device-side
+    # counts: `update` runs in every training step (train.py:146)
+    reference_cls = mod.SegmentationMetrics
+    mod.SegmentationMetrics = type("SegmentationMetrics", (_metrics.DeviceConfusion, reference_cls),
+                                   {"__doc__": reference_cls.__doc__, "__module__": "src.metrics"})
     sys.modules["src.metrics"] = mod
 
 

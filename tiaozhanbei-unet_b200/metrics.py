@@ -10,11 +10,19 @@
 Same names, argument meaning and error behaviour (e.g. focal with `ignore_index=None` raises the
 TypeError F.cross_entropy raises in the reference).  One forward launch computes the cross entropy, dice
 and focal sums in a single pass over the logits, one backward launch the gradient of their weighted sum;
-there is no CPU path.  The confusion-matrix half of src/metrics.py (`SegmentationMetrics`, sklearn,
-matplotlib) is host-side reporting and stays the reference's.
+there is no CPU path.
+
+    SegmentationMetrics(num_classes, ignore_index=None).update(pred, target)   src/metrics.py:9-45
+
+`update` runs in every step of the segmentation training loops (train.py:146): the reference copies the logits
+to the host, takes the argmax there and calls sklearn's confusion_matrix.  Here one kernel fuses the argmax with
+the C x C counts and accumulates them on the device; the matrix comes to the host when a `compute_*` method (or
+`.confusion_matrix`) is read, i.e. once per epoch.  The derived metrics (src/metrics.py:47-133) are the same
+numpy formulas; plotting stays the reference's.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 from torch import nn
 from torch.autograd.function import once_differentiable
@@ -127,3 +135,126 @@ def argmax_predictions(logits):
     z = logits.detach().float().contiguous()
     out = torch.empty(z.shape[0], z.shape[2], z.shape[3], dtype=torch.int64, device=z.device)
     return ops.argmax_channels(z, out)
+
+
+class DeviceConfusion:
+    """The state half of `SegmentationMetrics` (src/metrics.py:12-45) with the counts kept on the device.
+    `confusion_matrix` / `total_samples` read like the reference's attributes (numpy int64 [C, C] / int) and
+    synchronise; assigning to them (as `reset` does) is supported.  Also used as a mix-in over the reference's own
+    class by `dropin.launch`, whose `compute_*` methods then run unmodified."""
+
+    def __init__(self, num_classes, ignore_index=None):
+        if num_classes > 8:
+            raise NotImplementedError("at most 8 classes are supported by the confusion kernel")
+        self.num_classes = num_classes
+        self.ignore_index = ignore_index
+        self.reset()
+
+    def reset(self):
+        self._cm_host = np.zeros((self.num_classes, self.num_classes), dtype=np.int64)
+        self._kept_host = 0
+        self._dev = None           # [C * C + 1] int64: the counts since the last read, and the kept pixels
+
+    def _flush(self):
+        if self._dev is not None:
+            vals = self._dev.cpu().numpy()
+            self._cm_host = self._cm_host + vals[:-1].reshape(self.num_classes, self.num_classes)
+            self._kept_host += int(vals[-1])
+            self._dev = None
+
+    @property
+    def confusion_matrix(self):
+        self._flush()
+        return self._cm_host
+
+    @confusion_matrix.setter
+    def confusion_matrix(self, value):
+        self._flush()
+        self._cm_host = np.asarray(value, dtype=np.int64)
+
+    @property
+    def total_samples(self):
+        self._flush()
+        return self._kept_host
+
+    @total_samples.setter
+    def total_samples(self, value):
+        self._flush()
+        self._kept_host = int(value)
+
+    def update(self, pred, target):
+        """pred: (N, C, H, W) logits or (N, H, W) class indices; target: (N, H, W) labels — CUDA tensors."""
+        if not pred.is_cuda or not target.is_cuda:
+            raise RuntimeError("pred and target must be CUDA tensors: the confusion kernel has no CPU path")
+        if pred.dim() == 4:
+            if pred.shape[1] != self.num_classes:
+                # (torch.argmax over more channels than classes: indices >= num_classes fall out of the matrix,
+                # which the kernel handles for index input)
+                pred = argmax_predictions(pred)
+            else:
+                pred = pred.detach().float().contiguous()
+        if pred.dtype != torch.float32:
+            pred = pred.detach().long().contiguous()
+        target = target.detach().long().contiguous()
+        if target.numel() == 0:
+            return
+        if self._dev is None or self._dev.device != target.device:
+            self._flush()
+            self._dev = ops.zero_(torch.empty(self.num_classes * self.num_classes + 1, dtype=torch.int64,
+                                              device=target.device))
+        ops.class_confusion(pred, target, self.num_classes, self.ignore_index, self._dev[:-1], self._dev[-1:])
+
+
+class SegmentationMetrics(DeviceConfusion):
+    """src/metrics.py:9-133 without the plotting: same constructor, `update`, `compute_*` and
+    `compute_all_metrics` keys; every ratio guards its denominator with max(., 1e-8) like the reference."""
+
+    def _parts(self):
+        cm = self.confusion_matrix
+        return np.diag(cm), cm.sum(axis=1), cm.sum(axis=0)      # hits, pixels per true class, per predicted class
+
+    def compute_iou(self, per_class=True):
+        tp, rows, cols = self._parts()
+        iou = tp / np.maximum(rows + cols - tp, 1e-8)
+        return iou if per_class else np.nanmean(iou)
+
+    def compute_dice(self, per_class=True):
+        tp, rows, cols = self._parts()
+        dice = 2 * tp / np.maximum(rows + cols, 1e-8)
+        return dice if per_class else np.nanmean(dice)
+
+    def compute_pixel_accuracy(self):
+        cm = self.confusion_matrix
+        return np.diag(cm).sum() / max(cm.sum(), 1e-8)
+
+    def compute_mean_accuracy(self):
+        tp, rows, _ = self._parts()
+        return np.nanmean(tp / np.maximum(rows, 1e-8))
+
+    def compute_precision_recall_f1(self, per_class=True):
+        tp, rows, cols = self._parts()
+        precision = tp / np.maximum(tp + (cols - tp), 1e-8)
+        recall = tp / np.maximum(tp + (rows - tp), 1e-8)
+        f1 = 2 * precision * recall / np.maximum(precision + recall, 1e-8)
+        if per_class:
+            return precision, recall, f1
+        return np.nanmean(precision), np.nanmean(recall), np.nanmean(f1)
+
+    def compute_all_metrics(self):
+        iou, dice = self.compute_iou(), self.compute_dice()
+        precision, recall, f1 = self.compute_precision_recall_f1()
+        return {
+            "iou_per_class": iou, "mean_iou": np.nanmean(iou),
+            "dice_per_class": dice, "mean_dice": np.nanmean(dice),
+            "pixel_accuracy": self.compute_pixel_accuracy(), "mean_accuracy": self.compute_mean_accuracy(),
+            "precision_per_class": precision, "recall_per_class": recall, "f1_per_class": f1,
+            "mean_precision": np.nanmean(precision), "mean_recall": np.nanmean(recall), "mean_f1": np.nanmean(f1),
+            "confusion_matrix": self.confusion_matrix,
+        }
+
+
+def compute_metrics_from_predictions(predictions, targets, num_classes, class_names=None):
+    """src/metrics.py:209-230: all metrics of (N, C, H, W) / (N, H, W) predictions against (N, H, W) labels."""
+    calc = SegmentationMetrics(num_classes)
+    calc.update(predictions, targets)         # (the reference updates image by image: the same counts)
+    return calc.compute_all_metrics()

@@ -403,6 +403,32 @@ def pixel_confusion(pred, truth, include, thresholds, counts, truth_threshold=0.
     return counts
 
 
+def class_confusion(pred, target, num_classes, ignore_index, cm, kept):
+    """cm[t, p] += 1 / kept += pixels (see include/unetk.h); pred: NCHW fp32 logits or int64 [N, ...] indices."""
+    _chk(target, torch.int64, "target"); _chk(cm, torch.int64, "cm"); _chk(kept, torch.int64, "kept")
+    if cm.numel() != num_classes * num_classes or kept.numel() != 1:
+        raise ValueError("class_confusion: cm must hold num_classes^2 values, kept one")
+    n = target.shape[0] if target.dim() > 0 else 0
+    per = target.numel() // n if n else 0
+    has_ignore = ignore_index is not None
+    ii = int(ignore_index) if has_ignore else 0
+    if pred.dtype == f32:
+        _chk(pred, f32, "pred")
+        if pred.dim() != target.dim() + 1 or pred.shape[0] != n or pred.shape[1] != num_classes \
+                or pred.numel() != n * num_classes * per:
+            raise ValueError(f"class_confusion: logits {tuple(pred.shape)} do not match target {tuple(target.shape)} "
+                             f"with {num_classes} classes")
+        _lib.call("unetk_class_confusion", _p(pred), None, _p(target), n, num_classes, per, ii, int(has_ignore),
+                  _p(cm), _p(kept), _s())
+    else:
+        _chk(pred, torch.int64, "pred")
+        if pred.numel() != target.numel():
+            raise ValueError("class_confusion: predictions and target differ in size")
+        _lib.call("unetk_class_confusion", None, _p(pred), _p(target), n, num_classes, per, ii, int(has_ignore),
+                  _p(cm), _p(kept), _s())
+    return cm
+
+
 def select_kth(x, k, out2=None, work=None):
     """(k-th, (k+1)-th) smallest values of the fp32 tensor x (0-based rank, NaN last) -> fp32 [2] on the device."""
     _chk(x, f32, "x")
