@@ -74,7 +74,7 @@ def _resize(x, size, out_u8, out_f32, mean, std):
 def resize_u8(images, size, device=None):
     """`PIL.Image.resize((S, S), BILINEAR)` (what transforms.Resize does to a PIL image) on uint8 pixels:
     RGB [H, W, 3] / [N, H, W, 3] or single-channel [H, W] / [N, H, W]; same layout back, on the device."""
-    x = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(images)))
+    x = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.array(images))
     rgb = x.dim() >= 3 and x.shape[-1] == 3
     x, single = _as_u8_batch(x, 3 if rgb else 1, device)
     out, _ = _resize(x, size, True, False, None, None)
