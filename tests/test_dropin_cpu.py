@@ -125,3 +125,56 @@ def test_reference_segmentation_train_script_runs_on_top_of_this_package(tmp_pat
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+REF_KOLEKTOR_TRAIN = "/root/reference/train_kolektorsdd.py"
+
+
+def _make_kolektor_tree(root, folders=4, per_folder=3, h=60, w=30):
+    """kosNN/PartK.jpg + PartK_label.bmp (src/kolektorsdd_dataset.py:44-58)."""
+    from PIL import Image
+    rng = np.random.default_rng(2)
+    for f in range(folders):
+        d = os.path.join(root, f"kos{f + 1:02d}")
+        os.makedirs(d, exist_ok=True)
+        for k in range(per_folder):
+            Image.fromarray(rng.integers(0, 255, (h, w), dtype=np.uint8)).save(os.path.join(d, f"Part{k}.jpg"))
+            label = np.zeros((h, w), dtype=np.uint8)
+            label[10:20, 5:15] = 1 + (k % 2)
+            Image.fromarray(label).save(os.path.join(d, f"Part{k}_label.bmp"))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_KOLEKTOR_TRAIN), reason="reference sources only exist in the build container")
+def test_reference_kolektor_train_script_runs_on_top_of_this_package(tmp_path, monkeypatch):
+    """train_kolektorsdd.py (3 classes, 2:1 strips, class weights 1/50/50 by default, bilinear decoders here): same
+    wiring as the Gear script, stops at the loud no-CPU-path error of the first step."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU wiring test")
+    pytest.importorskip("torchvision")
+    pytest.importorskip("sklearn")
+    from tiaozhanbei_unet_b200 import _lib
+    from tiaozhanbei_unet_b200.dropin import launch
+    data = str(tmp_path / "KolektorSDD")
+    _make_kolektor_tree(data)
+    names = ("model", "train_utils", "matplotlib", "seaborn", "src", "src.model", "src.metrics", "src.utils",
+             "src.kolektorsdd_dataset")
+    saved_modules = {k: sys.modules.get(k) for k in names}
+    saved_argv, saved_path = list(sys.argv), list(sys.path)
+    monkeypatch.chdir(os.path.dirname(REF_KOLEKTOR_TRAIN))
+    try:
+        with pytest.raises((_lib.UnetkError, RuntimeError)) as e:
+            launch.run(REF_KOLEKTOR_TRAIN, ["--data_root", data, "--image_height", "64", "--image_width", "32",
+                                            "--epochs", "1", "--batch_size", "2", "--num_workers", "0", "--bilinear",
+                                            "--save_dir", str(tmp_path / "out"), "--device", "cpu"])
+        assert "CUDA" in str(e.value) or "CPU" in str(e.value)
+        import src.metrics as sm
+        assert sm.CombinedSegmentationLoss.__module__ == "tiaozhanbei_unet_b200.metrics"
+    finally:
+        sys.argv[:] = saved_argv
+        sys.path[:] = saved_path
+        for k, v in saved_modules.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
