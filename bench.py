@@ -361,7 +361,8 @@ def run_ours(args):
                        "streams": "decoder chains on 2 streams, weight gradients on side streams (engine.py)",
                        "weights": "reference initialiser, seed 42"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "train_utils.train_epoch(model, loader of pinned host batches, criterion, optimizer, device, epoch)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
