@@ -535,7 +535,11 @@ def test_train_epoch_prefetch_matches_the_step_loop(cuda_device):
         count += n
     for key, want in zip(("total_loss", "recon_loss", "seg_loss"), tot):
         want /= count
-        assert abs(got[key] - want) <= 1e-3 * abs(want), (key, got[key], want)
+        # (two runs of the same step differ in the last bits — atomics — and bf16 storage turns some of those into
+        # rounding flips: the small focal term moves by a few 1e-4; a stale batch would move the reconstruction
+        # term, whose batches differ by up to 9x, by tens of percent)
+        tol = 5e-3 if key == "seg_loss" else 1e-3
+        assert abs(got[key] - want) <= tol * abs(want), (key, got[key], want)
     # every batch is different, so a wrong / stale batch in any step would show: the five per-step losses differ
     assert len({round(float(((b["image"] ** 2).mean())), 6) for b in batches}) == len(batches)
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
