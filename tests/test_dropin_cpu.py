@@ -178,3 +178,56 @@ def test_reference_kolektor_train_script_runs_on_top_of_this_package(tmp_path, m
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+REF_TEST = "/root/reference/src/test.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TEST), reason="reference sources only exist in the build container")
+def test_reference_test_script_loads_our_checkpoint(tmp_path, monkeypatch, capsys):
+    """src/test.py: dataset with anomalous test images + masks, AnomalyUNet from OUR module, a checkpoint in the
+    reference's dict layout (src/utils.py:37-58) loaded by the reference's own load_checkpoint with strict keys,
+    then test_model stops at the loud no-CPU-path error of the first forward."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU wiring test")
+    pytest.importorskip("torchvision")
+    from PIL import Image
+    from tiaozhanbei_unet_b200 import _lib
+    from tiaozhanbei_unet_b200.dropin import launch
+    from tiaozhanbei_unet_b200.model import AnomalyUNet
+    data = str(tmp_path / "mvtec")
+    _make_mvtec_tree(data)
+    rng = np.random.default_rng(3)
+    for sub, mode in (("test/scratch", "rgb"), ("ground_truth/scratch", "mask")):
+        d = os.path.join(data, "synth", sub)
+        os.makedirs(d, exist_ok=True)
+        for i in range(2):
+            if mode == "rgb":
+                Image.fromarray(rng.integers(0, 255, (40, 40, 3), dtype=np.uint8)).save(os.path.join(d, f"{i:03d}.png"))
+            else:
+                m = np.zeros((40, 40), dtype=np.uint8)
+                m[5:15, 5:15] = 255
+                Image.fromarray(m).save(os.path.join(d, f"{i:03d}_mask.png"))
+    ckpt = str(tmp_path / "ckpt.pth")
+    torch.manual_seed(0)
+    torch.save({"epoch": 3, "model_state_dict": AnomalyUNet(3).state_dict(), "optimizer_state_dict": {}, "loss": 0.25}, ckpt)
+    saved_modules = {k: sys.modules.get(k) for k in ("model", "train_utils", "utils", "dataset", "matplotlib", "seaborn")}
+    saved_argv, saved_path = list(sys.argv), list(sys.path)
+    monkeypatch.chdir(os.path.dirname(REF_TEST))
+    try:
+        with pytest.raises((_lib.UnetkError, RuntimeError)) as e:
+            launch.run(REF_TEST, ["--data_root", data, "--category", "synth", "--image_size", "32", "--batch_size", "2",
+                                  "--num_workers", "0", "--model", "anomaly_unet", "--checkpoint", ckpt,
+                                  "--threshold", "0.5", "--output_dir", str(tmp_path / "res"), "--device", "cpu"])
+        assert "CUDA" in str(e.value) or "CPU" in str(e.value)
+        out = capsys.readouterr().out
+        assert "Test samples: 4" in out and "epoch 3, loss 0.2500" in out and "Testing model..." in out
+    finally:
+        sys.argv[:] = saved_argv
+        sys.path[:] = saved_path
+        for k, v in saved_modules.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
