@@ -231,3 +231,46 @@ def test_reference_test_script_loads_our_checkpoint(tmp_path, monkeypatch, capsy
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+REF_SEG_TEST = "/root/reference/test.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SEG_TEST), reason="reference sources only exist in the build container")
+def test_reference_segmentation_test_script_loads_our_checkpoint(tmp_path, monkeypatch, capsys):
+    """Root test.py (Gear evaluation): 4-class SegmentationUNet from OUR module + a checkpoint in the reference's dict
+    layout through the reference's load_checkpoint, then evaluate_model stops at the loud no-CPU-path error."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU wiring test")
+    pytest.importorskip("torchvision")
+    pytest.importorskip("sklearn")
+    from tiaozhanbei_unet_b200 import _lib
+    from tiaozhanbei_unet_b200.dropin import launch
+    from tiaozhanbei_unet_b200.model import SegmentationUNet
+    data = str(tmp_path / "Gear")
+    _make_gear_tree(data)
+    ckpt = str(tmp_path / "seg.pth")
+    torch.manual_seed(0)
+    torch.save({"epoch": 7, "model_state_dict": SegmentationUNet(3, 4).state_dict(), "optimizer_state_dict": {}, "loss": 0.125}, ckpt)
+    names = ("model", "train_utils", "matplotlib", "seaborn", "src", "src.model", "src.metrics", "src.utils",
+             "src.gear_dataset")
+    saved_modules = {k: sys.modules.get(k) for k in names}
+    saved_argv, saved_path = list(sys.argv), list(sys.path)
+    monkeypatch.chdir(os.path.dirname(REF_SEG_TEST))
+    try:
+        with pytest.raises((_lib.UnetkError, RuntimeError)) as e:
+            launch.run(REF_SEG_TEST, ["--data_root", data, "--image_size", "32", "--batch_size", "2", "--num_workers", "0",
+                                      "--model", "seg_unet", "--checkpoint", ckpt, "--save_dir", str(tmp_path / "res"),
+                                      "--device", "cpu"])
+        assert "CUDA" in str(e.value) or "CPU" in str(e.value)
+        out = capsys.readouterr().out
+        assert "epoch 7" in out and "0.1250" in out and "Model parameters: 31,0" in out
+    finally:
+        sys.argv[:] = saved_argv
+        sys.path[:] = saved_path
+        for k, v in saved_modules.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
