@@ -222,5 +222,8 @@ def test_segmentation_metrics_update_is_bit_exact(cuda_device, kw):
     assert got["pixel_accuracy"] == tp.sum() / max((2 * cm).sum(), 1e-8)
     m.reset()
     assert m.total_samples == 0 and not m.confusion_matrix.any()
+    m.update(logits, target.to(dev))                                               # host tensors are moved, not refused
+    m.update(torch.argmax(logits, dim=1), target)
+    np.testing.assert_array_equal(m.confusion_matrix, 2 * cm)
     full = M.compute_metrics_from_predictions(logits.to(dev), target.to(dev), c)
     np.testing.assert_array_equal(full["confusion_matrix"], E.class_confusion(logits.numpy(), target.numpy(), c)[0])

@@ -183,9 +183,13 @@ class DeviceConfusion:
         self._kept_host = int(value)
 
     def update(self, pred, target):
-        """pred: (N, C, H, W) logits or (N, H, W) class indices; target: (N, H, W) labels — CUDA tensors."""
+        """pred: (N, C, H, W) logits or (N, H, W) class indices; target: (N, H, W) labels.  Host tensors (the
+        reference accepts them) are copied to the GPU: the counting itself has no CPU path."""
         if not pred.is_cuda or not target.is_cuda:
-            raise RuntimeError("pred and target must be CUDA tensors: the confusion kernel has no CPU path")
+            if not torch.cuda.is_available():
+                raise RuntimeError("pred and target must be CUDA tensors: the confusion kernel has no CPU path")
+            dev = pred.device if pred.is_cuda else (target.device if target.is_cuda else torch.device("cuda"))
+            pred, target = pred.to(dev), target.to(dev)
         if pred.dim() == 4:
             if pred.shape[1] != self.num_classes:
                 # (torch.argmax over more channels than classes: indices >= num_classes fall out of the matrix,
