@@ -161,8 +161,8 @@ def _geometry(flip, angle, w, h):
     m[2], m[5] = m[0] * x + m[1] * y + m[2], m[3] * x + m[4] * y + m[5]
     m[2] += cx
     m[5] += cy
-    if m[1] == 0 and m[3] == 0:
-        raise NotImplementedError("rotation angles that reduce to a pure scale are not supported")
+    # (angles so small that sin rounds to 0 make Pillow take its scale-only path, which samples the same pixels as
+    # the fixed-point formula below: identity for cos = 1, the 180 degree mirror for cos = -1)
     return [1, int(flip), _fix16(m[0]), _fix16(m[1]), _fix16(m[2] + m[0] * 0.5 + m[1] * 0.5),
             _fix16(m[3]), _fix16(m[4]), _fix16(m[5] + m[3] * 0.5 + m[4] * 0.5)]
 
