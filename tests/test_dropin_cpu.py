@@ -14,6 +14,13 @@ sys.path.insert(0, ROOT)
 REF_TRAIN = "/root/reference/src/train.py"
 
 
+def _drop_plot_stubs():
+    """The launcher's stand-ins for matplotlib / seaborn sub-modules must not outlive a test."""
+    for k in [k for k in sys.modules if k.split(".")[0] in ("matplotlib", "seaborn")]:
+        if getattr(sys.modules[k], "__file__", None) is None:
+            del sys.modules[k]
+
+
 def _make_mvtec_tree(root, category="synth", n_train=4, n_test=2, size=40):
     from PIL import Image
     rng = np.random.default_rng(0)
@@ -58,6 +65,7 @@ def test_reference_train_script_runs_on_top_of_this_package(tmp_path, monkeypatc
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+        _drop_plot_stubs()
 
 
 REF_SEG_TRAIN = "/root/reference/train.py"
@@ -125,6 +133,7 @@ def test_reference_segmentation_train_script_runs_on_top_of_this_package(tmp_pat
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+        _drop_plot_stubs()
 
 
 REF_KOLEKTOR_TRAIN = "/root/reference/train_kolektorsdd.py"
@@ -178,6 +187,7 @@ def test_reference_kolektor_train_script_runs_on_top_of_this_package(tmp_path, m
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+        _drop_plot_stubs()
 
 
 REF_TEST = "/root/reference/src/test.py"
@@ -231,6 +241,7 @@ def test_reference_test_script_loads_our_checkpoint(tmp_path, monkeypatch, capsy
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+        _drop_plot_stubs()
 
 
 REF_SEG_TEST = "/root/reference/test.py"
@@ -274,3 +285,4 @@ def test_reference_segmentation_test_script_loads_our_checkpoint(tmp_path, monke
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+        _drop_plot_stubs()

@@ -45,7 +45,12 @@ class _Anything:
 
 def _stub(name):
     mod = types.ModuleType(name)
-    mod.__getattr__ = lambda attr: _Anything()
+
+    def absorb(attr):
+        if attr.startswith("__"):          # no fake __file__ / __path__ / __spec__: tools that scan sys.modules read them
+            raise AttributeError(attr)
+        return _Anything()
+    mod.__getattr__ = absorb
     sys.modules[name] = mod
     return mod
 
