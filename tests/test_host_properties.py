@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import preprocess_oracle as P  # noqa: E402
 
-SETTINGS = dict(max_examples=60, deadline=None)
+SETTINGS = dict(max_examples=60, deadline=None, derandomize=True, database=None)      # same examples every run
 
 
 @settings(**SETTINGS)
@@ -39,7 +39,7 @@ def test_resize_tables_equal_the_oracles(a, b):
     assert np.array_equal(ops.resize_nearest_table(a, b), P.nearest_table(a, b))
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True, database=None)
 @given(h=st.integers(1, 40), w=st.integers(1, 40), oh=st.integers(1, 40), ow=st.integers(1, 40), seed=st.integers(0, 999))
 def test_resize_oracle_equals_pillow_for_any_size(h, w, oh, ow, seed):
     from PIL import Image
@@ -68,7 +68,7 @@ def test_rotation_coefficients_equal_the_oracles(angle, w, h, flip):
         assert g[0] == 1 and tuple(g[2:]) == P.affine_fixed_coeffs(P.rotate_matrix(a, w, h))
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True, database=None)
 @given(angle=st.floats(-180, 180), seed=st.integers(0, 999), h=st.integers(2, 48), w=st.integers(2, 48))
 def test_rotation_oracle_equals_pillow_for_any_angle(angle, seed, h, w):
     from PIL import Image
