@@ -10,8 +10,9 @@ script is launched with torch.distributed.run, one rank per GPU; the batch is sh
 (weak scaling: 16 images per GPU) and gradients are averaged with bucketed NCCL all-reduce.
 
 One JSON line on stdout (rank 0).  `value` = images/s with the batch already resident in HBM;
-`e2e` = the same loop through the public API with pinned HOST batches: H2D copy of image+mask and
-D2H read of the three loss scalars inside the timed region.  `roofline` = the dominant kernel
+`e2e` = the same steps through the public API — train_utils.train_epoch, the call src/train.py makes — over a
+loader of pinned HOST batches: H2D copy of image+mask and D2H read of the three loss scalars of every step inside
+the timed region.  `roofline` = the dominant kernel
 family (tcgen05 conv3x3 implicit GEMM: fwd + dgrad + wgrad launches), algorithmic FLOPs / CUDA-event
 time of exactly those launches, measured in an instrumented pass of the same step.
 """
