@@ -143,24 +143,37 @@ def cpu_reference_rate(steps, warmup, budget_s):
         run(b, 2 + i)
     times = [run(b, 2 + warmup + i) for i in range(steps)]
     rate = b / statistics.median(times)
+    cpu_reference_rate.last_step_ms = 1e3 * statistics.median(times)
     return rate, threads, f"AnomalyUNet train step (fwd+loss+bwd+Adam, fp32) on {b} of the {PER_GPU_BATCH} images of a 256x256 batch, " \
                           f"{steps} timed steps after {warmup} warm-up, median"
 
 
+def workload_config(world):
+    """`config` of the JSON line: the same dict on both arms (the reference arm times the same workload)."""
+    return {"workload": "AnomalyUNet train 256x256, CombinedLoss(MSE+focal), Adam lr1e-3 wd1e-4 — BASELINE configs[1]",
+            "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world,
+            "parallelism": f"dp{world} (batch-sharded, bucketed NCCL all-reduce overlapped with backward, local BN)",
+            "l2": "no explicit flush: one step streams ~8 GB of activations, far beyond the 126 MB L2",
+            "streams": "decoder chains on 2 streams, weight gradients on side streams (engine.py)",
+            "weights": "reference initialiser, seed 42"}
+
+
 def run_reference(args):
+    """The reference's algorithm for this path on the box's host cores (all threads), K timed steps after W warm-up
+    steps exactly as asked; every step is a bounded sample of the workload's batch (see `cpu_baseline.sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 1))
-    rate, threads, sample = cpu_reference_rate(steps, warmup, budget_s=150.0)
+    t0 = time.perf_counter()
+    rate, threads, sample = cpu_reference_rate(args.steps, args.warmup, budget_s=150.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "AnomalyUNet train 256x256, CombinedLoss(MSE+focal), Adam — BASELINE configs[1]",
-                   "per_gpu_batch": PER_GPU_BATCH, "device": "host CPU (reference algorithm, PyTorch fp32 ops)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": cpu_reference_rate.last_step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "device": "host CPU (reference algorithm restated in oracle/unet_oracle.py, PyTorch fp32 ops)",
+                         "wall_s": round(time.perf_counter() - t0, 1)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -355,12 +368,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "AnomalyUNet train 256x256, CombinedLoss(MSE+focal), Adam lr1e-3 wd1e-4 — BASELINE configs[1]",
-                       "per_gpu_batch": B, "global_batch": B * world,
-                       "parallelism": f"dp{world} (batch-sharded, bucketed NCCL all-reduce overlapped with backward, local BN)",
-                       "l2": "no explicit flush: one step streams ~8 GB of activations, far beyond the 126 MB L2",
-                       "streams": "decoder chains on 2 streams, weight gradients on side streams (engine.py)",
-                       "weights": "reference initialiser, seed 42"},
+            "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "api": "train_utils.train_epoch(model, loader of pinned host batches, criterion, optimizer, device, epoch)"},

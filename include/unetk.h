@@ -73,7 +73,9 @@ typedef struct {
   float* shift;
   float* mean;
   float* invstd;
-  float count;               /* N*H*W */
+  double count;              /* N*H*W (x world size with synchronised statistics): exact beyond 2^24 */
+  double inv_count;          /* 1 / count: written by the library at launch, callers leave it 0 */
+  float unbias;              /* count / (count - 1) for running_var's unbiased variance: likewise written at launch */
   float eps;
   float momentum;
 } unetk_bn_finalize_args;
@@ -84,6 +86,10 @@ const char* unetk_last_error(void);
 int unetk_check_device(void);
 /* cudaMemsetAsync on the caller's stream (zeroing statistics / gradient accumulators). */
 int unetk_memset_zero(void* ptr, size_t bytes, void* stream);
+/* Diagnostics (tools/timeline.py): a one-thread kernel that stores the GPU's %globaltimer (ns) into *slot when
+ * everything enqueued before it on `stream` has finished.  Works inside CUDA-graph capture, so a replayed
+ * step can be laid out kernel by kernel and stream by stream without a profiler. */
+int unetk_debug_stamp(uint64_t* slot, void* stream);
 
 /* ---- nn.Conv2d(Cin, Cout, 3, padding=1, bias=False): src/model.py:14,17 -------------------- */
 /* y[n,h,w,co] = sum_{tap,ci} cat(src1,src2)[n,h+dy,w+dx,ci] * Wf[co][tap][ci]   (tcgen05 implicit

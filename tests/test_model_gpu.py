@@ -544,3 +544,101 @@ def test_train_epoch_prefetch_matches_the_step_loop(cuda_device):
     assert len({round(float(((b["image"] ** 2).mean())), 6) for b in batches}) == len(batches)
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         assert torch.allclose(p1, p2, rtol=0, atol=2e-6), k
+
+
+def test_gradient_accumulation_adds_up(cuda_device):
+    """Two backward passes before the optimizer step (gradient accumulation, or zero_grad(set_to_none=False)):
+    `.grad` is a view of the engine's flat gradient buffer, which the second backward rewrites — the engine must
+    hand autograd the new gradients in fresh storage so that AccumulateGrad leaves old + new, here checked against
+    the oracle's two gradients (head-side tensors tightly, the rest by direction / norm like every gradient test)."""
+    from tiaozhanbei_unet_b200 import train_utils
+    dev = cuda_device
+    arch = "anomaly_unet"
+    sd = O.synthetic_state_dict(arch, seed=5, device=dev)
+    m = _model(arch, {k: v.clone() for k, v in sd.items()}, dev).train()
+    crit = train_utils.CombinedLoss()
+    opt = train_utils.get_optimizer(m, "adam", 1e-3, 0.0)
+    batches = [_inputs(11, 2, 32, 32, dev), _inputs(12, 2, 32, 32, dev)]
+    opt.zero_grad()
+    firsts = None
+    for image, mask in batches:
+        _train_step_ours(m, arch, image, mask, crit)
+        if firsts is None:
+            firsts = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    torch.cuda.synchronize()
+    eng = m._engine()
+    # the accumulated gradients still live in the flat buffer (one fused optimizer launch)
+    assert all(p.grad.untyped_storage().data_ptr() == eng.flat_g.untyped_storage().data_ptr() for p in m.parameters())
+    # running statistics differ between the two oracle steps: replay them in order on one state dict
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    total = None
+    for image, mask in batches:
+        _, g = O.train_step(ref_sd, image, mask, arch=arch)
+        total = g if total is None else {k: total[k] + g[k] for k in g}
+    _check_grads(m.named_parameters(), total, "accumulated")
+    # and it is NOT twice the last gradient nor the last gradient alone (the failure modes of aliased storage)
+    k = "outc_seg.conv.weight"
+    got = dict(m.named_parameters())[k].grad
+    _, g_last = O.train_step({kk: v.clone() for kk, v in sd.items()}, *batches[1], arch=arch)
+    assert (got - 2 * g_last[k]).norm() > 0.05 * got.norm() and (got - g_last[k]).norm() > 0.05 * got.norm()
+    assert (got - firsts[k] - g_last[k]).norm() <= 5e-2 * got.norm()
+    # zero_grad(set_to_none=False) keeps the views; the next backward must give that step's gradient alone
+    opt.zero_grad(set_to_none=False)
+    _train_step_ours(m, arch, *batches[0], crit)
+    torch.cuda.synchronize()
+    assert (dict(m.named_parameters())[k].grad - firsts[k]).norm() <= 5e-2 * firsts[k].norm()
+    opt.step()
+    torch.cuda.synchronize()
+
+
+def test_backward_after_any_other_forward_raises(cuda_device):
+    """The BatchNorm statistics / scale / shift and the packed weights are per engine: a forward of ANOTHER shape or
+    an eval forward between a training forward and its backward invalidates them, and backward must say so instead
+    of using the wrong statistics."""
+    from tiaozhanbei_unet_b200 import train_utils
+    dev = cuda_device
+    m = _model("anomaly_unet", O.synthetic_state_dict("anomaly_unet", seed=2), dev).train()
+    crit = train_utils.CombinedLoss()
+    image, mask = _inputs(1, 2, 32, 32, dev)
+    other, _ = _inputs(2, 1, 48, 32, dev)
+    for intruder in ("train_other_shape", "eval_same_shape"):
+        m.train()
+        r, a = m(image)
+        loss = crit(r, a, image, mask)["total_loss"]
+        if intruder == "train_other_shape":
+            with torch.no_grad():
+                m(other)
+        else:
+            m.eval()
+            with torch.no_grad():
+                m(image)
+            m.train()
+        with pytest.raises(RuntimeError, match="another forward"):
+            loss.backward()
+    # and the normal order still works afterwards
+    r, a = m(image)
+    crit(r, a, image, mask)["total_loss"].backward()
+    torch.cuda.synchronize()
+
+
+def test_plan_cache_is_lru(cuda_device):
+    """Four live input shapes (train, ragged train, validation, ragged validation) must not evict the training plan
+    every epoch: the cache holds UNETK_MAX_PLANS (4) plans and drops the least recently used one."""
+    from tiaozhanbei_unet_b200 import engine as E
+    dev = cuda_device
+    m = _model("unet", O.synthetic_state_dict("unet", seed=2), dev).eval()
+    eng = m._engine()
+    shapes = [(2, 32, 32), (1, 32, 32), (2, 16, 48), (1, 16, 48)]
+    assert E.MAX_PLANS >= 4
+    with torch.no_grad():
+        for n, h, w in shapes:
+            m(torch.zeros(n, 3, h, w, device=dev))
+        train_plan = eng.plans[shapes[0]]
+        m(torch.zeros(*((shapes[0][0], 3) + shapes[0][1:]), device=dev))       # touch the oldest: now most recent
+        for i in range(E.MAX_PLANS - 3):
+            m(torch.zeros(1, 3, 16 * (i + 1), 64, device=dev))                 # new shapes until one must go
+        m(torch.zeros(3, 3, 16, 16, device=dev))
+    assert eng.plans.get(shapes[0]) is train_plan, "the most recently used plan was evicted"
+    assert shapes[1] not in eng.plans, "the least recently used plan should have been evicted"
+    assert len(eng.plans) == E.MAX_PLANS
+    torch.cuda.synchronize()

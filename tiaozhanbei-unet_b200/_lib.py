@@ -20,6 +20,7 @@ SIGNATURES = {
     "unetk_last_error": (c_char_p, []),
     "unetk_check_device": (I, []),
     "unetk_memset_zero": (I, [P, Z, P]),
+    "unetk_debug_stamp": (I, [P, P]),
     "unetk_conv3x3_fwd": (I, [P, I, P, I, P, P, P, P, P, I, I, I, I, I, I, I, P]),
     "unetk_conv3x3_dgrad": (I, [P, I, P, P, I, I, P, I, I, P, P, I, I, I, I, I, P]),
     "unetk_conv3x3_wgrad": (I, [P, P, I, P, I, P, I, I, I, I, I, I, P]),
@@ -92,7 +93,8 @@ class BnFinalizeArgs(ctypes.Structure):
     """Mirror of `unetk_bn_finalize_args` (include/unetk.h)."""
     _fields_ = [("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p),
                 ("running_var", c_void_p), ("num_batches_tracked", c_void_p), ("scale", c_void_p), ("shift", c_void_p),
-                ("mean", c_void_p), ("invstd", c_void_p), ("count", ctypes.c_float), ("eps", ctypes.c_float),
+                ("mean", c_void_p), ("invstd", c_void_p), ("count", ctypes.c_double), ("inv_count", ctypes.c_double),
+                ("unbias", ctypes.c_float), ("eps", ctypes.c_float),
                 ("momentum", ctypes.c_float)]
 
 
@@ -128,10 +130,45 @@ def last_error() -> str:
     return msg.decode() if msg else ""
 
 
+class Timeline:
+    """Diagnostics (tools/timeline.py): a %globaltimer stamp before and after every C-ABI call, on the call's
+    own stream.  Stamps are kernels, so they are captured into the engine's CUDA graphs and every replay
+    rewrites the buffer: read `intervals()` after a synchronize."""
+
+    def __init__(self, device, capacity=8192):
+        import torch
+        self.buf = torch.zeros(2 * capacity, dtype=torch.int64, device=device)
+        self.capacity = capacity
+        self.calls = []          # (name, stream handle, note)
+        self.note = ""
+
+    def stamp(self, name, stream, fn, args):
+        i = len(self.calls)
+        if i >= self.capacity:
+            return fn(*args)
+        self.calls.append((name, stream or 0, self.note))
+        lib, base = get(), self.buf.data_ptr()
+        lib.unetk_debug_stamp(base + 16 * i, stream)
+        rc = fn(*args)
+        lib.unetk_debug_stamp(base + 16 * i + 8, stream)
+        return rc
+
+    def intervals(self):
+        """[(name, stream, note, start_ns, end_ns)] of the LAST execution of every recorded call."""
+        t = self.buf.cpu().view(-1, 2).tolist()
+        return [(n, s, note, t[i][0], t[i][1]) for i, (n, s, note) in enumerate(self.calls)]
+
+
+timeline = None   # set to a Timeline to record (tools/timeline.py)
+
+
 def call(name: str, *args) -> None:
     """Call an int-returning entry point and raise UnetkError on a non-zero code."""
     global _launches, _kernel_launches
-    rc = getattr(get(), name)(*args)
+    if timeline is not None:
+        rc = timeline.stamp(name, args[-1], getattr(get(), name), args)
+    else:
+        rc = getattr(get(), name)(*args)
     _launches += 1
     if name != "unetk_memset_zero":
         _kernel_launches += 1

@@ -29,6 +29,21 @@ int unetk_memset_zero(void* ptr, size_t bytes, void* stream) {
   return UNETK_OK;
 }
 
+__global__ void debug_stamp_kernel(uint64_t* slot) {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+int unetk_debug_stamp(uint64_t* slot, void* stream) {
+  if (slot == nullptr) {
+    unetk::set_last_error("debug_stamp: null pointer");
+    return UNETK_ERR_ARG;
+  }
+  debug_stamp_kernel<<<1, 1, 0, S(stream)>>>(slot);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
 int unetk_conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wf, void* y,
                       float* stats, const float* scale, const float* shift, int relu, int n, int h,
                       int w, int cout, int h2, int w2, void* stream) {

@@ -52,12 +52,16 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
                                    float* running_var, long long* num_batches_tracked,
                                    float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                   int C, float count, float eps, float momentum) {
+                                   int C, double count, float eps, float momentum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (c >= C) return;
-  const float mean = stats[c] / count;
-  float var = stats[C + c] / count - mean * mean;
+  // E[x^2] - E[x]^2 from the fp32 batch sums, evaluated in double: the pixel count stays exact beyond 2^24
+  // (synchronised BatchNorm over 8 ranks at 512^2) and the subtraction itself adds no rounding; what
+  // cancellation is left is that of the fp32 partial sums (relative 1e-7 * mean^2 / var)
+  const double mean_d = static_cast<double>(stats[c]) / count;
+  const float mean = static_cast<float>(mean_d);
+  float var = static_cast<float>(static_cast<double>(stats[C + c]) / count - mean_d * mean_d);
   var = fmaxf(var, 0.f);
   const float invstd = rsqrtf(var + eps);
   const float sc = gamma[c] * invstd;
@@ -66,7 +70,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
   mean_out[c] = mean;
   invstd_out[c] = invstd;
   if (running_mean != nullptr) {
-    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    const float unbiased = count > 1.0 ? static_cast<float>(var * (count / (count - 1.0))) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
   }
@@ -93,8 +97,11 @@ __device__ __forceinline__ void bn_finalize8(const BnFinalizeArgs& f, int C, int
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cg * 8 + j;
-    const float mean = f.stats[c] / f.count;
-    float var = f.stats[C + c] / f.count - mean * mean;
+    // see bn_finalize_kernel; every thread of the grid runs this for its 8 channels, so the reciprocal of the
+    // count comes from the host (two DMULs and a DFMA per channel instead of two double divisions)
+    const double mean_d = static_cast<double>(f.stats[c]) * f.inv_count;
+    const float mean = static_cast<float>(mean_d);
+    float var = static_cast<float>(static_cast<double>(f.stats[C + c]) * f.inv_count - mean_d * mean_d);
     var = fmaxf(var, 0.f);
     const float invstd = rsqrtf(var + f.eps);
     sc[j] = f.gamma[c] * invstd;
@@ -105,7 +112,7 @@ __device__ __forceinline__ void bn_finalize8(const BnFinalizeArgs& f, int C, int
       f.mean[c] = mean;
       f.invstd[c] = invstd;
       if (f.running_mean != nullptr) {
-        const float unbiased = f.count > 1.f ? var * f.count / (f.count - 1.f) : var;
+        const float unbiased = var * f.unbias;
         f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
         f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unbiased;
       }
@@ -468,7 +475,7 @@ int bn_finalize(const float* stats, const float* gamma, const float* beta, float
                 float* invstd, int C, double count, float eps, float momentum, cudaStream_t s) {
   UNETK_CHECK_ARG(stats && gamma && beta && scale && shift && mean && invstd, "bn_finalize: null pointer");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean,
-                                                     invstd, C, static_cast<float>(count), eps, momentum);
+                                                     invstd, C, count, eps, momentum);
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -492,12 +499,19 @@ int bnrelu_apply(const void* y, const float* scale, const float* shift, void* a,
   return UNETK_OK;
 }
 
+// inv_count / unbias are derived here, at launch, from count: callers only fill count
+static BnFinalizeArgs with_reciprocals(BnFinalizeArgs f) {
+  f.inv_count = 1.0 / f.count;
+  f.unbias = f.count > 1.0 ? static_cast<float>(f.count / (f.count - 1.0)) : 1.f;
+  return f;
+}
+
 static int check_fin(const BnFinalizeArgs* f, int C, const char* who) {
   UNETK_CHECK_ARG(f && f->stats && f->gamma && f->beta && f->scale && f->shift && f->mean && f->invstd,
                   "%s: incomplete BatchNorm finalize arguments", who);
   UNETK_CHECK_ARG((f->running_mean == nullptr) == (f->running_var == nullptr), "%s: running_mean and running_var go together", who);
   UNETK_CHECK_ARG(C / 8 <= kEwThreads, "%s: at most %d channels", who, 8 * kEwThreads);
-  UNETK_CHECK_ARG(f->count >= 1.f, "%s: empty batch", who);
+  UNETK_CHECK_ARG(f->count >= 1.0, "%s: empty batch", who);
   return UNETK_OK;
 }
 
@@ -507,7 +521,7 @@ int bnrelu_apply_fin(const void* y, const BnFinalizeArgs* fin, void* a, long npi
   if (int e = check_fin(fin, C, "bnrelu_apply_fin")) return e;
   const long nvec = npix * (C / 8);
   UNETK_CUDA(launch_pdl(bnrelu_apply_kernel<true>, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s, static_cast<const uint4*>(y), nullptr, nullptr,
-                                                                        static_cast<uint4*>(a), nvec, C / 8, *fin));
+                                                                        static_cast<uint4*>(a), nvec, C / 8, with_reciprocals(*fin)));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -521,7 +535,7 @@ int bnrelu_pool_fin(const void* y, const BnFinalizeArgs* fin, void* a, void* poo
   const long nvec = static_cast<long>(N) * (H / 2) * (W / 2) * (C / 8);
   UNETK_CUDA(launch_pdl(bnrelu_pool_kernel<true>, dim3(ew_grid(nvec, C / 8)), dim3(kEwThreads), 0, s, static_cast<const uint4*>(y), nullptr, nullptr,
                                                                        static_cast<uint4*>(a), static_cast<uint4*>(pooled),
-                                                                       static_cast<uint2*>(idx), N, H, W, C / 8, 1, *fin));
+                                                                       static_cast<uint2*>(idx), N, H, W, C / 8, 1, with_reciprocals(*fin)));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }

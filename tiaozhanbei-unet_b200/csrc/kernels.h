@@ -31,7 +31,9 @@ struct BnFinalizeArgs {
   float* shift;
   float* mean;
   float* invstd;
-  float count;               // N*H*W
+  double count;              // N*H*W (x world size with synchronised statistics): exact beyond 2^24
+  double inv_count;          // 1 / count: written by the library at launch, callers leave it 0
+  float unbias;              // count / (count - 1) for running_var's unbiased variance: likewise written at launch
   float eps;
   float momentum;
 };

@@ -56,11 +56,20 @@ GRAPH_DDP = os.environ.get("UNETK_GRAPH_DDP", "0") == "1"
 # next layer instead of queueing in front of them.
 OVERLAP_WGRAD = os.environ.get("UNETK_OVERLAP_WGRAD", "1") != "0"
 PARALLEL_DECODERS = os.environ.get("UNETK_PARALLEL_DECODERS", "1") != "0"
+# Plans (activations, scratch, CUDA graphs of one input shape) kept alive at once, least recently used evicted:
+# train batch, ragged last train batch, validation batch, ragged last validation batch.
+MAX_PLANS = max(1, int(os.environ.get("UNETK_MAX_PLANS", "4")))
 ALIGN = 64  # elements; keeps every slice 256-byte aligned
 
 
 def _align(n):
     return (n + ALIGN - 1) // ALIGN * ALIGN
+
+
+def _note(text):
+    """Label the following C-ABI calls in a tools/timeline.py recording (no-op otherwise)."""
+    if _lib.timeline is not None:
+        _lib.timeline.note = text
 
 
 def param_layout(named_params):
@@ -95,7 +104,6 @@ class Plan:
 
     def __init__(self, eng, n, h, w, device):
         self.n, self.h, self.w = n, h, w
-        self.generation = 0
         bf = torch.bfloat16
 
         def act(lvl, c):
@@ -263,6 +271,10 @@ class Engine:
         self.pack_done = None
         self.weights_dirty = True
         self.fold_dirty = True
+        # bumped by EVERY forward (any shape, train or eval): the BatchNorm scale / shift / mean / invstd, the
+        # statistics and the packed weights are per engine, not per plan, so any later forward invalidates the
+        # saved state a pending backward needs
+        self.generation = 0
         m = module
         self.convbn = []
         self.encoder = []
@@ -309,7 +321,8 @@ class Engine:
             return
         if device.type != "cuda":
             raise _lib.UnetkError("this implementation has no CPU path: move the model and inputs to a CUDA (sm_100a) device")
-        rc = _lib.get().unetk_check_device()
+        with torch.cuda.device(device):
+            rc = _lib.get().unetk_check_device()
         if rc != 0:
             raise _lib.UnetkError(_lib.last_error())
         self.device = device
@@ -495,14 +508,15 @@ class Engine:
 
     def plan_for(self, n, h, w):
         key = (n, h, w)
-        pl = self.plans.get(key)
+        pl = self.plans.pop(key, None)
         if pl is None:
             if h < 16 or w < 16:
                 raise ValueError(f"input size {h}x{w} is too small: four 2x2 poolings need at least 16x16")
-            if len(self.plans) >= 3:      # e.g. train batch, last ragged batch, validation batch
-                self.plans.pop(next(iter(self.plans)))
+            while len(self.plans) >= MAX_PLANS:      # least recently used first (dicts keep insertion order)
+                old = self.plans.pop(next(iter(self.plans)))
+                old.graphs.clear()                   # drop the captured graphs (and their memory pools) with it
             pl = Plan(self, n, h, w, self.device)
-            self.plans[key] = pl
+        self.plans[key] = pl                         # (re)insert at the most-recently-used end
         return pl
 
     # ------------------------------------------------------------------------------------------
@@ -523,10 +537,14 @@ class Engine:
 
     def forward(self, x, training):
         x = self._check_input(x)
+        with torch.cuda.device(x.device):      # kernels go to the tensors' device, whatever the caller's current one
+            return self._forward(x, training)
+
+    def _forward(self, x, training):
         self.ensure(x.device)
         n, _, h, w = x.shape
         pl = self.plan_for(n, h, w)
-        pl.generation += 1
+        self.generation += 1
         sig = self._version_sig()
         if training or sig != getattr(self, "_vsig", None):
             self.mark_weights_dirty()
@@ -540,7 +558,7 @@ class Engine:
             pl.static_outs = None
         if training:
             self.fold_dirty = True   # running statistics moved
-        return outs, pl, pl.generation
+        return outs, pl, self.generation
 
     def _forward_graphed(self, pl, x, training):
         """Forward through a captured graph (see USE_GRAPHS): the image is copied into the plan's static
@@ -570,7 +588,10 @@ class Engine:
         return [o.clone() for o in outs] if replayed else outs
 
     def _bn_train(self, L, y, a, count, pool=None):
-        mom = L.bn.momentum if L.bn.momentum is not None else 0.1
+        if L.bn.momentum is None:
+            raise NotImplementedError("BatchNorm momentum=None (cumulative moving average) is not supported: the "
+                                      "reference uses nn.BatchNorm2d's default momentum 0.1 (src/model.py:15,18)")
+        mom = L.bn.momentum
         if self.sync_bn is not None:
             # synchronised BatchNorm: statistics over the GLOBAL batch (sum of the per-rank sums, global count),
             # i.e. exactly the single-process reference on the concatenated batch
@@ -607,6 +628,7 @@ class Engine:
         n = pl.n
         for l, (c1, c2) in enumerate(self.encoder):
             e = pl.enc[l]
+            _note(f"fwd enc{l}")
             count = n * (pl.h >> l) * (pl.w >> l)
             if l == 0 and self._first_tc():
                 ops.image_to_nhwc64(x, pl.x64)
@@ -632,6 +654,7 @@ class Engine:
             ct, c1, c2 = self.decoders[d][0][k]
             lv = 3 - k
             s = pl.dec[d][k]
+            _note(f"fwd dec{d}.up{k + 1}")
             t = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
             count = n * (pl.h >> lv) * (pl.w >> lv)
             if ct is None:
@@ -765,9 +788,27 @@ class Engine:
         return c
 
     def backward(self, pl, generation, grad_outs, outs):
-        if generation != pl.generation:
-            raise RuntimeError("backward() after another forward() through the same model and input shape: the saved "
-                               "activations of this graph were overwritten (only one live graph per shape is supported)")
+        if generation != self.generation:
+            raise RuntimeError("backward() after another forward() through the same model (any input shape, training "
+                               "or eval): the saved activations / BatchNorm statistics of this graph were overwritten "
+                               "(only one live graph per model is supported)")
+        with torch.cuda.device(self.device):
+            # Gradient accumulation (a second backward before the optimizer step, zero_grad(set_to_none=False)):
+            # `.grad` is then already a view of flat_g, which the kernels below overwrite.  Keep the old sums,
+            # hand autograd the new gradients in fresh storage and let its AccumulateGrad add them up.
+            fs = self.flat_g.untyped_storage().data_ptr()
+            accumulate = any(p.grad is not None and p.grad.untyped_storage().data_ptr() == fs for p in self.params)
+            if accumulate:
+                old = self.flat_g.clone()
+            grads = self._backward(pl, grad_outs, outs)
+            if accumulate:
+                new = self.flat_g.clone()
+                self.flat_g.copy_(old)
+                grads = [new[self.offsets[k]: self.offsets[k] + p.numel()].view(p.shape)
+                         for k, p in zip(self.param_names, self.params)]
+            return grads
+
+    def _backward(self, pl, grad_outs, outs):
         pl.alloc_grads()
         graphed = (self._graphs_ok() and pl.static_outs is not None and (self.ddp is None or GRAPH_DDP))
         if not graphed:
@@ -823,6 +864,7 @@ class Engine:
             ct, c1, c2 = stages[k]
             lv = 3 - k
             s = pl.dec[d][k]
+            _note(f"bwd dec{d}.up{k + 1}")
             if k == 3:
                 ops.head_bwd(s["a2"], head.w, grads[d], outs[d], V(ch.d_t, s["a2"]), head.g_w, head.g_b, head.sigmoid,
                              bn=ctx(pl, c2, s["y2"], kind="head"))
@@ -910,6 +952,7 @@ class Engine:
         for l in reversed(range(5)):
             c1, c2 = self.encoder[l]
             e = pl.enc[l]
+            _note(f"bwd enc{l}")
             d_a1 = V(ch.d_a1, e["a1"])
             iy, d_y = ch.take_y(e["y2"])
             self._bn_apply_bwd(pl, c2, pl.d_skip[l], e["y2"], d_y)
@@ -941,6 +984,7 @@ class Engine:
         for c in chains:
             if c.last_w is not None:
                 s0.wait_event(c.last_w)       # every weight gradient is in the staging buffer
+        _note("bwd unpack")
         scale = 1.0
         if self.ddp is not None:
             scale = self.ddp.finish(self)

@@ -21,6 +21,8 @@ def _p(t):
 
 
 def _s():
+    # the CURRENT device's current stream: every public wrapper below runs under _on_tensor_device, which makes
+    # the tensors' device current first
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -224,7 +226,7 @@ def bnrelu_apply(y, scale, shift, a):
 def bn_finalize_args(stats, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd, count, eps, momentum):
     """Host-side `unetk_bn_finalize_args` for bnrelu_apply_fin / bnrelu_pool_fin."""
     f = _lib.BnFinalizeArgs(_p(stats), _p(gamma), _p(beta), _p(rm), _p(rv), _p(nbt), _p(scale), _p(shift), _p(mean),
-                            _p(invstd), float(count), float(eps), float(momentum))
+                            _p(invstd), float(count), 0.0, 0.0, float(eps), float(momentum))
     f._keep = (stats, gamma, beta, rm, rv, nbt, scale, shift, mean, invstd)
     return f
 
@@ -581,3 +583,33 @@ def nhwc_to_nchw(a, out):
     n, h, w, c = a.shape
     _lib.call("unetk_nhwc_to_nchw", _p(a), _p(out), n, c, h, w, _s())
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# device guard
+# ---------------------------------------------------------------------------------------------
+def _on_tensor_device(fn):
+    """Run `fn` with its first tensor argument's device current: _s() and the library's own device checks look
+    at the current device, so a model on cuda:1 under a caller whose current device is cuda:0 would otherwise
+    launch on device 0's stream with device-1 pointers."""
+    import functools
+
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+
+    return guarded
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and not _name.startswith("_") and getattr(_fn, "__module__", None) == __name__ \
+            and _name not in ("timing_enabled", "enable_conv_timing", "collect_conv_timing", "conv_timing_by_kernel",
+                              "resize_coeffs", "resize_nearest_table", "bn_ctx", "bn_finalize_args"):
+        globals()[_name] = _on_tensor_device(_fn)
+del _name, _fn
