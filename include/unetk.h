@@ -186,6 +186,14 @@ int unetk_bn_bwd_apply(const void* da, const void* y, const float* scale, const 
 /* ---- OutConv = nn.Conv2d(64, n_out, 1) (+ torch.sigmoid): src/model.py:69-75,201,208 ------- */
 int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, int n, int h, int w_,
                    int c, int n_out, int sigmoid, void* stream);
+/* The same on the RAW output y of the last conv3x3: the training-mode BatchNorm of that layer (batch statistics
+ * finalized as in unetk_bnrelu_apply_fin, running statistics updated) + ReLU are applied on the fly, the activation
+ * rounded to bf16 as the stand-alone pass would have stored it; the activated tensor is never written
+ * (src/model.py:18-19 feeding :200-201 / :207-208). */
+int unetk_head_fwd_bn(const void* y, const unetk_bn_finalize_args* fin, const float* w, const float* b, float* out,
+                      int n, int h, int w_, int c, int n_out, int sigmoid, void* stream);
+/* a == NULL (forward went through unetk_head_fwd_bn): the activation is recomputed from bn->y / scale / shift.
+ * bn->sums != NULL: the first pass of that BatchNorm's backward (see unetk_bn_ctx) is fused in. */
 int unetk_head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da,
                    float* dw, float* db, int n, int h, int w_, int c, int n_out, int sigmoid,
                    const unetk_bn_ctx* bn, void* stream);

@@ -363,6 +363,42 @@ def test_head(cuda_device, n_out, sigmoid):
         torch.cuda.synchronize()
         assert torch.equal(da2, da3)
         _close(fused, ref_sums, 5e-3, "head_bwd fused BN reduction")
+        # a=None: the activation recomputed from y (forward went through head_fwd_bn) -- bit for bit the same
+        da4 = torch.empty_like(a); dw4 = torch.empty_like(dw); db4 = torch.empty_like(db); fused4 = torch.zeros(128, device=dev)
+        ops.head_bwd(a2, wt, dout, out, da3, dw, db, sigmoid)
+        ops.head_bwd(None, wt, dout, out, da4, dw4, db4, sigmoid, bn=ops.bn_ctx(yb, scale_case, sh, mu, iv, fused4))
+        torch.cuda.synchronize()
+        assert torch.equal(da4, da3)
+        _close(dw4, dw, 1e-4, "head_bwd(a=None) dw")       # (fp32 atomics: the order differs between launches)
+        _close(db4, db, 1e-4, "head_bwd(a=None) db")
+        _close(fused4, ref_sums, 5e-3, "head_bwd(a=None) fused BN reduction")
+        da5 = torch.empty_like(a)
+        ops.head_bwd(None, wt, dout, out, da5, dw4, db4, sigmoid, bn=ops.bn_ctx(yb, scale_case, sh, mu, iv, None))
+        torch.cuda.synchronize()
+        assert torch.equal(da5, da3)
+
+    # head_fwd_bn == bnrelu_apply_fin + head_fwd, bit for bit (outputs, saved BatchNorm constants, running statistics)
+    count = n * h * w
+    y32 = _nchw(yb)
+    stats = torch.cat([y32.sum((0, 2, 3)), (y32 * y32).sum((0, 2, 3))]).contiguous()
+    gamma = (torch.rand(64, generator=g) + 0.5).to(dev); beta = (torch.randn(64, generator=g) * 0.2).to(dev)
+    res = []
+    for fused_head in (False, True):
+        rm, rv, nbt = torch.zeros(64, device=dev), torch.ones(64, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
+        aux = [torch.empty(64, device=dev) for _ in range(4)]
+        fin = ops.bn_finalize_args(stats, gamma, beta, rm, rv, nbt, *aux, count, 1e-5, 0.1)
+        o = torch.empty(n, n_out, h, w, device=dev)
+        if fused_head:
+            ops.head_fwd_bn(yb, fin, wt, b, o, sigmoid)
+        else:
+            act = torch.empty_like(yb)
+            ops.bnrelu_apply_fin(yb, fin, act)
+            ops.head_fwd(act, wt, b, o, sigmoid)
+        torch.cuda.synchronize()
+        res.append([o, rm, rv, nbt] + aux)
+    for t0, t1 in zip(*res):
+        assert torch.equal(t0, t1)
+    assert int(res[1][3]) == 1
 
 
 def test_adam_and_layout(cuda_device):

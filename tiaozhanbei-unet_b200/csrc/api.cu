@@ -140,6 +140,10 @@ int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, in
                    int c, int n_out, int sigmoid, void* stream) {
   return unetk::head_fwd(a, w, b, out, n, h, w_, c, n_out, sigmoid, S(stream));
 }
+int unetk_head_fwd_bn(const void* y, const unetk_bn_finalize_args* fin, const float* w, const float* b, float* out,
+                      int n, int h, int w_, int c, int n_out, int sigmoid, void* stream) {
+  return unetk::head_fwd_bn(y, reinterpret_cast<const unetk::BnFinalizeArgs*>(fin), w, b, out, n, h, w_, c, n_out, sigmoid, S(stream));
+}
 int unetk_head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da,
                    float* dw, float* db, int n, int h, int w_, int c, int n_out, int sigmoid,
                    const unetk_bn_ctx* bn, void* stream) {

@@ -47,33 +47,12 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 // torch semantics (nn.BatchNorm2d, training): biased variance for normalisation, unbiased for
 // running_var, momentum 0.1, num_batches_tracked += 1.
 // ----------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean,
-                                   float* running_var, long long* num_batches_tracked,
-                                   float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                   int C, double count, float eps, float momentum) {
+__global__ void bn_finalize_kernel(const BnFinalizeArgs f, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+  if (c == 0 && f.num_batches_tracked != nullptr) *f.num_batches_tracked += 1;
   if (c >= C) return;
-  // E[x^2] - E[x]^2 from the fp32 batch sums, evaluated in double: the pixel count stays exact beyond 2^24
-  // (synchronised BatchNorm over 8 ranks at 512^2) and the subtraction itself adds no rounding; what
-  // cancellation is left is that of the fp32 partial sums (relative 1e-7 * mean^2 / var)
-  const double mean_d = static_cast<double>(stats[c]) / count;
-  const float mean = static_cast<float>(mean_d);
-  float var = static_cast<float>(static_cast<double>(stats[C + c]) / count - mean_d * mean_d);
-  var = fmaxf(var, 0.f);
-  const float invstd = rsqrtf(var + eps);
-  const float sc = gamma[c] * invstd;
-  scale[c] = sc;
-  shift[c] = beta[c] - mean * sc;
-  mean_out[c] = mean;
-  invstd_out[c] = invstd;
-  if (running_mean != nullptr) {
-    const float unbiased = count > 1.0 ? static_cast<float>(var * (count / (count - 1.0))) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
-  }
+  float sc, sh;
+  bn_finalize1(f, C, c, true, sc, sh);      // the arithmetic every fused consumer uses: bit-identical constants
 }
 
 // Eval mode: fold running statistics into (scale, shift).
@@ -95,29 +74,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 __device__ __forceinline__ void bn_finalize8(const BnFinalizeArgs& f, int C, int cg, bool writer,
                                              float (&sc)[8], float (&sh)[8]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    // see bn_finalize_kernel; every thread of the grid runs this for its 8 channels, so the reciprocal of the
-    // count comes from the host (two DMULs and a DFMA per channel instead of two double divisions)
-    const double mean_d = static_cast<double>(f.stats[c]) * f.inv_count;
-    const float mean = static_cast<float>(mean_d);
-    float var = static_cast<float>(static_cast<double>(f.stats[C + c]) * f.inv_count - mean_d * mean_d);
-    var = fmaxf(var, 0.f);
-    const float invstd = rsqrtf(var + f.eps);
-    sc[j] = f.gamma[c] * invstd;
-    sh[j] = f.beta[c] - mean * sc[j];
-    if (writer) {
-      f.scale[c] = sc[j];
-      f.shift[c] = sh[j];
-      f.mean[c] = mean;
-      f.invstd[c] = invstd;
-      if (f.running_mean != nullptr) {
-        const float unbiased = var * f.unbias;
-        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
-        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unbiased;
-      }
-    }
-  }
+  for (int j = 0; j < 8; ++j) bn_finalize1(f, C, cg * 8 + j, writer, sc[j], sh[j]);
   if (writer && cg == 0 && f.num_batches_tracked != nullptr) *f.num_batches_tracked += 1;
 }
 
@@ -474,8 +431,10 @@ int bn_finalize(const float* stats, const float* gamma, const float* beta, float
                 float* running_var, long long* nbt, float* scale, float* shift, float* mean,
                 float* invstd, int C, double count, float eps, float momentum, cudaStream_t s) {
   UNETK_CHECK_ARG(stats && gamma && beta && scale && shift && mean && invstd, "bn_finalize: null pointer");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean,
-                                                     invstd, C, count, eps, momentum);
+  UNETK_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running_mean and running_var go together");
+  UNETK_CHECK_ARG(count >= 1.0, "bn_finalize: empty batch");
+  BnFinalizeArgs f{stats, gamma, beta, running_mean, running_var, nbt, scale, shift, mean, invstd, count, 0.0, 0.f, eps, momentum};
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(with_reciprocals(f), C);
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
@@ -497,13 +456,6 @@ int bnrelu_apply(const void* y, const float* scale, const float* shift, void* a,
                                                                          static_cast<uint4*>(a), nvec, C / 8, BnFinalizeArgs{}));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
-}
-
-// inv_count / unbias are derived here, at launch, from count: callers only fill count
-static BnFinalizeArgs with_reciprocals(BnFinalizeArgs f) {
-  f.inv_count = 1.0 / f.count;
-  f.unbias = f.count > 1.0 ? static_cast<float>(f.count / (f.count - 1.0)) : 1.f;
-  return f;
 }
 
 static int check_fin(const BnFinalizeArgs* f, int C, const char* who) {
@@ -587,7 +539,14 @@ int bn_bwd_reduce(const void* da, const void* y, const float* scale, const float
   const long nvec = npix * (C / 8);
   // full grid (8 blocks per SM): at 4 per SM the two read streams ran at 3.9 TB/s, latency bound; an
   // unrolled variant with four loads in flight per thread was slower still (3.2 TB/s)
-  const int grid = ew_grid(nvec, C / 8);
+  // ... but every block ends with 2*C global atomics, so the deep layers (few pixels, many channels: 16x16x1024
+  // x 16 images is 2 vectors per thread of a full grid against 2.4 M atomics) get a grid with at least 16
+  // vectors per thread
+  int grid = ew_grid(nvec, C / 8);
+  {
+    const long want = (nvec + 16L * kEwThreads - 1) / (16L * kEwThreads);
+    if (want < grid) grid = ew_grid(want * kEwThreads, C / 8);
+  }
   UNETK_CUDA(launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(kEwThreads), 2 * C * sizeof(float), s, static_cast<const uint4*>(da), static_cast<const uint4*>(y),
                                                                       scale, shift, mean, invstd, sums, nvec, C / 8));
   UNETK_CUDA(cudaGetLastError());

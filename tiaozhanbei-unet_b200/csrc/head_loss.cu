@@ -18,15 +18,28 @@ namespace unetk {
 constexpr int kHeadC = 64;
 constexpr int kHeadMaxOut = 4;
 
+// BN: `a` is the RAW output y of the last conv; the kernel applies that layer's training-mode BatchNorm (finalize
+// folded in, see bn_finalize1) + ReLU on the fly, rounding the activation to bf16 exactly as the stand-alone
+// BN+ReLU pass would have stored it -- the activated tensor of the last layer is never written (a 134 MB read +
+// 134 MB write pass per decoder at 16 x 256^2 that sat, un-overlapped, at the end of the forward pass).
+template <bool BN>
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const float* __restrict__ b,
-                float* __restrict__ out, long npix_total, long hw, int n_out, int sigmoid) {
+                float* __restrict__ out, long npix_total, long hw, int n_out, int sigmoid, const BnFinalizeArgs fin) {
   __shared__ float sw[kHeadMaxOut * kHeadC];
   __shared__ float sb[kHeadMaxOut];
+  __shared__ float ssc[BN ? kHeadC : 1], ssh[BN ? kHeadC : 1];
   pdl_trigger();
   pdl_wait();
   for (int i = threadIdx.x; i < n_out * kHeadC; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < n_out) sb[threadIdx.x] = b[threadIdx.x];
+  if (BN && threadIdx.x < kHeadC) {
+    float sc, sh;
+    bn_finalize1(fin, kHeadC, threadIdx.x, blockIdx.x == 0, sc, sh);
+    ssc[threadIdx.x] = sc;
+    ssh[threadIdx.x] = sh;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && fin.num_batches_tracked != nullptr) *fin.num_batches_tracked += 1;
+  }
   __syncthreads();
   for (long p = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; p < npix_total;
        p += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -35,7 +48,12 @@ head_fwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const 
     for (int v = 0; v < 8; ++v) {
       const uint4 u = ldg_nc_v4(a + p * 8 + v);
       const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-      const float x[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+      float x[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+      if (BN) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          x[k] = __bfloat162float(__float2bfloat16(fmaxf(fmaf(x[k], ssc[v * 8 + k], ssh[v * 8 + k]), 0.f)));
+      }
 #pragma unroll
       for (int j = 0; j < kHeadMaxOut; ++j) {
         if (j < n_out) {
@@ -60,8 +78,10 @@ head_fwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w, const 
 // 8 lanes cover one pixel (16-byte vectors of 8 channels), a warp covers 4 pixels per step and every
 // thread keeps four steps in flight; weights and the dW partial sums live in registers.
 // ----------------------------------------------------------------------------------------------
-// Optional fusion (bn_y != nullptr): first pass of the BatchNorm+ReLU backward of the layer that
+// Optional fusion (bn_sums != nullptr): first pass of the BatchNorm+ReLU backward of the layer that
 // produced `a` (y = its raw conv output): sums[0..64) += sum g, sums[64..128) += sum g*xhat.
+// a == nullptr (the forward pass used head_fwd_bn and never stored the activation): a is recomputed from
+// bn_y as bf16(relu(y*scale + shift)), bit for bit what head_fwd_bn fed the 1x1 convolution.
 template <int NOUT>
 __global__ void __launch_bounds__(256, 2)
 head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
@@ -74,13 +94,18 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
   __shared__ float sdw[NOUT * kHeadC];
   __shared__ float sdb[NOUT];
   __shared__ float sbn[2 * kHeadC];
+  __shared__ float sysc[2 * kHeadC];
   pdl_trigger();
   pdl_wait();
+  const bool bn = bn_sums != nullptr;
+  const bool from_y = a == nullptr;
   for (int i = threadIdx.x; i < NOUT * kHeadC; i += blockDim.x) sdw[i] = 0.f;
   if (threadIdx.x < NOUT) sdb[threadIdx.x] = 0.f;
-  if (threadIdx.x < 2 * kHeadC) sbn[threadIdx.x] = 0.f;
+  if (threadIdx.x < 2 * kHeadC) {
+    sbn[threadIdx.x] = 0.f;
+    if (from_y) sysc[threadIdx.x] = threadIdx.x < kHeadC ? bn_scale[threadIdx.x] : bn_shift[threadIdx.x - kHeadC];
+  }
   __syncthreads();
-  const bool bn = bn_y != nullptr;
   const int lane = threadIdx.x & 31;
   const int cg = lane & 7;          // channel group: channels 8*cg .. 8*cg+7
   const int pl = lane >> 3;         // pixel slot inside the warp step
@@ -97,6 +122,10 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
     s1[k] = s2[k] = 0.f;
     if (bn && bn_scale[cg * 8 + k] == 0.f) degenerate = true;
   }
+  const uint4* __restrict__ src = from_y ? bn_y : a;
+  // (scale, shift of this thread's 8 channels stay in shared memory: the kernel sits at its register cap)
+  const float* ysc = sysc + cg * 8;
+  const float* ysh = sysc + kHeadC + cg * 8;
 #pragma unroll
   for (int j = 0; j < NOUT; ++j) {
     gb[j] = 0.f;
@@ -117,7 +146,7 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
     for (int u = 0; u < U; ++u) {
       const long p = base + u * 4 + pl;
       ok[u] = p < npix_total;
-      av[u] = ok[u] ? ldg_nc_v4(a + p * 8 + cg) : make_uint4(0, 0, 0, 0);
+      av[u] = ok[u] ? ldg_nc_v4(src + p * 8 + cg) : make_uint4(0, 0, 0, 0);
       const long n = ok[u] ? p / hw : 0, r = ok[u] ? p - n * hw : 0;
 #pragma unroll
       for (int j = 0; j < NOUT; ++j) {
@@ -135,6 +164,11 @@ head_bwd_kernel(const uint4* __restrict__ a, const float* __restrict__ w,
       float x[8], g[8];
       const float2 f0 = unpack_bf16x2(av[u].x), f1 = unpack_bf16x2(av[u].y), f2 = unpack_bf16x2(av[u].z), f3 = unpack_bf16x2(av[u].w);
       x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y; x[4] = f2.x; x[5] = f2.y; x[6] = f3.x; x[7] = f3.y;
+      if (from_y) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          x[k] = ok[u] ? __bfloat162float(__float2bfloat16(fmaxf(fmaf(x[k], ysc[k], ysh[k]), 0.f))) : 0.f;
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] = 0.f;
 #pragma unroll
@@ -547,14 +581,33 @@ int head_fwd(const void* a, const float* w, const float* b, float* out, int N, i
   UNETK_CHECK_ARG(C == kHeadC, "head_fwd: input channels must be 64 (got %d)", C);
   UNETK_CHECK_ARG(n_out >= 1 && n_out <= kHeadMaxOut, "head_fwd: 1..4 output channels supported (got %d)", n_out);
   const long hw = static_cast<long>(H) * W, np = hw * N;
-  UNETK_CUDA(launch_pdl(head_fwd_kernel, dim3(ew_blocks(np, 256)), dim3(256), 0, s, static_cast<const uint4*>(a), w, b, out, np, hw, n_out, sigmoid));
+  UNETK_CUDA(launch_pdl(head_fwd_kernel<false>, dim3(ew_blocks(np, 256)), dim3(256), 0, s, static_cast<const uint4*>(a), w, b, out, np, hw, n_out, sigmoid,
+                        BnFinalizeArgs{}));
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int head_fwd_bn(const void* y, const BnFinalizeArgs* fin, const float* w, const float* b, float* out, int N, int H,
+                int W, int C, int n_out, int sigmoid, cudaStream_t s) {
+  UNETK_CHECK_ARG(y && fin && w && b && out, "head_fwd_bn: null pointer");
+  UNETK_CHECK_ARG(C == kHeadC, "head_fwd_bn: input channels must be 64 (got %d)", C);
+  UNETK_CHECK_ARG(n_out >= 1 && n_out <= kHeadMaxOut, "head_fwd_bn: 1..4 output channels supported (got %d)", n_out);
+  UNETK_CHECK_ARG(fin->stats && fin->gamma && fin->beta && fin->scale && fin->shift && fin->mean && fin->invstd,
+                  "head_fwd_bn: incomplete BatchNorm finalize arguments");
+  UNETK_CHECK_ARG((fin->running_mean == nullptr) == (fin->running_var == nullptr), "head_fwd_bn: running_mean and running_var go together");
+  UNETK_CHECK_ARG(fin->count >= 1.0, "head_fwd_bn: empty batch");
+  const long hw = static_cast<long>(H) * W, np = hw * N;
+  UNETK_CUDA(launch_pdl(head_fwd_kernel<true>, dim3(ew_blocks(np, 256)), dim3(256), 0, s, static_cast<const uint4*>(y), w, b, out, np, hw, n_out, sigmoid,
+                        with_reciprocals(*fin)));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
 }
 
 int head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da, float* dw,
              float* db, int N, int H, int W, int C, int n_out, int sigmoid, const BnReduceCtx* bn, cudaStream_t s) {
-  UNETK_CHECK_ARG(a && w && dout && da && dw && db, "head_bwd: null pointer");
+  UNETK_CHECK_ARG(w && dout && da && dw && db, "head_bwd: null pointer");
+  UNETK_CHECK_ARG(a != nullptr || (bn != nullptr && bn->y && bn->scale && bn->shift),
+                  "head_bwd: without the stored activation the BatchNorm context (y, scale, shift) is required");
   UNETK_CHECK_ARG(!sigmoid || out, "head_bwd: sigmoid backward needs the forward output");
   UNETK_CHECK_ARG(C == kHeadC, "head_bwd: input channels must be 64 (got %d)", C);
   UNETK_CHECK_ARG(n_out >= 1 && n_out <= kHeadMaxOut, "head_bwd: 1..4 output channels supported");
@@ -566,11 +619,12 @@ int head_bwd(const void* a, const float* w, const float* dout, const float* out,
   if (blocks > cap) blocks = cap;
   const uint4* a4 = static_cast<const uint4*>(a);
   uint4* da4 = static_cast<uint4*>(da);
-  const bool fuse = bn != nullptr && bn->y != nullptr;
-  UNETK_CHECK_ARG(!fuse || (bn->scale && bn->shift && bn->mean && bn->invstd && bn->sums), "head_bwd: incomplete BatchNorm context");
-  const uint4* by = fuse ? static_cast<const uint4*>(bn->y) : nullptr;
-  const float* b1 = fuse ? bn->scale : nullptr; const float* b2 = fuse ? bn->shift : nullptr;
-  const float* b3 = fuse ? bn->mean : nullptr;  const float* b4 = fuse ? bn->invstd : nullptr;
+  const bool fuse = bn != nullptr && bn->y != nullptr && bn->sums != nullptr;     // + BatchNorm-backward sums
+  const bool ctx = bn != nullptr && bn->y != nullptr && (fuse || a == nullptr);
+  UNETK_CHECK_ARG(!fuse || (bn->scale && bn->shift && bn->mean && bn->invstd), "head_bwd: incomplete BatchNorm context");
+  const uint4* by = ctx ? static_cast<const uint4*>(bn->y) : nullptr;
+  const float* b1 = ctx ? bn->scale : nullptr; const float* b2 = ctx ? bn->shift : nullptr;
+  const float* b3 = ctx ? bn->mean : nullptr;  const float* b4 = ctx ? bn->invstd : nullptr;
   float* b5 = fuse ? bn->sums : nullptr;
   switch (n_out) {
     case 1: UNETK_CUDA(launch_pdl(head_bwd_kernel<1>, dim3(blocks), dim3(256), 0, s, a4, w, dout, out, da4, dw, db, np, hw, sigmoid, by, b1, b2, b3, b4, b5)); break;

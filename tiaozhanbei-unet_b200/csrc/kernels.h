@@ -38,6 +38,41 @@ struct BnFinalizeArgs {
   float momentum;
 };
 
+// inv_count / unbias are derived at launch from count: callers only fill count
+inline BnFinalizeArgs with_reciprocals(BnFinalizeArgs f) {
+  f.inv_count = 1.0 / f.count;
+  f.unbias = f.count > 1.0 ? static_cast<float>(f.count / (f.count - 1.0)) : 1.f;
+  return f;
+}
+
+#ifdef __CUDACC__
+// (scale, shift) of channel c from the batch sums, exactly as bn_finalize_kernel (elementwise.cu) computes
+// them: E[x^2] - E[x]^2 in double from the fp32 sums with the host's reciprocal of the count (two DMULs and a
+// DFMA instead of two double divisions: every thread of the consuming kernel runs this).  `writer` threads
+// also store scale / shift / mean / invstd for the backward pass and update the running statistics
+// (num_batches_tracked is the caller's: one thread only).
+__device__ __forceinline__ void bn_finalize1(const BnFinalizeArgs& f, int C, int c, bool writer, float& sc, float& sh) {
+  const double mean_d = static_cast<double>(f.stats[c]) * f.inv_count;
+  const float mean = static_cast<float>(mean_d);
+  float var = static_cast<float>(static_cast<double>(f.stats[C + c]) * f.inv_count - mean_d * mean_d);
+  var = fmaxf(var, 0.f);
+  const float invstd = rsqrtf(var + f.eps);
+  sc = f.gamma[c] * invstd;
+  sh = f.beta[c] - mean * sc;
+  if (writer) {
+    f.scale[c] = sc;
+    f.shift[c] = sh;
+    f.mean[c] = mean;
+    f.invstd[c] = invstd;
+    if (f.running_mean != nullptr) {
+      const float unbiased = var * f.unbias;
+      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unbiased;
+    }
+  }
+}
+#endif
+
 // igemm.cu — K-major implicit GEMMs (tcgen05)
 int conv3x3_fwd(const void* src1, int c1, const void* src2, int c2, const void* wpk, void* y,
                 float* stats, const float* scale, const float* shift, int relu, int n, int h, int w,
@@ -91,6 +126,8 @@ int nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, cudaStr
 int nhwc_to_nchw(const void* in, float* out, int N, int C, int H, int W, cudaStream_t s);
 
 // head_loss.cu
+int head_fwd_bn(const void* y, const BnFinalizeArgs* fin, const float* w, const float* b, float* out, int N, int H,
+                int W, int C, int n_out, int sigmoid, cudaStream_t s);
 int head_fwd(const void* a, const float* w, const float* b, float* out, int N, int H, int W, int C,
              int n_out, int sigmoid, cudaStream_t s);
 int head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da, float* dw,

@@ -19,11 +19,12 @@ contiguous range.
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import torch
 
 from . import _lib, ops, packing
-
-import os
 
 # Which producers of an activation gradient also run the first pass (per-channel sums) of the BatchNorm
 # backward of the layer below them: "head" (default: the 1x1 head backward already holds the activation in
@@ -40,6 +41,10 @@ FIRST_FWD_TC = os.environ.get("UNETK_FIRST_FWD_TC", "1") != "0"
 # BN+ReLU(+pool) kernel instead of a separate dependent launch per layer.
 FUSE_BN_FINALIZE = os.environ.get("UNETK_FUSE_BN_FINALIZE", "1") != "0"
 SPLIT_PACK = os.environ.get("UNETK_SPLIT_PACK", "1") != "0"
+# Training forward: the BatchNorm + ReLU of every decoder's LAST conv is applied inside the 1x1 head kernel (and
+# recomputed from the raw conv output in the head's backward), so that layer's activated tensor is never
+# written or re-read: one full-resolution pass less per decoder, at the un-overlapped end of the forward pass.
+HEAD_FUSE_BN = os.environ.get("UNETK_HEAD_FUSE_BN", "1") != "0"
 # CUDA graphs: the plan is static (same kernels, same buffers every step), so after one eager warm-up call
 # the whole forward (and backward) launch sequence, side streams included, is captured once per input shape
 # and replayed with ONE call: Python enqueue drops from 6.5-10 ms per step (host dependent) to 2.8 ms (loss,
@@ -56,6 +61,20 @@ GRAPH_DDP = os.environ.get("UNETK_GRAPH_DDP", "0") == "1"
 # next layer instead of queueing in front of them.
 OVERLAP_WGRAD = os.environ.get("UNETK_OVERLAP_WGRAD", "1") != "0"
 PARALLEL_DECODERS = os.environ.get("UNETK_PARALLEL_DECODERS", "1") != "0"
+# The tensor-core kernels are persistent (one CTA per SM for the whole launch), so kernels of different streams
+# that are ready together run one after the other, in the order the hardware picks them.  The chains whose
+# kernels other work waits for (forward, data gradients) run on high-priority streams owned by the engine;
+# weight gradients, weight packing and gradient un-packing stay at the default (lowest) priority and fill
+# the holes.  Off by default: measured on a B200 (B=16 @256^2, 8 runs each way) the step takes 10.0-10.2 ms either way -- the
+# backward pass is bound by the sum of its tensor-core kernels, not by their order -- and the default keeps
+# everything on the caller's stream.
+PRIORITY_STREAMS = os.environ.get("UNETK_PRIORITY_STREAMS", "0") == "1"
+# Release a weight-gradient launch as soon as its inputs exist (with the data gradient of the same layer,
+# not after it); only sensible together with PRIORITY_STREAMS, which lets the data gradient go first.
+WGRAD_EARLY = os.environ.get("UNETK_WGRAD_EARLY", "0") == "1"
+# Slots of the d_y / d_up scratch per backward chain: a chain may run this many layers ahead of the (lower
+# priority, hence later) weight gradients that still read them before it has to wait for one.
+GRAD_SLOTS = max(2, int(os.environ.get("UNETK_GRAD_SLOTS", "2")))
 # Plans (activations, scratch, CUDA graphs of one input shape) kept alive at once, least recently used evicted:
 # train batch, ragged last train batch, validation batch, ragged last validation batch.
 MAX_PLANS = max(1, int(os.environ.get("UNETK_MAX_PLANS", "4")))
@@ -141,6 +160,7 @@ class Plan:
         self.bnctx = {}
         self.fused = set()
         self.drop_mask = None
+        self.head_fused = False   # the last training forward applied the final BatchNorm inside the head kernels
         self.static_outs = None   # outputs owned by the forward graph (backward reads them)
         self.graphs = {}          # "train" / "eval" / "bwd" -> _GraphState
         self.x_in = None          # static copy of the input image (graph replays read it)
@@ -156,10 +176,10 @@ class Plan:
         # scratch per backward chain (one per decoder; the encoder continues on chain 0), all of the
         # largest (full resolution, 64 channel) size: d_t = running decoder gradient d(a2) of the current
         # stage, d_a1 = gradient wrt a DoubleConv's inner activation, d_y = gradient wrt a raw conv output,
-        # d_up = gradient wrt an up-sampled tensor.  d_y / d_up have two slots each: the weight gradient
+        # d_up = gradient wrt an up-sampled tensor.  d_y / d_up have GRAD_SLOTS slots each: the weight gradient
         # that reads slot i runs on a side stream while the chain already fills slot i^1.
-        self.scratch = [{"d_t": act(0, 64), "d_a1": act(0, 64), "d_y": [act(0, 64), act(0, 64)],
-                         "d_up": [act(0, 64), act(0, 64)]} for _ in range(self.n_dec)]
+        self.scratch = [{"d_t": act(0, 64), "d_a1": act(0, 64), "d_y": [act(0, 64) for _ in range(GRAD_SLOTS)],
+                         "d_up": [act(0, 64) for _ in range(GRAD_SLOTS)]} for _ in range(self.n_dec)]
         self.d_p = act(1, 64)       # gradient wrt a pooled tensor (max size)
         self.fc_scratch = torch.empty(64 * 9 * 64, dtype=torch.float32, device=self.d_p.device)   # first conv dW[co][tap][64]
         self.grads_ready = True
@@ -215,18 +235,28 @@ class _Chain:
         self.stream, self.wstream = stream, wstream
         self.d_t, self.d_a1 = scratch["d_t"], scratch["d_a1"]
         self.d_y, self.d_up = scratch["d_y"], scratch["d_up"]
-        self.free_y, self.free_up = [None, None], [None, None]   # events after which a slot may be overwritten
+        self.free_y, self.free_up = [None] * len(self.d_y), [None] * len(self.d_up)   # events after which a slot may be overwritten
         self.slot_y = self.slot_up = 0
         self.last_w = None                                       # last event recorded on the side stream
 
-    def side(self, fn):
-        """Run the weight-gradient launches of `fn` on the side stream, after everything enqueued on the
-        chain's stream so far (the data gradient of the same layer included)."""
-        if self.wstream is None:
-            fn()
+    def mark(self):
+        """Event on the chain's stream at this point (an earlier release point for side()), or None."""
+        if self.wstream is None or not WGRAD_EARLY:
             return None
         ev = torch.cuda.Event()
         ev.record(self.stream)
+        return ev
+
+    def side(self, fn, after=None):
+        """Run the weight-gradient launches of `fn` on the side stream, after everything enqueued on the
+        chain's stream so far (the data gradient of the same layer included) or after the event `after`."""
+        if self.wstream is None:
+            fn()
+            return None
+        ev = after
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
         self.wstream.wait_event(ev)
         with torch.cuda.stream(self.wstream):
             fn()
@@ -242,11 +272,11 @@ class _Chain:
         return slot, Plan.view(bufs[slot], like)
 
     def take_y(self, like):
-        self.slot_y ^= 1
+        self.slot_y = (self.slot_y + 1) % len(self.d_y)
         return self._take(self.d_y, self.free_y, self.slot_y, like)
 
     def take_up(self, like):
-        self.slot_up ^= 1
+        self.slot_up = (self.slot_up + 1) % len(self.d_up)
         return self._take(self.d_up, self.free_up, self.slot_up, like)
 
 
@@ -264,17 +294,19 @@ class Engine:
         self.fuse_check = []      # (layer, relative error) records of UNETK_FUSE_CHECK=1
         self.wstreams = []        # side streams of the weight gradients, one per backward chain (OVERLAP_WGRAD)
         self.dstreams = []        # side streams of the second, third... decoder (PARALLEL_DECODERS)
+        self.hstream = None       # high-priority stream of the critical chain (PRIORITY_STREAMS)
         self.pstream = None       # side stream packing the decoders' weights (SPLIT_PACK)
         self.ustream = None       # side stream un-packing the decoders' gradients during the encoder's backward
         self.sync_bn = None       # process group for synchronised BatchNorm statistics (distributed.attach(sync_bn=True))
         self.bottleneck_dropout = 0.0   # SegmentationUNet: nn.Dropout2d(p) on the bottleneck (src/model.py:130,146)
-        self.pack_done = None
+        self.pack_done0 = self.pack_done4 = self.pack_done = None
         self.weights_dirty = True
         self.fold_dirty = True
         # bumped by EVERY forward (any shape, train or eval): the BatchNorm scale / shift / mean / invstd, the
         # statistics and the packed weights are per engine, not per plan, so any later forward invalidates the
         # saved state a pending backward needs
         self.generation = 0
+        self.staging_clean = False     # gradient staging buffer zeroed by the last training forward
         m = module
         self.convbn = []
         self.encoder = []
@@ -354,13 +386,14 @@ class Engine:
         chunk = _lib.get().unetk_permute_chunk_elems()
         pack = packing.PermuteTable(chunk)
         unpack_enc, unpack_dec = packing.PermuteTable(chunk), packing.PermuteTable(chunk)
-        # conv3x3 weight packing in two groups: the encoder's (needed first, packed on the caller's stream) and
-        # the decoders' (packed on a side stream under the encoder's forward pass)
+        # conv3x3 weight packing / gradient un-packing in three groups: 0 = encoder levels 0-3 (a quarter of the
+        # encoder's weights, needed first: packed on the caller's stream), 1 = the bottleneck level (three quarters)
+        # and 2 = the decoders, both packed on a side stream under the first levels of the forward pass; the
+        # un-packing mirrors it (groups 2 and 1 under the encoder's backward, only group 0 after its end)
         n_enc_layers = 2 * len(self.encoder)
-        conv_pack_enc = packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32))
-        conv_pack_dec = packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32))
-        conv_unpack_enc = packing.ConvTable(lambda cout, cin: cout)
-        conv_unpack_dec = packing.ConvTable(lambda cout, cin: cout)
+        n_early = n_enc_layers - 2
+        conv_pack_g = [packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32)) for _ in range(3)]
+        conv_unpack_g = [packing.ConvTable(lambda cout, cin: cout) for _ in range(3)]
         pdict = dict(zip(self.param_names, self.params))
         wsize = 0
 
@@ -380,9 +413,9 @@ class Engine:
         handled = set()
         for li, L in enumerate(self.convbn):
             c = L.cout
-            conv_pack = conv_pack_enc if li < n_enc_layers else conv_pack_dec
+            grp = 0 if li < n_early else (1 if li < n_enc_layers else 2)
+            conv_pack, conv_unpack = conv_pack_g[grp], conv_unpack_g[grp]
             unpack = unpack_enc if li < n_enc_layers else unpack_dec
-            conv_unpack = conv_unpack_enc if li < n_enc_layers else conv_unpack_dec
             L.stats = self.bn_stats_all[2 * co: 2 * co + 2 * c]
             L.sums = self.bn_sums_all[2 * co: 2 * co + 2 * c]
             L.scale = self.bn_aux[4 * co: 4 * co + c]
@@ -446,13 +479,28 @@ class Engine:
         for obj, attr, off, n in wplan:
             setattr(obj, attr, self.wpack[off: off + n])
         self.pack_table = pack.finalize(device)
-        self.unpack_tables = (unpack_enc.finalize(device), unpack_dec.finalize(device))
-        self.conv_pack_tables = (conv_pack_enc.finalize(device), conv_pack_dec.finalize(device))
-        self.conv_unpack_tables = (conv_unpack_enc.finalize(device), conv_unpack_dec.finalize(device))
+        self.unpack_tables = (unpack_enc.finalize(device), None, unpack_dec.finalize(device))
+        self.conv_pack_tables = tuple(t.finalize(device) for t in conv_pack_g)
+        self.conv_unpack_tables = tuple(t.finalize(device) for t in conv_unpack_g)
 
     def mark_weights_dirty(self):
         self.weights_dirty = True
         self.fold_dirty = True
+
+    @contextlib.contextmanager
+    def _critical(self):
+        """Run the enclosed launches on the engine's high-priority stream, forked from / joined to the caller's
+        current stream (see PRIORITY_STREAMS)."""
+        if not PRIORITY_STREAMS or ops.timing_enabled():
+            yield
+            return
+        user = torch.cuda.current_stream(self.device)
+        if self.hstream is None:
+            self.hstream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.hstream.wait_stream(user)
+        with torch.cuda.stream(self.hstream):
+            yield
+        user.wait_stream(self.hstream)
 
     def _version_sig(self):
         """Sum of autograd version counters: changes whenever torch code (load_state_dict, a stock
@@ -465,35 +513,70 @@ class Engine:
             v += L.rm._version + L.rv._version
         return v
 
-    def _pack_weights(self, split=True):
-        """fp32 master weights -> bf16 kernel layouts.  The encoder's on the caller's stream; the decoders'
-        (2/3 of the bytes) on a side stream that the decoder chains wait for (self.pack_done)."""
-        self.pack_done = None
+    def _pack_weights(self, split=True, zero_staging=False):
+        """fp32 master weights -> bf16 kernel layouts.  Only the first conv's (tiny) weights on the caller's
+        stream; the rest on a side stream in the order the forward pass needs them -- encoder levels 0-3
+        (self.pack_done0, waited for by the second conv), the bottleneck level (self.pack_done4), the decoders
+        (self.pack_done) -- so the first convolution starts right away and the packing (memory bound) runs
+        under the convolutions (tensor bound).
+        zero_staging (training forward): the same side stream also zeroes the gradient staging buffer and the
+        BatchNorm-backward sums for the backward pass that follows (173 MB: 26 us that used to sit between the
+        loss and the first backward kernel)."""
+        self.pack_done0 = self.pack_done4 = self.pack_done = None
+        if zero_staging:
+            # the BatchNorm batch sums of the forward pass that follows: zeroed here, before the side stream is
+            # forked (60 KB; queued behind the packing kernels' thousands of blocks it took 30 us instead of 3)
+            ops.zero_(self.bn_stats_all)
+
+        def zero():
+            ops.zero_(self.gstage)
+            ops.zero_(self.bn_sums_all)
+            self.staging_clean = True
+
         if not self.weights_dirty:
+            if zero_staging:
+                zero()
             return
-        first = self.encoder[0][0]
-        if self._first_tc():
-            ops.first_conv_pack(first.w, first.wf0)
-        ops.pack_conv_weights(self.conv_pack_tables[0], self.flat_p, self.wpack)     # encoder conv3x3 layers (tiled)
-
-        def decoders():
-            ops.pack_conv_weights(self.conv_pack_tables[1], self.flat_p, self.wpack)
-            ops.permute_batched(self.pack_table, self.flat_p, self.wpack)            # transposed convs
-
-        if split and SPLIT_PACK and not ops.timing_enabled():
+        side = split and SPLIT_PACK and not ops.timing_enabled()
+        if side:
             s0 = torch.cuda.current_stream(self.device)
             if self.pstream is None:
                 self.pstream = torch.cuda.Stream(device=self.device)
             ev = torch.cuda.Event()
             ev.record(s0)                       # the optimizer's parameter update is on the caller's stream
             self.pstream.wait_event(ev)
+        first = self.encoder[0][0]
+        if self._first_tc():
+            ops.first_conv_pack(first.w, first.wf0)
+
+        def rest(record):
+            ops.pack_conv_weights(self.conv_pack_tables[0], self.flat_p, self.wpack)     # encoder levels 0-3 (tiled)
+            self.pack_done0 = record()
+            ops.pack_conv_weights(self.conv_pack_tables[1], self.flat_p, self.wpack)     # bottleneck level
+            self.pack_done4 = record()
+            ops.pack_conv_weights(self.conv_pack_tables[2], self.flat_p, self.wpack)     # decoders
+            ops.permute_batched(self.pack_table, self.flat_p, self.wpack)                # transposed convs
+            if zero_staging:
+                zero()
+            self.pack_done = record()
+
+        if side:
+            def record():
+                e = torch.cuda.Event()
+                e.record(self.pstream)
+                return e
             with torch.cuda.stream(self.pstream):
-                decoders()
-                self.pack_done = torch.cuda.Event()
-                self.pack_done.record(self.pstream)
+                rest(record)
         else:
-            decoders()
+            rest(lambda: None)
         self.weights_dirty = False
+
+    def _wait_pack(self, which):
+        """Make the current stream wait for a stage of the side-stream weight packing (see _pack_weights)."""
+        ev = getattr(self, which)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            setattr(self, which, None)
 
     def _first_tc(self):
         return FIRST_FWD_TC and self.n_channels <= 8 and self.encoder[0][0].cout == 64
@@ -552,8 +635,12 @@ class Engine:
         if self._graphs_ok():
             outs = self._forward_graphed(pl, x, training)
         else:
-            self._pack_weights()
-            outs = self._forward_train(pl, x) if training else self._forward_eval(pl, x)
+            with self._critical() if training else contextlib.nullcontext():
+                self._pack_weights(zero_staging=training)
+                outs = self._forward_train(pl, x) if training else self._forward_eval(pl, x)
+            user = torch.cuda.current_stream(self.device)
+            for o in outs:
+                o.record_stream(user)       # allocated on the engine's stream, consumed on the caller's
             pl.x = x
             pl.static_outs = None
         if training:
@@ -574,8 +661,9 @@ class Engine:
         if training:
             def body():
                 self.weights_dirty = True       # the optimizer moved the weights: re-pack inside the graph
-                self._pack_weights()
-                return self._forward_train(pl, pl.x_in)
+                with self._critical():
+                    self._pack_weights(zero_staging=True)
+                    return self._forward_train(pl, pl.x_in)
         else:
             self._pack_weights(split=False)     # only when something changed the weights; not part of the graph
             self._fold()
@@ -584,34 +672,51 @@ class Engine:
                 return self._forward_eval(pl, pl.x_in, fold=False)
         outs, replayed = st.run(body)
         self.weights_dirty = False
+        if training:
+            self.staging_clean = True       # (a replay ran the captured memsets)
         pl.static_outs = outs if replayed else None
-        return [o.clone() for o in outs] if replayed else outs
+        if replayed:
+            return [o.clone() for o in outs]
+        user = torch.cuda.current_stream(self.device)
+        for o in outs:
+            o.record_stream(user)           # eager call: allocated on the engine's stream, consumed on the caller's
+        return outs
 
-    def _bn_train(self, L, y, a, count, pool=None):
+    def _bn_count(self, L, count):
+        """Pixel count behind L.stats; with synchronised BatchNorm the statistics are first summed over the
+        ranks (global batch = exactly the single-process reference on the concatenated batch)."""
         if L.bn.momentum is None:
             raise NotImplementedError("BatchNorm momentum=None (cumulative moving average) is not supported: the "
                                       "reference uses nn.BatchNorm2d's default momentum 0.1 (src/model.py:15,18)")
-        mom = L.bn.momentum
         if self.sync_bn is not None:
-            # synchronised BatchNorm: statistics over the GLOBAL batch (sum of the per-rank sums, global count),
-            # i.e. exactly the single-process reference on the concatenated batch
             import torch.distributed as dist
             dist.all_reduce(L.stats, op=dist.ReduceOp.SUM, group=self.sync_bn[0])
             count = count * self.sync_bn[1]
+        return count
+
+    def _fin(self, L, count):
+        """unetk_bn_finalize_args of layer L (cached: the pointers and the count are fixed per plan)."""
+        mom = L.bn.momentum
+        key = (count, L.bn.eps, mom, L.rm.data_ptr(), L.rv.data_ptr(), L.stats.data_ptr(), L.gamma.data_ptr())
+        fin = L.__dict__.get("_fin")
+        if fin is None or fin[0] != key:
+            fin = (key, ops.bn_finalize_args(L.stats, L.gamma, L.beta, L.rm, L.rv, L.nbt, L.scale, L.shift, L.mean,
+                                             L.invstd, count, L.bn.eps, mom))
+            L._fin = fin
+        return fin[1]
+
+    def _bn_train(self, L, y, a, count, pool=None):
+        count = self._bn_count(L, count)
+        mom = L.bn.momentum
         if FUSE_BN_FINALIZE:
-            key = (count, L.bn.eps, mom, L.rm.data_ptr(), L.rv.data_ptr(), L.stats.data_ptr(), L.gamma.data_ptr())
-            fin = L.__dict__.get("_fin")
-            if fin is None or fin[0] != key:
-                fin = (key, ops.bn_finalize_args(L.stats, L.gamma, L.beta, L.rm, L.rv, L.nbt, L.scale, L.shift, L.mean,
-                                                 L.invstd, count, L.bn.eps, mom))
-                L._fin = fin
+            fin = self._fin(L, count)
             if pool is None:
-                ops.bnrelu_apply_fin(y, fin[1], a)
+                ops.bnrelu_apply_fin(y, fin, a)
             elif y.shape[1] % 2 or y.shape[2] % 2:    # floor pooling leaves the last row / column outside every window
-                ops.bnrelu_apply_fin(y, fin[1], a)
+                ops.bnrelu_apply_fin(y, fin, a)
                 ops.bnrelu_pool(a, None, None, None, pool[0], pool[1], apply=False)
             else:
-                ops.bnrelu_pool_fin(y, fin[1], a, pool[0], pool[1])
+                ops.bnrelu_pool_fin(y, fin, a, pool[0], pool[1])
             return
         ops.bn_finalize(L.stats, L.gamma, L.beta, L.rm, L.rv, L.nbt, L.scale, L.shift, L.mean, L.invstd,
                         count, L.bn.eps, mom)
@@ -624,11 +729,13 @@ class Engine:
             ops.bnrelu_pool(y, L.scale, L.shift, a, pool[0], pool[1], apply=True)
 
     def _forward_train(self, pl, x):
-        ops.zero_(self.bn_stats_all)
+        # (self.bn_stats_all was zeroed by _pack_weights(zero_staging=True))
         n = pl.n
         for l, (c1, c2) in enumerate(self.encoder):
             e = pl.enc[l]
             _note(f"fwd enc{l}")
+            if l == 4:
+                self._wait_pack("pack_done4")
             count = n * (pl.h >> l) * (pl.w >> l)
             if l == 0 and self._first_tc():
                 ops.image_to_nhwc64(x, pl.x64)
@@ -638,6 +745,8 @@ class Engine:
             else:
                 ops.conv3x3_fwd(pl.enc[l - 1]["p"], None, c1.wf, e["y1"], stats=c1.stats)
             self._bn_train(c1, e["y1"], e["a1"], count)
+            if l == 0:
+                self._wait_pack("pack_done0")
             ops.conv3x3_fwd(e["a1"], None, c2.wf, e["y2"], stats=c2.stats)
             self._bn_train(c2, e["y2"], e["a2"], count, pool=(e["p"], e["idx"]) if l < 4 else None)
         pl.drop_mask = None
@@ -664,11 +773,21 @@ class Engine:
             ops.conv3x3_fwd(pl.enc[lv]["a2"], s["up"], c1.wf, s["y1"], stats=c1.stats)
             self._bn_train(c1, s["y1"], s["a1"], count)
             ops.conv3x3_fwd(s["a1"], None, c2.wf, s["y2"], stats=c2.stats)
-            self._bn_train(c2, s["y2"], s["a2"], count)
+            if k < 3 or not pl.head_fused:
+                self._bn_train(c2, s["y2"], s["a2"], count)
 
-        return self._run_decoders(pl, x, stage)
+        def head(d, out):
+            hd = self.decoders[d][1]
+            if not pl.head_fused:
+                return ops.head_fwd(pl.dec[d][3]["a2"], hd.w, hd.b, out, hd.sigmoid)
+            c2 = self.decoders[d][0][3][2]
+            count = self._bn_count(c2, n * pl.h * pl.w)
+            ops.head_fwd_bn(pl.dec[d][3]["y2"], self._fin(c2, count), hd.w, hd.b, out, hd.sigmoid)
 
-    def _run_decoders(self, pl, x, stage, parallel=True):
+        pl.head_fused = HEAD_FUSE_BN and FUSE_BN_FINALIZE and all(st[3][2].cout == 64 for st, _ in self.decoders)
+        return self._run_decoders(pl, x, stage, head=head)
+
+    def _run_decoders(self, pl, x, stage, parallel=True, head=None):
         """Decoder stages + heads.  The decoders of an AnomalyUNet are independent given the encoder, so in
         training they run on parallel streams, enqueued stage by stage: the memory-bound BatchNorm/ReLU
         passes of one decoder share the SMs with the tensor-bound convolutions of the other (12.0 -> 11.0 ms
@@ -678,9 +797,11 @@ class Engine:
         outs = [torch.empty(pl.n, head.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device) for _, head in self.decoders]
         streams = self._decoder_streams(n_dec if parallel else 1) * (1 if parallel else n_dec)
         s0 = streams[0]
-        if self.pack_done is not None:          # decoder weights are packed on a side stream
-            s0.wait_event(self.pack_done)
-            self.pack_done = None
+        for which in ("pack_done0", "pack_done4", "pack_done"):     # decoder weights are packed on a side stream
+            ev = getattr(self, which)
+            if ev is not None:
+                s0.wait_event(ev)
+                setattr(self, which, None)
         if n_dec > 1 and streams[1] is not s0:
             ev = torch.cuda.Event()
             ev.record(s0)
@@ -691,9 +812,11 @@ class Engine:
                 with torch.cuda.stream(streams[d]):
                     if k < 4:
                         stage(d, k)
+                    elif head is not None:
+                        head(d, outs[d])
                     else:
-                        head = self.decoders[d][1]
-                        ops.head_fwd(pl.dec[d][3]["a2"], head.w, head.b, outs[d], head.sigmoid)
+                        hd = self.decoders[d][1]
+                        ops.head_fwd(pl.dec[d][3]["a2"], hd.w, hd.b, outs[d], hd.sigmoid)
         for st in streams[1:]:
             if st is not s0:
                 ev = torch.cuda.Event()
@@ -708,7 +831,7 @@ class Engine:
         if n_dec == 1 or not PARALLEL_DECODERS or ops.timing_enabled():
             return [s0] * n_dec
         while len(self.dstreams) < n_dec - 1:
-            self.dstreams.append(torch.cuda.Stream(device=self.device))
+            self.dstreams.append(torch.cuda.Stream(device=self.device, priority=-1 if PRIORITY_STREAMS else 0))
         return [s0] + self.dstreams[: n_dec - 1]
 
     def _fold(self):
@@ -718,11 +841,14 @@ class Engine:
             self.fold_dirty = False
 
     def _forward_eval(self, pl, x, fold=True):
+        pl.head_fused = False
         if fold:
             self._fold()
         n = pl.n
         for l, (c1, c2) in enumerate(self.encoder):
             e = pl.enc[l]
+            if l == 4:
+                self._wait_pack("pack_done4")
             if l == 0 and self._first_tc():
                 ops.image_to_nhwc64(x, pl.x64)
                 ops.conv3x3_fwd(pl.x64, None, c1.wf0, e["a1"], scale=c1.scale, shift=c1.shift, relu=True,
@@ -732,6 +858,8 @@ class Engine:
                 ops.bnrelu_apply(e["y1"], c1.scale, c1.shift, e["a1"])
             else:
                 ops.conv3x3_fwd(pl.enc[l - 1]["p"], None, c1.wf, e["a1"], scale=c1.scale, shift=c1.shift, relu=True)
+            if l == 0:
+                self._wait_pack("pack_done0")
             ops.conv3x3_fwd(e["a1"], None, c2.wf, e["a2"], scale=c2.scale, shift=c2.shift, relu=True)
             if l < 4:
                 ops.bnrelu_pool(e["a2"], None, None, None, e["p"], None, apply=False)
@@ -809,6 +937,10 @@ class Engine:
             return grads
 
     def _backward(self, pl, grad_outs, outs):
+        if not self.staging_clean:          # not preceded by a training forward of this engine (cannot happen
+            ops.zero_(self.gstage)          # through autograd; kept for direct callers)
+            ops.zero_(self.bn_sums_all)
+        self.staging_clean = False
         pl.alloc_grads()
         graphed = (self._graphs_ok() and pl.static_outs is not None and (self.ddp is None or GRAPH_DDP))
         if not graphed:
@@ -835,6 +967,10 @@ class Engine:
         return self.grad_views()
 
     def _backward_body(self, pl, grads, outs):
+        with self._critical():
+            return self._backward_chains(pl, grads, outs)
+
+    def _backward_chains(self, pl, grads, outs):
         V = Plan.view
         ctx = self._ctx
         n_dec = len(self.decoders)
@@ -848,8 +984,6 @@ class Engine:
             self.wstreams.append(torch.cuda.Stream(device=self.device))
         chains = [_Chain(streams[d], self.wstreams[d if parallel else 0] if overlap else None, pl.scratch[d])
                   for d in range(n_dec)]
-        ops.zero_(self.gstage)
-        ops.zero_(self.bn_sums_all)
         if parallel:
             ev = torch.cuda.Event()
             ev.record(s0)
@@ -866,29 +1000,37 @@ class Engine:
             s = pl.dec[d][k]
             _note(f"bwd dec{d}.up{k + 1}")
             if k == 3:
-                ops.head_bwd(s["a2"], head.w, grads[d], outs[d], V(ch.d_t, s["a2"]), head.g_w, head.g_b, head.sigmoid,
-                             bn=ctx(pl, c2, s["y2"], kind="head"))
+                bnc = ctx(pl, c2, s["y2"], kind="head")
+                if bnc is None and pl.head_fused:       # no fused reduction, but the activation comes from y2
+                    bnc = pl.bnctx.get((c2.name, "y-only"))
+                    if bnc is None:
+                        bnc = pl.bnctx[(c2.name, "y-only")] = ops.bn_ctx(s["y2"], c2.scale, c2.shift, c2.mean, c2.invstd, None)
+                ops.head_bwd(None if pl.head_fused else s["a2"], head.w, grads[d], outs[d], V(ch.d_t, s["a2"]), head.g_w,
+                             head.g_b, head.sigmoid, bn=bnc)
             d_t = V(ch.d_t, s["a2"])
             d_a1 = V(ch.d_a1, s["a1"])
             skip = pl.enc[lv]["a2"]
             # second conv of the DoubleConv
             iy, d_y = ch.take_y(s["y2"])
             self._bn_apply_bwd(pl, c2, d_t, s["y2"], d_y)
+            mk = ch.mark()
             ops.conv3x3_dgrad(d_y, c2.wd, d_a1, bn=ctx(pl, c1, s["y1"]))
-            ch.free_y[iy] = ch.side(lambda: ops.conv3x3_wgrad(d_y, s["a1"], None, c2.g_w))
+            ch.free_y[iy] = ch.side(lambda: ops.conv3x3_wgrad(d_y, s["a1"], None, c2.g_w), mk)
             # first conv: two sources (skip, up)
             iy, d_y1 = ch.take_y(s["y1"])
             iu, d_up = ch.take_up(s["up"])
             self._bn_apply_bwd(pl, c1, d_a1, s["y1"], d_y1)
+            mk = ch.mark()
             bias_grad = ct.g_bias if ct is not None else None     # transposed-conv bias gradient = column sums of d_up
             if parallel and d > 0:      # own skip-gradient buffer: summed by the encoder's pool backward
                 ops.conv3x3_dgrad(d_y1, c1.wd, pl.d_skipx[d - 1][lv], acc1=False, dx2=d_up, acc2=False, stats=bias_grad)
             else:
                 ops.conv3x3_dgrad(d_y1, c1.wd, pl.d_skip[lv], acc1=skip_written[lv], dx2=d_up, acc2=False, stats=bias_grad)
                 skip_written[lv] = True
-            ch.free_y[iy] = ch.side(lambda: ops.conv3x3_wgrad(d_y1, skip, s["up"], c1.g_w))
+            ch.free_y[iy] = ch.side(lambda: ops.conv3x3_wgrad(d_y1, skip, s["up"], c1.g_w), mk)
             # transposed conv
             t_in = pl.dec[d][k - 1]["a2"] if k > 0 else pl.enc[4]["a2"]
+            mk = ch.mark()
             if ct is None:              # bilinear up-sampling: no parameters, gather backward
                 if k > 0:
                     ops.upsample2x_bwd(d_up, V(ch.d_t, t_in), accumulate=False)
@@ -914,7 +1056,7 @@ class Engine:
                 if parallel:
                     bottleneck_done = torch.cuda.Event()
                     bottleneck_done.record(ch.stream)
-            ch.free_up[iu] = ch.side(lambda: ops.convt2x2_wgrad(t_in, d_up, ct.g_w))
+            ch.free_up[iu] = ch.side(lambda: ops.convt2x2_wgrad(t_in, d_up, ct.g_w), mk)
 
         # decoders: enqueued stage by stage so that parallel chains advance together
         for k in reversed(range(4)):
@@ -933,6 +1075,7 @@ class Engine:
         # the decoders' gradients are final: re-lay them out on a side stream under the encoder's backward
         # (without data parallelism; with it the buckets are still being all-reduced)
         early_unpack = None
+        early_bottleneck = False
         if self.ddp is None and overlap:
             if self.ustream is None:
                 self.ustream = torch.cuda.Stream(device=self.device)
@@ -943,7 +1086,7 @@ class Engine:
                 if c.last_w is not None:
                     self.ustream.wait_event(c.last_w)
             with torch.cuda.stream(self.ustream):
-                self._unpack(1, 1.0)
+                self._unpack(2, 1.0)
                 early_unpack = torch.cuda.Event()
                 early_unpack.record(self.ustream)
         ch = chains[0]
@@ -956,10 +1099,12 @@ class Engine:
             d_a1 = V(ch.d_a1, e["a1"])
             iy, d_y = ch.take_y(e["y2"])
             self._bn_apply_bwd(pl, c2, pl.d_skip[l], e["y2"], d_y)
+            mk = ch.mark()
             ops.conv3x3_dgrad(d_y, c2.wd, d_a1, bn=ctx(pl, c1, e["y1"]))
-            ch.free_y[iy] = ch.side(lambda d_y=d_y, e=e, c2=c2: ops.conv3x3_wgrad(d_y, e["a1"], None, c2.g_w))
+            ch.free_y[iy] = ch.side(lambda d_y=d_y, e=e, c2=c2: ops.conv3x3_wgrad(d_y, e["a1"], None, c2.g_w), mk)
             iy, d_y = ch.take_y(e["y1"])
             self._bn_apply_bwd(pl, c1, d_a1, e["y1"], d_y)
+            mk = ch.mark()
             if l == 0:
                 def first_wgrad(d_y=d_y, c1=c1):
                     if self.n_channels <= 8 and FIRST_WGRAD_TC:
@@ -968,7 +1113,7 @@ class Engine:
                         ops.first_conv_wgrad_tc(pl.x64, d_y, pl.fc_scratch, c1.g_w)
                     else:
                         ops.first_conv_wgrad(pl.x, d_y, c1.g_w)
-                ch.free_y[iy] = ch.side(first_wgrad)
+                ch.free_y[iy] = ch.side(first_wgrad, mk)
             else:
                 src = pl.enc[l - 1]["p"]
                 d_p = V(pl.d_p, src)
@@ -978,9 +1123,18 @@ class Engine:
                                 extra=pl.d_skipx[0][l - 1] if parallel else None,
                                 bn=ctx(pl, self.encoder[l - 1][1], pl.enc[l - 1]["y2"]))
                 skip_written[l - 1] = True
-                ch.free_y[iy] = ch.side(lambda d_y=d_y, src=src, c1=c1: ops.conv3x3_wgrad(d_y, src, None, c1.g_w))
+                ch.free_y[iy] = ch.side(lambda d_y=d_y, src=src, c1=c1: ops.conv3x3_wgrad(d_y, src, None, c1.g_w), mk)
             if self.ddp is not None and l in (3, 0):
                 self.ddp.segment_ready(self, ("enc", l), [ch.last_w] if ch.last_w is not None else [])
+            if l == 4 and early_unpack is not None and ch.last_w is not None:
+                # the bottleneck level holds three quarters of the encoder's weights: un-pack its gradients under
+                # the rest of the encoder's backward too
+                self.ustream.wait_event(ch.last_w)
+                with torch.cuda.stream(self.ustream):
+                    self._unpack(1, 1.0)
+                    early_unpack = torch.cuda.Event()
+                    early_unpack.record(self.ustream)
+                early_bottleneck = True
         for c in chains:
             if c.last_w is not None:
                 s0.wait_event(c.last_w)       # every weight gradient is in the staging buffer
@@ -991,12 +1145,17 @@ class Engine:
         if early_unpack is not None:
             s0.wait_event(early_unpack)       # the decoders' gradients were re-laid-out under the encoder's backward
         else:
+            self._unpack(2, scale)
+        if not early_bottleneck:
             self._unpack(1, scale)
         self._unpack(0, scale)
         return self.grad_views()
 
     def _unpack(self, part, scale):
         """Staged gradients ([Cout][tap][Cin] conv weights, ...) -> `.grad` in the reference layouts, for the
-        encoder's (part 0) or the decoders' (part 1) parameters."""
-        ops.unpack_conv_grads(self.conv_unpack_tables[part], self.gstage, self.flat_g, scale)
-        ops.permute_batched(self.unpack_tables[part], self.gstage, self.flat_g, scale)
+        parameters of encoder levels 0-3 (part 0), of the bottleneck level's convolutions (part 1) or of the
+        decoders (part 2)."""
+        if self.conv_unpack_tables[part].n_desc:
+            ops.unpack_conv_grads(self.conv_unpack_tables[part], self.gstage, self.flat_g, scale)
+        if self.unpack_tables[part] is not None:
+            ops.permute_batched(self.unpack_tables[part], self.gstage, self.flat_g, scale)

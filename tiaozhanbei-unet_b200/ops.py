@@ -88,7 +88,8 @@ def _timed(flops, tag, name, *args):
 
 
 def bn_ctx(y, scale, shift, mean, invstd, sums):
-    """Host-side `unetk_bn_ctx` for the kernels that can fuse the BatchNorm-backward reduction."""
+    """Host-side `unetk_bn_ctx` for the kernels that can fuse the BatchNorm-backward reduction (sums=None: only
+    the layer's y / scale / shift, for head_bwd(a=None))."""
     c = _lib.BnCtx(_p(y), _p(scale), _p(shift), _p(mean), _p(invstd), _p(sums))
     c._keep = (y, scale, shift, mean, invstd, sums)
     return c
@@ -283,9 +284,24 @@ def head_fwd(a, w, b, out, sigmoid):
     return out
 
 
+def head_fwd_bn(y, fin, w, b, out, sigmoid):
+    """out = act(conv1x1(relu(BatchNorm_train(y)))) with the statistics finalize folded in (see bn_finalize_args);
+    the activated tensor is not stored."""
+    import ctypes
+    _chk(y, bf16, "y"); _chk(out, f32, "out")
+    n, h, ww, c = y.shape
+    _lib.call("unetk_head_fwd_bn", _p(y), ctypes.byref(fin), _p(w), _p(b), _p(out), n, h, ww, c, out.shape[1], int(sigmoid), _s())
+    return out
+
+
 def head_bwd(a, w, dout, out, da, dw, db, sigmoid, bn=None):
-    _chk(a, bf16, "a"); _chk(dout, f32, "dout"); _chk(da, bf16, "da")
-    n, h, ww, c = a.shape
+    """a=None: the activation is recomputed from the BatchNorm context `bn` (forward used head_fwd_bn)."""
+    _chk(dout, f32, "dout"); _chk(da, bf16, "da")
+    if a is not None:
+        _chk(a, bf16, "a")
+    elif bn is None:
+        raise _lib.UnetkError("head_bwd: without the stored activation a BatchNorm context is required")
+    n, h, ww, c = da.shape
     _lib.call("unetk_head_bwd", _p(a), _p(w), _p(dout), _p(out), _p(da), _p(dw), _p(db), n, h, ww, c,
               dout.shape[1], int(sigmoid), _bn(bn), _s())
 
