@@ -263,11 +263,9 @@ def run_ours(args):
     resident = [(a.to(dev), b.to(dev)) for a, b in host]
 
     def step(image, mask):
-        recon, amap = model(image)
-        ld = criterion(recon, amap, image, mask)
-        optimizer.zero_grad()
-        ld["total_loss"].backward()
-        optimizer.step()
+        # the loop body of src/train_utils.py:122-135 (forward, CombinedLoss, zero_grad, backward, optimizer step)
+        # through the package's public entry point for it
+        train_utils.train_step(model, criterion, optimizer, image, mask)
 
     def sync_all():
         torch.cuda.synchronize()

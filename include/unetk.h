@@ -192,6 +192,19 @@ int unetk_head_fwd(const void* a, const float* w, const float* b, float* out, in
  * (src/model.py:18-19 feeding :200-201 / :207-208). */
 int unetk_head_fwd_bn(const void* y, const unetk_bn_finalize_args* fin, const float* w, const float* b, float* out,
                       int n, int h, int w_, int c, int n_out, int sigmoid, void* stream);
+/* Output stage of one AnomalyUNet decoder for a training step, in ONE pass over y (csrc/head_fused.cu):
+ * unetk_head_fwd_bn (+sigmoid) + this decoder's term of CombinedLoss (src/train_utils.py:30-44) + unetk_head_bwd
+ * with the BatchNorm-backward sums.  which = 0: reconstruction decoder, squared error against target = the image
+ * [n, n_out, h, w]; which = 1: segmentation decoder, focal loss against target = the mask [n, 1, h, w].
+ * out (nullable): the sigmoid outputs.  da: gradient w.r.t. the activated tensor (bf16 NHWC); dw / db / bn_sums are
+ * ACCUMULATED into (zero them first).  out3 = {total, recon, seg}: each launch writes its own term, the launch of a
+ * step that finishes second also writes total = recon_weight * recon + seg_weight * seg.  work: zeroed once by the
+ * caller (unetk_head_loss_workspace_bytes), shared by the two launches of a step, self-cleaning. */
+size_t unetk_head_loss_workspace_bytes(void);
+int unetk_head_loss_bwd(const void* y, const unetk_bn_finalize_args* fin, const float* w, const float* b,
+                        const float* target, float* out, void* da, float* dw, float* db, float* bn_sums, void* work,
+                        size_t work_bytes, float* out3, int which, int n, int h, int w_, int c, int n_out,
+                        float recon_weight, float seg_weight, float alpha, float gamma, void* stream);
 /* a == NULL (forward went through unetk_head_fwd_bn): the activation is recomputed from bn->y / scale / shift.
  * bn->sums != NULL: the first pass of that BatchNorm's backward (see unetk_bn_ctx) is fused in. */
 int unetk_head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da,

@@ -42,10 +42,17 @@ def shard(r):
 
 
 image, mask = (t.to(dev) for t in shard(rank))
-r_, a_ = m(image)
-ld = crit(r_, a_, image, mask)
-opt.zero_grad()
-ld["total_loss"].backward()
+FUSED = "--fused" in sys.argv           # the one-sequence training step (Engine.train_step) instead of model / criterion / backward
+if FUSED and not SYNC_BN:
+    assert train_utils._fusable(m, crit, image, mask)
+    for _ in range(3):                  # eager call, graph capture (forward half; the all-reduces stay eager), replay
+        opt.zero_grad()
+        m._engine().train_step(image, mask, (crit.recon_weight, crit.seg_weight, crit.focal_alpha, crit.focal_gamma))
+else:
+    r_, a_ = m(image)
+    ld = crit(r_, a_, image, mask)
+    opt.zero_grad()
+    ld["total_loss"].backward()
 torch.cuda.synchronize()
 flat = m._engine().flat_g
 # 1) identical on all ranks

@@ -653,3 +653,92 @@ def test_plan_cache_is_lru(cuda_device):
     assert shapes[1] not in eng.plans, "the least recently used plan should have been evicted"
     assert len(eng.plans) == E.MAX_PLANS
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 32, 32), (3, 64, 48), (1, 36, 52)])
+def test_fused_train_step_matches_the_plain_path(cuda_device, n, h, w):
+    """train_utils.train_step on this package's AnomalyUNet + CombinedLoss runs forward, loss and backward as one
+    launch sequence with each decoder's head, loss term and head backward in ONE kernel (csrc/head_fused.cu).  The
+    arithmetic is the plain path's (model(x) -> criterion -> backward), element for element, so losses, the
+    gradients next to the heads, the BatchNorm buffers and three optimizer steps (eager call, graph capture, graph
+    replay) must agree with it; the deep gradients are compared like everywhere else (direction / norm: two runs
+    of the SAME path already differ there through the order of the fp32 atomics)."""
+    from tiaozhanbei_unet_b200 import train_utils
+    dev = cuda_device
+    arch = "anomaly_unet"
+    sd = O.synthetic_state_dict(arch, seed=9, device=dev)
+    batches = [_inputs(40 + i, n, h, w, dev) for i in range(3)]
+
+    def run(fused):
+        m = _model(arch, {k: v.clone() for k, v in sd.items()}, dev).train()
+        crit = train_utils.CombinedLoss(recon_weight=0.7, seg_weight=1.3)
+        # (a tiny learning rate: Adam's first steps move every weight by +-lr whatever the gradient's size, which
+        # turns the last-bit differences of two runs -- fp32 atomics -- into different weights)
+        opt = train_utils.get_optimizer(m, "adam", 1e-7, 1e-4)
+        losses, first_grads = [], None
+        for image, mask in batches:
+            if fused:
+                assert train_utils._fusable(m, crit, image, mask)
+                ld = train_utils.train_step(m, crit, opt, image, mask)
+            else:
+                r, a = m(image)
+                ld = crit(r, a, image, mask)
+                opt.zero_grad()
+                ld["total_loss"].backward()
+                opt.step()
+            losses.append([float(ld[k]) for k in ("total_loss", "recon_loss", "seg_loss")])
+            assert tuple(losses[-1]) == pytest.approx(crit.last_values(), rel=1e-6)
+            if first_grads is None:
+                first_grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+        torch.cuda.synchronize()
+        return m, losses, first_grads
+
+    m_plain, l_plain, g_plain = run(False)
+    m_fused, l_fused, g_fused = run(True)
+    for a, b in zip(l_plain, l_fused):
+        # (two runs of the SAME path differ in the last bits -- atomics -- and bf16 storage turns some of those into
+        # rounding flips: the small focal term moves by a few 1e-3, see test_train_epoch_prefetch_matches_the_step_loop)
+        for va, vb, tol in zip(a, b, (1e-3, 1e-3, 5e-3)):
+            assert abs(va - vb) <= tol * abs(va), (l_plain, l_fused)
+    assert abs(l_plain[0][0] - l_fused[0][0]) <= 2e-5 * abs(l_plain[0][0])     # same weights, same kernels' arithmetic
+    assert abs(l_fused[0][0] - (0.7 * l_fused[0][1] + 1.3 * l_fused[0][2])) <= 1e-5 * abs(l_fused[0][0])
+    for k in g_plain:
+        gp, gf = g_plain[k], g_fused[k]
+        cos = ((gp * gf).sum() / (gp.norm() * gf.norm() + 1e-30)).item()
+        assert cos >= GRAD_COS and abs(gp.norm().item() - gf.norm().item()) <= GRAD_NORM * gp.norm().item(), (k, cos)
+        if k.startswith(HEAD_KEYS):
+            assert (gp - gf).norm() <= 2e-3 * gp.norm(), k
+    sp, sf = m_plain.state_dict(), m_fused.state_dict()
+    for k in sp:
+        if k.endswith("num_batches_tracked"):
+            assert int(sp[k]) == int(sf[k]) == 3
+        elif O.is_buffer(k):
+            assert torch.allclose(sp[k], sf[k], rtol=2e-2, atol=1e-4), k
+    # and against the oracle, like the plain path's own test
+    ref_losses, ref_grads = O.train_step({k: v.clone() for k, v in sd.items()}, *batches[0], arch=arch)
+    want = 0.7 * ref_losses["recon_loss"] + 1.3 * ref_losses["seg_loss"]
+    assert abs(l_fused[0][0] - want) <= LOSS_REL * abs(want)
+    assert abs(l_fused[0][1] - ref_losses["recon_loss"]) <= LOSS_REL * abs(ref_losses["recon_loss"])
+    for k in ("outc_recon.conv.bias", "outc_seg.conv.bias", "outc_seg.conv.weight"):
+        gr = ref_grads[k] * (0.7 if "recon" in k else 1.3)
+        assert (g_fused[k] - gr).norm() <= GRAD_REL_HEAD * gr.norm(), k
+
+
+def test_fused_train_step_falls_back_when_it_does_not_apply(cuda_device):
+    """UNet, a frozen parameter, eval mode or a foreign criterion take the plain path of train_step."""
+    from tiaozhanbei_unet_b200 import train_utils
+    dev = cuda_device
+    image, mask = _inputs(3, 2, 32, 32, dev)
+    crit = train_utils.CombinedLoss()
+    m = _model("anomaly_unet", O.synthetic_state_dict("anomaly_unet", seed=2), dev).train()
+    assert train_utils._fusable(m, crit, image, mask)
+    assert not train_utils._fusable(m, torch.nn.MSELoss(), image, mask)
+    assert not train_utils._fusable(m.eval(), crit, image, mask)
+    m.train()
+    m.outc_seg.conv.bias.requires_grad_(False)
+    assert not train_utils._fusable(m, crit, image, mask)
+    opt = train_utils.get_optimizer(m, "adam", 1e-3, 1e-4)
+    ld = train_utils.train_step(m, crit, opt, image, mask)          # plain path: autograd leaves the frozen bias alone
+    torch.cuda.synchronize()
+    assert m.outc_seg.conv.bias.grad is None and m.outc_seg.conv.weight.grad is not None
+    assert torch.isfinite(ld["total_loss"]).item()

@@ -43,6 +43,8 @@ SIGNATURES = {
     "unetk_bn_bwd_apply": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, P]),
     "unetk_head_fwd": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "unetk_head_fwd_bn": (I, [P, P, P, P, P, I, I, I, I, I, I, P]),
+    "unetk_head_loss_workspace_bytes": (Z, []),
+    "unetk_head_loss_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, Z, P, I, I, I, I, I, I, F, F, F, F, P]),
     "unetk_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, I, I, P, P]),
     "unetk_combined_loss_workspace_bytes": (Z, []),
     "unetk_combined_loss": (I, [P, P, P, P, P, P, P, P, Z, L, L, F, F, F, F, P]),

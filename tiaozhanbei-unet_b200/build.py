@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(CSRC, "build")
 LIB = os.path.join(BUILD, "libunetk.so")
-SOURCES = ["runtime.cu", "igemm.cu", "wgrad.cu", "elementwise.cu", "head_loss.cu", "first_conv.cu", "seg_loss.cu",
+SOURCES = ["runtime.cu", "igemm.cu", "wgrad.cu", "elementwise.cu", "head_loss.cu", "head_fused.cu", "first_conv.cu", "seg_loss.cu",
            "eval_metrics.cu", "preprocess.cu", "optim.cu", "api.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "unetk.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -144,6 +144,14 @@ int unetk_head_fwd_bn(const void* y, const unetk_bn_finalize_args* fin, const fl
                       int n, int h, int w_, int c, int n_out, int sigmoid, void* stream) {
   return unetk::head_fwd_bn(y, reinterpret_cast<const unetk::BnFinalizeArgs*>(fin), w, b, out, n, h, w_, c, n_out, sigmoid, S(stream));
 }
+size_t unetk_head_loss_workspace_bytes(void) { return unetk::head_loss_workspace_bytes(); }
+int unetk_head_loss_bwd(const void* y, const unetk_bn_finalize_args* fin, const float* w, const float* b,
+                        const float* target, float* out, void* da, float* dw, float* db, float* bn_sums, void* work,
+                        size_t work_bytes, float* out3, int which, int n, int h, int w_, int c, int n_out,
+                        float recon_weight, float seg_weight, float alpha, float gamma, void* stream) {
+  return unetk::head_loss_bwd(y, reinterpret_cast<const unetk::BnFinalizeArgs*>(fin), w, b, target, out, da, dw, db, bn_sums,
+                              work, work_bytes, out3, which, n, h, w_, c, n_out, recon_weight, seg_weight, alpha, gamma, S(stream));
+}
 int unetk_head_bwd(const void* a, const float* w, const float* dout, const float* out, void* da,
                    float* dw, float* db, int n, int h, int w_, int c, int n_out, int sigmoid,
                    const unetk_bn_ctx* bn, void* stream) {

@@ -51,7 +51,8 @@ inline BnFinalizeArgs with_reciprocals(BnFinalizeArgs f) {
 // DFMA instead of two double divisions: every thread of the consuming kernel runs this).  `writer` threads
 // also store scale / shift / mean / invstd for the backward pass and update the running statistics
 // (num_batches_tracked is the caller's: one thread only).
-__device__ __forceinline__ void bn_finalize1(const BnFinalizeArgs& f, int C, int c, bool writer, float& sc, float& sh) {
+__device__ __forceinline__ void bn_finalize1(const BnFinalizeArgs& f, int C, int c, bool writer, float& sc, float& sh,
+                                             float* mean_out = nullptr, float* invstd_out = nullptr) {
   const double mean_d = static_cast<double>(f.stats[c]) * f.inv_count;
   const float mean = static_cast<float>(mean_d);
   float var = static_cast<float>(static_cast<double>(f.stats[C + c]) * f.inv_count - mean_d * mean_d);
@@ -59,6 +60,8 @@ __device__ __forceinline__ void bn_finalize1(const BnFinalizeArgs& f, int C, int
   const float invstd = rsqrtf(var + f.eps);
   sc = f.gamma[c] * invstd;
   sh = f.beta[c] - mean * sc;
+  if (mean_out != nullptr) *mean_out = mean;
+  if (invstd_out != nullptr) *invstd_out = invstd;
   if (writer) {
     f.scale[c] = sc;
     f.shift[c] = sh;
@@ -126,6 +129,11 @@ int nchw_to_nhwc(const float* in, void* out, int N, int C, int H, int W, cudaStr
 int nhwc_to_nchw(const void* in, float* out, int N, int C, int H, int W, cudaStream_t s);
 
 // head_loss.cu
+size_t head_loss_workspace_bytes();
+int head_loss_bwd(const void* y, const BnFinalizeArgs* fin, const float* w, const float* b, const float* target,
+                  float* out, void* da, float* dw, float* db, float* bn_sums, void* work, size_t work_bytes,
+                  float* out3, int which, int N, int H, int W, int C, int n_out, float recon_weight, float seg_weight,
+                  float alpha, float gamma, cudaStream_t s);
 int head_fwd_bn(const void* y, const BnFinalizeArgs* fin, const float* w, const float* b, float* out, int N, int H,
                 int W, int C, int n_out, int sigmoid, cudaStream_t s);
 int head_fwd(const void* a, const float* w, const float* b, float* out, int N, int H, int W, int C,

@@ -161,6 +161,10 @@ class Plan:
         self.fused = set()
         self.drop_mask = None
         self.head_fused = False   # the last training forward applied the final BatchNorm inside the head kernels
+        self.chains_flow = False  # train_step(): the decoder streams were not joined between forward and backward
+        self.fused_loss = None    # train_step(): {"mask", "cfg", "work", "out3", "want_outs"} while its launches are enqueued
+        self.m_in = None          # static copy of the mask (train_step graph replays read it)
+        self.out3 = None          # static (total, recon, seg) of train_step
         self.static_outs = None   # outputs owned by the forward graph (backward reads them)
         self.graphs = {}          # "train" / "eval" / "bwd" -> _GraphState
         self.x_in = None          # static copy of the input image (graph replays read it)
@@ -299,7 +303,8 @@ class Engine:
         self.ustream = None       # side stream un-packing the decoders' gradients during the encoder's backward
         self.sync_bn = None       # process group for synchronised BatchNorm statistics (distributed.attach(sync_bn=True))
         self.bottleneck_dropout = 0.0   # SegmentationUNet: nn.Dropout2d(p) on the bottleneck (src/model.py:130,146)
-        self.pack_done0 = self.pack_done4 = self.pack_done = None
+        self.pack_done0 = self.pack_done4 = self.pack_done = self.zero_done = None
+        self._pack_pending = None
         self.weights_dirty = True
         self.fold_dirty = True
         # bumped by EVERY forward (any shape, train or eval): the BatchNorm scale / shift / mean / invstd, the
@@ -515,61 +520,75 @@ class Engine:
 
     def _pack_weights(self, split=True, zero_staging=False):
         """fp32 master weights -> bf16 kernel layouts.  Only the first conv's (tiny) weights on the caller's
-        stream; the rest on a side stream in the order the forward pass needs them -- encoder levels 0-3
-        (self.pack_done0, waited for by the second conv), the bottleneck level (self.pack_done4), the decoders
-        (self.pack_done) -- so the first convolution starts right away and the packing (memory bound) runs
-        under the convolutions (tensor bound).
-        zero_staging (training forward): the same side stream also zeroes the gradient staging buffer and the
-        BatchNorm-backward sums for the backward pass that follows (173 MB: 26 us that used to sit between the
-        loss and the first backward kernel)."""
-        self.pack_done0 = self.pack_done4 = self.pack_done = None
+        stream; the rest on a side stream, staged the way the forward pass needs it: encoder levels 0-3 at once
+        (self.pack_done0, waited for by the second conv); the bottleneck level (self.pack_done4) and the decoders
+        (self.pack_done) only after encoder level 1 (_pack_rest) -- packing is memory bound, and under the
+        full-resolution BatchNorm passes of the first two levels it doubled their time, while the deeper levels are
+        tensor bound and hide it.
+        zero_staging (training forward): the side stream finally zeroes the gradient staging buffer and the
+        BatchNorm-backward sums for the backward pass that follows (self.zero_done; 173 MB: 26 us that used to sit
+        between the loss and the first backward kernel)."""
+        self.pack_done0 = self.pack_done4 = self.pack_done = self.zero_done = None
+        self._pack_pending = None
         if zero_staging:
             # the BatchNorm batch sums of the forward pass that follows: zeroed here, before the side stream is
             # forked (60 KB; queued behind the packing kernels' thousands of blocks it took 30 us instead of 3)
             ops.zero_(self.bn_stats_all)
-
-        def zero():
-            ops.zero_(self.gstage)
-            ops.zero_(self.bn_sums_all)
-            self.staging_clean = True
-
-        if not self.weights_dirty:
-            if zero_staging:
-                zero()
-            return
         side = split and SPLIT_PACK and not ops.timing_enabled()
-        if side:
-            s0 = torch.cuda.current_stream(self.device)
-            if self.pstream is None:
-                self.pstream = torch.cuda.Stream(device=self.device)
-            ev = torch.cuda.Event()
-            ev.record(s0)                       # the optimizer's parameter update is on the caller's stream
-            self.pstream.wait_event(ev)
-        first = self.encoder[0][0]
-        if self._first_tc():
-            ops.first_conv_pack(first.w, first.wf0)
-
-        def rest(record):
-            ops.pack_conv_weights(self.conv_pack_tables[0], self.flat_p, self.wpack)     # encoder levels 0-3 (tiled)
-            self.pack_done0 = record()
-            ops.pack_conv_weights(self.conv_pack_tables[1], self.flat_p, self.wpack)     # bottleneck level
-            self.pack_done4 = record()
-            ops.pack_conv_weights(self.conv_pack_tables[2], self.flat_p, self.wpack)     # decoders
-            ops.permute_batched(self.pack_table, self.flat_p, self.wpack)                # transposed convs
-            if zero_staging:
-                zero()
-            self.pack_done = record()
-
-        if side:
-            def record():
-                e = torch.cuda.Event()
-                e.record(self.pstream)
-                return e
-            with torch.cuda.stream(self.pstream):
-                rest(record)
-        else:
-            rest(lambda: None)
+        if side and self.pstream is None:
+            self.pstream = torch.cuda.Stream(device=self.device)
+        dirty = self.weights_dirty
+        if dirty:
+            first = self.encoder[0][0]
+            if side:
+                self._fork_pack_stream()            # (the optimizer's parameter update is on the caller's stream)
+            if self._first_tc():
+                ops.first_conv_pack(first.w, first.wf0)
+            with torch.cuda.stream(self.pstream) if side else contextlib.nullcontext():
+                ops.pack_conv_weights(self.conv_pack_tables[0], self.flat_p, self.wpack)     # encoder levels 0-3 (tiled)
+                if side:
+                    self.pack_done0 = self._record(self.pstream)
+        self._pack_pending = (side, dirty, zero_staging)
+        if not side:
+            self._pack_rest()
         self.weights_dirty = False
+
+    def _fork_pack_stream(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.pstream.wait_event(ev)
+
+    @staticmethod
+    def _record(stream):
+        e = torch.cuda.Event()
+        e.record(stream)
+        return e
+
+    def _pack_rest(self):
+        """Second half of _pack_weights: bottleneck level, decoders, transposed convs, staging memsets."""
+        if self._pack_pending is None:
+            return
+        side, dirty, zero_staging = self._pack_pending
+        self._pack_pending = None
+        if not (dirty or zero_staging):
+            return
+        if side:
+            self._fork_pack_stream()
+        with torch.cuda.stream(self.pstream) if side else contextlib.nullcontext():
+            if dirty:
+                ops.pack_conv_weights(self.conv_pack_tables[1], self.flat_p, self.wpack)     # bottleneck level
+                if side:
+                    self.pack_done4 = self._record(self.pstream)
+                ops.pack_conv_weights(self.conv_pack_tables[2], self.flat_p, self.wpack)     # decoders
+                ops.permute_batched(self.pack_table, self.flat_p, self.wpack)                # transposed convs
+                if side:
+                    self.pack_done = self._record(self.pstream)
+            if zero_staging:
+                ops.zero_(self.gstage)
+                ops.zero_(self.bn_sums_all)
+                self.staging_clean = True
+                if side:
+                    self.zero_done = self._record(self.pstream)
 
     def _wait_pack(self, which):
         """Make the current stream wait for a stage of the side-stream weight packing (see _pack_weights)."""
@@ -749,6 +768,8 @@ class Engine:
                 self._wait_pack("pack_done0")
             ops.conv3x3_fwd(e["a1"], None, c2.wf, e["y2"], stats=c2.stats)
             self._bn_train(c2, e["y2"], e["a2"], count, pool=(e["p"], e["idx"]) if l < 4 else None)
+            if l == 1:
+                self._pack_rest()
         pl.drop_mask = None
         if self.bottleneck_dropout > 0.0:
             # F.dropout2d(x5, p, training=True): one Bernoulli(1-p)/(1-p) factor per (image, channel), drawn from
@@ -776,25 +797,35 @@ class Engine:
             if k < 3 or not pl.head_fused:
                 self._bn_train(c2, s["y2"], s["a2"], count)
 
+        fl = pl.fused_loss          # set by train_step(): the heads also compute CombinedLoss and their own backward
+
         def head(d, out):
             hd = self.decoders[d][1]
             if not pl.head_fused:
                 return ops.head_fwd(pl.dec[d][3]["a2"], hd.w, hd.b, out, hd.sigmoid)
             c2 = self.decoders[d][0][3][2]
             count = self._bn_count(c2, n * pl.h * pl.w)
-            ops.head_fwd_bn(pl.dec[d][3]["y2"], self._fin(c2, count), hd.w, hd.b, out, hd.sigmoid)
+            fin = self._fin(c2, count)
+            y2 = pl.dec[d][3]["y2"]
+            if fl is None:
+                return ops.head_fwd_bn(y2, fin, hd.w, hd.b, out, hd.sigmoid)
+            rw, sw, alpha, gamma = fl["cfg"]
+            ops.head_loss_bwd(y2, fin, hd.w, hd.b, x if d == 0 else fl["mask"], out, Plan.view(pl.scratch[d]["d_t"], y2),
+                              hd.g_w, hd.g_b, c2.sums, fl["work"], fl["out3"], d, rw, sw, alpha, gamma)
 
-        pl.head_fused = HEAD_FUSE_BN and FUSE_BN_FINALIZE and all(st[3][2].cout == 64 for st, _ in self.decoders)
-        return self._run_decoders(pl, x, stage, head=head)
+        pl.head_fused = fl is not None or (HEAD_FUSE_BN and FUSE_BN_FINALIZE
+                                           and all(st[3][2].cout == 64 for st, _ in self.decoders))
+        return self._run_decoders(pl, x, stage, head=head, want_outs=fl is None or fl["want_outs"])
 
-    def _run_decoders(self, pl, x, stage, parallel=True, head=None):
+    def _run_decoders(self, pl, x, stage, parallel=True, head=None, want_outs=True):
         """Decoder stages + heads.  The decoders of an AnomalyUNet are independent given the encoder, so in
         training they run on parallel streams, enqueued stage by stage: the memory-bound BatchNorm/ReLU
         passes of one decoder share the SMs with the tensor-bound convolutions of the other (12.0 -> 11.0 ms
         per step together with the backward chains).  Eval mode folds BatchNorm into the conv epilogue, is
         tensor bound throughout and measured slower on two streams (2.90 -> 3.05 ms): one stream."""
         n_dec = len(self.decoders)
-        outs = [torch.empty(pl.n, head.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device) for _, head in self.decoders]
+        outs = [torch.empty(pl.n, hd.n_out, pl.h, pl.w, dtype=torch.float32, device=x.device) if want_outs else None
+                for _, hd in self.decoders]
         streams = self._decoder_streams(n_dec if parallel else 1) * (1 if parallel else n_dec)
         s0 = streams[0]
         for which in ("pack_done0", "pack_done4", "pack_done"):     # decoder weights are packed on a side stream
@@ -808,6 +839,10 @@ class Engine:
             for st in streams[1:]:
                 st.wait_event(ev)
         for k in range(5):
+            if k == 4 and self.zero_done is not None:      # the heads of train_step() add into the zeroed staging buffers
+                for st in {id(st): st for st in streams}.values():
+                    st.wait_event(self.zero_done)
+                self.zero_done = None
             for d in range(n_dec):
                 with torch.cuda.stream(streams[d]):
                     if k < 4:
@@ -817,12 +852,28 @@ class Engine:
                     else:
                         hd = self.decoders[d][1]
                         ops.head_fwd(pl.dec[d][3]["a2"], hd.w, hd.b, outs[d], hd.sigmoid)
+        if pl.fused_loss is not None and pl.fused_loss["flow"] and not want_outs and self._same_backward_streams(pl, streams):
+            # train_step(): every decoder's backward chain continues on the stream its forward ran on -- no join
+            # here, no fork there: the decoder that is ahead runs on into its backward pass instead of idling until
+            # the other one's head is done (225 us at 16 x 256^2)
+            pl.chains_flow = True
+            return outs
+        pl.chains_flow = False
         for st in streams[1:]:
             if st is not s0:
                 ev = torch.cuda.Event()
                 ev.record(st)
                 s0.wait_event(ev)
         return outs
+
+    def _backward_streams(self, pl):
+        n_dec = len(self.decoders)
+        # (odd sizes: the pool backward cannot add the second decoder's skip gradient to the last row / column)
+        return (self._decoder_streams(n_dec) if n_dec == 2 and pl.all_even
+                else [torch.cuda.current_stream(self.device)] * n_dec)
+
+    def _same_backward_streams(self, pl, streams):
+        return [s.cuda_stream for s in self._backward_streams(pl)] == [s.cuda_stream for s in streams]
 
     def _decoder_streams(self, n_dec):
         """[current stream, side streams...]; all the current stream when parallel decoders are off or the
@@ -863,6 +914,9 @@ class Engine:
             ops.conv3x3_fwd(e["a1"], None, c2.wf, e["a2"], scale=c2.scale, shift=c2.shift, relu=True)
             if l < 4:
                 ops.bnrelu_pool(e["a2"], None, None, None, e["p"], None, apply=False)
+            if l == 1:
+                self._pack_rest()
+
         def stage(d, k):
             ct, c1, c2 = self.decoders[d][0][k]
             lv = 3 - k
@@ -936,6 +990,117 @@ class Engine:
                          for k, p in zip(self.param_names, self.params)]
             return grads
 
+    # ------------------------------------------------------------------------------------------
+    # fused training step (AnomalyUNet + CombinedLoss)
+    # ------------------------------------------------------------------------------------------
+    def can_fuse_step(self):
+        """train_step() covers the two-decoder AnomalyUNet graph with 64-channel last layers, no dropout, local
+        BatchNorm statistics and every parameter trainable."""
+        return (self.arch == "anomaly_unet" and len(self.decoders) == 2 and self.bottleneck_dropout == 0.0
+                and self.sync_bn is None and FUSE_BN_FINALIZE and not FUSE_CHECK
+                and all(st[3][2].cout == 64 for st, _ in self.decoders)
+                and self.decoders[0][1].sigmoid and self.decoders[1][1].sigmoid and self.decoders[1][1].n_out == 1
+                and self.decoders[0][1].n_out in (1, 3)
+                and all(p.requires_grad for p in self.module.parameters()))
+
+    def train_step(self, x, mask, cfg, want_outs=False):
+        """Forward, CombinedLoss (cfg = recon_weight, seg_weight, focal_alpha, focal_gamma) and backward of one
+        batch as ONE launch sequence (one CUDA graph per input shape): what src/train_utils.py:122-132 does with
+        `model(images)`, `criterion(...)` and `total_loss.backward()`, with each decoder's head, its loss term and
+        the head's backward in a single kernel (csrc/head_fused.cu).  Sets every parameter's `.grad` (a view of
+        the flat gradient buffer, replacing what was there) and returns (out3, outs): the device tensor
+        (total, recon, seg) and, if asked for, the two sigmoid outputs."""
+        x = self._check_input(x)
+        if not mask.is_cuda or mask.dtype != torch.float32:
+            raise _lib.UnetkError("train_step: the mask must be a float32 CUDA tensor")
+        mask = mask.contiguous()
+        with torch.cuda.device(x.device):
+            self.ensure(x.device)
+            n, _, h, w = x.shape
+            if tuple(mask.shape) != (n, 1, h, w):
+                raise ValueError(f"train_step: mask must be {(n, 1, h, w)}, got {tuple(mask.shape)}")
+            pl = self.plan_for(n, h, w)
+            self.generation += 1
+            self.mark_weights_dirty()
+            self._vsig = self._version_sig()
+            pl.alloc_grads()
+            if pl.out3 is None:
+                pl.out3 = torch.zeros(3, dtype=torch.float32, device=x.device)
+                pl.loss_work = ops.head_loss_workspace(x.device)
+            cfg = tuple(float(v) for v in cfg)
+            graphs = self._graphs_ok()
+
+            whole = self.ddp is None or GRAPH_DDP       # NCCL all-reduces stay outside the capture by default
+            # forward and backward enqueued back to back (both eager, or one capture): the decoder chains need no join
+            flow = whole or not graphs
+
+            def phases(xs, ms):
+                pl.fused_loss = {"mask": ms, "cfg": cfg, "work": pl.loss_work, "out3": pl.out3, "want_outs": want_outs,
+                                 "flow": flow}
+                try:
+                    with self._critical():
+                        self._pack_weights(zero_staging=True)
+                        outs = self._forward_train(pl, xs)
+                    yield outs
+                    self.staging_clean = False
+                    self._backward_body(pl, None, None)
+                    yield None
+                finally:
+                    pl.fused_loss = None
+
+            if not graphs:
+                ph = phases(x, mask)
+                outs = next(ph)
+                pl.x = x
+                next(ph)
+                ph.close()
+            else:
+                if pl.x_in is None:
+                    pl.x_in = torch.empty_like(x)
+                if pl.m_in is None:
+                    pl.m_in = torch.empty_like(mask)
+                pl.x_in.copy_(x)
+                pl.m_in.copy_(mask)
+                pl.x = pl.x_in
+                key = ("step" if whole else "step_fwd", cfg, want_outs)
+                st = pl.graphs.get(key)
+                if st is None:
+                    st = pl.graphs[key] = _GraphState()
+                keep = {}
+
+                def body():
+                    ph = phases(pl.x_in, pl.m_in)
+                    outs = next(ph)
+                    if whole:
+                        next(ph)
+                        ph.close()
+                    else:
+                        keep["ph"] = ph
+                    return outs
+                outs, replayed = st.run(body)
+                if not whole:
+                    ph = keep.get("ph")
+                    if ph is None:                          # replayed: only the backward half runs eagerly
+                        pl.fused_loss = {"mask": pl.m_in, "cfg": cfg, "work": pl.loss_work, "out3": pl.out3, "want_outs": want_outs,
+                                         "flow": False}
+                        pl.chains_flow = False
+                        try:
+                            self.staging_clean = False
+                            self._backward_body(pl, None, None)
+                        finally:
+                            pl.fused_loss = None
+                    else:
+                        next(ph)
+                        ph.close()
+                if want_outs and replayed:
+                    outs = [o.clone() for o in outs]
+            self.weights_dirty = False
+            self.fold_dirty = True
+            self.staging_clean = False
+            for p, v in zip(self.params, self.grad_views()):
+                p.grad = v
+            return pl.out3.clone(), (outs if want_outs else None)
+
     def _backward(self, pl, grad_outs, outs):
         if not self.staging_clean:          # not preceded by a training forward of this engine (cannot happen
             ops.zero_(self.gstage)          # through autograd; kept for direct callers)
@@ -974,9 +1139,7 @@ class Engine:
         V = Plan.view
         ctx = self._ctx
         n_dec = len(self.decoders)
-        # (odd sizes: the pool backward cannot add the second decoder's skip gradient to the last row / column)
-        streams = (self._decoder_streams(n_dec) if n_dec == 2 and pl.all_even
-                   else [torch.cuda.current_stream(self.device)] * n_dec)
+        streams = self._backward_streams(pl)
         s0 = streams[0]
         parallel = n_dec == 2 and streams[1] is not s0
         overlap = OVERLAP_WGRAD and not ops.timing_enabled()
@@ -984,7 +1147,7 @@ class Engine:
             self.wstreams.append(torch.cuda.Stream(device=self.device))
         chains = [_Chain(streams[d], self.wstreams[d if parallel else 0] if overlap else None, pl.scratch[d])
                   for d in range(n_dec)]
-        if parallel:
+        if parallel and not (pl.fused_loss is not None and pl.chains_flow):
             ev = torch.cuda.Event()
             ev.record(s0)
             streams[1].wait_event(ev)
@@ -999,7 +1162,9 @@ class Engine:
             lv = 3 - k
             s = pl.dec[d][k]
             _note(f"bwd dec{d}.up{k + 1}")
-            if k == 3:
+            if k == 3 and pl.fused_loss is not None:
+                pl.fused.add(c2.name)       # head_loss_bwd left dA in the chain's d_t and the BatchNorm sums in c2.sums
+            elif k == 3:
                 bnc = ctx(pl, c2, s["y2"], kind="head")
                 if bnc is None and pl.head_fused:       # no fused reduction, but the activation comes from y2
                     bnc = pl.bnctx.get((c2.name, "y-only"))

@@ -294,6 +294,25 @@ def head_fwd_bn(y, fin, w, b, out, sigmoid):
     return out
 
 
+def head_loss_workspace(device):
+    return torch.zeros(_lib.get().unetk_head_loss_workspace_bytes(), dtype=torch.uint8, device=device)
+
+
+def head_loss_bwd(y, fin, w, b, target, out, da, dw, db, bn_sums, work, out3, which, rw, sw, alpha, gamma):
+    """One decoder's output stage of a training step in one pass (include/unetk.h: unetk_head_loss_bwd)."""
+    import ctypes
+    _chk(y, bf16, "y"); _chk(target, f32, "target"); _chk(da, bf16, "da"); _chk(out3, f32, "out3")
+    n, h, ww, c = y.shape
+    n_out = w.shape[0]
+    if tuple(target.shape) != (n, n_out, h, ww):
+        raise ValueError(f"head_loss_bwd: target must be {(n, n_out, h, ww)}, got {tuple(target.shape)}")
+    if out is not None:
+        _chk(out, f32, "out")
+    _lib.call("unetk_head_loss_bwd", _p(y), ctypes.byref(fin), _p(w), _p(b), _p(target), _p(out), _p(da), _p(dw), _p(db),
+              _p(bn_sums), _p(work), work.numel(), _p(out3), int(which), n, h, ww, c, n_out, float(rw), float(sw),
+              float(alpha), float(gamma), _s())
+
+
 def head_bwd(a, w, dout, out, da, dw, db, sigmoid, bn=None):
     """a=None: the activation is recomputed from the BatchNorm context `bn` (forward used head_fwd_bn)."""
     _chk(dout, f32, "dout"); _chk(da, bf16, "da")

@@ -272,6 +272,48 @@ def _device_batches(loader, device):
         k += 1
 
 
+FUSED_STEP = __import__("os").environ.get("UNETK_FUSED_STEP", "1") != "0"
+
+
+def _fusable(model, criterion, images, masks):
+    """The loop body of src/train_utils.py:122-135 can run as Engine.train_step: this package's AnomalyUNet in
+    training mode, this package's CombinedLoss, float32 CUDA batches of matching shapes, autograd on."""
+    from .model import AnomalyUNet
+    if not (FUSED_STEP and type(model) is AnomalyUNet and type(criterion) is CombinedLoss and model.training
+            and torch.is_grad_enabled()):
+        return False
+    if not (torch.is_tensor(images) and torch.is_tensor(masks) and images.is_cuda and masks.is_cuda
+            and images.dtype == torch.float32 and masks.dtype == torch.float32 and images.dim() == 4 and masks.dim() == 4
+            and masks.shape == (images.shape[0], 1, images.shape[2], images.shape[3])
+            and not images.requires_grad and not masks.requires_grad):
+        return False
+    p0 = next(model.parameters())
+    return p0.device == images.device and model._engine().can_fuse_step()
+
+
+def train_step(model, criterion, optimizer, images, masks):
+    """One iteration of the reference's training loop body (src/train_utils.py:122-135): forward, CombinedLoss,
+    `optimizer.zero_grad()`, backward, `optimizer.step()`.  Returns the loss dict (0-d device tensors, detached:
+    the backward pass has already run).  For this package's AnomalyUNet + CombinedLoss the forward pass, the loss
+    and the backward pass are ONE launch sequence (Engine.train_step: each decoder's 1x1 head, its loss term and the
+    head's backward are a single kernel, and nothing separates the forward from the backward CUDA graph); any other
+    combination takes the plain path below, which is also what `model(x)` / `criterion(...)` / `.backward()` called
+    one by one do."""
+    if _fusable(model, criterion, images, masks):
+        optimizer.zero_grad()
+        out3, _ = model._engine().train_step(images, masks, (criterion.recon_weight, criterion.seg_weight,
+                                                              criterion.focal_alpha, criterion.focal_gamma))
+        criterion._last = out3
+        optimizer.step()
+        return {"total_loss": out3[0], "recon_loss": out3[1], "seg_loss": out3[2]}
+    reconstruction, anomaly_map = model(images)
+    loss_dict = criterion(reconstruction, anomaly_map, images, masks)
+    optimizer.zero_grad()
+    loss_dict["total_loss"].backward()
+    optimizer.step()
+    return loss_dict
+
+
 def train_epoch(model, train_loader, criterion, optimizer, device, epoch):
     """Train for one epoch; returns the same dict of three running averages as the reference."""
     model.train()
@@ -289,12 +331,7 @@ def train_epoch(model, train_loader, criterion, optimizer, device, epoch):
 
     pending = None
     for batch, images, masks in _device_batches(pbar, device):
-        reconstruction, anomaly_map = model(images)
-        loss_dict = criterion(reconstruction, anomaly_map, images, masks)
-        total_loss = loss_dict["total_loss"]
-        optimizer.zero_grad()
-        total_loss.backward()
-        optimizer.step()
+        loss_dict = train_step(model, criterion, optimizer, images, masks)
         current = (_loss_values_later(criterion, loss_dict), images.size(0))
         if pending is not None:
             account(pending)        # the previous step's losses: its copy finished while this step was enqueued

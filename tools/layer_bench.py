@@ -159,11 +159,7 @@ mask = (torch.rand(B, 1, H, H, generator=g) > 0.95).float().to(dev)
 
 
 def step():
-    r, a = m(image)
-    ld = crit(r, a, image, mask)
-    opt.zero_grad()
-    ld["total_loss"].backward()
-    opt.step()
+    train_utils.train_step(m, crit, opt, image, mask)
 
 
 n0 = _lib.launch_count()

@@ -19,10 +19,6 @@ g = torch.Generator().manual_seed(0)
 image = torch.randn(16, 3, 256, 256, generator=g).to(dev)
 mask = (torch.rand(16, 1, 256, 256, generator=g) > 0.95).float().to(dev)
 for _ in range(int(os.environ.get("STEPS", "2"))):
-    r, a = m(image)
-    ld = crit(r, a, image, mask)
-    opt.zero_grad()
-    ld["total_loss"].backward()
-    opt.step()
+    train_utils.train_step(m, crit, opt, image, mask)
 torch.cuda.synchronize()
 print("done", crit.last_values())

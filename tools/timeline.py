@@ -19,6 +19,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+# (UNETK_FUSED_STEP=0 in the environment lays out the unfused model(x) / criterion / backward sequence instead)
 TENSOR = ("unetk_conv3x3_fwd", "unetk_conv3x3_dgrad", "unetk_conv3x3_wgrad", "unetk_convt2x2_fwd", "unetk_convt2x2_dgrad",
           "unetk_convt2x2_wgrad", "unetk_first_conv_wgrad_tc")
 
@@ -61,11 +62,7 @@ def main():
     mask = (torch.rand(args.batch, 1, args.size, args.size, generator=g) > 0.95).float().to(dev)
 
     def step():
-        recon, amap = model(image)
-        ld = crit(recon, amap, image, mask)
-        opt.zero_grad()
-        ld["total_loss"].backward()
-        opt.step()
+        train_utils.train_step(model, crit, opt, image, mask)
 
     step()                                   # eager warm-up (plans, streams)
     torch.cuda.synchronize()
