@@ -700,20 +700,23 @@ def test_fused_train_step_matches_the_plain_path(cuda_device, n, h, w):
         # rounding flips: the small focal term moves by a few 1e-3, see test_train_epoch_prefetch_matches_the_step_loop)
         for va, vb, tol in zip(a, b, (1e-3, 1e-3, 5e-3)):
             assert abs(va - vb) <= tol * abs(va), (l_plain, l_fused)
-    assert abs(l_plain[0][0] - l_fused[0][0]) <= 2e-5 * abs(l_plain[0][0])     # same weights, same kernels' arithmetic
+    assert abs(l_plain[0][0] - l_fused[0][0]) <= 5e-4 * abs(l_plain[0][0])     # same weights, same arithmetic, other atomics order
     assert abs(l_fused[0][0] - (0.7 * l_fused[0][1] + 1.3 * l_fused[0][2])) <= 1e-5 * abs(l_fused[0][0])
     for k in g_plain:
         gp, gf = g_plain[k], g_fused[k]
         cos = ((gp * gf).sum() / (gp.norm() * gf.norm() + 1e-30)).item()
         assert cos >= GRAD_COS and abs(gp.norm().item() - gf.norm().item()) <= GRAD_NORM * gp.norm().item(), (k, cos)
         if k.startswith(HEAD_KEYS):
-            assert (gp - gf).norm() <= 2e-3 * gp.norm(), k
+            # (not tighter: the batch statistics are sums of fp32 atomics, their last bits move the BatchNorm scale /
+            # shift, and an activation that rounds to +0 instead of a tiny positive value flips its ReLU mask; the
+            # kernels themselves are compared on identical inputs in test_ops_gpu.py::test_head_loss_bwd_is_the_unfused_sequence)
+            assert (gp - gf).norm() <= GRAD_REL_HEAD * gp.norm(), k
     sp, sf = m_plain.state_dict(), m_fused.state_dict()
     for k in sp:
         if k.endswith("num_batches_tracked"):
             assert int(sp[k]) == int(sf[k]) == 3
-        elif O.is_buffer(k):
-            assert torch.allclose(sp[k], sf[k], rtol=2e-2, atol=1e-4), k
+        elif O.is_buffer(k):      # (the bound of test_train_step_matches_oracle)
+            assert (sp[k] - sf[k]).abs().max().item() <= 5e-2 * (sp[k].abs().max().item() + 1e-3), k
     # and against the oracle, like the plain path's own test
     ref_losses, ref_grads = O.train_step({k: v.clone() for k, v in sd.items()}, *batches[0], arch=arch)
     want = 0.7 * ref_losses["recon_loss"] + 1.3 * ref_losses["seg_loss"]

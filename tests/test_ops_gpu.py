@@ -431,3 +431,82 @@ def test_adam_and_layout(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(nh, x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
     assert torch.equal(back, x.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 12, 20), (1, 33, 7), (3, 64, 64)])
+def test_head_loss_bwd_is_the_unfused_sequence(cuda_device, n, h, w):
+    """unetk_head_loss_bwd (one pass: BatchNorm + ReLU + 1x1 head + sigmoid + loss term + head backward + BatchNorm-
+    backward sums) against the kernels it replaces, launched one by one: head_fwd_bn -> combined_loss -> head_bwd.
+    Same arithmetic element for element except for the order of the 64-term dot product of the 1x1 conv (eight lanes
+    per pixel here, one thread per pixel in head_fwd): outputs agree to the last bits of fp32, dA to a rare bf16
+    rounding flip, the atomically accumulated sums to fp32 noise; the BatchNorm constants and running statistics are
+    bit-identical."""
+    _lib, ops, packing = _mods()
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(77)
+    rw, sw, alpha, gamma = 0.7, 1.3, 0.25, 2.0
+    image = torch.rand(n, 3, h, w, generator=g).to(dev)
+    mask = (torch.rand(n, 1, h, w, generator=g) > 0.9).float().to(dev)
+    count = n * h * w
+    ys, fins, heads, buf = [], [], [], []
+    for d, n_out in enumerate((3, 1)):
+        yb = _nhwc((torch.randn(n, 64, h, w, generator=g) * 1.5 + 0.2).to(dev))
+        y32 = _nchw(yb)
+        stats = torch.cat([y32.sum((0, 2, 3)), (y32 * y32).sum((0, 2, 3))]).contiguous()
+        gamma_ = (torch.rand(64, generator=g) + 0.5).to(dev); beta = (torch.randn(64, generator=g) * 0.2).to(dev)
+        if d == 1:
+            gamma_[3] = 0.0          # a degenerate channel (scale == 0) takes the direct route through y
+        ys.append((yb, stats, gamma_, beta))
+        heads.append(((torch.randn(n_out, 64, generator=g) / 8).to(dev), torch.randn(n_out, generator=g).to(dev)))
+
+    def make_fin(d):
+        yb, stats, gamma_, beta = ys[d]
+        rm, rv, nbt = torch.zeros(64, device=dev), torch.ones(64, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
+        aux = [torch.empty(64, device=dev) for _ in range(4)]
+        return ops.bn_finalize_args(stats, gamma_, beta, rm, rv, nbt, *aux, count, 1e-5, 0.1), (rm, rv, nbt, aux)
+
+    # unfused reference sequence
+    outs, ref = [], []
+    for d in range(2):
+        fin, keep = make_fin(d)
+        o = torch.empty(n, heads[d][0].shape[0], h, w, device=dev)
+        ops.head_fwd_bn(ys[d][0], fin, heads[d][0], heads[d][1], o, True)
+        outs.append(o); ref.append(keep)
+    d_r, d_a = torch.empty_like(outs[0]), torch.empty_like(outs[1])
+    out3_ref = torch.empty(3, device=dev)
+    ops.combined_loss(outs[0], outs[1], image, mask, d_r, d_a, out3_ref, ops.combined_loss_workspace(dev), rw, sw, alpha, gamma)
+    ref_b = []
+    for d, dout in enumerate((d_r, d_a)):
+        rm, rv, nbt, aux = ref[d]
+        da = torch.empty_like(ys[d][0]); dw = torch.empty_like(heads[d][0]); db = torch.empty_like(heads[d][1])
+        sums = torch.zeros(128, device=dev)
+        ops.head_bwd(None, heads[d][0], dout, outs[d], da, dw, db, True, bn=ops.bn_ctx(ys[d][0], aux[0], aux[1], aux[2], aux[3], sums))
+        ref_b.append((da, dw, db, sums))
+    # fused, twice (the workspace cleans itself up)
+    work = ops.head_loss_workspace(dev)
+    for rep in range(2):
+        out3 = torch.zeros(3, device=dev)
+        got = []
+        for d in range(2):
+            fin, keep = make_fin(d)
+            o = torch.empty_like(outs[d]) if rep == 0 else None
+            da = torch.empty_like(ys[d][0]); dw = torch.zeros_like(heads[d][0]); db = torch.zeros_like(heads[d][1])
+            sums = torch.zeros(128, device=dev)
+            ops.head_loss_bwd(ys[d][0], fin, heads[d][0], heads[d][1], image if d == 0 else mask, o, da, dw, db, sums, work, out3,
+                              d, rw, sw, alpha, gamma)
+            got.append((o, da, dw, db, sums, keep))
+        torch.cuda.synchronize()
+        for d in range(2):
+            o, da, dw, db, sums, (rm, rv, nbt, aux) = got[d]
+            if o is not None:
+                assert torch.allclose(o, outs[d], rtol=0, atol=2e-6)
+            _close(_nchw(da), _nchw(ref_b[d][0]), 8e-3, "fused dA")      # (one bf16 ulp of the largest element)
+            assert (da != ref_b[d][0]).float().mean().item() < 2e-2
+            _close(dw, ref_b[d][1], 1e-4, "fused dw")
+            _close(db, ref_b[d][2], 1e-4, "fused db")
+            _close(sums, ref_b[d][3], 5e-3, "fused BN sums")
+            assert int(nbt) == 1 and torch.equal(rm, ref[d][0]) and torch.equal(rv, ref[d][1])
+            for t0, t1 in zip(aux, ref[d][3]):
+                assert torch.equal(t0, t1)
+        assert torch.allclose(out3, out3_ref, rtol=1e-5, atol=1e-7), (out3, out3_ref)
+        assert abs(float(out3[0]) - (rw * float(out3[1]) + sw * float(out3[2]))) <= 1e-6 * abs(float(out3[0]))

@@ -18,8 +18,7 @@
 // reading the same 134 MB tensor, plus the boundary between the forward and the backward CUDA graph).
 //
 // Thread mapping as head_bwd_kernel: 8 lanes cover one pixel (16-byte vectors of 8 channels), a warp covers
-// 4 pixels per step.  The 1x1 weights live in shared memory (the kernel sits at its register cap; the
-// registers go to loads in flight instead).
+// 4 pixels per step.  The 1x1 weights live in shared memory, and so do the loads in flight (cp.async ring).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -36,7 +35,23 @@ struct HeadLossWork {            // zero-initialised once by the caller; self-cl
   double partial[2][kFMaxBlocks];
 };
 
-template <int NOUT, int LOSS, int U>   // LOSS 0: squared error against `target`, 1: focal BCE
+// cp.async (LDGSTS) helpers: 16 / 4 bytes global -> shared, zero-filled when !ok (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool ok) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// D: depth of the per-lane prefetch ring.  The kernel sits at its register cap (two blocks of 256 threads per SM:
+// 40 accumulators per thread for dW and the BatchNorm sums), so loads in flight cannot live in registers: with four
+// 16-byte loads per thread it ran at 2.3 TB/s, latency bound.  Every lane instead keeps D steps of its own
+// 16-byte vector (and the warp D steps of its 4 x NOUT targets) in flight through cp.async into a private ring
+// in shared memory -- a lane only ever reads back what it issued itself, so no barrier is involved.
+template <int NOUT, int LOSS, int D>   // LOSS 0: squared error against `target`, 1: focal BCE
 __global__ void __launch_bounds__(256, 2)
 head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, const float* __restrict__ w,
                      const float* __restrict__ b, const float* __restrict__ target, float* __restrict__ out,
@@ -51,6 +66,8 @@ head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, cons
   __shared__ float ssum[2 * kFC];
   __shared__ float sloss[8];
   __shared__ bool is_last;
+  __shared__ uint4 yring[8 * D * 32];      // [warp][slot][lane]
+  __shared__ float tring[8 * D * 32];      // [warp][slot][pixel slot * 8 + j]
   pdl_trigger();
   pdl_wait();
   for (int i = threadIdx.x; i < NOUT * kFC; i += blockDim.x) {
@@ -93,33 +110,46 @@ head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, cons
   float lsum = 0.f;
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
-  for (long base = warp * (4 * U); base < npix_total; base += nwarps * (4 * U)) {
-    uint4 yv[U];
-    float tg[U][NOUT];
-    bool ok[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long p = base + u * 4 + pl;
-      ok[u] = p < npix_total;
-      yv[u] = ok[u] ? ldg_nc_v4(y + p * 8 + cg) : make_uint4(0, 0, 0, 0);
-      const long n = ok[u] ? p / hw : 0, r = ok[u] ? p - n * hw : 0;
-#pragma unroll
-      for (int j = 0; j < NOUT; ++j) tg[u][j] = ok[u] ? __ldg(target + (n * NOUT + j) * hw + r) : 0.f;
+  uint4* myy = yring + (threadIdx.x >> 5) * (D * 32) + lane;
+  float* myt = tring + (threadIdx.x >> 5) * (D * 32);
+  // step i of this warp covers the four pixels (warp + i * nwarps) * 4 + {0..3}
+  auto issue = [&](long i, int slot) {
+    const long p = (warp + i * nwarps) * 4 + pl;
+    const bool okp = p < npix_total;
+    cp_async16(myy + slot * 32, y + (okp ? p : 0) * 8 + cg, okp);
+    if (cg < NOUT) {
+      const long n = okp ? p / hw : 0, r = okp ? p - n * hw : 0;
+      cp_async4(myt + slot * 32 + lane, target + (n * NOUT + cg) * hw + r, okp);
     }
+    cp_async_commit();
+  };
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+  for (int s = 0; s < D; ++s) issue(s, s);
+  int slot = 0;
+  for (long i = 0; (warp + i * nwarps) * 4 < npix_total; ++i) {
+    cp_async_wait<D - 1>();
+    __syncwarp();                      // (the targets of a pixel were fetched by its lanes 0..NOUT-1)
+    const long p = (warp + i * nwarps) * 4 + pl;
+    const bool oku = p < npix_total;
+    const uint4 yq0 = myy[slot * 32];
+    float tgt[NOUT];
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) tgt[j] = myt[slot * 32 + pl * 8 + j];
+    __syncwarp();
+    issue(i + D, slot);                // refill the slot just read
+    slot = (slot + 1 == D) ? 0 : slot + 1;
+    {
       float x[8], g[8];
       {
-        const float2 f0 = unpack_bf16x2(yv[u].x), f1 = unpack_bf16x2(yv[u].y), f2 = unpack_bf16x2(yv[u].z), f3 = unpack_bf16x2(yv[u].w);
+        const float2 f0 = unpack_bf16x2(yq0.x), f1 = unpack_bf16x2(yq0.y), f2 = unpack_bf16x2(yq0.z), f3 = unpack_bf16x2(yq0.w);
         x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y; x[4] = f2.x; x[5] = f2.y; x[6] = f3.x; x[7] = f3.y;
       }
       // BatchNorm + ReLU, rounded to bf16 exactly as the stand-alone pass would have stored the activation
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        x[k] = ok[u] ? __bfloat162float(__float2bfloat16(fmaxf(fmaf(x[k], wsc[k], wsh[k]), 0.f))) : 0.f;
+        x[k] = oku ? __bfloat162float(__float2bfloat16(fmaxf(fmaf(x[k], wsc[k], wsh[k]), 0.f))) : 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] = 0.f;
-      const long p = base + u * 4 + pl;
 #pragma unroll
       for (int j = 0; j < NOUT; ++j) {
         // 1x1 conv: this lane's 8 channels, then the 8 lanes of the pixel
@@ -130,7 +160,7 @@ head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, cons
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         const float pr = 1.f / (1.f + __expf(-(acc + sb[j])));
-        const float t = tg[u][j];
+        const float t = tgt[j];
         float dldp, term;
         if (LOSS == 0) {
           const float d = pr - t;
@@ -148,12 +178,12 @@ head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, cons
           const float omg1 = (gamma == 2.f) ? om : ((om > 0.f) ? powf(om, gamma - 1.f) : 0.f);
           dldp = gcoef * alpha * (omg + gamma * omg1 * pt * bce) * dbce;
         }
-        const float dl = ok[u] ? dldp * pr * (1.f - pr) : 0.f;      // through the sigmoid
-        if (cg == 0 && ok[u]) {
+        const float dl = oku ? dldp * pr * (1.f - pr) : 0.f;      // through the sigmoid
+        if (cg == 0 && oku) {
           lsum += term;
           gb[j] += dl;
         }
-        if (out != nullptr && cg == j && ok[u]) {
+        if (out != nullptr && cg == j && oku) {
           const long n = p / hw;
           out[(n * NOUT + j) * hw + (p - n * hw)] = pr;
         }
@@ -163,7 +193,7 @@ head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, cons
           gw[j][k] = fmaf(dl, x[k], gw[j][k]);
         }
       }
-      if (ok[u]) {
+      if (oku) {
         uint4 o4;
         o4.x = pack_bf16x2(g[0], g[1]); o4.y = pack_bf16x2(g[2], g[3]);
         o4.z = pack_bf16x2(g[4], g[5]); o4.w = pack_bf16x2(g[6], g[7]);
@@ -193,6 +223,7 @@ head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, cons
       }
     }
   }
+  cp_async_wait<0>();
   // fold the four pixel slots of the warp, then one shared atomic per (j, channel) per warp
 #pragma unroll
   for (int j = 0; j < NOUT; ++j) {
@@ -301,13 +332,13 @@ int head_loss_bwd(const void* y, const BnFinalizeArgs* fin, const float* w, cons
   HeadLossWork* wk = static_cast<HeadLossWork*>(work);
   const dim3 grid(static_cast<unsigned int>(blocks)), block(256);
   if (which == 1)
-    UNETK_CUDA(launch_pdl(head_loss_bwd_kernel<1, 1, 4>, grid, block, 0, s, y4, f, w, b, target, out, da4, dw, db, bn_sums, wk, out3,
+    UNETK_CUDA(launch_pdl(head_loss_bwd_kernel<1, 1, 8>, grid, block, 0, s, y4, f, w, b, target, out, da4, dw, db, bn_sums, wk, out3,
                           which, np, hw, gcoef, recon_weight, seg_weight, alpha, gamma));
   else if (n_out == 3)
-    UNETK_CUDA(launch_pdl(head_loss_bwd_kernel<3, 0, 4>, grid, block, 0, s, y4, f, w, b, target, out, da4, dw, db, bn_sums, wk, out3,
+    UNETK_CUDA(launch_pdl(head_loss_bwd_kernel<3, 0, 8>, grid, block, 0, s, y4, f, w, b, target, out, da4, dw, db, bn_sums, wk, out3,
                           which, np, hw, gcoef, recon_weight, seg_weight, alpha, gamma));
   else
-    UNETK_CUDA(launch_pdl(head_loss_bwd_kernel<1, 0, 4>, grid, block, 0, s, y4, f, w, b, target, out, da4, dw, db, bn_sums, wk, out3,
+    UNETK_CUDA(launch_pdl(head_loss_bwd_kernel<1, 0, 8>, grid, block, 0, s, y4, f, w, b, target, out, da4, dw, db, bn_sums, wk, out3,
                           which, np, hw, gcoef, recon_weight, seg_weight, alpha, gamma));
   UNETK_CUDA(cudaGetLastError());
   return UNETK_OK;
