@@ -5,7 +5,7 @@ amplifies chaotically through 26 BatchNorm layers -- does not blur the compariso
 import os
 import sys
 
-os.environ["UNETK_FUSE_BN_REDUCE"] = "all"
+os.environ.setdefault("UNETK_FUSE_BN_REDUCE", "all")
 os.environ["UNETK_FUSE_CHECK"] = "1"
 import torch
 
@@ -18,7 +18,7 @@ from tiaozhanbei_unet_b200.model import AnomalyUNet, UNet  # noqa: E402
 dev = torch.device("cuda:0")
 bad = 0
 for arch, n, h, w in [("unet", 2, 32, 32), ("anomaly_unet", 2, 32, 32), ("anomaly_unet", 3, 64, 48), ("unet", 2, 128, 128),
-                      ("anomaly_unet", 4, 256, 256)]:
+                      ("anomaly_unet", 1, 52, 76), ("anomaly_unet", 4, 256, 256)]:
     sd = O.synthetic_state_dict(arch, seed=1, device=dev)
     model = (AnomalyUNet(3) if arch == "anomaly_unet" else UNet(3, 1))
     model.load_state_dict(sd)

@@ -510,3 +510,51 @@ def test_head_loss_bwd_is_the_unfused_sequence(cuda_device, n, h, w):
                 assert torch.equal(t0, t1)
         assert torch.allclose(out3, out3_ref, rtol=1e-5, atol=1e-7), (out3, out3_ref)
         assert abs(float(out3[0]) - (rw * float(out3[1]) + sw * float(out3[2]))) <= 1e-6 * abs(float(out3[0]))
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_tma_store_epilogue_is_bit_identical(cuda_device, mode, monkeypatch):
+    """UNETK_TMA_STORE: the epilogue stages its bf16 tile in swizzled shared memory and writes it with bulk tensor
+    stores (clipped at the image border / the second destination's extent; pixel shuffle through a 5-D map for the
+    transposed conv) instead of per-thread stores.  Same values, bit for bit, on full and ragged tiles."""
+    _lib, ops, packing = _mods()
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(5)
+
+    def bf(*shape):
+        return (torch.randn(*shape, generator=g) * 0.5).to(dev).to(torch.bfloat16)
+
+    def run_all():
+        out = []
+        for n, h, w, c1, c2, cout in [(2, 16, 16, 64, 0, 64), (1, 20, 28, 64, 64, 128), (2, 16, 24, 128, 0, 256)]:
+            s1 = bf(n, h, w, c1)
+            s2 = bf(n, h - 1, w - 1, c2) if c2 else None           # the second source one row / column short (F.pad path)
+            wf, wd = bf(cout * 9 * (c1 + c2)), bf((c1 + c2) * 9 * cout)
+            y = torch.zeros(n, h, w, cout, dtype=torch.bfloat16, device=dev)
+            stats = torch.zeros(2 * cout, device=dev)
+            ops.conv3x3_fwd(s1, s2, wf, y, stats=stats)
+            dx1 = torch.zeros(n, h, w, c1, dtype=torch.bfloat16, device=dev)
+            dx2 = torch.zeros(n, h - 1, w - 1, c2, dtype=torch.bfloat16, device=dev) if c2 else None
+            ops.conv3x3_dgrad(y, wd, dx1, False, dx2, False)
+            out += [y, stats, dx1] + ([dx2] if c2 else [])
+        for n, h, w, cin, cout in [(2, 8, 8, 128, 64), (1, 12, 20, 256, 128)]:
+            a = bf(n, h, w, cin)
+            wt = bf(4 * cout * cin)
+            bias = torch.randn(cout, generator=g).to(dev)
+            up = torch.zeros(n, 2 * h, 2 * w, cout, dtype=torch.bfloat16, device=dev)
+            ops.convt2x2_fwd(a, wt, bias, up)
+            out.append(up)
+        torch.cuda.synchronize()
+        return out
+
+    monkeypatch.setenv("UNETK_TMA_STORE", "0")
+    g.manual_seed(5)
+    ref = run_all()
+    monkeypatch.setenv("UNETK_TMA_STORE", mode)
+    g.manual_seed(5)
+    got = run_all()
+    for i, (a, b) in enumerate(zip(ref, got)):
+        if a.dtype == torch.float32:          # BatchNorm sums: atomics
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-4), i
+        else:
+            assert torch.equal(a, b), i

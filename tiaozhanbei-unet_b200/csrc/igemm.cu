@@ -48,6 +48,7 @@ struct IgemmParams {
   __nv_bfloat16* out2;
   int ldc1, ldc2;
   int acc1, acc2;       // 1: read-modify-write (gradient accumulation)
+  int tma1, tma2;       // 1: this destination is written by TMA stores from a swizzled staging tile (tmO1 / tmO2)
   float* stats;         // nullable: per-column sums for columns [stats_from, Ntot), stats[col - stats_from]
   float* stats_sq;      // nullable: per-column sums of squares, same indexing
   int stats_from;
@@ -84,7 +85,7 @@ constexpr int kSubW = 8;                      // sub-tile: 8 wide x 16 tall = 12
 //        N=64 -> 33 % tensor-pipe activity with everything else waiting on the MMA), so halving the B
 //        bytes per CTA is what lifts the tensor pipe: 256x256 pair tiles read A 4 KB + B 4 KB per
 //        128-cycle instruction.
-template <int BN, int SUBS, int CTAS>
+template <int BN, int SUBS, int CTAS, bool BNRED = false, int EPW_ = 4, bool OSTG = false>
 struct IgemmCfg {
   static constexpr int kBNLocal = BN / CTAS;
   static constexpr int kBBytes = kBNLocal * 128;
@@ -92,21 +93,33 @@ struct IgemmCfg {
   static constexpr int kBudget = 196 * 1024;
   // halo buffers in flight (a third buffer for the narrow BN = 64 tiles was measured: no change)
   static constexpr int kNumABufs = 2;
-  static constexpr int kFit = (kBudget - kNumABufs * kABufBytes) / kBBytes;
+  // BNRED: the tile of the producing layer's raw output y that belongs to the OUTPUT tile (region x BN columns),
+  // fetched by TMA while the tile's MMAs run: one 64-channel chunk = (8*SUBS x 16 pixels) x 128 B
+  static constexpr int kYChunkBytes = SUBS * 16 * 1024;
+  static constexpr int kYBytes = (BN / 64) * kYChunkBytes;
+  static constexpr int kNumYBufs = BNRED ? (BN == 64 ? 2 : 1) : 0;     // narrow tiles are epilogue bound: two in flight
+  // Output staging for the TMA stores: per epilogue warp two buffers of SUBS x (32 pixel rows x 64 channels)
+  static constexpr int kOWarpBytes = 2 * SUBS * 4096;
+  static constexpr int kOBytes = OSTG ? EPW_ * kOWarpBytes : 0;
+  static constexpr int kFit = (kBudget - kNumABufs * kABufBytes - kNumYBufs * kYBytes - kOBytes) / kBBytes;
   static constexpr int kBStages = kFit > 16 ? 16 : kFit;
   static constexpr int kTmemCols = 2 * SUBS * BN;    // 2 accumulator stages x SUBS sub-tiles
-  static constexpr int kSmemMain = kNumABufs * kABufBytes + kBStages * kBBytes;
-  static constexpr int kNumBars = 2 * kNumABufs + 2 * kBStages + 4;
-  static_assert(kTmemCols <= 512 && kBStages >= 4, "bad igemm configuration");
+  static constexpr int kSmemMain = kNumABufs * kABufBytes + kBStages * kBBytes + kNumYBufs * kYBytes + kOBytes;
+  static constexpr int kNumBars = 2 * kNumABufs + 2 * kBStages + 4 + 4;
+  static_assert(kTmemCols <= 512 && kBStages >= 3, "bad igemm configuration");
 };
 
 // BNRED: the epilogue also runs the first pass of the BatchNorm+ReLU backward of the layer that produced
 //        the activation whose gradient this kernel completes (IgemmParams::bn_*), see unetk_bn_ctx.
-template <int BN, int SUBS, int CTAS, bool BNRED, int EPW>
+// OSTG: the kernel has output staging tiles and writes the destinations flagged in IgemmParams::tma1/2 by TMA
+template <int BN, int SUBS, int CTAS, bool BNRED, int EPW, bool OSTG>
 __global__ void __launch_bounds__(igemm_threads(EPW), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-             const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
-  using Cfg = IgemmCfg<BN, SUBS, CTAS>;
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+             const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2, const IgemmParams p) {
+  using Cfg = IgemmCfg<BN, SUBS, CTAS, BNRED, EPW, OSTG>;
+  static_assert(!(BNRED && OSTG), "the BatchNorm-reduction variants keep per-thread stores (no room for staging)");
+  constexpr int kNumYBufs = Cfg::kNumYBufs;
   constexpr int kBStages = Cfg::kBStages;
   constexpr int kABufBytes = Cfg::kABufBytes;
   constexpr int kNumABufs = Cfg::kNumABufs;
@@ -117,6 +130,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kNumABufs * kABufBytes;
+  uint8_t* sY = sB + kBStages * Cfg::kBBytes;            // BNRED only (1 KB aligned: every region above is)
+  uint8_t* sO = sY + kNumYBufs * Cfg::kYBytes;           // output staging of the epilogue warps
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kSmemMain);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kNumABufs;
@@ -124,8 +139,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
   uint64_t* b_empty = b_full + kBStages;
   uint64_t* tfull = b_empty + kBStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* colbuf = reinterpret_cast<float*>(tempty + 4);  // affine: [2][Ntot]; stats: [4][2][BN]
+  uint64_t* yfull = tempty + 2;
+  uint64_t* yempty = yfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yempty + 2);
+  float* colbuf = reinterpret_cast<float*>(yempty + 4);  // affine: [2][Ntot]; stats: [4][2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -146,7 +163,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], EPW * CTAS);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(&yfull[i], 1);
+      mbar_init(&yempty[i], EPW);         // this CTA's epilogue warps
     }
+    if (BNRED) tma_prefetch_desc(&tmY);
+    if (p.tma1) tma_prefetch_desc(&tmO1);
+    if (p.tma2) tma_prefetch_desc(&tmO2);
     fence_barrier_init();
   }
   if (CTAS == 2) cluster_sync_all();     // pair TMEM allocation needs both CTAs resident
@@ -189,7 +211,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      for (int t = tile0; t < total_tiles; t += tile_step) {
+      int pit = 0;
+      for (int t = tile0; t < total_tiles; t += tile_step, ++pit) {
         // region-fastest order: CTAs running together share the weight tile (and the statistics slot)
         const int nb = t / region_slots;
         int m = (t - nb * region_slots) * CTAS + static_cast<int>(rank);
@@ -230,6 +253,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               bph ^= 1;
             }
           }
+        }
+        if constexpr (BNRED) {
+          // the y tile of this OUTPUT tile, for its epilogue: issued behind the tile's operand loads, i.e. while
+          // its MMAs run; the buffer is free once the epilogue that last read it is done
+          const int yb = (kNumYBufs == 2) ? (pit & 1) : 0;
+          const uint32_t yph = (kNumYBufs == 2) ? ((pit >> 1) & 1) : (pit & 1);
+          mbar_wait(&yempty[yb], yph ^ 1);
+          mbar_expect_tx(&yfull[yb], Cfg::kYBytes);
+#pragma unroll
+          for (int cc = 0; cc < BN / 64; ++cc)
+            tma_load_5d(sY + yb * Cfg::kYBytes + cc * Cfg::kYChunkBytes, &tmY, &yfull[yb], nb * BN + cc * 64, x0, y0, n0, 0);
         }
       }
     }
@@ -308,7 +342,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     int cur_nb = -1;
     // add this warp's partial column sums of column block `nbk` to the global statistics
     auto flush_stats = [&](int nbk) {
-      for (int c = half; c < BN / 32; c += EPW / 4) {
+      for (int c = 2 * half; c < BN / 32; c += ((c & 1) ? 2 * (EPW / 4) - 1 : 1)) {      // the 32-column chunks of this warp's 64-column blocks
         const int i = c * 32 + lane;
         const int col = nbk * BN + i;
         if (col >= p.stats_from) {
@@ -326,6 +360,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
     };
     const int sx = row & 7;   // pixel inside the 8 x 16 sub-tile
     const int sy = row >> 3;
+    int obuf = 0;             // staging buffer of the next TMA store
     int it = 0;
     for (int t = tile0; t < total_tiles; t += tile_step, ++it) {
       const int acc = it & 1;
@@ -353,19 +388,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
       }
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
+      const int yb = (kNumYBufs == 2) ? (it & 1) : 0;
+      if constexpr (BNRED) mbar_wait(&yfull[yb], (kNumYBufs == 2) ? ((it >> 1) & 1) : (it & 1));
       if (live) {
 #pragma unroll 1
-        for (int ch = half; ch < BN / 32; ch += EPW / 4) {
+        for (int c64 = half; c64 < BN / 64; c64 += EPW / 4) {
+        // One 64-column block = one destination = (with TMA stores) one 128-byte-row staging tile per sub-tile:
+        // the warp's 32 pixel rows x 64 channels, SWIZZLE_128B, written by conflict-free 16-byte shared stores and
+        // sent by ONE bulk tensor store.  Per-thread global stores touch 32 different lines per instruction
+        // (33 L1 data-pipe wavefronts each, the pipe the tensor core fetches its operands through: ncu,
+        // profiles/ncu_igemm64_r02_summary.txt); accumulating destinations keep them (read-modify-write).
+        // Optional (OSTG kernels, UNETK_TMA_STORE): see launch_igemm for why it is not the default.
+        const bool second_dst = (BNRED || p.epi_mode != 0) ? false : (col0 + c64 * 64 >= p.split);
+        const bool use_tma = OSTG && (second_dst ? (p.tma2 != 0) : (p.tma1 != 0));
+        uint8_t* stg = sO + (warp - 2) * Cfg::kOWarpBytes + obuf * (SUBS * 4096);
+        if (use_tma) {
+          if (lane == 0) tma_store_wait_read<1>();       // the store that last read this buffer (two groups ago)
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          const int ch = c64 * 2 + hf;
           const int col = col0 + ch * 32;
-          // BNRED: fetch the producing layer's raw conv output under the TMEM load latency
+          // BNRED: the producing layer's raw conv output, from the TMA-fetched tile (SWIZZLE_128B rows of 64 channels,
+          // row = pixel (sy, sub*8 + sx) of the region, 16-byte column XOR (row & 7))
           uint4 yv[BNRED ? SUBS : 1][4];
           if constexpr (BNRED) {
 #pragma unroll
             for (int sub = 0; sub < SUBS; ++sub) {
-              const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + xs[sub];
-              const uint4* src = reinterpret_cast<const uint4*>(p.bn_y + pix * p.ldc1 + col);
+              const int ry_ = sy * kRegionW + sub * kSubW + sx;
+              const uint8_t* src = sY + yb * Cfg::kYBytes + (ch >> 1) * Cfg::kYChunkBytes + ry_ * 128;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) yv[sub][g] = valids[sub] ? ldg_nc_v4(src + g) : make_uint4(0, 0, 0, 0);
+              for (int g = 0; g < 4; ++g)
+                yv[sub][g] = *reinterpret_cast<const uint4*>(src + ((((ch & 1) * 4 + g) ^ (ry_ & 7)) << 4));
             }
           }
           float v2[SUBS][32];
@@ -456,12 +511,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               }
             }
             uint4* d4 = reinterpret_cast<uint4*>(dst);
+            uint8_t* srow = stg + sub * 4096 + lane * 128;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = v[g * 8 + j];
-              if (accum) {
+              if (accum && !use_tma) {
                 const uint4 o = d4[g];
                 const float2 o0 = unpack_bf16x2(o.x), o1 = unpack_bf16x2(o.y);
                 const float2 o2 = unpack_bf16x2(o.z), o3 = unpack_bf16x2(o.w);
@@ -473,7 +529,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
               w.y = pack_bf16x2(f[2], f[3]);
               w.z = pack_bf16x2(f[4], f[5]);
               w.w = pack_bf16x2(f[6], f[7]);
-              d4[g] = w;
+              if (use_tma) *reinterpret_cast<uint4*>(srow + (((hf * 4 + g) ^ (lane & 7)) << 4)) = w;
+              else d4[g] = w;
               if constexpr (BNRED) {
                 // g = the STORED (accumulated, bf16-rounded) gradient masked by the ReLU of the producing
                 // layer; keep g in v[] and g * xhat in gx[] for the column reduction below
@@ -504,15 +561,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ C
             wbuf[BN + ch * 32 + lane] += cs2;
           }
         }
+        if (use_tma) {
+          fence_proxy_async_smem();          // the staging tile, written through the generic proxy, is read by the TMA
+          __syncwarp();
+          if (lane == 0) {
+            const int colb = col0 + c64 * 64;
+            const int yw = ry * kRegionH + q * 4;           // first of this warp's four pixel rows
+#pragma unroll
+            for (int sub = 0; sub < SUBS; ++sub) {
+              const int xw = rx * kRegionW + sub * kSubW;
+              if (p.epi_mode == 0) {
+                if (second_dst) tma_store_5d(&tmO2, stg + sub * 4096, colb - p.split, xw, yw, n, 0);
+                else tma_store_5d(&tmO1, stg + sub * 4096, colb, xw, yw, n, 0);
+              } else {                                      // transposed conv: pixel shuffle (co, kx, x, ky, n*H + y)
+                const int tap = colb / p.cout_t;
+                tma_store_5d(&tmO1, stg + sub * 4096, colb - tap * p.cout_t, tap & 1, xw, tap >> 1, yw);
+              }
+            }
+            tma_store_commit();
+          }
+          obuf ^= 1;
+        }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CTAS == 2) mbar_arrive_cluster(&tempty[acc], 0);   // the leader's MMA warp waits on its own barrier
         else mbar_arrive(&tempty[acc]);
+        if (BNRED) mbar_arrive(&yempty[yb]);                   // this CTA's producer may refill the y tile
       }
     }
     if (p.stats != nullptr && cur_nb >= 0) flush_stats(cur_nb);
+    if (OSTG && lane == 0) tma_store_wait<0>();      // shared memory must outlive the bulk stores that read it
   }
   __syncwarp();
   tc_fence_before();
@@ -594,12 +675,12 @@ struct IgemmLaunch {
   IgemmParams p;
 };
 
-template <int BN, int SUBS, int CTAS, bool BNRED, int EPW = 4>
-static int launch_cfg(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB, const IgemmParams& p,
-                      int grid, size_t colbytes, cudaStream_t stream) {
-  using Cfg = IgemmCfg<BN, SUBS, CTAS>;
+template <int BN, int SUBS, int CTAS, bool BNRED, int EPW = 4, bool OSTG = false>
+static int launch_cfg(const CUtensorMap* tm, const IgemmParams& p, int grid, size_t colbytes, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BN, SUBS, CTAS, BNRED, EPW, OSTG>;
+  const CUtensorMap &tmA1 = tm[0], &tmA2 = tm[1], &tmB = tm[2], &tmY = tm[3], &tmO1 = tm[4], &tmO2 = tm[5];
   const size_t smem = 1024 + Cfg::kSmemMain + (Cfg::kNumBars + 2) * 8 + colbytes;
-  auto kern = igemm_kernel<BN, SUBS, CTAS, BNRED, EPW>;
+  auto kern = igemm_kernel<BN, SUBS, CTAS, BNRED, EPW, OSTG>;
   UNETK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -615,7 +696,7 @@ static int launch_cfg(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CU
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  UNETK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA1, tmA2, tmB, p));
+  UNETK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA1, tmA2, tmB, tmY, tmO1, tmO2, p));
   return UNETK_OK;
 }
 
@@ -633,11 +714,10 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
   p.c1_chunks = L.c1 / 64;
   p.c2_chunks = L.c2 / 64;
   // configuration: CTA pairs with 256-wide column blocks where the layer is wide enough
-  static const bool pair_ok = (getenv("UNETK_IGEMM_1CTA") == nullptr);
-  int bn, subs, ctas;
-  if (pair_ok && p.Ntot % 256 == 0) { bn = 256; subs = 1; ctas = 2; }
-  else if (pair_ok) { bn = (p.Ntot % 128 == 0) ? 128 : 64; subs = 2; ctas = 2; }
-  else { bn = (p.Ntot % 128 == 0) ? 128 : 64; subs = 2; ctas = 1; }
+  int bn, subs;
+  const int ctas = 2;
+  if (p.Ntot % 256 == 0) { bn = 256; subs = 1; }
+  else { bn = (p.Ntot % 128 == 0) ? 128 : 64; subs = 2; }
   const int region_w = kSubW * subs;
   p.regions_x = (p.W + region_w - 1) / region_w;
   p.regions_y = (p.H + kRegionH - 1) / kRegionH;
@@ -670,14 +750,47 @@ static int launch_igemm(IgemmLaunch& L, cudaStream_t stream) {
   const size_t colbytes = (p.stats != nullptr ? static_cast<size_t>(8) * bn + (p.bn_y != nullptr ? 4 * static_cast<size_t>(p.Ntot) : 0)
                                               : (use_colbuf ? static_cast<size_t>(2) * p.Ntot : 0)) * sizeof(float);
   const bool red = p.bn_y != nullptr;
+  CUtensorMap tmY = tmA1;
+  if (red) {      // y of the layer whose BatchNorm backward is fused: same pixel grid and columns as the output
+    UNETK_CHECK_ARG((reinterpret_cast<uintptr_t>(p.bn_y) & 15) == 0, "igemm: bn_ctx.y must be 16-byte aligned");
+    if ((e = make_act_tmap(&tmY, p.bn_y, p.n_img, p.H, p.W, p.Ntot, region_w, kRegionH, 1))) return e;
+  }
+  // TMA stores (see the epilogue): every non-accumulating destination made of whole 64-channel blocks; box =
+  // one epilogue warp's 8 x 4 pixels x 64 channels
+  // UNETK_TMA_STORE: 0 = never (default), 1 = every eligible destination, 2 = the transposed conv's pixel-shuffle
+  // store only.  Measured on a B200 inside the training step (B=16 @256^2, two runs of 40 steps each): 10.15 / 10.20 ms
+  // without, 10.17 / 10.17 ms with (1), 10.19 / 10.22 ms with (2) -- no gain: the staging tiles cost B-operand
+  // stages (9 -> 7 for 256-wide tiles, 14 -> 6 for 128-wide ones) and the stores share the TMA unit with the operand
+  // loads; under the board's power cap the saved L1 wavefronts do not show.  (Read per launch: tests toggle it.)
+  const char* tma_env = getenv("UNETK_TMA_STORE");
+  const int tma_mode = tma_env ? atoi(tma_env) : 0;
+  CUtensorMap tmO1 = tmA1, tmO2 = tmA1;
+  p.tma1 = p.tma2 = 0;
+  if (tma_mode == 1 && !red && p.epi_mode == 0) {
+    const bool two = p.split < p.Ntot;
+    if (!p.acc1 && p.ldc1 % 64 == 0 && p.split % 64 == 0) {
+      if ((e = make_act_tmap(&tmO1, p.out1, p.n_img, p.H, p.W, p.ldc1, kSubW, 4, 1))) return e;
+      p.tma1 = 1;
+    }
+    if (two && !p.acc2 && p.ldc2 % 64 == 0 && p.split % 64 == 0 && (reinterpret_cast<uintptr_t>(p.out2) & 15) == 0) {
+      if ((e = make_act_tmap(&tmO2, p.out2, p.n_img, p.H2, p.W2, p.ldc2, kSubW, 4, 1))) return e;
+      p.tma2 = 1;
+    }
+  } else if (tma_mode >= 1 && !red && p.epi_mode == 1 && p.cout_t % 64 == 0) {
+    if ((e = make_act_tmap_up2(&tmO1, p.out1, 1, p.H, p.W, p.cout_t, kSubW, 4, 1))) return e;
+    p.tma1 = 1;
+  }
+  const CUtensorMap tm[6] = {tmA1, tmA2, tmB, tmY, tmO1, tmO2};
+  const bool ostg = p.tma1 || p.tma2;
 #define UNETK_IGEMM_LAUNCH(BN_, SUBS_, CTAS_)                                                             \
-  (red ? launch_cfg<BN_, SUBS_, CTAS_, true>(tmA1, tmA2, tmB, p, grid, colbytes, stream)                 \
-       : launch_cfg<BN_, SUBS_, CTAS_, false>(tmA1, tmA2, tmB, p, grid, colbytes, stream))
+  (red ? launch_cfg<BN_, SUBS_, CTAS_, true>(tm, p, grid, colbytes, stream)                              \
+       : ostg ? launch_cfg<BN_, SUBS_, CTAS_, false, 4, true>(tm, p, grid, colbytes, stream)             \
+              : launch_cfg<BN_, SUBS_, CTAS_, false>(tm, p, grid, colbytes, stream))
   if (bn == 256 && p.epi_mode == 1 && !red)      // transposed-conv forward: epilogue bound, eight epilogue warps
-    return launch_cfg<256, 1, 2, false, 8>(tmA1, tmA2, tmB, p, grid, colbytes, stream);
+    return ostg ? launch_cfg<256, 1, 2, false, 8, true>(tm, p, grid, colbytes, stream)
+                : launch_cfg<256, 1, 2, false, 8>(tm, p, grid, colbytes, stream);
   if (bn == 256) return UNETK_IGEMM_LAUNCH(256, 1, 2);
-  if (ctas == 2) return bn == 128 ? UNETK_IGEMM_LAUNCH(128, 2, 2) : UNETK_IGEMM_LAUNCH(64, 2, 2);
-  return bn == 128 ? UNETK_IGEMM_LAUNCH(128, 2, 1) : UNETK_IGEMM_LAUNCH(64, 2, 1);
+  return bn == 128 ? UNETK_IGEMM_LAUNCH(128, 2, 2) : UNETK_IGEMM_LAUNCH(64, 2, 2);
 #undef UNETK_IGEMM_LAUNCH
 }
 

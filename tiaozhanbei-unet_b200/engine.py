@@ -32,6 +32,7 @@ from . import _lib, ops, packing
 # pool backward: measured slower at B=16 @256^2, the extra global loads sit on the epilogue's critical
 # path), "0" (stand-alone reductions everywhere).
 FUSE_BN_REDUCE = os.environ.get("UNETK_FUSE_BN_REDUCE", "head")
+DEEP_PIXELS = int(os.environ.get("UNETK_FUSE_DEEP_PIXELS", "65536"))
 FUSE_CHECK = os.environ.get("UNETK_FUSE_CHECK", "0") == "1"
 FIRST_WGRAD_TC = os.environ.get("UNETK_FIRST_WGRAD_TC", "1") != "0"
 # The first conv (Cin = 3) as the 64 -> 64 tcgen05 layer on the channel-padded bf16 image (0.19 -> ~0.12 ms
@@ -960,7 +961,9 @@ class Engine:
     def _ctx(pl, L, y, kind="igemm"):
         """unetk_bn_ctx for the producer of layer L's activation gradient, or None when that producer does
         not fuse the reduction."""
-        if FUSE_BN_REDUCE != "all" and not (FUSE_BN_REDUCE == "head" and kind == "head"):
+        npix = y.numel() // y.shape[-1]
+        if not (FUSE_BN_REDUCE == "all" or kind == "head" and FUSE_BN_REDUCE in ("head", "conv", "deep")
+                or kind == "igemm" and (FUSE_BN_REDUCE == "conv" or FUSE_BN_REDUCE == "deep" and npix <= DEEP_PIXELS)):
             return None
         pl.fused.add(L.name)
         key = (L.name, y.data_ptr())
@@ -1286,7 +1289,7 @@ class Engine:
                 # the skip gradient of level l-1 is complete after this accumulation
                 ops.maxpool_bwd(d_p, pl.enc[l - 1]["idx"], pl.d_skip[l - 1], accumulate=skip_written[l - 1],
                                 extra=pl.d_skipx[0][l - 1] if parallel else None,
-                                bn=ctx(pl, self.encoder[l - 1][1], pl.enc[l - 1]["y2"]))
+                                bn=ctx(pl, self.encoder[l - 1][1], pl.enc[l - 1]["y2"], kind="pool"))
                 skip_written[l - 1] = True
                 ch.free_y[iy] = ch.side(lambda d_y=d_y, src=src, c1=c1: ops.conv3x3_wgrad(d_y, src, None, c1.g_w), mk)
             if self.ddp is not None and l in (3, 0):
