@@ -112,19 +112,28 @@ head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, cons
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
   uint4* myy = yring + (threadIdx.x >> 5) * (D * 32) + lane;
   float* myt = tring + (threadIdx.x >> 5) * (D * 32);
-  // step i of this warp covers the four pixels (warp + i * nwarps) * 4 + {0..3}
-  auto issue = [&](long i, int slot) {
-    const long p = (warp + i * nwarps) * 4 + pl;
-    const bool okp = p < npix_total;
-    cp_async16(myy + slot * 32, y + (okp ? p : 0) * 8 + cg, okp);
-    if (cg < NOUT) {
-      const long n = okp ? p / hw : 0, r = okp ? p - n * hw : 0;
-      cp_async4(myt + slot * 32 + lane, target + (n * NOUT + cg) * hw + r, okp);
-    }
+  // step i of this warp covers the four pixels (warp + i * nwarps) * 4 + {0..3}.  (image, offset) of the pixel the next
+  // issue() fetches are carried from step to step: a 64-bit division per step and lane was a quarter of the
+  // kernel's instructions, and the kernel is issue bound
+  const long pstep = nwarps * 4;
+  const long dq = pstep / hw, dr = pstep - dq * hw;
+  long ip = warp * 4 + pl;                   // pixel of the next issue()
+  long in = ip / hw, ir = ip - in * hw;
+  auto issue = [&](int slot) {
+    const bool okp = ip < npix_total;
+    cp_async16(myy + slot * 32, y + (okp ? ip : 0) * 8 + cg, okp);
+    if (cg < NOUT) cp_async4(myt + slot * 32 + lane, target + (okp ? (in * NOUT + cg) * hw + ir : 0), okp);
     cp_async_commit();
+    ip += pstep;
+    in += dq;
+    ir += dr;
+    if (ir >= hw) {
+      ir -= hw;
+      ++in;
+    }
   };
 #pragma unroll
-  for (int s = 0; s < D; ++s) issue(s, s);
+  for (int s = 0; s < D; ++s) issue(s);
   int slot = 0;
   for (long i = 0; (warp + i * nwarps) * 4 < npix_total; ++i) {
     cp_async_wait<D - 1>();
@@ -136,7 +145,7 @@ head_loss_bwd_kernel(const uint4* __restrict__ y, const BnFinalizeArgs fin, cons
 #pragma unroll
     for (int j = 0; j < NOUT; ++j) tgt[j] = myt[slot * 32 + pl * 8 + j];
     __syncwarp();
-    issue(i + D, slot);                // refill the slot just read
+    issue(slot);                       // refill the slot just read (step i + D)
     slot = (slot + 1 == D) ? 0 : slot + 1;
     {
       float x[8], g[8];

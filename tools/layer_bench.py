@@ -138,6 +138,21 @@ log(f"head_bwd {t:.3f} ms  {2*nbytes/t/1e6:.0f} GB/s")
 ctx = ops.bn_ctx(y, sc, sh, sh, sc, sums)
 t = timeit(lambda: ops.head_bwd(y, hw, out, out, a, dwh, dbh, True, bn=ctx))
 log(f"head_bwd+bnred {t:.3f} ms  {2*nbytes/t/1e6:.0f} GB/s")
+# the fused output stage of the training step (head + loss term + head backward + BatchNorm-backward sums)
+_stats = torch.cat([y.float().sum((0, 1, 2)), (y.float() ** 2).sum((0, 1, 2))]).contiguous()
+_g, _b = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+_rm, _rv, _nbt = torch.zeros(64, device=dev), torch.ones(64, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
+_aux = [torch.empty(64, device=dev) for _ in range(4)]
+_fin = ops.bn_finalize_args(_stats, _g, _b, _rm, _rv, _nbt, *_aux, B * H * H, 1e-5, 0.1)
+_work, _out3 = ops.head_loss_workspace(dev), torch.zeros(3, device=dev)
+_img, _msk = torch.rand(B, 3, H, H, device=dev), (torch.rand(B, 1, H, H, device=dev) > 0.95).float()
+_hw1, _hb1 = torch.randn(1, 64, device=dev), torch.zeros(1, device=dev)
+_dw1, _db1 = torch.zeros(1, 64, device=dev), torch.zeros(1, device=dev)
+_s128 = torch.zeros(128, device=dev)
+t = timeit(lambda: ops.head_loss_bwd(y, _fin, hw, hb, _img, None, a, dwh, dbh, _s128, _work, _out3, 0, 1.0, 1.0, 0.25, 2.0))
+log(f"head_loss_bwd<3, mse> {t:.3f} ms  {(2*nbytes + _img.numel()*4)/t/1e6:.0f} GB/s")
+t2 = timeit(lambda: ops.head_loss_bwd(y, _fin, _hw1, _hb1, _msk, None, a, _dw1, _db1, _s128, _work, _out3, 1, 1.0, 1.0, 0.25, 2.0))
+log(f"head_loss_bwd<1, focal> {t2:.3f} ms  {(2*nbytes + _msk.numel()*4)/t2/1e6:.0f} GB/s")
 dp_ = bf(B, H // 2, H // 2, 64)
 idx8 = torch.randint(0, 4, (B, H // 2, H // 2, 64), dtype=torch.uint8, device=dev)
 t = timeit(lambda: ops.maxpool_bwd(dp_, idx8, a, accumulate=True))
