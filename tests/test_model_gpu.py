@@ -745,3 +745,29 @@ def test_fused_train_step_falls_back_when_it_does_not_apply(cuda_device):
     torch.cuda.synchronize()
     assert m.outc_seg.conv.bias.grad is None and m.outc_seg.conv.weight.grad is not None
     assert torch.isfinite(ld["total_loss"]).item()
+
+
+def test_fused_train_step_can_return_the_outputs(cuda_device):
+    """Engine.train_step(want_outs=True) also stores the two sigmoid outputs (a caller that logs reconstructions):
+    they are the plain training-mode forward's, and the gradients do not change."""
+    from tiaozhanbei_unet_b200 import train_utils
+    dev = cuda_device
+    sd = O.synthetic_state_dict("anomaly_unet", seed=4, device=dev)
+    image, mask = _inputs(8, 2, 48, 32, dev)
+    cfg = (1.0, 1.0, 0.25, 2.0)
+    m1 = _model("anomaly_unet", {k: v.clone() for k, v in sd.items()}, dev).train()
+    r, a = m1(image)
+    m2 = _model("anomaly_unet", {k: v.clone() for k, v in sd.items()}, dev).train()
+    for _ in range(3):      # eager, capture, replay
+        m2.load_state_dict(sd)          # (same weights and running statistics every time)
+        out3, outs = m2._engine().train_step(image, mask, cfg, want_outs=True)
+        torch.cuda.synchronize()
+        assert torch.allclose(outs[0], r.detach(), rtol=0, atol=2e-3) and torch.allclose(outs[1], a.detach(), rtol=0, atol=2e-3)
+        ld = train_utils.CombinedLoss()(r.detach(), a.detach(), image, mask)
+        assert abs(float(out3[0]) - float(ld["total_loss"])) <= 1e-3 * float(ld["total_loss"])
+    m3 = _model("anomaly_unet", {k: v.clone() for k, v in sd.items()}, dev).train()
+    m3._engine().train_step(image, mask, cfg)
+    torch.cuda.synchronize()
+    for (k, p2), (_, p3) in zip(m2.named_parameters(), m3.named_parameters()):
+        if k.startswith(HEAD_KEYS):
+            assert (p2.grad - p3.grad).norm() <= GRAD_REL_HEAD * p3.grad.norm(), k
