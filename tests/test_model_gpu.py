@@ -762,7 +762,10 @@ def test_fused_train_step_can_return_the_outputs(cuda_device):
         m2.load_state_dict(sd)          # (same weights and running statistics every time)
         out3, outs = m2._engine().train_step(image, mask, cfg, want_outs=True)
         torch.cuda.synchronize()
-        assert torch.allclose(outs[0], r.detach(), rtol=0, atol=2e-3) and torch.allclose(outs[1], a.detach(), rtol=0, atol=2e-3)
+        # (two runs of the same forward differ through the atomics' order, amplified by bf16 storage: the bounds of
+        # every other output comparison in this file)
+        _check_out(outs[0], r.detach(), "train_step reconstruction")
+        _check_out(outs[1], a.detach(), "train_step anomaly map")
         ld = train_utils.CombinedLoss()(r.detach(), a.detach(), image, mask)
         assert abs(float(out3[0]) - float(ld["total_loss"])) <= 1e-3 * float(ld["total_loss"])
     m3 = _model("anomaly_unet", {k: v.clone() for k, v in sd.items()}, dev).train()
