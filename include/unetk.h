@@ -355,6 +355,21 @@ int unetk_pack_conv_weights(const void* descs, int n_desc, int n_blocks, const f
                             void* stream);
 int unetk_unpack_conv_grads(const void* descs, int n_desc, int n_blocks, int max_cin, const float* gstage,
                             float* flat_g, float scale, void* stream);
+/* The tail of the training step (src/train_utils.py:131-135: `optimizer.zero_grad()`, `backward()` leaving `.grad`,
+ * `optimizer.step()`) for a group of tensors in ONE pass: staged gradient * hyper[8] -> g (`.grad`, reference
+ * layout), the optimizer update of unetk_adam_step (same arithmetic, bit for bit) on p / m / v, the new weights ->
+ * their bf16 kernel layouts in wpack, and zeroes over the staging range it has read.  descs: 64-byte records
+ * {int64 off, wf_off, wd_off; int32 kind (0 plain, 1 conv3x3 OIHW, 2 ConvTranspose2d [ci][co][2][2]), cout, cin,
+ * block_begin, pad[6]} (tiaozhanbei-unet_b200/packing.py: UpdateTable); conv / transposed-conv tensors need
+ * channel counts that are multiples of 32.  hyper: DEVICE float[9] = {lr, beta1, beta2, eps, weight_decay,
+ * 1 - beta1^step, sqrt(1 - beta2^step), first step (0 / 1), gradient scale} -- device memory so that the launch can
+ * be replayed from a CUDA graph with a new step count; unetk_set_floats (values passed by value in the launch)
+ * fills it.  n_blocks = work units of the table (32 x 32 channel tiles, 2048-element chunks); max_blocks > 0 bounds
+ * the grid (the blocks then walk the units), for launches that run beside other streams' kernels. */
+int unetk_fused_update(const void* descs, int n_desc, int n_blocks, int max_blocks, float* p, float* g, float* m, float* v,
+                       float* gstage, void* wpack, const float* hyper, int mode, void* stream);
+int unetk_update_plain_chunk_elems(void);
+int unetk_set_floats(float* dst, const float* host_vals, int n, void* stream);
 int unetk_nchw_to_nhwc(const float* in, void* out, int n, int c, int h, int w, void* stream);
 int unetk_nhwc_to_nchw(const void* in, float* out, int n, int c, int h, int w, void* stream);
 

@@ -43,7 +43,16 @@ def shard(r):
 
 image, mask = (t.to(dev) for t in shard(rank))
 FUSED = "--fused" in sys.argv           # the one-sequence training step (Engine.train_step) instead of model / criterion / backward
-if FUSED and not SYNC_BN:
+UPDATE = "--update" in sys.argv         # ... with the optimizer step inside it (unetk_fused_update after the all-reduces)
+if UPDATE and not SYNC_BN:
+    # (a tiny learning rate: the third step's gradients are still comparable with the oracle at the initial weights)
+    opt = train_utils.get_optimizer(m, "adam", 1e-9, 0.0)
+    assert train_utils._fusable(m, crit, image, mask) and train_utils.FUSED_UPDATE
+    for _ in range(3):
+        train_utils.train_step(m, crit, opt, image, mask)
+    eng = m._engine()
+    assert eng.gstage_zero and not eng.weights_dirty and float(opt.state_dict()["state"][0]["step"]) == 3.0
+elif FUSED and not SYNC_BN:
     assert train_utils._fusable(m, crit, image, mask)
     for _ in range(3):                  # eager call, graph capture (forward half; the all-reduces stay eager), replay
         opt.zero_grad()
@@ -62,6 +71,22 @@ dist.all_gather(allc, chk)
 same = all(torch.equal(allc[0], c) for c in allc)
 ok = same
 msg = f"identical across ranks: {same}; reduced {red.bytes_reduced / 1e6:.1f} MB in buckets"
+if UPDATE and not SYNC_BN:
+    # the updated weights are identical on every rank, their packed bf16 copies are current, the staging buffer is zero
+    eng = m._engine()
+    pc = torch.stack([eng.flat_p.double().sum(), eng.flat_p.double().abs().sum()])
+    allp = [torch.zeros_like(pc) for _ in range(world)]
+    dist.all_gather(allp, pc)
+    same_p = all(torch.equal(allp[0], c) for c in allp)
+    have = eng.wpack.clone()
+    eng.weights_dirty = True
+    eng._pack_weights(split=False)
+    torch.cuda.synchronize()
+    packed = torch.equal(have.view(torch.int16), eng.wpack.view(torch.int16))
+    clean = not eng.gstage.any().item()
+    moved = (eng.flat_p - torch.cat([torch.nn.functional.pad(sd[k].to(dev).flatten(), (0, (-sd[k].numel()) % 64)) for k in eng.param_names])).abs().max().item()
+    ok = ok and same_p and packed and clean and 0.0 < moved < 1e-7
+    msg += f"; after 3 fused updates: weights identical across ranks {same_p}, packed copies current {packed}, staging zero {clean}, max |dp| {moved:.1e}"
 if rank == 0:
     if SYNC_BN:      # the reference on the concatenated global batch (mean loss over all images)
         im = torch.cat([shard(r)[0] for r in range(world)]).to(dev)
@@ -102,7 +127,8 @@ if rank == 0:
                      if k.endswith(("running_mean", "running_var")))
         ok = ok and dev_rs < 5e-2
         msg += f", running-stat rel dev {dev_rs:.2e}"
-opt.step()
+if not UPDATE:
+    opt.step()
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -92,6 +92,22 @@ def test_packing_recipes_are_the_documented_permutations():
     assert arr.dtype.itemsize == 64 and chunks == 18 + 3 and arr[1]["chunk_begin"] == 18
 
 
+def test_update_table_layout():
+    """Descriptor table of unetk_fused_update (packing.UpdateTable): 64-byte records, block ranges per tensor."""
+    from tiaozhanbei_unet_b200 import packing
+    tab = packing.UpdateTable(2048)
+    tab.add_plain(0, 5000)                         # 3 chunks of 2048
+    tab.add_conv(5056, 0, 64 * 64 * 9, 64, 64)     # 2 x 2 tiles of 32 x 32
+    tab.add_convt(50000, 100000, 200000, 128, 64)  # [cin 128][cout 64][2][2]: 4 x 2 tiles
+    arr, blocks = tab.numpy()
+    assert arr.dtype.itemsize == 64 and blocks == 3 + 4 + 8
+    assert list(arr["block_begin"]) == [0, 3, 7] and list(arr["kind"]) == [0, 1, 2]
+    assert (arr["cout"][0], arr["cout"][1], arr["cin"][1], arr["cout"][2], arr["cin"][2]) == (5000, 64, 64, 64, 128)
+    assert list(arr["wf_off"]) == [-1, 0, 100000] and list(arr["wd_off"]) == [-1, 64 * 64 * 9, 200000]
+    with pytest.raises(ValueError):
+        tab.add_conv(0, 0, 0, 48, 64)
+
+
 def test_no_cpu_fallback():
     from tiaozhanbei_unet_b200 import train_utils
     from tiaozhanbei_unet_b200.model import UNet, Up

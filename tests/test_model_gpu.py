@@ -774,3 +774,125 @@ def test_fused_train_step_can_return_the_outputs(cuda_device):
     for (k, p2), (_, p3) in zip(m2.named_parameters(), m3.named_parameters()):
         if k.startswith(HEAD_KEYS):
             assert (p2.grad - p3.grad).norm() <= GRAD_REL_HEAD * p3.grad.norm(), k
+
+
+@pytest.mark.parametrize("kind", ["adam", "adamw", "sgd"])
+def test_fused_update_is_the_unfused_sequence(cuda_device, kind):
+    """unetk_fused_update (one pass per parameter group: staged gradient -> `.grad`, optimizer update, new weights ->
+    packed bf16 layouts, staging range zeroed) against the three passes it replaces on the same buffers
+    (unpack_conv_grads / permute_batched, adam_step, pack_conv_weights / permute_batched / first_conv_pack):
+    bit for bit, over every tensor of an AnomalyUNet, for two consecutive steps (first-step flag, bias corrections)
+    and a gradient scale != 1 (the data-parallel average)."""
+    from tiaozhanbei_unet_b200 import ops, train_utils
+    dev = cuda_device
+    m = _model("anomaly_unet", O.synthetic_state_dict("anomaly_unet", seed=5), dev).train()
+    eng = m._engine()
+    eng.ensure(torch.device(dev))
+    opt_a = train_utils.get_optimizer(m, kind, 3e-3, 1e-2)
+    opt_b = train_utils.get_optimizer(m, kind, 3e-3, 1e-2)
+    g = torch.Generator(device=dev).manual_seed(11)
+    p0 = eng.flat_p.clone()
+    scale = 0.25
+    ref = {}
+    # --- the separate passes (twice), starting from p0 ---
+    stages = [torch.randn(eng.total, device=dev, generator=g) * 1e-2 for _ in range(2)]
+    for step in range(2):
+        eng.gstage.copy_(stages[step])
+        for part in (2, 1, 0):
+            eng._unpack(part, scale)
+        for p, v in zip(eng.params, eng.grad_views()):
+            p.grad = v
+        ref[("g", step)] = eng.flat_g.clone()
+        opt_a.step()
+        eng.weights_dirty = True
+        eng._pack_weights(split=False)
+        ref[("p", step)], ref[("w", step)] = eng.flat_p.clone(), eng.wpack.clone()
+        ref[("m", step)] = [b.clone() for b in opt_a._flat]
+    torch.cuda.synchronize()
+    # --- the fused pass (twice), from the same start ---
+    eng.flat_p.copy_(p0)
+    eng.wpack.zero_()
+    eng.flat_g.zero_()
+    for p in eng.params:
+        p.grad = None
+    for step in range(2):
+        eng.gstage.copy_(stages[step])
+        upd = opt_b.fused_update_args(eng)
+        assert upd is not None
+        vals = list(upd.values)
+        vals[8] = scale
+        ops.set_floats(eng.hyper, vals)
+        eng._upd = upd
+        for tag in (("dec", 1), ("dec", 0), ("enc", 3), ("enc", 0)):        # the order the backward pass finishes them in
+            eng._update_segment(tag)
+        eng._upd = None
+        torch.cuda.synchronize()
+        assert torch.equal(eng.flat_g, ref[("g", step)]), f"{kind} step {step}: gradients"
+        assert torch.equal(eng.flat_p, ref[("p", step)]), f"{kind} step {step}: parameters"
+        for a, b in zip(opt_b._flat, ref[("m", step)]):
+            assert torch.equal(a, b), f"{kind} step {step}: optimizer state"
+        assert torch.equal(eng.wpack.view(torch.int16), ref[("w", step)].view(torch.int16)), f"{kind} step {step}: packed weights"
+        for k, p in zip(eng.param_names, eng.params):       # every parameter's staging range is zero again
+            o = eng.offsets[k]
+            assert not eng.gstage[o: o + p.numel()].any(), k
+    sa, sb = opt_a.state_dict(), opt_b.state_dict()
+    if kind != "sgd":
+        assert float(sa["state"][0]["step"]) == float(sb["state"][0]["step"]) == 2.0
+
+
+def test_fused_update_inside_train_step(cuda_device):
+    """train_utils.train_step with this package's optimizer: the optimizer step runs inside the backward pass
+    (Engine.train_step(update=...)).  Deterministic invariants after eager, captured and replayed steps: the packed
+    bf16 weights the next step will read are exactly pack(current fp32 weights), the staging buffer is zero, the
+    step count advances, a learning-rate change and weights written by torch code in between (load_state_dict)
+    are picked up; and the trajectory agrees with the separate optimizer.step() path like two runs of one path do."""
+    from tiaozhanbei_unet_b200 import train_utils
+    dev = cuda_device
+    arch = "anomaly_unet"
+    sd = O.synthetic_state_dict(arch, seed=12, device=dev)
+    batches = [_inputs(70 + i, 2, 32, 48, dev) for i in range(5)]
+
+    def run(fused_update):
+        old = train_utils.FUSED_UPDATE
+        train_utils.FUSED_UPDATE = fused_update
+        try:
+            m = _model(arch, {k: v.clone() for k, v in sd.items()}, dev).train()
+            crit = train_utils.CombinedLoss()
+            opt = train_utils.get_optimizer(m, "adam", 1e-7, 1e-4)
+            eng = m._engine()
+            losses = []
+            for i, (image, mask) in enumerate(batches):
+                if i == 3:
+                    opt.param_groups[0]["lr"] = 2e-7
+                    m.load_state_dict({k: v.clone() for k, v in sd.items()})      # torch writes the weights in place
+                ld = train_utils.train_step(m, crit, opt, image, mask)
+                losses.append(float(ld["total_loss"]))
+                if fused_update:
+                    torch.cuda.synchronize()
+                    assert eng.gstage_zero and not eng.weights_dirty
+                    assert not eng.gstage.any(), f"step {i}: staging buffer not zero"
+                    have = eng.wpack.clone()
+                    eng.weights_dirty = True
+                    eng._pack_weights(split=False)
+                    torch.cuda.synchronize()
+                    assert torch.equal(have.view(torch.int16), eng.wpack.view(torch.int16)), f"step {i}: stale packed weights"
+                    assert all(p.grad is not None and p.grad.data_ptr() == eng.flat_g.data_ptr() + 4 * eng.offsets[k]
+                               for k, p in zip(eng.param_names, eng.params))
+            torch.cuda.synchronize()
+            assert float(opt.state_dict()["state"][0]["step"]) == len(batches)
+            return m, losses
+        finally:
+            train_utils.FUSED_UPDATE = old
+
+    m_sep, l_sep = run(False)
+    m_fus, l_fus = run(True)
+    for a, b in zip(l_sep, l_fus):
+        assert abs(a - b) <= 1e-3 * abs(a), (l_sep, l_fus)
+    # steps 0 and 3 start from the same weights (and BatchNorm buffers close to each other): same loss up to the atomics
+    assert abs(l_fus[0] - l_sep[0]) <= 5e-4 * abs(l_sep[0])
+    moved = 0.0
+    for (k, a), (_, b) in zip(m_sep.named_parameters(), m_fus.named_parameters()):
+        # lr 1e-7..2e-7, five steps: every weight moved by at most ~1e-6; a stale or mis-laid-out update would show
+        assert (a - b).abs().max().item() <= 2e-6, k
+        moved = max(moved, (a - sd[k]).abs().max().item())
+    assert moved > 0

@@ -77,6 +77,9 @@ SIGNATURES = {
     "unetk_permute_chunk_elems": (I, []),
     "unetk_pack_conv_weights": (I, [P, I, I, P, P, P]),
     "unetk_unpack_conv_grads": (I, [P, I, I, I, P, P, F, P]),
+    "unetk_fused_update": (I, [P, I, I, I, P, P, P, P, P, P, P, I, P]),
+    "unetk_update_plain_chunk_elems": (I, []),
+    "unetk_set_floats": (I, [P, P, I, P]),
     "unetk_nchw_to_nhwc": (I, [P, P, I, I, I, I, P]),
     "unetk_nhwc_to_nchw": (I, [P, P, I, I, I, I, P]),
 }

@@ -283,6 +283,14 @@ int unetk_unpack_conv_grads(const void* descs, int n_desc, int n_blocks, int max
   return unetk::unpack_conv_grads(descs, n_desc, n_blocks, max_cin, gstage, flat_g, scale, S(stream));
 }
 int unetk_permute_chunk_elems(void) { return unetk::permute_chunk_elems(); }
+int unetk_fused_update(const void* descs, int n_desc, int n_blocks, int max_blocks, float* p, float* g, float* m, float* v,
+                       float* gstage, void* wpack, const float* hyper, int mode, void* stream) {
+  return unetk::fused_update(descs, n_desc, n_blocks, max_blocks, p, g, m, v, gstage, wpack, hyper, mode, S(stream));
+}
+int unetk_update_plain_chunk_elems(void) { return unetk::update_plain_chunk_elems(); }
+int unetk_set_floats(float* dst, const float* host_vals, int n, void* stream) {
+  return unetk::set_floats(dst, host_vals, n, S(stream));
+}
 int unetk_nchw_to_nhwc(const float* in, void* out, int n, int c, int h, int w, void* stream) {
   return unetk::nchw_to_nhwc(in, out, n, c, h, w, S(stream));
 }

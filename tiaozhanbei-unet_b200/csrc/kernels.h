@@ -199,5 +199,9 @@ int pack_conv_weights(const void* descs, int n_desc, int n_blocks, const float* 
                       cudaStream_t s);
 int unpack_conv_grads(const void* descs, int n_desc, int n_blocks, int max_cin, const float* gstage,
                       float* flat_g, float scale, cudaStream_t s);
+int fused_update(const void* descs, int n_desc, int n_blocks, int max_blocks, float* p, float* g, float* m, float* v,
+                 float* gstage, void* wpack, const float* hyper, int mode, cudaStream_t s);
+int update_plain_chunk_elems();
+int set_floats(float* dst, const float* host_vals, int n, cudaStream_t s);
 
 }  // namespace unetk

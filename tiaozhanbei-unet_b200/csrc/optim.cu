@@ -17,21 +17,22 @@ namespace unetk {
 __device__ __forceinline__ float adam_update1(float p, float g, float& m, float& v, float lr, float beta1, float beta2,
                                               float eps, float wd, float step_size, float bc2_sqrt, float grad_scale,
                                               int mode, int first_step) {
-  float gg = g * grad_scale;
+  float gg = __fmul_rn(g, grad_scale);
   if (mode == 0) {
     gg = fmaf(wd, p, gg);
   } else if (mode == 1) {
-    p *= (1.f - lr * wd);
+    p = __fmul_rn(p, __fsub_rn(1.f, __fmul_rn(lr, wd)));
   }
   if (mode == 2) {
     gg = fmaf(wd, p, gg);
     m = first_step ? gg : fmaf(beta1, m, gg);
-    return p - lr * m;
+    return __fmaf_rn(-lr, m, p);
   }
-  m = m + (1.f - beta1) * (gg - m);                  // lerp_, as torch does
-  v = beta2 * v + (1.f - beta2) * gg * gg;            // mul_ + addcmul_
-  const float denom = sqrtf(v) / bc2_sqrt + eps;
-  return p - step_size * (m / denom);                 // addcdiv_
+  // explicit roundings (no compiler-chosen contractions): the stand-alone and the fused kernels agree bit for bit
+  m = __fmaf_rn(1.f - beta1, __fsub_rn(gg, m), m);                                    // lerp_, as torch does
+  v = __fmaf_rn(__fmul_rn(1.f - beta2, gg), gg, __fmul_rn(beta2, v));                 // mul_ + addcmul_
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps);
+  return __fmaf_rn(-step_size, __fdiv_rn(m, denom), p);                               // addcdiv_
 }
 
 // Two float4 groups per thread and iteration: eight 16-byte loads in flight before the first store (one group
@@ -191,6 +192,236 @@ unpack_conv_grads_kernel(const ConvPackDesc* __restrict__ descs, int n_desc, con
     dst[i] = row[tap * pitch + ci] * scale;
   }
 }
+
+// ----------------------------------------------------------------------------------------------
+// Fused parameter update: ONE pass over a group of tensors does what used to be three --
+//   (1) staged gradient -> `.grad` in the reference layout, times the data-parallel average,
+//   (2) the optimizer step (adam_update1: bit-identical arithmetic to adam_step_kernel),
+//   (3) the new fp32 weights -> the bf16 kernel layouts the NEXT forward / backward pass reads,
+// and zeroes the staging range it has read (the weight-gradient kernels accumulate into it with
+// red.global.add), so the next step needs neither a packing pass nor a memset.  36 bytes per conv
+// weight instead of 8 (un-pack) + 28 (Adam) + 8 (pack) + 4 (memset), in one launch per group that
+// the engine releases as soon as the group's gradients are final, under the rest of the backward pass.
+// The hyper-parameters come from device memory (hyper[]: the launch is part of a CUDA graph whose
+// replays see a new step count / learning rate every time).
+// ----------------------------------------------------------------------------------------------
+struct UpdateDesc {
+  long long off;      // element offset of the tensor in the flat p / g / m / v / staging buffers
+  long long wf_off;   // bf16 element offset in wpack: conv Wf[co][tap][ci] | convT Wt[tap][co][ci]
+  long long wd_off;   //                               conv Wd[ci][8-tap][co] | convT Wtd[ci][tap][co]
+  int kind;           // 0 plain (same layout everywhere, no packed copy), 1 conv3x3 OIHW, 2 convT [ci][co][2][2]
+  int cout, cin;      // plain: cout = number of elements
+  int block_begin;    // first work unit of this tensor
+  int pad[6];
+};
+static_assert(sizeof(UpdateDesc) == 64, "UpdateDesc layout is part of the C ABI");
+
+constexpr int kUpdPlainChunk = 2048;
+constexpr int kUpdPitch9 = 289;                  // conv3x3 tile: [32 co][32 ci x 9 taps], odd pitch
+constexpr int kUpdPitch4 = 129;                  // transposed-conv tile: [32 ci][32 co x 4 taps]
+constexpr int kUpdMaxDesc = 128;
+
+struct Hyper {
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale;
+  int first_step;
+};
+
+__device__ __forceinline__ Hyper load_hyper(const float* __restrict__ h) {
+  Hyper y;
+  y.lr = h[0]; y.beta1 = h[1]; y.beta2 = h[2]; y.eps = h[3]; y.wd = h[4]; y.bc1 = h[5]; y.bc2_sqrt = h[6];
+  y.first_step = h[7] != 0.f;
+  y.grad_scale = h[8];
+  return y;
+}
+
+// Staged gradients of one tile (ROWS rows of 32 contiguous floats, row i at gtile + i * row_stride) -> the shared
+// tile, transposed into the parameter layout (slot(row, c) = position of element c of row `row`), and zeroes over
+// what was read.  Every thread issues all of its 16-byte loads before the first store (the staging rows are 128-byte
+// pieces a few KB apart: DRAM latency is what this pass waits for).
+template <int ROWS, typename Slot>
+__device__ __forceinline__ void stage_tile(float* __restrict__ gtile, int row_stride, float* tile, Slot slot) {
+  constexpr int PER = ROWS * 8 / 256;           // float4 groups per thread: 9 / 4
+  static_assert(ROWS * 8 % 256 == 0, "tile size");
+  float4 val[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int q = threadIdx.x + k * 256;
+    val[k] = *reinterpret_cast<const float4*>(gtile + (q >> 3) * row_stride + (q & 7) * 4);
+  }
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int q = threadIdx.x + k * 256;
+    const int row = q >> 3, c = (q & 7) * 4;
+    *reinterpret_cast<float4*>(gtile + row * row_stride + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    tile[slot(row, c)] = val[k].x;
+    tile[slot(row, c + 1)] = val[k].y;
+    tile[slot(row, c + 2)] = val[k].z;
+    tile[slot(row, c + 3)] = val[k].w;
+  }
+}
+
+// 32 rows x ROWLEN contiguous fp32 parameters (row r at p + r * row_stride); tile[r * (ROWLEN + 1) + j] holds the
+// element's staged gradient on entry and its new value on exit (same thread, same slot: updated in place).
+template <int ROWLEN>
+__device__ __forceinline__ void update_rows(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                            float* __restrict__ v, int row_stride, float* tile, const Hyper& y, int mode) {
+  constexpr int Q = ROWLEN / 4;                 // float4 groups per row
+  constexpr int PER = 32 * Q / 256;             // groups per thread: 9 / 4
+  static_assert(32 * Q % 256 == 0, "tile size");
+  const float step_size = y.lr / y.bc1;
+  constexpr int U = (PER % 3 == 0) ? 3 : 2;     // groups in flight per thread: 9 / 6 16-byte loads before the first store
+#pragma unroll
+  for (int k0 = 0; k0 < PER; k0 += U) {
+    float4 pv[U], mv[U], vv[U];
+    int at[U];                                  // (offsets inside the tile's 32 rows: < 2^31)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = threadIdx.x + (k0 + u) * 256;
+      const int r = q / Q, j4 = q - r * Q;
+      at[u] = r * row_stride + j4 * 4;
+      pv[u] = *reinterpret_cast<const float4*>(p + at[u]);
+      mv[u] = *reinterpret_cast<const float4*>(m + at[u]);
+      vv[u] = (mode != 2) ? *reinterpret_cast<const float4*>(v + at[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = threadIdx.x + (k0 + u) * 256;
+      const int r = q / Q, j = (q - r * Q) * 4;
+      float* slot = tile + r * (ROWLEN + 1) + j;
+      float4 gg;
+      gg.x = slot[0] * y.grad_scale;
+      gg.y = slot[1] * y.grad_scale;
+      gg.z = slot[2] * y.grad_scale;
+      gg.w = slot[3] * y.grad_scale;
+      pv[u].x = adam_update1(pv[u].x, gg.x, mv[u].x, vv[u].x, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+      pv[u].y = adam_update1(pv[u].y, gg.y, mv[u].y, vv[u].y, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+      pv[u].z = adam_update1(pv[u].z, gg.z, mv[u].z, vv[u].z, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+      pv[u].w = adam_update1(pv[u].w, gg.w, mv[u].w, vv[u].w, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+      *reinterpret_cast<float4*>(g + at[u]) = gg;
+      *reinterpret_cast<float4*>(p + at[u]) = pv[u];
+      *reinterpret_cast<float4*>(m + at[u]) = mv[u];
+      if (mode != 2) *reinterpret_cast<float4*>(v + at[u]) = vv[u];
+      slot[0] = pv[u].x; slot[1] = pv[u].y; slot[2] = pv[u].z; slot[3] = pv[u].w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 4)
+fused_update_kernel(const UpdateDesc* __restrict__ descs, int n_desc, int n_units, float* __restrict__ p,
+                    float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* __restrict__ gstage,
+                    __nv_bfloat16* __restrict__ wpack, const float* __restrict__ hyper, int mode) {
+  __shared__ float tile[32 * kUpdPitch9];
+  __shared__ int begins[kUpdMaxDesc];
+  for (int i = threadIdx.x; i < n_desc; i += blockDim.x) begins[i] = descs[i].block_begin;
+  const Hyper y = load_hyper(hyper);
+  __syncthreads();
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    int lo = 0, hi = n_desc - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (begins[mid] <= unit) lo = mid; else hi = mid - 1;
+    }
+    const long long off = descs[lo].off;
+    const int kind = descs[lo].kind, cout = descs[lo].cout, cin = descs[lo].cin;
+    const int tix = unit - begins[lo];
+    if (kind == 0) {
+      const float step_size = y.lr / y.bc1;
+      const int begin = tix * kUpdPlainChunk;
+      const int end = min(begin + kUpdPlainChunk, cout);
+      for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+        const long long a = off + i;
+        const float gv = gstage[a] * y.grad_scale;
+        gstage[a] = 0.f;
+        float mm = m[a], vv = (mode != 2) ? v[a] : 0.f;
+        g[a] = gv;
+        p[a] = adam_update1(p[a], gv, mm, vv, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+        m[a] = mm;
+        if (mode != 2) v[a] = vv;
+      }
+      continue;                   // (no shared-memory tile involved)
+    }
+    const long long wf_off = descs[lo].wf_off, wd_off = descs[lo].wd_off;
+    if (kind == 1) {
+      // conv3x3: 32 output channels x 32 input channels x 9 taps.  staged dW[co][tap][ci]; parameter OIHW
+      const int tiles_ci = cin / 32;
+      const int co0 = (tix / tiles_ci) * 32, ci0 = (tix % tiles_ci) * 32;
+      // staged row i = r * 9 + tap (rows of one output channel are consecutive taps, cin apart)
+      stage_tile<288>(gstage + off + static_cast<long long>(co0) * 9 * cin + ci0, cin, tile,
+                      [](int row, int c) { const int r = row / 9; return r * kUpdPitch9 + c * 9 + (row - r * 9); });
+      __syncthreads();
+      const long long pb = off + (static_cast<long long>(co0) * cin + ci0) * 9;
+      update_rows<288>(p + pb, g + pb, m + pb, mode != 2 ? v + pb : v, cin * 9, tile, y, mode);
+      __syncthreads();
+      for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
+        const int c = i & 31, rt = i >> 5;
+        const int r = rt / 9, tap = rt - r * 9;
+        wpack[wf_off + (static_cast<long long>(co0 + r) * 9 + tap) * cin + ci0 + c] = __float2bfloat16(tile[r * kUpdPitch9 + c * 9 + tap]);
+      }
+      for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
+        const int r = i & 31, ct = i >> 5;
+        const int c = ct / 9, tapf = ct - c * 9;
+        wpack[wd_off + (static_cast<long long>(ci0 + c) * 9 + tapf) * cout + co0 + r] = __float2bfloat16(tile[r * kUpdPitch9 + c * 9 + (8 - tapf)]);
+      }
+    } else {
+      // transposed conv 2x2: 32 input channels x 32 output channels x 4 taps.  staged dW[co][tap][ci]; parameter [ci][co][tap]
+      const int tiles_co = cout / 32;
+      const int ci0 = (tix / tiles_co) * 32, co0 = (tix % tiles_co) * 32;
+      // staged row i = c * 4 + tap holds 32 input channels r: tile[r][c * 4 + tap]
+      stage_tile<128>(gstage + off + static_cast<long long>(co0) * 4 * cin + ci0, cin, tile,
+                      [](int row, int c) { return c * kUpdPitch4 + row; });
+      __syncthreads();
+      const long long pb = off + (static_cast<long long>(ci0) * cout + co0) * 4;
+      update_rows<128>(p + pb, g + pb, m + pb, mode != 2 ? v + pb : v, cout * 4, tile, y, mode);
+      __syncthreads();
+      for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) {
+        const int r = i & 31, ct = i >> 5;
+        const int c = ct >> 2, tap = ct & 3;
+        wpack[wf_off + (static_cast<long long>(tap) * cout + co0 + c) * cin + ci0 + r] = __float2bfloat16(tile[r * kUpdPitch4 + ct]);
+      }
+      for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) {
+        const int c = i & 31, rt = i >> 5;     // rt = r * 4 + tap
+        const int r = rt >> 2, tap = rt & 3;
+        wpack[wd_off + (static_cast<long long>(ci0 + r) * 4 + tap) * cout + co0 + c] = __float2bfloat16(tile[r * kUpdPitch4 + c * 4 + tap]);
+      }
+    }
+    __syncthreads();        // the tile is reused by the next unit
+  }
+}
+
+struct FloatVals { float v[16]; };
+__global__ void set_floats_kernel(float* dst, FloatVals vals, int n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+
+int set_floats(float* dst, const float* host_vals, int n, cudaStream_t s) {
+  UNETK_CHECK_ARG(dst && host_vals && n > 0 && n <= 16, "set_floats: 1..16 values");
+  FloatVals vals{};
+  for (int i = 0; i < n; ++i) vals.v[i] = host_vals[i];
+  set_floats_kernel<<<1, 32, 0, s>>>(dst, vals, n);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int fused_update(const void* descs, int n_desc, int n_blocks, int max_blocks, float* p, float* g, float* m, float* v,
+                 float* gstage, void* wpack, const float* hyper, int mode, cudaStream_t s) {
+  UNETK_CHECK_ARG(descs && p && g && m && gstage && wpack && hyper && n_desc > 0 && n_blocks > 0, "fused_update: bad arguments");
+  UNETK_CHECK_ARG(mode >= 0 && mode <= 2, "fused_update: unknown mode %d", mode);
+  UNETK_CHECK_ARG(mode == 2 || v != nullptr, "fused_update: second-moment buffer missing");
+  UNETK_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                    reinterpret_cast<uintptr_t>(v)) & 15) == 0, "fused_update: buffers must be 16-byte aligned");
+  // max_blocks > 0: a bounded grid that walks the work units (a launch that runs beside the backward pass must leave
+  // the SMs' block slots to the kernels other streams wait for); 0: one block per unit
+  const int grid = (max_blocks > 0 && max_blocks < n_blocks) ? max_blocks : n_blocks;
+  UNETK_CHECK_ARG(n_desc <= kUpdMaxDesc, "fused_update: at most %d tensors per launch", kUpdMaxDesc);
+  UNETK_CUDA(cudaFuncSetAttribute(fused_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  fused_update_kernel<<<grid, 256, 0, s>>>(static_cast<const UpdateDesc*>(descs), n_desc, n_blocks, p, g, m, v, gstage,
+                                          static_cast<__nv_bfloat16*>(wpack), hyper, mode);
+  UNETK_CUDA(cudaGetLastError());
+  return UNETK_OK;
+}
+
+int update_plain_chunk_elems() { return kUpdPlainChunk; }
+
 
 int pack_conv_weights(const void* descs, int n_desc, int n_blocks, const float* flat_p, void* wpack,
                       cudaStream_t s) {

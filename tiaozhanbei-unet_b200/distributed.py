@@ -70,10 +70,16 @@ class GradReducer:
             self._total = eng.total
         return self.segments
 
-    def segment_ready(self, eng, tag, also_after=None):
+    def segment_ready(self, eng, tag, also_after=None, then=None):
         """Reduce the bucket `tag` once the current stream (and the events `also_after`, recorded on the
-        engine's side streams) have finished writing it."""
+        engine's side streams) have finished writing it.  then(): launches that consume the reduced bucket
+        (Engine.train_step's fused parameter update), enqueued on the reducer's stream right behind the all-reduce."""
         if self.world == 1:
+            if then is not None:
+                cur = torch.cuda.current_stream(eng.gstage.device)
+                for e in (also_after or ()):
+                    cur.wait_event(e)
+                then()
             return
         a, b = self._segments(eng)[tag]
         view = eng.gstage[a:b]
@@ -87,15 +93,28 @@ class GradReducer:
                 self.stream.wait_event(ev)
                 for e in (also_after or ()):
                     self.stream.wait_event(e)
-                self.works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                if then is not None:
+                    work.wait()             # orders the reducer's STREAM behind the all-reduce (the host does not block)
+                    then()
+                    self.tail = torch.cuda.Event()
+                    self.tail.record(self.stream)
+                else:
+                    self.works.append(work)
         else:
             self.works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if then is not None:
+                self.works.pop().wait()
+                then()
 
     def finish(self, eng) -> float:
         """Make the current stream wait for all outstanding reductions; returns the averaging factor."""
         for w in self.works:
             w.wait()
         self.works = []
+        if getattr(self, "tail", None) is not None:      # launches enqueued behind the all-reduces (segment_ready(then=...))
+            torch.cuda.current_stream(eng.gstage.device).wait_event(self.tail)
+            self.tail = None
         return 1.0 / self.world
 
 

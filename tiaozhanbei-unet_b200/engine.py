@@ -79,6 +79,11 @@ GRAD_SLOTS = max(2, int(os.environ.get("UNETK_GRAD_SLOTS", "2")))
 # Plans (activations, scratch, CUDA graphs of one input shape) kept alive at once, least recently used evicted:
 # train batch, ragged last train batch, validation batch, ragged last validation batch.
 MAX_PLANS = max(1, int(os.environ.get("UNETK_MAX_PLANS", "4")))
+# Grid bound of a fused parameter update that runs beside the backward pass (blocks of 256 threads walking the work
+# units; 0 = one block per unit).  Measured (B=16 @256^2, 100 steps, two runs each): 74 -> 10.42-10.45 ms, 148 -> 10.29-10.30,
+# 296 -> 10.17-10.26, 0 -> 10.14-10.18 (update off: 10.18-10.24): a shorter-lived launch disturbs the chain less than a
+# bounded one that lingers.
+UPDATE_SIDE_BLOCKS = int(os.environ.get("UNETK_UPDATE_SIDE_BLOCKS", "0"))
 ALIGN = 64  # elements; keeps every slice 256-byte aligned
 
 
@@ -313,6 +318,8 @@ class Engine:
         # saved state a pending backward needs
         self.generation = 0
         self.staging_clean = False     # gradient staging buffer zeroed by the last training forward
+        self.gstage_zero = False       # ... or by the fused parameter update of the last train_step (which zeroes what it reads)
+        self._upd = None               # train_step(update=...): the optimizer state its backward pass updates in place
         m = module
         self.convbn = []
         self.encoder = []
@@ -400,6 +407,16 @@ class Engine:
         n_early = n_enc_layers - 2
         conv_pack_g = [packing.ConvTable(lambda cout, cin: (cout // 32) * (cin // 32)) for _ in range(3)]
         conv_unpack_g = [packing.ConvTable(lambda cout, cin: cout) for _ in range(3)]
+        # the fused parameter update (un-pack + optimizer + re-pack in one pass, train_step) works on the segments the
+        # backward pass finishes -- and the data-parallel reducer all-reduces -- one after the other: each decoder,
+        # encoder levels 3-4 (nine tenths of the encoder's weights), the rest of the encoder
+        upd_g = {tag: packing.UpdateTable(_lib.get().unetk_update_plain_chunk_elems())
+                 for tag in [("dec", d) for d in range(len(self.decoders))] + [("enc", 3), ("enc", 0)]}
+
+        def upd_of(li):
+            if li >= n_enc_layers:
+                return upd_g[("dec", (li - n_enc_layers) // 8)]
+            return upd_g[("enc", 3) if li >= 6 else ("enc", 0)]
         pdict = dict(zip(self.param_names, self.params))
         wsize = 0
 
@@ -441,19 +458,23 @@ class Engine:
             if L.first:
                 L.g_w = self._slice(self.gstage, wk)            # written in OIHW directly
                 unpack.add(self.offsets[wk], self.offsets[wk], *packing.identity(n))
+                upd_of(li).add_plain(self.offsets[wk], n)       # (its packed copy: first_conv_pack after the update)
                 wplan.append((L, "wf0", walloc(64 * 9 * 64), 64 * 9 * 64))   # Wf[64][9][64], zero beyond Cin
             else:
                 L.g_w = self._slice(self.gstage, wk, (n,))      # [Cout][tap][Cin]
                 of, od = walloc(n), walloc(n)
                 conv_unpack.add(self.offsets[wk], self.offsets[wk], 0, L.cout, cin)
                 conv_pack.add(self.offsets[wk], of, od, L.cout, cin)
+                upd_of(li).add_conv(self.offsets[wk], of, od, L.cout, cin)
                 wplan.append((L, "wf", of, n))
                 wplan.append((L, "wd", od, n))
             for k in (gk, bk):
                 unpack.add(self.offsets[k], self.offsets[k], *packing.identity(pdict[k].numel()))
+                upd_of(li).add_plain(self.offsets[k], pdict[k].numel())
             handled.update((wk, gk, bk))
         unpack = unpack_dec
-        for stages, head in self.decoders:
+        for d, (stages, head) in enumerate(self.decoders):
+            upd = upd_g[("dec", d)]
             for ct, _, _ in stages:
                 if ct is None:                # bilinear stage: no parameters
                     continue
@@ -469,6 +490,8 @@ class Engine:
                 wplan.append((ct, "wd", od, n))
                 unpack.add(self.offsets[wk], self.offsets[wk], *packing.convt_grad_unpack(ct.cin, ct.cout))
                 unpack.add(self.offsets[bk], self.offsets[bk], *packing.identity(ct.cout))
+                upd.add_convt(self.offsets[wk], of, od, ct.cin, ct.cout)
+                upd.add_plain(self.offsets[bk], ct.cout)
                 handled.update((wk, bk))
             wk, bk = head.name + ".weight", head.name + ".bias"
             head.w = self._slice(self.flat_p, wk, (head.n_out, 64))
@@ -477,6 +500,8 @@ class Engine:
             head.g_b = self._slice(self.gstage, bk)
             unpack.add(self.offsets[wk], self.offsets[wk], *packing.identity(head.n_out * 64))
             unpack.add(self.offsets[bk], self.offsets[bk], *packing.identity(head.n_out))
+            upd.add_plain(self.offsets[wk], head.n_out * 64)
+            upd.add_plain(self.offsets[bk], head.n_out)
             handled.update((wk, bk))
         missing = set(self.param_names) - handled
         if missing:
@@ -488,6 +513,15 @@ class Engine:
         self.unpack_tables = (unpack_enc.finalize(device), None, unpack_dec.finalize(device))
         self.conv_pack_tables = tuple(t.finalize(device) for t in conv_pack_g)
         self.conv_unpack_tables = tuple(t.finalize(device) for t in conv_unpack_g)
+        self.update_tables = {tag: t.finalize(device) for tag, t in upd_g.items()}
+        # a segment's update runs right behind the segment's all-reduce: it must stay inside the reduced range
+        from .distributed import segment_ranges
+        ranges = segment_ranges(self.param_names, self.offsets, self.total, len(self.decoders))
+        for tag, t in upd_g.items():
+            lo, hi = ranges[tag]
+            if any(not (lo <= e[0] and e[0] + e[7] <= hi) for e in t.entries):
+                raise _lib.UnetkError(f"update segment {tag} does not match the parameter range {lo}..{hi} of the same tag")
+        self.hyper = torch.zeros(16, dtype=torch.float32, device=device)     # unetk_fused_update's hyper-parameters
 
     def mark_weights_dirty(self):
         self.weights_dirty = True
@@ -590,6 +624,16 @@ class Engine:
                 self.staging_clean = True
                 if side:
                     self.zero_done = self._record(self.pstream)
+
+    def _begin_update_step(self):
+        """What is left of _pack_weights(zero_staging=True) when the previous train_step ended in fused updates:
+        the packed weights are current and the staging buffer is zero; only the two small BatchNorm sum regions
+        (forward statistics, backward sums) are cleared."""
+        self.pack_done0 = self.pack_done4 = self.pack_done = self.zero_done = None
+        self._pack_pending = None
+        ops.zero_(self.bn_stats_all)
+        ops.zero_(self.bn_sums_all)
+        self.staging_clean = True
 
     def _wait_pack(self, which):
         """Make the current stream wait for a stage of the side-stream weight packing (see _pack_weights)."""
@@ -1006,13 +1050,20 @@ class Engine:
                 and self.decoders[0][1].n_out in (1, 3)
                 and all(p.requires_grad for p in self.module.parameters()))
 
-    def train_step(self, x, mask, cfg, want_outs=False):
+    def train_step(self, x, mask, cfg, want_outs=False, update=None):
         """Forward, CombinedLoss (cfg = recon_weight, seg_weight, focal_alpha, focal_gamma) and backward of one
         batch as ONE launch sequence (one CUDA graph per input shape): what src/train_utils.py:122-132 does with
         `model(images)`, `criterion(...)` and `total_loss.backward()`, with each decoder's head, its loss term and
         the head's backward in a single kernel (csrc/head_fused.cu).  Sets every parameter's `.grad` (a view of
         the flat gradient buffer, replacing what was there) and returns (out3, outs): the device tensor
-        (total, recon, seg) and, if asked for, the two sigmoid outputs."""
+        (total, recon, seg) and, if asked for, the two sigmoid outputs.
+
+        update (optim.FusedOptimizer.fused_update_args): the `optimizer.step()` of src/train_utils.py:133 becomes
+        part of the same launch sequence -- as soon as the gradients of a parameter group are final (decoders, then
+        the bottleneck level, then the rest of the encoder) ONE kernel writes the group's `.grad`, applies the
+        optimizer, re-packs the new weights for the next step's kernels and zeroes the gradient staging range
+        (unetk_fused_update), under the rest of the backward pass.  The next step then starts with its first
+        convolution: no packing pass, no memset."""
         x = self._check_input(x)
         if not mask.is_cuda or mask.dtype != torch.float32:
             raise _lib.UnetkError("train_step: the mask must be a float32 CUDA tensor")
@@ -1024,14 +1075,30 @@ class Engine:
                 raise ValueError(f"train_step: mask must be {(n, 1, h, w)}, got {tuple(mask.shape)}")
             pl = self.plan_for(n, h, w)
             self.generation += 1
-            self.mark_weights_dirty()
-            self._vsig = self._version_sig()
+            sig = self._version_sig()
+            if update is None or sig != getattr(self, "_vsig", None):
+                self.mark_weights_dirty()   # (a fused update leaves freshly packed weights behind; torch code that
+            self._vsig = sig                #  wrote a parameter in place since then shows in the version counters)
             pl.alloc_grads()
             if pl.out3 is None:
                 pl.out3 = torch.zeros(3, dtype=torch.float32, device=x.device)
                 pl.loss_work = ops.head_loss_workspace(x.device)
             cfg = tuple(float(v) for v in cfg)
             graphs = self._graphs_ok()
+            if update is not None:
+                # outside the captured sequence: packed weights only if something else changed the parameters, a
+                # memset only if the previous backward pass was not followed by a fused update, this step's
+                # hyper-parameters (step count, learning rate, 1 / world size)
+                if self.weights_dirty:
+                    self._pack_weights(split=False)
+                if not self.gstage_zero:
+                    ops.zero_(self.gstage)
+                vals = list(update.values)
+                vals[8] = 1.0 / self.ddp.world if self.ddp is not None else 1.0
+                ops.set_floats(self.hyper, vals)
+            self._upd = update
+            upd_key = None if update is None else (update.mode, update.m.data_ptr(),
+                                                   0 if update.v is None else update.v.data_ptr())
 
             whole = self.ddp is None or GRAPH_DDP       # NCCL all-reduces stay outside the capture by default
             # forward and backward enqueued back to back (both eager, or one capture): the decoder chains need no join
@@ -1042,7 +1109,10 @@ class Engine:
                                  "flow": flow}
                 try:
                     with self._critical():
-                        self._pack_weights(zero_staging=True)
+                        if update is None:
+                            self._pack_weights(zero_staging=True)
+                        else:
+                            self._begin_update_step()
                         outs = self._forward_train(pl, xs)
                     yield outs
                     self.staging_clean = False
@@ -1065,7 +1135,7 @@ class Engine:
                 pl.x_in.copy_(x)
                 pl.m_in.copy_(mask)
                 pl.x = pl.x_in
-                key = ("step" if whole else "step_fwd", cfg, want_outs)
+                key = ("step" if whole else "step_fwd", cfg, want_outs, upd_key)
                 st = pl.graphs.get(key)
                 if st is None:
                     st = pl.graphs[key] = _GraphState()
@@ -1097,9 +1167,11 @@ class Engine:
                         ph.close()
                 if want_outs and replayed:
                     outs = [o.clone() for o in outs]
+            self._upd = None
             self.weights_dirty = False
             self.fold_dirty = True
             self.staging_clean = False
+            self.gstage_zero = update is not None
             for p, v in zip(self.params, self.grad_views()):
                 p.grad = v
             return pl.out3.clone(), (outs if want_outs else None)
@@ -1109,6 +1181,8 @@ class Engine:
             ops.zero_(self.gstage)          # through autograd; kept for direct callers)
             ops.zero_(self.bn_sums_all)
         self.staging_clean = False
+        self.gstage_zero = False
+        self._upd = None                    # (left set if a train_step(update=...) raised half way)
         pl.alloc_grads()
         graphed = (self._graphs_ok() and pl.static_outs is not None and (self.ddp is None or GRAPH_DDP))
         if not graphed:
@@ -1231,6 +1305,10 @@ class Engine:
             for d in reversed(range(n_dec)):
                 with torch.cuda.stream(chains[d].stream):
                     decoder_stage(d, k, chains[d])
+        upd = self._upd is not None
+        side_updates = upd and self.ddp is None and overlap     # (with a reducer the updates follow the all-reduces)
+        if side_updates and self.ustream is None:
+            self.ustream = torch.cuda.Stream(device=self.device)
         for d in reversed(range(n_dec)):
             ch = chains[d]
             done = None
@@ -1239,12 +1317,23 @@ class Engine:
                 done.record(ch.stream)
                 s0.wait_event(done)
             if self.ddp is not None:
-                self.ddp.segment_ready(self, ("dec", d), [e for e in (done, ch.last_w) if e is not None])
+                self.ddp.segment_ready(self, ("dec", d), [e for e in (done, ch.last_w) if e is not None],
+                                       then=(lambda d=d: self._update_segment(("dec", d), side=True)) if upd else None)
+            elif side_updates:
+                # this decoder's gradients are final: its parameters are updated (and re-packed) on a side stream
+                # while the other decoder and the encoder are still in their backward pass
+                self.ustream.wait_event(done if done is not None else self._record(s0))
+                if ch.last_w is not None:
+                    self.ustream.wait_event(ch.last_w)
+                with torch.cuda.stream(self.ustream):
+                    self._update_segment(("dec", d), side=True)
+            elif upd:
+                self._update_segment(("dec", d))
         # the decoders' gradients are final: re-lay them out on a side stream under the encoder's backward
         # (without data parallelism; with it the buckets are still being all-reduced)
         early_unpack = None
         early_bottleneck = False
-        if self.ddp is None and overlap:
+        if self.ddp is None and overlap and not upd:
             if self.ustream is None:
                 self.ustream = torch.cuda.Stream(device=self.device)
             ev = torch.cuda.Event()
@@ -1293,7 +1382,20 @@ class Engine:
                 skip_written[l - 1] = True
                 ch.free_y[iy] = ch.side(lambda d_y=d_y, src=src, c1=c1: ops.conv3x3_wgrad(d_y, src, None, c1.g_w), mk)
             if self.ddp is not None and l in (3, 0):
-                self.ddp.segment_ready(self, ("enc", l), [ch.last_w] if ch.last_w is not None else [])
+                self.ddp.segment_ready(self, ("enc", l), [ch.last_w] if ch.last_w is not None else [],
+                                       then=(lambda l=l: self._update_segment(("enc", l), side=l == 3)) if upd else None)
+            elif upd and l == 3:
+                # levels 3-4 hold nine tenths of the encoder's weights: updated under the rest of the encoder's backward
+                if side_updates:
+                    self.ustream.wait_event(self._record(ch.stream))      # (the data gradients that read the packed weights)
+                    if ch.last_w is not None:
+                        self.ustream.wait_event(ch.last_w)
+                    with torch.cuda.stream(self.ustream):
+                        self._update_segment(("enc", 3), side=True)
+                else:
+                    if ch.last_w is not None:
+                        ch.stream.wait_event(ch.last_w)
+                    self._update_segment(("enc", 3))
             if l == 4 and early_unpack is not None and ch.last_w is not None:
                 # the bottleneck level holds three quarters of the encoder's weights: un-pack its gradients under
                 # the rest of the encoder's backward too
@@ -1309,7 +1411,13 @@ class Engine:
         _note("bwd unpack")
         scale = 1.0
         if self.ddp is not None:
-            scale = self.ddp.finish(self)
+            scale = self.ddp.finish(self)     # (with fused updates: the last segment's update ran behind its all-reduce)
+        if upd:
+            if side_updates:
+                s0.wait_event(self._record(self.ustream))
+            if self.ddp is None:
+                self._update_segment(("enc", 0))
+            return self.grad_views()
         if early_unpack is not None:
             s0.wait_event(early_unpack)       # the decoders' gradients were re-laid-out under the encoder's backward
         else:
@@ -1318,6 +1426,17 @@ class Engine:
             self._unpack(1, scale)
         self._unpack(0, scale)
         return self.grad_views()
+
+    def _update_segment(self, tag, side=False):
+        """train_step(update=...): the gradients of segment `tag` are final (and all-reduced): ONE kernel writes its
+        `.grad`, applies the optimizer, re-packs the new weights and zeroes the staging range (unetk_fused_update).
+        side: the launch runs beside the rest of the backward pass (optional grid bound, UPDATE_SIDE_BLOCKS)."""
+        u = self._upd
+        ops.fused_update(self.update_tables[tag], self.flat_p, self.flat_g, u.m, u.v, self.gstage, self.wpack, self.hyper,
+                         u.mode, max_blocks=UPDATE_SIDE_BLOCKS if side else 0)
+        if tag == ("enc", 0) and self._first_tc():
+            first = self.encoder[0][0]
+            ops.first_conv_pack(first.w, first.wf0)
 
     def _unpack(self, part, scale):
         """Staged gradients ([Cout][tap][Cin] conv weights, ...) -> `.grad` in the reference layouts, for the

@@ -606,6 +606,33 @@ def unpack_conv_grads(table, gstage, flat_g, scale=1.0):
               _p(gstage), _p(flat_g), scale, _s())
 
 
+def fused_update(table, p, g, m, v, gstage, wpack, hyper, mode, max_blocks=0):
+    """table: packing.UpdateTable.  Staged gradients -> g, optimizer update of p / m / v, new weights -> wpack, zeroes
+    over the staging ranges read; hyper: device float32[>= 9] (see include/unetk.h: unetk_fused_update)."""
+    if table.n_desc == 0:
+        return
+    for t, name in ((p, "p"), (g, "g"), (m, "m"), (gstage, "gstage"), (hyper, "hyper")):
+        _chk(t, f32, name)
+    if v is not None:
+        _chk(v, f32, "v")
+    _chk(wpack, bf16, "wpack")
+    if not (p.numel() == g.numel() == m.numel() == gstage.numel() and p.numel() >= table.max_end) or hyper.numel() < 9:
+        raise _lib.UnetkError("fused_update: flat buffers of different sizes / shorter than the table's tensors")
+    _lib.call("unetk_fused_update", _p(table.device_descs), table.n_desc, table.n_blocks, max_blocks, _p(p), _p(g), _p(m), _p(v),
+              _p(gstage), _p(wpack), _p(hyper), mode, _s())
+
+
+def set_floats(dst, values):
+    """dst[:len(values)] = values (at most 16 floats, passed by value inside the launch: no host buffer to keep alive)."""
+    import ctypes
+    _chk(dst, f32, "dst")
+    n = len(values)
+    if not 0 < n <= 16 or dst.numel() < n:
+        raise _lib.UnetkError("set_floats: 1..16 values into a buffer that holds them")
+    arr = (ctypes.c_float * n)(*[float(x) for x in values])
+    _lib.call("unetk_set_floats", _p(dst), ctypes.cast(arr, ctypes.c_void_p), n, _s())
+
+
 def nchw_to_nhwc(x, out):
     _chk(x, f32, "x"); _chk(out, bf16, "out")
     n, c, h, w = x.shape

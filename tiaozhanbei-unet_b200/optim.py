@@ -16,6 +16,15 @@ from . import ops
 _MODE = {"adam": 0, "adamw": 1, "sgd": 2}
 
 
+class _FusedUpdate:
+    """m / v: flat moment buffers laid out like the engine's flat parameter buffer; values: the nine floats of
+    unetk_fused_update's hyper[] (index 8, the gradient scale, is filled in by the engine)."""
+    __slots__ = ("m", "v", "mode", "values")
+
+    def __init__(self, m, v, mode, values):
+        self.m, self.v, self.mode, self.values = m, v, mode, values
+
+
 class FusedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, kind, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8, momentum=0.9, engine=None):
         if kind not in _MODE:
@@ -72,6 +81,50 @@ class FusedOptimizer(torch.optim.Optimizer):
                     st[name] = view
             if "step" not in st and self.kind != "sgd":
                 st["step"] = torch.tensor(0.0, dtype=torch.float32)
+
+    # -- step as part of Engine.train_step ---------------------------------------------------------
+    def fused_update_args(self, eng):
+        """Everything Engine.train_step(update=...) needs to run this optimizer's step inside the backward pass
+        (unetk_fused_update: one kernel per parameter group un-packs the gradients, updates the parameters and
+        re-packs the new weights), or None if this optimizer does not own exactly the engine's flat parameter
+        buffer.  Advances the step count like step() does: call it once per training step, then do NOT call step()."""
+        import math
+        import numpy as np
+        if eng is None or eng is not self._engine or eng.flat_p is None or len(self.param_groups) != 1:
+            return None
+        group = self.param_groups[0]
+        params = group["params"]
+        key = (eng.flat_p.data_ptr(), len(params))
+        if getattr(self, "_fused_ok_key", None) != key:
+            ok = len(params) == len(eng.params)
+            base = eng.flat_p.data_ptr()
+            for p, q, k in zip(params, eng.params, eng.param_names) if ok else ():
+                if p is not q or p.data_ptr() != base + eng.offsets[k] * 4 or not p.requires_grad:
+                    ok = False
+                    break
+            self._fused_ok_key, self._fused_ok = key, ok
+        if not self._fused_ok or group.get("maximize") or group.get("amsgrad") or group.get("nesterov") or group.get("dampening"):
+            return None
+        first = self._names()[0] not in self.state[eng.params[0]]
+        self._ensure_flat_state(eng)
+        f32 = lambda x: float(np.float32(x))
+        lr, wd = f32(group["lr"]), f32(group["weight_decay"])
+        if self.kind == "sgd":
+            mom = f32(group["momentum"])
+            step = 1 if first else 2
+            values = [lr, mom, 0.0, 0.0, wd, f32(1.0 - math.pow(mom, step)), 1.0, float(first), 1.0]
+            return _FusedUpdate(self._flat[0], None, 2, values)
+        states = [self.state[p] for p in eng.params]
+        step = self._step_of(states[0]) + 1
+        t = torch.tensor(float(step), dtype=torch.float32)
+        for st in states:
+            st["step"] = t
+        b1, b2 = (f32(b) for b in group["betas"])
+        # the same double-precision bias corrections unetk_adam_step derives from its float arguments
+        bc1 = f32(1.0 - math.pow(b1, step))
+        bc2_sqrt = f32(math.sqrt(1.0 - math.pow(b2, step)))
+        values = [lr, b1, b2, f32(group["eps"]), wd, bc1, bc2_sqrt, float(step == 1), 1.0]
+        return _FusedUpdate(self._flat[0], self._flat[1], _MODE[self.kind], values)
 
     # -- step ------------------------------------------------------------------------------------
     @torch.no_grad()

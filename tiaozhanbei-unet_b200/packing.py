@@ -113,3 +113,50 @@ class ConvTable:
         self.n_desc, self.n_blocks = len(self.entries), blk
         self.device_descs = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
         return self
+
+
+# ---- fused parameter update (unetk_fused_update) ------------------------------------------------------
+UPDATE_DESC_DTYPE = np.dtype([("off", "<i8"), ("wf_off", "<i8"), ("wd_off", "<i8"), ("kind", "<i4"), ("cout", "<i4"),
+                              ("cin", "<i4"), ("block_begin", "<i4"), ("pad", "<i4", (6,))])
+assert UPDATE_DESC_DTYPE.itemsize == 64
+KIND_PLAIN, KIND_CONV3X3, KIND_CONVT = 0, 1, 2
+
+
+class UpdateTable:
+    """Tensors one unetk_fused_update launch covers: `off` = the tensor's offset in the flat parameter / gradient /
+    moment / staging buffers, `wf_off` / `wd_off` = where its two packed bf16 copies live in the weight pack."""
+
+    def __init__(self, plain_chunk: int):
+        self.plain_chunk = plain_chunk
+        self.entries = []
+        self.device_descs = None
+        self.n_desc = self.n_blocks = self.max_end = 0
+
+    def add_plain(self, off, n):
+        self.entries.append((off, -1, -1, KIND_PLAIN, n, 0, (n + self.plain_chunk - 1) // self.plain_chunk, n))
+
+    def add_conv(self, off, wf_off, wd_off, cout, cin):
+        if cout % 32 or cin % 32:
+            raise ValueError("fused update of a conv3x3 weight needs channel counts that are multiples of 32")
+        self.entries.append((off, wf_off, wd_off, KIND_CONV3X3, cout, cin, (cout // 32) * (cin // 32), cout * cin * 9))
+
+    def add_convt(self, off, wf_off, wd_off, cin, cout):
+        if cout % 32 or cin % 32:
+            raise ValueError("fused update of a transposed-conv weight needs channel counts that are multiples of 32")
+        self.entries.append((off, wf_off, wd_off, KIND_CONVT, cout, cin, (cout // 32) * (cin // 32), cout * cin * 4))
+
+    def numpy(self):
+        arr = np.zeros(len(self.entries), dtype=UPDATE_DESC_DTYPE)
+        blk = 0
+        for i, (off, wf, wd, kind, cout, cin, blocks, _) in enumerate(self.entries):
+            arr[i]["off"], arr[i]["wf_off"], arr[i]["wd_off"] = off, wf, wd
+            arr[i]["kind"], arr[i]["cout"], arr[i]["cin"], arr[i]["block_begin"] = kind, cout, cin, blk
+            blk += blocks
+        return arr, blk
+
+    def finalize(self, device):
+        arr, blocks = self.numpy()
+        self.n_desc, self.n_blocks = len(self.entries), blocks
+        self.max_end = max((e[0] + e[7] for e in self.entries), default=0)
+        self.device_descs = torch.from_numpy(arr.view(np.uint8).copy()).to(device)
+        return self

@@ -273,6 +273,7 @@ def _device_batches(loader, device):
 
 
 FUSED_STEP = __import__("os").environ.get("UNETK_FUSED_STEP", "1") != "0"
+FUSED_UPDATE = __import__("os").environ.get("UNETK_FUSED_UPDATE", "1") != "0"
 
 
 def _fusable(model, criterion, images, masks):
@@ -300,11 +301,19 @@ def train_step(model, criterion, optimizer, images, masks):
     combination takes the plain path below, which is also what `model(x)` / `criterion(...)` / `.backward()` called
     one by one do."""
     if _fusable(model, criterion, images, masks):
+        eng = model._engine()
+        update = None
+        if FUSED_UPDATE and isinstance(optimizer, FusedOptimizer):
+            # this package's optimizer on the model's flat parameter buffer: its step runs inside the backward pass,
+            # group by group as the gradients become final (Engine.train_step, unetk_fused_update)
+            eng.ensure(images.device)
+            update = optimizer.fused_update_args(eng)
         optimizer.zero_grad()
-        out3, _ = model._engine().train_step(images, masks, (criterion.recon_weight, criterion.seg_weight,
-                                                              criterion.focal_alpha, criterion.focal_gamma))
+        out3, _ = eng.train_step(images, masks, (criterion.recon_weight, criterion.seg_weight,
+                                                 criterion.focal_alpha, criterion.focal_gamma), update=update)
         criterion._last = out3
-        optimizer.step()
+        if update is None:
+            optimizer.step()
         return {"total_loss": out3[0], "recon_loss": out3[1], "seg_loss": out3[2]}
     reconstruction, anomaly_map = model(images)
     loss_dict = criterion(reconstruction, anomaly_map, images, masks)

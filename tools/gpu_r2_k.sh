@@ -1,0 +1,16 @@
+#!/bin/bash
+# fused parameter update (unetk_fused_update inside train_step): tests, step time with / without, timeline
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_model_gpu.py -x -q -m gpu -p no:cacheprovider -k "fused or ddp or accumulation or checkpoint or curve" > gpurun_out/pytest_gpu_k.log 2>&1; echo "pytest exit $?"
+tail -n 5 gpurun_out/pytest_gpu_k.log
+for mode in 1 0; do
+UNETK_FUSED_UPDATE=$mode timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-inference > gpurun_out/bench_upd$mode.json 2> gpurun_out/bench_upd$mode.err; echo "bench (update=$mode) exit $?"
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_upd$mode.json"))
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["loss"], d["gpu_launches"])
+PY
+done
+timeout 300 python tools/update_bench.py 2>&1 | tee gpurun_out/update_bench.log
+timeout 300 python tools/timeline.py --out gpurun_out/timeline_r02_update.txt > gpurun_out/timeline_update.log 2>&1; echo "timeline exit $?"
+head -n 50 gpurun_out/timeline_update.log | cut -c1-220
