@@ -1,0 +1,10 @@
+#!/bin/bash
+# full GPU suite + smoke + bench, then the ncu launch list of the bench command
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"
+tail -n 3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"
+tail -n 2 gpurun_out/smoke.log | cut -c1-300
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+cut -c1-300 gpurun_out/bench.json
+bash tools/gpu_ncu_launches.sh r02b
