@@ -217,8 +217,8 @@ struct UpdateDesc {
 static_assert(sizeof(UpdateDesc) == 64, "UpdateDesc layout is part of the C ABI");
 
 constexpr int kUpdPlainChunk = 2048;
-constexpr int kUpdPitch9 = 289;                  // conv3x3 tile: [32 co][32 ci x 9 taps], odd pitch
-constexpr int kUpdPitch4 = 129;                  // transposed-conv tile: [32 ci][32 co x 4 taps]
+constexpr int kUpdPitch9 = 290;                  // conv3x3 tile: [32 co][32 ci x 9 taps]; even pitch: 8-byte shared accesses
+constexpr int kUpdPitch4 = 130;                  // transposed-conv tile: [32 ci][32 co x 4 taps]
 constexpr int kUpdMaxDesc = 128;
 
 struct Hyper {
@@ -260,7 +260,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ gtile, int row_st
   }
 }
 
-// 32 rows x ROWLEN contiguous fp32 parameters (row r at p + r * row_stride); tile[r * (ROWLEN + 1) + j] holds the
+// 32 rows x ROWLEN contiguous fp32 parameters (row r at p + r * row_stride); tile[r * (ROWLEN + 2) + j] holds the
 // element's staged gradient on entry and its new value on exit (same thread, same slot: updated in place).
 template <int ROWLEN>
 __device__ __forceinline__ void update_rows(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
@@ -287,12 +287,13 @@ __device__ __forceinline__ void update_rows(float* __restrict__ p, float* __rest
     for (int u = 0; u < U; ++u) {
       const int q = threadIdx.x + (k0 + u) * 256;
       const int r = q / Q, j = (q - r * Q) * 4;
-      float* slot = tile + r * (ROWLEN + 1) + j;
+      float2* slot = reinterpret_cast<float2*>(tile + r * (ROWLEN + 2) + j);      // (even offset: 8-byte aligned)
+      const float2 g01 = slot[0], g23 = slot[1];
       float4 gg;
-      gg.x = slot[0] * y.grad_scale;
-      gg.y = slot[1] * y.grad_scale;
-      gg.z = slot[2] * y.grad_scale;
-      gg.w = slot[3] * y.grad_scale;
+      gg.x = g01.x * y.grad_scale;
+      gg.y = g01.y * y.grad_scale;
+      gg.z = g23.x * y.grad_scale;
+      gg.w = g23.y * y.grad_scale;
       pv[u].x = adam_update1(pv[u].x, gg.x, mv[u].x, vv[u].x, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
       pv[u].y = adam_update1(pv[u].y, gg.y, mv[u].y, vv[u].y, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
       pv[u].z = adam_update1(pv[u].z, gg.z, mv[u].z, vv[u].z, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
@@ -301,7 +302,8 @@ __device__ __forceinline__ void update_rows(float* __restrict__ p, float* __rest
       *reinterpret_cast<float4*>(p + at[u]) = pv[u];
       *reinterpret_cast<float4*>(m + at[u]) = mv[u];
       if (mode != 2) *reinterpret_cast<float4*>(v + at[u]) = vv[u];
-      slot[0] = pv[u].x; slot[1] = pv[u].y; slot[2] = pv[u].z; slot[3] = pv[u].w;
+      slot[0] = make_float2(pv[u].x, pv[u].y);
+      slot[1] = make_float2(pv[u].z, pv[u].w);
     }
   }
 }
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(256, 4)
 fused_update_kernel(const UpdateDesc* __restrict__ descs, int n_desc, int n_units, float* __restrict__ p,
                     float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* __restrict__ gstage,
                     __nv_bfloat16* __restrict__ wpack, const float* __restrict__ hyper, int mode) {
-  __shared__ float tile[32 * kUpdPitch9];
+  __shared__ __align__(16) float tile[32 * kUpdPitch9];
   __shared__ int begins[kUpdMaxDesc];
   for (int i = threadIdx.x; i < n_desc; i += blockDim.x) begins[i] = descs[i].block_begin;
   const Hyper y = load_hyper(hyper);
@@ -328,6 +330,34 @@ fused_update_kernel(const UpdateDesc* __restrict__ descs, int n_desc, int n_unit
       const float step_size = y.lr / y.bc1;
       const int begin = tix * kUpdPlainChunk;
       const int end = min(begin + kUpdPlainChunk, cout);
+      if (end - begin == kUpdPlainChunk) {
+        // a full chunk (tensor offsets are 256-byte aligned): two 16-byte groups per thread, every load before the first store
+        constexpr int G = kUpdPlainChunk / 4 / 256;
+        float4 gv[G], pv[G], mv[G], vv[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          const long long a = off + begin + (threadIdx.x + k * 256) * 4;
+          gv[k] = *reinterpret_cast<const float4*>(gstage + a);
+          pv[k] = *reinterpret_cast<const float4*>(p + a);
+          mv[k] = *reinterpret_cast<const float4*>(m + a);
+          vv[k] = (mode != 2) ? *reinterpret_cast<const float4*>(v + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+          const long long a = off + begin + (threadIdx.x + k * 256) * 4;
+          gv[k].x *= y.grad_scale; gv[k].y *= y.grad_scale; gv[k].z *= y.grad_scale; gv[k].w *= y.grad_scale;
+          pv[k].x = adam_update1(pv[k].x, gv[k].x, mv[k].x, vv[k].x, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+          pv[k].y = adam_update1(pv[k].y, gv[k].y, mv[k].y, vv[k].y, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+          pv[k].z = adam_update1(pv[k].z, gv[k].z, mv[k].z, vv[k].z, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+          pv[k].w = adam_update1(pv[k].w, gv[k].w, mv[k].w, vv[k].w, y.lr, y.beta1, y.beta2, y.eps, y.wd, step_size, y.bc2_sqrt, 1.f, mode, y.first_step);
+          *reinterpret_cast<float4*>(gstage + a) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(g + a) = gv[k];
+          *reinterpret_cast<float4*>(p + a) = pv[k];
+          *reinterpret_cast<float4*>(m + a) = mv[k];
+          if (mode != 2) *reinterpret_cast<float4*>(v + a) = vv[k];
+        }
+        continue;
+      }
       for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
         const long long a = off + i;
         const float gv = gstage[a] * y.grad_scale;
@@ -352,15 +382,26 @@ fused_update_kernel(const UpdateDesc* __restrict__ descs, int n_desc, int n_unit
       const long long pb = off + (static_cast<long long>(co0) * cin + ci0) * 9;
       update_rows<288>(p + pb, g + pb, m + pb, mode != 2 ? v + pb : v, cin * 9, tile, y, mode);
       __syncthreads();
-      for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
-        const int c = i & 31, rt = i >> 5;
+      // packed copies, eight bf16 (16 bytes) per store: Wf[co][tap][ci0 + 8 q ..], Wd[ci][8 - tap][co0 + 8 q ..]
+      for (int i = threadIdx.x; i < 32 * 9 * 4; i += blockDim.x) {
+        const int q = i & 3, rt = i >> 2;
         const int r = rt / 9, tap = rt - r * 9;
-        wpack[wf_off + (static_cast<long long>(co0 + r) * 9 + tap) * cin + ci0 + c] = __float2bfloat16(tile[r * kUpdPitch9 + c * 9 + tap]);
+        const float* src = tile + r * kUpdPitch9 + q * 72 + tap;          // element c = 8 q + e at + 9 e
+        uint4 w;
+        w.x = pack_bf16x2(src[0], src[9]);  w.y = pack_bf16x2(src[18], src[27]);
+        w.z = pack_bf16x2(src[36], src[45]); w.w = pack_bf16x2(src[54], src[63]);
+        *reinterpret_cast<uint4*>(wpack + wf_off + (static_cast<long long>(co0 + r) * 9 + tap) * cin + ci0 + q * 8) = w;
       }
-      for (int i = threadIdx.x; i < 32 * 288; i += blockDim.x) {
-        const int r = i & 31, ct = i >> 5;
+      for (int i = threadIdx.x; i < 32 * 9 * 4; i += blockDim.x) {
+        const int q = i & 3, ct = i >> 2;
         const int c = ct / 9, tapf = ct - c * 9;
-        wpack[wd_off + (static_cast<long long>(ci0 + c) * 9 + tapf) * cout + co0 + r] = __float2bfloat16(tile[r * kUpdPitch9 + c * 9 + (8 - tapf)]);
+        const float* src = tile + (q * 8) * kUpdPitch9 + c * 9 + (8 - tapf);   // element r = 8 q + e at + pitch e
+        uint4 w;
+        w.x = pack_bf16x2(src[0], src[kUpdPitch9]);
+        w.y = pack_bf16x2(src[2 * kUpdPitch9], src[3 * kUpdPitch9]);
+        w.z = pack_bf16x2(src[4 * kUpdPitch9], src[5 * kUpdPitch9]);
+        w.w = pack_bf16x2(src[6 * kUpdPitch9], src[7 * kUpdPitch9]);
+        *reinterpret_cast<uint4*>(wpack + wd_off + (static_cast<long long>(ci0 + c) * 9 + tapf) * cout + co0 + q * 8) = w;
       }
     } else {
       // transposed conv 2x2: 32 input channels x 32 output channels x 4 taps.  staged dW[co][tap][ci]; parameter [ci][co][tap]
@@ -373,15 +414,26 @@ fused_update_kernel(const UpdateDesc* __restrict__ descs, int n_desc, int n_unit
       const long long pb = off + (static_cast<long long>(ci0) * cout + co0) * 4;
       update_rows<128>(p + pb, g + pb, m + pb, mode != 2 ? v + pb : v, cout * 4, tile, y, mode);
       __syncthreads();
-      for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) {
-        const int r = i & 31, ct = i >> 5;
+      // Wt[tap][co][ci0 + 8 q ..] and Wtd[ci][tap][co0 + 8 q ..], 16 bytes per store
+      for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) {
+        const int q = i & 3, ct = i >> 2;      // ct = c * 4 + tap
         const int c = ct >> 2, tap = ct & 3;
-        wpack[wf_off + (static_cast<long long>(tap) * cout + co0 + c) * cin + ci0 + r] = __float2bfloat16(tile[r * kUpdPitch4 + ct]);
+        const float* src = tile + (q * 8) * kUpdPitch4 + ct;                   // element r = 8 q + e at + pitch e
+        uint4 w;
+        w.x = pack_bf16x2(src[0], src[kUpdPitch4]);
+        w.y = pack_bf16x2(src[2 * kUpdPitch4], src[3 * kUpdPitch4]);
+        w.z = pack_bf16x2(src[4 * kUpdPitch4], src[5 * kUpdPitch4]);
+        w.w = pack_bf16x2(src[6 * kUpdPitch4], src[7 * kUpdPitch4]);
+        *reinterpret_cast<uint4*>(wpack + wf_off + (static_cast<long long>(tap) * cout + co0 + c) * cin + ci0 + q * 8) = w;
       }
-      for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) {
-        const int c = i & 31, rt = i >> 5;     // rt = r * 4 + tap
+      for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) {
+        const int q = i & 3, rt = i >> 2;      // rt = r * 4 + tap
         const int r = rt >> 2, tap = rt & 3;
-        wpack[wd_off + (static_cast<long long>(ci0 + r) * 4 + tap) * cout + co0 + c] = __float2bfloat16(tile[r * kUpdPitch4 + c * 4 + tap]);
+        const float* src = tile + r * kUpdPitch4 + q * 32 + tap;               // element c = 8 q + e at + 4 e
+        uint4 w;
+        w.x = pack_bf16x2(src[0], src[4]);   w.y = pack_bf16x2(src[8], src[12]);
+        w.z = pack_bf16x2(src[16], src[20]); w.w = pack_bf16x2(src[24], src[28]);
+        *reinterpret_cast<uint4*>(wpack + wd_off + (static_cast<long long>(ci0 + r) * 4 + tap) * cout + co0 + q * 8) = w;
       }
     }
     __syncthreads();        // the tile is reused by the next unit

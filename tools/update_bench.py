@@ -40,3 +40,12 @@ for part, name in ((("dec", 0), "decoder 0"), (("enc", 3), "encoder 3-4"), (("en
         print(f"fused_update {name:12s} {n / 1e6:6.2f} M params, {tab.n_blocks:5d} units, max_blocks {mb:4d}: {t * 1e3:7.1f} us  {36 * n / t / 1e6:7.0f} GB/s")
 t = timeit(lambda: ops.adam_step(eng.flat_p, eng.flat_g, upd.m, upd.v, 1e-3, 0.9, 0.999, 1e-8, 1e-4, 3))
 print(f"adam_step (all {eng.total / 1e6:.1f} M): {t * 1e3:.1f} us  {28 * eng.total / t / 1e6:.0f} GB/s")
+# control: the same kernel over the whole flat buffer as ONE "plain" tensor (no tiles, no packed copies: a streaming
+# pass of 36 bytes per element) -- what the tiled access pattern costs
+from tiaozhanbei_unet_b200 import packing  # noqa: E402
+from tiaozhanbei_unet_b200 import _lib  # noqa: E402
+ctl = packing.UpdateTable(_lib.get().unetk_update_plain_chunk_elems())
+ctl.add_plain(0, eng.total)
+ctl.finalize(dev)
+t = timeit(lambda: ops.fused_update(ctl, eng.flat_p, eng.flat_g, upd.m, upd.v, eng.gstage, eng.wpack, eng.hyper, upd.mode))
+print(f"fused_update, everything as one plain tensor ({eng.total / 1e6:.1f} M): {t * 1e3:.1f} us  {36 * eng.total / t / 1e6:.0f} GB/s")
