@@ -308,6 +308,51 @@ __device__ __forceinline__ void update_rows(float* __restrict__ p, float* __rest
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
+// The lines the NEXT work unit of this block will load (its staged gradient tile and its rows of p / m / v), pulled
+// into L2 while the current unit packs its weights: a block's loads then cost an L2 round trip instead of a DRAM one
+// (the kernel was latency bound at 42 % of the DRAM bandwidth with four blocks per SM: profiles/ncu_fused_update_r02_summary.txt).
+__device__ __forceinline__ void prefetch_unit(const UpdateDesc* __restrict__ descs, const int* begins, int n_desc, int unit,
+                                              const float* p, const float* m, const float* v, const float* gstage, int mode) {
+  int lo = 0, hi = n_desc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (begins[mid] <= unit) lo = mid; else hi = mid - 1;
+  }
+  const long long off = descs[lo].off;
+  const int kind = descs[lo].kind, cout = descs[lo].cout, cin = descs[lo].cin;
+  const int tix = unit - begins[lo];
+  if (kind == 0) return;                       // (small tensors)
+  int taps, rows;                              // rows of 128 bytes in the staging tile
+  long long gbase, pbase, prow;
+  if (kind == 1) {
+    const int tiles_ci = cin / 32;
+    const int co0 = (tix / tiles_ci) * 32, ci0 = (tix % tiles_ci) * 32;
+    taps = 9; rows = 288;
+    gbase = off + static_cast<long long>(co0) * 9 * cin + ci0;
+    pbase = off + (static_cast<long long>(co0) * cin + ci0) * 9;
+    prow = static_cast<long long>(cin) * 9;
+  } else {
+    const int tiles_co = cout / 32;
+    const int ci0 = (tix / tiles_co) * 32, co0 = (tix % tiles_co) * 32;
+    taps = 4; rows = 128;
+    gbase = off + static_cast<long long>(co0) * 4 * cin + ci0;
+    pbase = off + (static_cast<long long>(ci0) * cout + co0) * 4;
+    prow = static_cast<long long>(cout) * 4;
+  }
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    prefetch_l2(gstage + gbase + static_cast<long long>(i) * cin);
+    // the same count of 128-byte lines in each of p / m / v: 32 rows of `taps` lines
+    const long long a = pbase + (i / taps) * prow + (i % taps) * 32;
+    prefetch_l2(p + a);
+    prefetch_l2(m + a);
+    if (mode != 2) prefetch_l2(v + a);
+  }
+}
+
 __global__ void __launch_bounds__(256, 4)
 fused_update_kernel(const UpdateDesc* __restrict__ descs, int n_desc, int n_units, float* __restrict__ p,
                     float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* __restrict__ gstage,
@@ -382,6 +427,7 @@ fused_update_kernel(const UpdateDesc* __restrict__ descs, int n_desc, int n_unit
       const long long pb = off + (static_cast<long long>(co0) * cin + ci0) * 9;
       update_rows<288>(p + pb, g + pb, m + pb, mode != 2 ? v + pb : v, cin * 9, tile, y, mode);
       __syncthreads();
+      if (unit + static_cast<int>(gridDim.x) < n_units) prefetch_unit(descs, begins, n_desc, unit + gridDim.x, p, m, v, gstage, mode);
       // packed copies, eight bf16 (16 bytes) per store: Wf[co][tap][ci0 + 8 q ..], Wd[ci][8 - tap][co0 + 8 q ..]
       for (int i = threadIdx.x; i < 32 * 9 * 4; i += blockDim.x) {
         const int q = i & 3, rt = i >> 2;
@@ -414,6 +460,7 @@ fused_update_kernel(const UpdateDesc* __restrict__ descs, int n_desc, int n_unit
       const long long pb = off + (static_cast<long long>(ci0) * cout + co0) * 4;
       update_rows<128>(p + pb, g + pb, m + pb, mode != 2 ? v + pb : v, cout * 4, tile, y, mode);
       __syncthreads();
+      if (unit + static_cast<int>(gridDim.x) < n_units) prefetch_unit(descs, begins, n_desc, unit + gridDim.x, p, m, v, gstage, mode);
       // Wt[tap][co][ci0 + 8 q ..] and Wtd[ci][tap][co0 + 8 q ..], 16 bytes per store
       for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) {
         const int q = i & 3, ct = i >> 2;      // ct = c * 4 + tap
@@ -463,7 +510,10 @@ int fused_update(const void* descs, int n_desc, int n_blocks, int max_blocks, fl
                     reinterpret_cast<uintptr_t>(v)) & 15) == 0, "fused_update: buffers must be 16-byte aligned");
   // max_blocks > 0: a bounded grid that walks the work units (a launch that runs beside the backward pass must leave
   // the SMs' block slots to the kernels other streams wait for); 0: one block per unit
-  const int grid = (max_blocks > 0 && max_blocks < n_blocks) ? max_blocks : n_blocks;
+  // ... and at most four blocks per SM (what is resident at once): every block then walks several units and can
+  // prefetch its next one
+  int grid = (max_blocks > 0 && max_blocks < n_blocks) ? max_blocks : n_blocks;
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();
   UNETK_CHECK_ARG(n_desc <= kUpdMaxDesc, "fused_update: at most %d tensors per launch", kUpdMaxDesc);
   UNETK_CUDA(cudaFuncSetAttribute(fused_update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   fused_update_kernel<<<grid, 256, 0, s>>>(static_cast<const UpdateDesc*>(descs), n_desc, n_blocks, p, g, m, v, gstage,
