@@ -210,18 +210,24 @@ def measure_inference(torch, dist, world, rank, dev, timed):
     host_amap = torch.empty(e - b, 1, 512, 512, dtype=torch.float32).pin_memory()
     host_score = torch.empty(e - b, 512, 512, dtype=torch.float32).pin_memory()
 
-    def e2e(i):
+    def e2e_serial(i):
         amap, score = run(host.to(dev, non_blocking=True))
         host_amap.copy_(amap, non_blocking=True)
         host_score.copy_(score, non_blocking=True)
-    e2e(0)
-    ms_e2e = timed(e2e, k)
+    e2e_serial(0)
+    ms_serial = timed(e2e_serial, k)
+    # ... and through the package's entry point for that loop: utils.predict_batches pipelines copy-in, forward and
+    # copy-out over batches of the shard (two device slots, two side streams)
+    chunk = min(16, max(4, (e - b) // 4))
+    res = utils.predict_batches(m, host, chunk)
+    ms_e2e = timed(lambda i: utils.predict_batches(m, host, chunk, out=res), k)
     del m, x
     torch.cuda.empty_cache()
     return {"metric": "inference_images_per_sec_512x512", "value": total * k / (ms / 1e3), "unit": "img/s",
-            "e2e": total * k / (ms_e2e / 1e3), "ms_per_pass": ms / k,
+            "e2e": total * k / (ms_e2e / 1e3), "e2e_one_batch_serial": total * k / (ms_serial / 1e3), "ms_per_pass": ms / k,
+            "e2e_api": f"utils.predict_batches(model, pinned host images, batch_size={chunk})",
             "config": f"UNet(3,1) eval, sigmoid anomaly map + anomaly score, {total} images of 512x512 sharded {world}-way "
-                      f"({e - b} per GPU), no communication; e2e adds the H2D of the images and the D2H of both maps (pinned buffers)",
+                      f"({e - b} per GPU), no communication; e2e adds the H2D of the images and the D2H of both maps (pinned buffers), pipelined over batches by utils.predict_batches; e2e_one_batch_serial = copy in, one forward over the whole shard, copy out, on one stream",
             "e2e_h2d_bytes_per_pass": host.numel() * 4, "e2e_d2h_bytes_per_pass": (host_amap.numel() + host_score.numel()) * 4,
             "gflop_per_image": 385.34}
 

@@ -896,3 +896,35 @@ def test_fused_update_inside_train_step(cuda_device):
         assert (a - b).abs().max().item() <= 2e-6, k
         moved = max(moved, (a - sd[k]).abs().max().item())
     assert moved > 0
+
+
+@pytest.mark.parametrize("arch", ["unet", "anomaly_unet"])
+def test_predict_batches_is_the_batch_loop(cuda_device, arch):
+    """utils.predict_batches (the body of the reference's test_model loop, src/test.py:80-106, as a copy-in / compute /
+    copy-out pipeline over a host tensor) returns exactly what the batch-by-batch loop returns: ragged last batch,
+    slots reused more than once, both model kinds."""
+    from tiaozhanbei_unet_b200 import utils
+    dev = cuda_device
+    sd = O.synthetic_state_dict(arch, seed=6, device=dev)
+    m = _model(arch, {k: v.clone() for k, v in sd.items()}, dev).eval()
+    g = torch.Generator().manual_seed(21)
+    host = torch.randn(11, 3, 48, 80, generator=g)
+    got = utils.predict_batches(m, host, batch_size=3, want_reconstruction=True)
+    torch.cuda.synchronize()
+    assert got["anomaly_maps"].is_pinned() and got["anomaly_maps"].shape == (11, 1, 48, 80)
+    assert got["anomaly_scores"].shape == (11, 48, 80)
+    with torch.no_grad():
+        for b0 in range(0, 11, 3):
+            x = host[b0: b0 + 3].to(dev)
+            if arch == "anomaly_unet":
+                recon, amap = m(x)
+            else:
+                amap, recon = torch.sigmoid(m(x)), x
+            score = utils.compute_anomaly_score(recon, x)
+            assert torch.equal(got["anomaly_maps"][b0: b0 + 3], amap.cpu()), b0
+            assert torch.equal(got["anomaly_scores"][b0: b0 + 3], score.cpu()), b0
+            assert torch.equal(got["reconstructions"][b0: b0 + 3], recon.cpu()), b0
+    if arch == "unet":
+        assert float(got["anomaly_scores"].abs().max()) == 0.0       # reconstruction = images (src/test.py:93)
+    with pytest.raises(RuntimeError):
+        utils.predict_batches(m.train(), host)

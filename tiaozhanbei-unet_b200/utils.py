@@ -31,6 +31,85 @@ def compute_anomaly_score(reconstruction, original, method="mse"):
     return ops.anomaly_score(r, o, out, m)
 
 
+_predict_streams = {}
+
+
+def predict_batches(model, images, batch_size=16, method="mse", want_reconstruction=False, out=None):
+    """The per-batch body of the reference's `test_model` loop (src/test.py:80-106: `images.to(device)`, forward,
+    `sigmoid` for a plain UNet, `compute_anomaly_score`, `.cpu()` of every result) over a HOST tensor of images
+    [N, C, H, W] (pinned or not), as a three-stage pipeline: while batch k runs on the caller's stream, batch k+1 is
+    copied in and the results of batch k-1 are copied out on two side streams, through two device slots each.
+    Returns pinned host tensors {"anomaly_maps" [N, 1, H, W], "anomaly_scores" [N, H, W]} (+ "reconstructions" when
+    asked for; for a plain UNet the reference's dummy reconstruction is the input, so its score map is zero).
+    `out`: the dict of an earlier call, to be filled again (pinning the result buffers costs milliseconds).
+    The numbers are exactly those of the batch-by-batch loop (eval mode has no atomics)."""
+    from .model import AnomalyUNet
+    if model.training:
+        raise RuntimeError("predict_batches: put the model in eval() mode first")
+    if images.is_cuda or images.dim() != 4:
+        raise ValueError("predict_batches: images must be a host tensor [N, C, H, W]")
+    dev = next(model.parameters()).device
+    images = images.float().contiguous()
+    n, c, h, w = images.shape
+    batch_size = max(1, min(int(batch_size), n))
+    two = isinstance(model, AnomalyUNet)
+    shapes = {"anomaly_maps": (n, 1, h, w), "anomaly_scores": (n, h, w)}
+    if want_reconstruction:
+        shapes["reconstructions"] = (n, c, h, w)
+    if out is None:
+        out = {}
+    for key, shape in shapes.items():
+        t = out.get(key)
+        if t is None or tuple(t.shape) != shape or t.dtype != torch.float32 or t.is_cuda:
+            out[key] = torch.empty(shape, dtype=torch.float32).pin_memory()
+    with torch.cuda.device(dev), torch.no_grad():
+        main = torch.cuda.current_stream(dev)
+        if dev not in _predict_streams:
+            _predict_streams[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = _predict_streams[dev]
+        x_slot = [torch.empty(batch_size, c, h, w, dtype=torch.float32, device=dev) for _ in range(2)]
+        computed = [None, None]     # event: the forward pass that read x_slot[i] / wrote results[i] is done
+        copied_out = [None, None]   # event: results[i] have left the device
+        results = [None, None]
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        for k, b0 in enumerate(range(0, n, batch_size)):
+            i, nb = k & 1, min(batch_size, n - b0)
+            with torch.cuda.stream(s_in):
+                if computed[i] is not None:
+                    s_in.wait_event(computed[i])                 # the slot's previous batch has been consumed ...
+                    s_in.wait_event(copied_out[i])               # ... and copied out (a plain UNet's "reconstruction" IS the slot)
+                x = x_slot[i][:nb]
+                x.copy_(images[b0: b0 + nb], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(s_in)
+            main.wait_event(ready)
+            if copied_out[i] is not None:
+                main.wait_event(copied_out[i])                   # (results[i] are about to be replaced)
+            if two:
+                recon, amap = model(x)
+            else:
+                amap = torch.sigmoid(model(x))
+                recon = x
+            score = compute_anomaly_score(recon, x, method)
+            results[i] = (amap, score, recon)
+            computed[i] = torch.cuda.Event()
+            computed[i].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(computed[i])
+                out["anomaly_maps"][b0: b0 + nb].copy_(amap, non_blocking=True)
+                out["anomaly_scores"][b0: b0 + nb].copy_(score, non_blocking=True)
+                if want_reconstruction:
+                    out["reconstructions"][b0: b0 + nb].copy_(recon, non_blocking=True)
+                for t in (amap, score, recon):
+                    t.record_stream(s_out)
+                copied_out[i] = torch.cuda.Event()
+                copied_out[i].record(s_out)
+        main.wait_stream(s_out)
+        main.wait_stream(s_in)
+    return out
+
+
 def save_checkpoint(model, optimizer, epoch, loss, filepath):
     """Same four-key dict as the reference (src/utils.py:37-46)."""
     checkpoint = {
