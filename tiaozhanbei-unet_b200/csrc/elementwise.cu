@@ -6,6 +6,8 @@
 // autograd).  All tensors are NHWC bf16 with C a multiple of 8; every thread moves 16-byte
 // vectors (8 channels) and keeps its per-channel constants in registers: the grid-stride is a
 // multiple of C/8, so a thread always sees the same 8 channels.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -17,7 +19,12 @@ static inline int ew_grid(long nvec, int cgroups) {
   // total threads must be a multiple of the channel-group count (<= 256, divides 256 or is a
   // multiple of it handled by the caller's check)
   long blocks = (nvec + kEwThreads - 1) / kEwThreads;
-  const long cap = static_cast<long>(num_sms()) * 8;
+  // blocks of 256 threads per SM: half occupancy.  Stand-alone (tools/power_probe_ew.py, 64 ch @256^2) the passes run at
+  // 5.7 / 6.0 / 6.0 TB/s with 4 per SM against 5.5 / 5.7 / 5.9 with 8, at the same ~166 pJ per byte (the memory system, not
+  // the SMs, is what their energy goes to); inside the step (100 steps, five runs each way on two boxes) 4 per SM
+  // is 0.3-1 % faster: fewer resident blocks in the way of the tensor-core kernels they run beside.
+  static const int per_sm = [] { const char* e = getenv("UNETK_EW_BLOCKS_PER_SM"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 8 ? v : 4; }();
+  const long cap = static_cast<long>(num_sms()) * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   // (blocks * 256) % cgroups == 0 must hold: cgroups is a power of two <= 128 in this network, or

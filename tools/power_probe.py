@@ -92,14 +92,16 @@ def probe(name, fn, work, unit):
 
 
 log(f"# kernel families in a loop for {args.seconds:.0f} s each: burst = one call on an idle GPU, sustained = mean over the loop")
-a8 = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
-b8 = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
-probe("cuBLAS bf16 8192^3 (reference point)", lambda: torch.matmul(a8, b8), 2.0 * 8192 ** 3, "TF/s")
-del a8, b8
-src = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
-dst = torch.empty_like(src)
-probe("copy 2 GiB -> 2 GiB (reference point)", lambda: dst.copy_(src), 2.0 * src.numel() * 2, "GB/s")
-del src, dst
+ONLY_EW = os.environ.get("ONLY_EW", "0") == "1"        # tools/power_probe_ew.py: the bandwidth-bound kernels only
+if not ONLY_EW:
+    a8 = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
+    b8 = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
+    probe("cuBLAS bf16 8192^3 (reference point)", lambda: torch.matmul(a8, b8), 2.0 * 8192 ** 3, "TF/s")
+    del a8, b8
+    src = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+    dst = torch.empty_like(src)
+    probe("copy 2 GiB -> 2 GiB (reference point)", lambda: dst.copy_(src), 2.0 * src.numel() * 2, "GB/s")
+    del src, dst
 
 
 def conv_case(name, lvl, c1, c2, cout):
@@ -119,23 +121,24 @@ def conv_case(name, lvl, c1, c2, cout):
     probe(f"conv3x3_wgrad {name}", lambda: ops.conv3x3_wgrad(y, s1, s2, dw), flop, "TF/s")
 
 
-conv_case("up2.0 512->256 @64^2", 2, 256, 256, 256)
-conv_case("down3.3 512->512 @32^2", 3, 512, 0, 512)
-conv_case("up4.3 64->64 @256^2", 0, 64, 0, 64)
-conv_case("up4.0 128->64 @256^2", 0, 64, 64, 64)
-# transposed conv, the widest
-h = H >> 1
-a = bf(B, h, h, 128)
-wt = bf(4 * 64 * 128)
-bias = torch.zeros(64, device=dev)
-up = torch.empty(B, 2 * h, 2 * h, 64, dtype=torch.bfloat16, device=dev)
-da = torch.empty_like(a)
-dwt = torch.zeros(64 * 4 * 128, device=dev)
-fl = 2.0 * B * h * h * 128 * 4 * 64
-probe("convt2x2_fwd   up4 128->64", lambda: ops.convt2x2_fwd(a, wt, bias, up), fl, "TF/s")
-probe("convt2x2_dgrad up4", lambda: ops.convt2x2_dgrad(up, wt, da), fl, "TF/s")
-probe("convt2x2_wgrad up4", lambda: ops.convt2x2_wgrad(a, up, dwt), fl, "TF/s")
-del a, up, da
+if not ONLY_EW:
+    conv_case("up2.0 512->256 @64^2", 2, 256, 256, 256)
+    conv_case("down3.3 512->512 @32^2", 3, 512, 0, 512)
+    conv_case("up4.3 64->64 @256^2", 0, 64, 0, 64)
+    conv_case("up4.0 128->64 @256^2", 0, 64, 64, 64)
+    # transposed conv, the widest
+    h = H >> 1
+    a = bf(B, h, h, 128)
+    wt = bf(4 * 64 * 128)
+    bias = torch.zeros(64, device=dev)
+    up = torch.empty(B, 2 * h, 2 * h, 64, dtype=torch.bfloat16, device=dev)
+    da = torch.empty_like(a)
+    dwt = torch.zeros(64 * 4 * 128, device=dev)
+    fl = 2.0 * B * h * h * 128 * 4 * 64
+    probe("convt2x2_fwd   up4 128->64", lambda: ops.convt2x2_fwd(a, wt, bias, up), fl, "TF/s")
+    probe("convt2x2_dgrad up4", lambda: ops.convt2x2_dgrad(up, wt, da), fl, "TF/s")
+    probe("convt2x2_wgrad up4", lambda: ops.convt2x2_wgrad(a, up, dwt), fl, "TF/s")
+    del a, up, da
 # bandwidth kernels at full resolution
 y = bf(B, H, H, 64)
 act = torch.empty_like(y)
@@ -148,6 +151,8 @@ probe("bnrelu_apply 64ch @256^2", lambda: ops.bnrelu_apply(y, sc, sh, act), 2.0 
 probe("bn_bwd_reduce", lambda: ops.bn_bwd_reduce(act, y, sc, sh, sh, sc, sums), 2.0 * nb, "GB/s")
 probe("bn_bwd_apply", lambda: ops.bn_bwd_apply(act, y, sc, sh, sh, sc, sums, dy, dg, db), 3.0 * nb, "GB/s")
 del y, act, dy
+if ONLY_EW:
+    sys.exit(0)
 # whole step
 torch.manual_seed(42)
 m = AnomalyUNet(3).to(dev).train()
