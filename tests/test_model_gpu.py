@@ -208,9 +208,12 @@ def test_loss_kernels_match_reference_golden(cuda_device):
     torch.testing.assert_close(b2.grad, b3.grad, rtol=2e-3, atol=2e-8)
 
 
-def test_loss_curve_tracks_oracle(cuda_device):
+@pytest.mark.parametrize("fused", [False, True])
+def test_loss_curve_tracks_oracle(cuda_device, fused):
     """100 Adam steps from identical weights on fresh seeded batches: loss curves within 1 % (the bound
-    BASELINE.json's north star states)."""
+    BASELINE.json's north star states) -- through model(x) / criterion / backward / optimizer.step() called one by
+    one, and through train_utils.train_step (what train_epoch and bench.py run: one launch sequence with the
+    optimizer step inside the backward pass)."""
     from tiaozhanbei_unet_b200 import train_utils
     dev = cuda_device
     arch = "anomaly_unet"
@@ -225,16 +228,22 @@ def test_loss_curve_tracks_oracle(cuda_device):
     for step in range(1, 101):
         image = torch.randn(4, 3, 32, 32, generator=g).to(dev)
         mask = (torch.rand(4, 1, 32, 32, generator=g) > 0.95).float().to(dev)
-        r, a = m(image)
-        ld = crit(r, a, image, mask)
-        opt.zero_grad()
-        ld["total_loss"].backward()
-        opt.step()
+        if fused:
+            assert train_utils._fusable(m, crit, image, mask)
+            train_utils.train_step(m, crit, opt, image, mask)
+        else:
+            r, a = m(image)
+            ld = crit(r, a, image, mask)
+            opt.zero_grad()
+            ld["total_loss"].backward()
+            opt.step()
         ours.append(crit.last_values()[0])
         rl, _ = O.train_step(ref_sd, image, mask, arch=arch, opt_state=opt_state, step=step)
         refs.append(rl["total_loss"])
     worst = max(abs(a - b) / abs(b) for a, b in zip(ours, refs))
-    print(f"[parity] loss curve worst rel dev {worst:.3e}; first/last ours {ours[0]:.5f}/{ours[-1]:.5f} ref {refs[0]:.5f}/{refs[-1]:.5f}")
+    if fused:
+        assert m._engine().gstage_zero and float(opt.state_dict()["state"][0]["step"]) == 100.0
+    print(f"[parity] loss curve ({'train_step' if fused else 'plain'}) worst rel dev {worst:.3e}; first/last ours {ours[0]:.5f}/{ours[-1]:.5f} ref {refs[0]:.5f}/{refs[-1]:.5f}")
     assert worst <= 1e-2
 
 
