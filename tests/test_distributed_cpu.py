@@ -76,11 +76,19 @@ def _worker(rank, world, port, ret):
         mine = eng.gstage.clone()
         red = GradReducer()
         # same order as Engine.backward: decoders in reverse, then the two encoder halves
+        seen = {}
         for tag in (("dec", 1), ("dec", 0), ("enc", 3), ("enc", 0)):
-            red.segment_ready(eng, tag)
+            # then(): what consumes the reduced bucket (the fused parameter update) runs behind its all-reduce
+            a, b = red._segments(eng)[tag]
+            red.segment_ready(eng, tag, then=(lambda tag=tag, a=a, b=b: seen.__setitem__(tag, eng.gstage[a:b].clone()))
+                              if tag[0] == "enc" else None)
         scale = red.finish(eng)
         others = [torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
         expect = sum(others) / world
+        for tag, got in seen.items():
+            a, b = red._segments(eng)[tag]
+            assert torch.allclose(got * scale, expect[a:b], atol=1e-6), tag       # saw the REDUCED bucket
+        assert set(seen) == {("enc", 3), ("enc", 0)}
         ok = torch.allclose(eng.gstage * scale, expect, atol=1e-6) and abs(scale - 1.0 / world) < 1e-12
         ok = ok and red.bytes_reduced == total * 4 and not torch.equal(mine, eng.gstage)
         ret[rank] = bool(ok)

@@ -120,6 +120,52 @@ def test_no_cpu_fallback():
     assert isinstance(Up(128, 64, bilinear=True).up, torch.nn.Upsample)      # parameter-free up-sampling branch
 
 
+def test_fused_update_args_host_logic():
+    """optim.FusedOptimizer.fused_update_args (what Engine.train_step(update=...) is handed): the nine hyper-parameter
+    floats are the ones unetk_adam_step derives (float arguments, double bias corrections), the step count advances
+    like step() and rolls back, the moment buffers are the flat ones behind a torch-shaped state_dict; an optimizer
+    that does not own exactly the engine's parameters gets None.  Host logic only: a stand-in engine on the CPU."""
+    import math
+    import types
+    from tiaozhanbei_unet_b200.optim import FusedOptimizer
+    flat = torch.zeros(192)
+    names = ["a.weight", "a.bias"]
+    offsets = {"a.weight": 0, "a.bias": 128}
+    params = []
+    for k, shape in (("a.weight", (8, 12)), ("a.bias", (8,))):
+        p = torch.nn.Parameter(torch.zeros(shape))
+        n = p.numel()
+        p.data = flat[offsets[k]: offsets[k] + n].view(shape)
+        params.append(p)
+    eng = types.SimpleNamespace(flat_p=flat, params=params, param_names=names, offsets=offsets, total=192)
+    opt = FusedOptimizer(params, "adam", lr=3e-3, weight_decay=1e-2, engine=eng)
+    u = opt.fused_update_args(eng)
+    assert u is not None and u.mode == 0 and u.m.numel() == 192 and u.v.numel() == 192
+    f32 = lambda x: float(np.float32(x))
+    b1, b2 = f32(0.9), f32(0.999)
+    want = [f32(3e-3), b1, b2, f32(1e-8), f32(1e-2), f32(1.0 - math.pow(b1, 1)), f32(math.sqrt(1.0 - math.pow(b2, 1))), 1.0, 1.0]
+    assert u.values == want
+    sd = opt.state_dict()
+    assert float(sd["state"][0]["step"]) == 1.0 and sd["state"][1]["exp_avg"].shape == (8,)
+    assert opt.state[params[0]]["exp_avg"].data_ptr() == u.m.data_ptr()          # views of the flat buffer
+    u2 = opt.fused_update_args(eng)
+    assert u2.values[7] == 0.0 and u2.values[5] == f32(1.0 - math.pow(b1, 2)) and float(opt.state_dict()["state"][0]["step"]) == 2.0
+    u2.rollback()
+    assert float(opt.state_dict()["state"][0]["step"]) == 1.0
+    opt.param_groups[0]["lr"] = 1e-4
+    assert opt.fused_update_args(eng).values[0] == f32(1e-4)
+    # SGD: momentum in the beta1 slot, first-step flag from the missing momentum buffer
+    sgd = FusedOptimizer(params, "sgd", lr=0.1, weight_decay=0.0, engine=eng)
+    us = sgd.fused_update_args(eng)
+    assert us.mode == 2 and us.v is None and us.values[1] == f32(0.9) and us.values[7] == 1.0
+    assert sgd.fused_update_args(eng).values[7] == 0.0
+    # not this engine's parameters / another engine / two parameter groups: no fused update
+    assert FusedOptimizer(params[:1], "adam", 1e-3, 0.0, engine=eng).fused_update_args(eng) is None
+    assert opt.fused_update_args(types.SimpleNamespace(flat_p=flat)) is None
+    two = FusedOptimizer([{"params": params[:1]}, {"params": params[1:]}], "adam", 1e-3, 0.0, engine=eng)
+    assert two.fused_update_args(eng) is None
+
+
 def test_optimizer_state_dict_is_torch_shaped():
     from tiaozhanbei_unet_b200 import train_utils
     lin = torch.nn.Linear(4, 3)

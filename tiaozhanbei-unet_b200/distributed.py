@@ -63,6 +63,7 @@ class GradReducer:
         self.works = []
         self.segments = None
         self.bytes_reduced = 0
+        self.tail = None          # event behind the launches segment_ready(then=...) put on the reducer's stream
 
     def _segments(self, eng):
         if self.segments is None or self._total != eng.total:
@@ -112,7 +113,7 @@ class GradReducer:
         for w in self.works:
             w.wait()
         self.works = []
-        if getattr(self, "tail", None) is not None:      # launches enqueued behind the all-reduces (segment_ready(then=...))
+        if self.tail is not None:      # launches enqueued behind the all-reduces (segment_ready(then=...))
             torch.cuda.current_stream(eng.gstage.device).wait_event(self.tail)
             self.tail = None
         return 1.0 / self.world

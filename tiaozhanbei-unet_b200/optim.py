@@ -18,11 +18,12 @@ _MODE = {"adam": 0, "adamw": 1, "sgd": 2}
 
 class _FusedUpdate:
     """m / v: flat moment buffers laid out like the engine's flat parameter buffer; values: the nine floats of
-    unetk_fused_update's hyper[] (index 8, the gradient scale, is filled in by the engine)."""
-    __slots__ = ("m", "v", "mode", "values")
+    unetk_fused_update's hyper[] (index 8, the gradient scale, is filled in by the engine); rollback(): undo the
+    step count this update was handed out with (the launch sequence it was meant for raised)."""
+    __slots__ = ("m", "v", "mode", "values", "rollback")
 
-    def __init__(self, m, v, mode, values):
-        self.m, self.v, self.mode, self.values = m, v, mode, values
+    def __init__(self, m, v, mode, values, rollback=lambda: None):
+        self.m, self.v, self.mode, self.values, self.rollback = m, v, mode, values, rollback
 
 
 class FusedOptimizer(torch.optim.Optimizer):
@@ -115,16 +116,21 @@ class FusedOptimizer(torch.optim.Optimizer):
             values = [lr, mom, 0.0, 0.0, wd, f32(1.0 - math.pow(mom, step)), 1.0, float(first), 1.0]
             return _FusedUpdate(self._flat[0], None, 2, values)
         states = [self.state[p] for p in eng.params]
+        old_steps = [st.get("step") for st in states]
         step = self._step_of(states[0]) + 1
         t = torch.tensor(float(step), dtype=torch.float32)
         for st in states:
             st["step"] = t
+
+        def rollback():
+            for st, old in zip(states, old_steps):
+                st["step"] = old
         b1, b2 = (f32(b) for b in group["betas"])
         # the same double-precision bias corrections unetk_adam_step derives from its float arguments
         bc1 = f32(1.0 - math.pow(b1, step))
         bc2_sqrt = f32(math.sqrt(1.0 - math.pow(b2, step)))
         values = [lr, b1, b2, f32(group["eps"]), wd, bc1, bc2_sqrt, float(step == 1), 1.0]
-        return _FusedUpdate(self._flat[0], self._flat[1], _MODE[self.kind], values)
+        return _FusedUpdate(self._flat[0], self._flat[1], _MODE[self.kind], values, rollback)
 
     # -- step ------------------------------------------------------------------------------------
     @torch.no_grad()

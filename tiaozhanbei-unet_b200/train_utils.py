@@ -309,8 +309,13 @@ def train_step(model, criterion, optimizer, images, masks):
             eng.ensure(images.device)
             update = optimizer.fused_update_args(eng)
         optimizer.zero_grad()
-        out3, _ = eng.train_step(images, masks, (criterion.recon_weight, criterion.seg_weight,
-                                                 criterion.focal_alpha, criterion.focal_gamma), update=update)
+        try:
+            out3, _ = eng.train_step(images, masks, (criterion.recon_weight, criterion.seg_weight,
+                                                     criterion.focal_alpha, criterion.focal_gamma), update=update)
+        except BaseException:
+            if update is not None:
+                update.rollback()       # the optimizer step that was handed out did not run
+            raise
         criterion._last = out3
         if update is None:
             optimizer.step()
