@@ -849,30 +849,37 @@ def test_fused_update_is_the_unfused_sequence(cuda_device, kind):
         assert float(sa["state"][0]["step"]) == float(sb["state"][0]["step"]) == 2.0
 
 
-def test_fused_update_inside_train_step(cuda_device):
+@pytest.mark.parametrize("kind,bilinear,shape", [("adam", False, (2, 32, 48)), ("adamw", True, (2, 32, 32)), ("sgd", False, (1, 36, 52))])
+def test_fused_update_inside_train_step(cuda_device, kind, bilinear, shape):
     """train_utils.train_step with this package's optimizer: the optimizer step runs inside the backward pass
     (Engine.train_step(update=...)).  Deterministic invariants after eager, captured and replayed steps: the packed
     bf16 weights the next step will read are exactly pack(current fp32 weights), the staging buffer is zero, the
     step count advances, a learning-rate change and weights written by torch code in between (load_state_dict)
-    are picked up; and the trajectory agrees with the separate optimizer.step() path like two runs of one path do."""
+    are picked up; and the trajectory agrees with the separate optimizer.step() path like two runs of one path do.
+    Adam / AdamW / SGD; transposed-conv and bilinear (parameter-free up-sampling) decoders; an input size that is not
+    a multiple of 16 (serial decoder chains in backward)."""
     from tiaozhanbei_unet_b200 import train_utils
+    from tiaozhanbei_unet_b200.model import AnomalyUNet
     dev = cuda_device
     arch = "anomaly_unet"
-    sd = O.synthetic_state_dict(arch, seed=12, device=dev)
-    batches = [_inputs(70 + i, 2, 32, 48, dev) for i in range(5)]
+    sd = O.synthetic_state_dict(arch, seed=12, device=dev, bilinear=bilinear)
+    batches = [_inputs(70 + i, *shape, dev) for i in range(5)]
+    lr = 1e-7 if kind != "sgd" else 1e-9        # (SGD moves a weight by lr * gradient, Adam by ~lr)
 
     def run(fused_update):
         old = train_utils.FUSED_UPDATE
         train_utils.FUSED_UPDATE = fused_update
         try:
-            m = _model(arch, {k: v.clone() for k, v in sd.items()}, dev).train()
+            m = AnomalyUNet(3, bilinear=bilinear)
+            m.load_state_dict({k: v.clone() for k, v in sd.items()})
+            m = m.to(dev).train()
             crit = train_utils.CombinedLoss()
-            opt = train_utils.get_optimizer(m, "adam", 1e-7, 1e-4)
+            opt = train_utils.get_optimizer(m, kind, lr, 1e-4)
             eng = m._engine()
             losses = []
             for i, (image, mask) in enumerate(batches):
                 if i == 3:
-                    opt.param_groups[0]["lr"] = 2e-7
+                    opt.param_groups[0]["lr"] = 2 * lr
                     m.load_state_dict({k: v.clone() for k, v in sd.items()})      # torch writes the weights in place
                 ld = train_utils.train_step(m, crit, opt, image, mask)
                 losses.append(float(ld["total_loss"]))
@@ -888,7 +895,8 @@ def test_fused_update_inside_train_step(cuda_device):
                     assert all(p.grad is not None and p.grad.data_ptr() == eng.flat_g.data_ptr() + 4 * eng.offsets[k]
                                for k, p in zip(eng.param_names, eng.params))
             torch.cuda.synchronize()
-            assert float(opt.state_dict()["state"][0]["step"]) == len(batches)
+            if kind != "sgd":
+                assert float(opt.state_dict()["state"][0]["step"]) == len(batches)
             return m, losses
         finally:
             train_utils.FUSED_UPDATE = old
