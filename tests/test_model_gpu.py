@@ -23,6 +23,7 @@ tests/test_ops_gpu.py).  Hence, against the fp32 reference numbers:
 import os
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -945,3 +946,50 @@ def test_predict_batches_is_the_batch_loop(cuda_device, arch):
         assert float(got["anomaly_scores"].abs().max()) == 0.0       # reconstruction = images (src/test.py:93)
     with pytest.raises(RuntimeError):
         utils.predict_batches(m.train(), host)
+
+
+def test_train_validate_train_cycle(cuda_device):
+    """The loops of src/train.py:229-244 back to back: train_epoch (fused step, optimizer inside it) -> validate_epoch
+    (eval forward: must read the weights the last in-step update packed) -> train_epoch again.  The eval outputs after
+    training equal those of a FRESH model loaded from the trained state_dict bit for bit (eval mode has no atomics), so
+    the packed bf16 copies left behind by the fused update are exactly what a re-pack of the fp32 weights gives; the
+    second epoch continues from the first one's optimizer state."""
+    from tiaozhanbei_unet_b200 import train_utils
+    from tiaozhanbei_unet_b200.model import AnomalyUNet
+    dev = cuda_device
+    sd = O.synthetic_state_dict("anomaly_unet", seed=15, device=dev)
+    m = _model("anomaly_unet", {k: v.clone() for k, v in sd.items()}, dev)
+    crit = train_utils.CombinedLoss()
+    opt = train_utils.get_optimizer(m, "adam", 1e-4, 1e-4)
+    g = torch.Generator().manual_seed(3)
+
+    def batches(n, bs):
+        out = []
+        for i in range(n):
+            image = torch.randn(bs, 3, 32, 48, generator=g)
+            mask = (torch.rand(bs, 1, 32, 48, generator=g) > 0.9).float()
+            # (label 0 everywhere: with mixed labels the reference's validate_epoch ends in a ValueError, src/train_utils.py:216-219,
+            #  which this package reproduces -- tests/test_eval_gpu.py)
+            out.append({"image": image, "mask": mask, "label": torch.zeros(bs, dtype=torch.int64)})
+        return out
+
+    train_a, val, train_b = batches(4, 2), batches(2, 3), batches(3, 2)
+    r1 = train_utils.train_epoch(m, train_a, crit, opt, dev, 0)
+    eng = m._engine()
+    assert eng.gstage_zero and not eng.weights_dirty and float(opt.state_dict()["state"][0]["step"]) == 4.0
+    v1 = train_utils.validate_epoch(m, val, crit, dev)
+    assert not m.training and np.isfinite(v1["total_loss"])
+    # a fresh model with the trained weights gives the same evaluation outputs, bit for bit
+    fresh = AnomalyUNet(3)
+    fresh.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    fresh = fresh.to(dev).eval()
+    x = val[0]["image"].to(dev)
+    with torch.no_grad():
+        ra, aa = m(x)
+        rb, ab = fresh(x)
+    assert torch.equal(ra, rb) and torch.equal(aa, ab), "eval after the in-step update read stale packed weights"
+    r2 = train_utils.train_epoch(m, train_b, crit, opt, dev, 1)
+    torch.cuda.synchronize()
+    assert m.training and float(opt.state_dict()["state"][0]["step"]) == 7.0
+    assert all(np.isfinite(v) for v in list(r1.values()) + list(r2.values()))
+    assert eng.gstage_zero and not eng.gstage.any()
