@@ -993,3 +993,44 @@ def test_train_validate_train_cycle(cuda_device):
     assert m.training and float(opt.state_dict()["state"][0]["step"]) == 7.0
     assert all(np.isfinite(v) for v in list(r1.values()) + list(r2.values()))
     assert eng.gstage_zero and not eng.gstage.any()
+
+
+def test_checkpoint_resume_with_the_in_step_optimizer(cuda_device, tmp_path):
+    """save_checkpoint / load_checkpoint (src/utils.py:37-58) around fused training steps: the optimizer state the
+    in-step update keeps in flat buffers is what state_dict() writes; a new model + optimizer that loads the checkpoint
+    continues exactly where the first one stood (same moments, same step count), and the next fused step of both moves
+    the weights alike."""
+    from tiaozhanbei_unet_b200 import train_utils, utils
+    dev = cuda_device
+    sd = O.synthetic_state_dict("anomaly_unet", seed=18, device=dev)
+    batches = [_inputs(90 + i, 2, 32, 32, dev) for i in range(3)]
+    m1 = _model("anomaly_unet", {k: v.clone() for k, v in sd.items()}, dev).train()
+    crit = train_utils.CombinedLoss()
+    o1 = train_utils.get_optimizer(m1, "adam", 1e-6, 1e-4)
+    for image, mask in batches[:2]:
+        train_utils.train_step(m1, crit, o1, image, mask)
+    torch.cuda.synchronize()
+    path = str(tmp_path / "ckpt.pth")
+    utils.save_checkpoint(m1, o1, 2, 0.5, path)
+    m2 = _model("anomaly_unet", {k: v.clone() for k, v in sd.items()}, dev).train()
+    o2 = train_utils.get_optimizer(m2, "adam", 1e-3, 0.0)            # (hyper-parameters come back from the checkpoint)
+    epoch, loss = utils.load_checkpoint(m2, o2, path, dev)
+    assert (epoch, loss) == (2, 0.5) and o2.param_groups[0]["lr"] == 1e-6 and o2.param_groups[0]["weight_decay"] == 1e-4
+    s1, s2 = o1.state_dict()["state"], o2.state_dict()["state"]
+    assert len(s1) == len(s2) == 98
+    for i in s1:
+        assert float(s1[i]["step"]) == float(s2[i]["step"]) == 2.0
+        assert torch.equal(s1[i]["exp_avg"], s2[i]["exp_avg"].to(dev)) and torch.equal(s1[i]["exp_avg_sq"], s2[i]["exp_avg_sq"].to(dev))
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    image, mask = batches[2]
+    l1 = train_utils.train_step(m1, crit, o1, image, mask)
+    l2 = train_utils.train_step(m2, crit, o2, image, mask)
+    torch.cuda.synchronize()
+    assert abs(float(l1["total_loss"]) - float(l2["total_loss"])) <= 5e-4 * abs(float(l1["total_loss"]))
+    assert float(o1.state_dict()["state"][0]["step"]) == float(o2.state_dict()["state"][0]["step"]) == 3.0
+    e2 = m2._engine()
+    assert e2.gstage_zero and o2.state[e2.params[0]]["exp_avg"].data_ptr() == o2._flat[0].data_ptr()     # moved into the flat buffers
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        # one Adam step of 1e-6 each, from identical weights and moments: at most the sign of a few updates differs
+        assert (a - b).abs().max().item() <= 2.5e-6, k
