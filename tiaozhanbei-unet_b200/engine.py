@@ -12,6 +12,12 @@ kernels declared in include/unetk.h, in a fixed order on torch's current stream:
                     pool backward read-modify-write); weight gradients are staged in
                     [Cout][tap][Cin] and re-laid-out to the reference layouts by one launch.
 
+  train_step        forward, CombinedLoss, backward and (with this package's optimizer) the optimizer step as
+                    ONE captured launch sequence: the heads compute their loss term and their own backward in one
+                    kernel, and every parameter segment is un-packed, updated and re-packed by one kernel as soon
+                    as its gradients are final (unetk_fused_update), so that two consecutive steps have nothing
+                    between them.
+
 Parameters stay `nn.Parameter`s under the reference's attribute paths (state_dict identical);
 their storage is re-pointed to slices of ONE flat fp32 buffer so the optimizer step, the weight
 re-packing, the gradient un-packing and the data-parallel all-reduce are each one launch / one

@@ -6,6 +6,10 @@ vice versa — but whose step is ONE launch of unetk_adam_step over the model's 
 
 If the parameters are not (or no longer) views of an engine's flat buffer, or some gradients are
 missing, the same kernel is launched once per tensor instead.  There is no torch-op fallback.
+
+Inside train_utils.train_step (AnomalyUNet + CombinedLoss) step() is not called at all: fused_update_args()
+hands the engine the flat moment buffers and this step's hyper-parameters, and the update runs inside the
+backward pass, segment by segment (Engine.train_step(update=...), unetk_fused_update).
 """
 from __future__ import annotations
 
