@@ -1033,4 +1033,5 @@ def test_checkpoint_resume_with_the_in_step_optimizer(cuda_device, tmp_path):
     assert e2.gstage_zero and o2.state[e2.params[0]]["exp_avg"].data_ptr() == o2._flat[0].data_ptr()     # moved into the flat buffers
     for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         # one Adam step of 1e-6 each, from identical weights and moments: at most the sign of a few updates differs
-        assert (a - b).abs().max().item() <= 2.5e-6, k
+        # (|update| <= ~lr each; a checkpoint that failed to restore lr = 1e-6 or the moments would show as >= 1e-4)
+        assert (a - b).abs().max().item() <= 5e-6, k
